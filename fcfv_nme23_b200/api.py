@@ -1,0 +1,426 @@
+"""Host-side mirror of the reference's operator interface for the ported path.
+
+Same function names, argument order and meaning as the exported Julia functions
+(src/FCFV_NME23.jl:13,17):
+
+    ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τr, Formulation)
+    ElementAssemblyLoop / ElementAssemblyLoopNEW(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation)
+    ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, Formulation)
+
+Every floating-point operation happens in ``libfcfv_b200.so`` on the GPU (``lib.py``); this module
+only marshals arrays (NumPy, order='F' like Julia) and wraps results (SciPy CSC matrices with
+int64 indices play ``SparseMatrixCSC{Float64,Int64}``).  It is what ``julia/FCFV_B200.jl`` does
+with ``ccall``.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _L
+
+__all__ = [
+    "Handle", "handle_for", "mesh_geometry", "ComputeFCFV", "ElementAssemblyLoop", "ElementAssemblyLoopNEW",
+    "ComputeResidualsFCFV_Stokes_o1", "ph_residual", "ph_update_p", "ph_fusc", "formulation_id",
+]
+
+_FORMS = {"Gradient": _L.GRADIENT, "SymmetricGradient": _L.SYMMETRIC_GRADIENT}
+_TAU_MODES = {"REFERENCE": _L.TAU_REFERENCE, "FACE": _L.TAU_FACE}
+A_DEFAULT = 1.0   # module-level constant `A = 1.0` of src/DiscretisationFCFV_Stokes.jl:1-2
+
+
+def formulation_id(Formulation):
+    name = str(Formulation).lstrip(":")
+    if name not in _FORMS:
+        raise ValueError(f"Formulation must be :Gradient or :SymmetricGradient, got {Formulation!r}")
+    return _FORMS[name]
+
+
+class _Arg:
+    """Keeps the converted array alive for the duration of a call and yields its address."""
+
+    def __init__(self):
+        self.keep = []
+
+    def d(self, a, n=None):       # float64 input
+        return self._conv(a, np.float64, n)
+
+    def i(self, a, n=None):       # int64 input
+        return self._conv(a, np.int64, n)
+
+    def u8(self, a, n=None):
+        return self._conv(a, np.uint8, n)
+
+    def _conv(self, a, dtype, n):
+        if a is None:
+            return None
+        if isinstance(a, int):
+            return C.c_void_p(a)
+        if hasattr(a, "data_ptr"):   # torch tensor (host or device); caller guarantees layout
+            if n is not None and a.numel() < n:
+                raise ValueError(f"array has {a.numel()} entries, need {n}")
+            self.keep.append(a)
+            return C.c_void_p(a.data_ptr())
+        arr = np.asarray(a, dtype=dtype)
+        if arr.ndim > 1:
+            arr = np.asfortranarray(arr)
+            flat = arr.reshape(-1, order="F")
+        else:
+            flat = np.ascontiguousarray(arr)
+        if n is not None and flat.size < n:
+            raise ValueError(f"array has {flat.size} entries, need {n}")
+        self.keep.append(flat)
+        return C.c_void_p(flat.ctypes.data)
+
+
+def _out(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Handle:
+    """One GPU, one stream, all device-resident state (``fcfv_t``)."""
+
+    def __init__(self, device=0):
+        self.lib = _L.load()
+        self._h = C.c_void_p()
+        rc = self.lib.fcfv_create(C.byref(self._h), int(device))
+        if rc != _L.FCFV_OK:
+            raise _L.FCFVError(f"fcfv_create(device={device}) failed with status {rc}: no usable CUDA device "
+                               "(this library has no CPU fallback)")
+        self.device = int(device)
+        self.nel = self.nf = 0
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.fcfv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != _L.FCFV_OK:
+            raise _L.FCFVError(f"status {rc}: {self.lib.fcfv_last_error(self._h).decode()}")
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.fcfv_kernel_launches(self._h))
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.fcfv_device_bytes(self._h))
+
+    @property
+    def stream(self):
+        return self.lib.fcfv_stream(self._h)
+
+    def set_async(self, flag):
+        self.check(self.lib.fcfv_set_async(self._h, int(bool(flag))))
+
+    def sync(self):
+        self.check(self.lib.fcfv_sync(self._h))
+
+    # -- mesh ---------------------------------------------------------------------------------
+    def set_mesh(self, mesh):
+        a = _Arg()
+        nel, nf = int(mesh.nel), int(mesh.nf)
+        taue = mesh.τe if mesh.τe is not None else np.zeros(nel)
+        ntaue = int(np.size(taue)) if not hasattr(taue, "numel") else int(taue.numel())
+        self.check(self.lib.fcfv_set_mesh(
+            self._h, nel, nf, a.i(mesh.e2f, 3 * nel), a.i(mesh.bc, nf), a.d(mesh.Ω, nel), a.d(mesh.n_x, 3 * nel),
+            a.d(mesh.n_y, 3 * nel), a.d(mesh.Γ, 3 * nel), a.d(mesh.ke, nel), a.d(mesh.δ, nel), a.d(taue, nel), ntaue))
+        self.nel, self.nf = nel, nf
+        if mesh.τ is not None:
+            self.update_fields(tau=mesh.τ)
+        if getattr(mesh, "elem_owned", None) is not None or getattr(mesh, "face_owned", None) is not None:
+            self.set_ownership(mesh.elem_owned, mesh.face_owned, getattr(mesh, "nel_global", 0),
+                               getattr(mesh, "nf_global", 0), getattr(mesh, "tau_ref", None))
+
+    def update_fields(self, ke=None, delta=None, taue=None, tau=None):
+        a = _Arg()
+        nt = 0 if taue is None else int(np.size(taue))
+        self.check(self.lib.fcfv_update_fields(self._h, a.d(ke, self.nel), a.d(delta, self.nel), a.d(taue, self.nel),
+                                               nt, a.d(tau, self.nf)))
+
+    def set_ownership(self, elem_owned, face_owned, nel_global=0, nf_global=0, tau_ref=None):
+        a = _Arg()
+        self.check(self.lib.fcfv_set_ownership(self._h, a.u8(elem_owned, self.nel), a.u8(face_owned, self.nf),
+                                               int(nel_global or 0), int(nf_global or 0), a.d(tau_ref, self.nel)))
+
+    def geometry(self, nel, nf, nv, e2v, e2f, xv, yv, xf, yf, numbering, tau_r, tau=None):
+        a = _Arg()
+        Om, xc, yc = np.empty(nel), np.empty(nel), np.empty(nel)
+        nx, ny, G = (np.empty((nel, 3), order="F") for _ in range(3))
+        tau = np.zeros(nf) if tau is None else np.array(tau, dtype=np.float64)
+        self.check(self.lib.fcfv_geometry(self._h, nel, nf, nv, a.i(e2v, 3 * nel), a.i(e2f, 3 * nel), a.d(xv, nv), a.d(yv, nv),
+                                          a.d(xf, nf), a.d(yf, nf), int(numbering), float(tau_r), _out(Om), _out(xc), _out(yc),
+                                          _out(nx), _out(ny), _out(G), _out(tau)))
+        return Om, xc, yc, nx, ny, G, tau
+
+    # -- device-resident pipeline -------------------------------------------------------------
+    def set_sources(self, sex, sey):
+        a = _Arg()
+        self.check(self.lib.fcfv_set_sources(self._h, a.d(sex, self.nel), a.d(sey, self.nel)))
+
+    def set_face_data(self, VxDir=None, VyDir=None, sxx=None, syy=None, sxy=None, syx=None):
+        a = _Arg()
+        self.check(self.lib.fcfv_set_face_data(self._h, *[a.d(x, self.nf) for x in (VxDir, VyDir, sxx, syy, sxy, syx)]))
+
+    def set_solution(self, Vxh, Vyh, Pe):
+        a = _Arg()
+        self.check(self.lib.fcfv_set_solution(self._h, a.d(Vxh, self.nf), a.d(Vyh, self.nf), a.d(Pe, self.nel)))
+
+    def set_local(self, alpha, beta, Z):
+        a = _Arg()
+        self.check(self.lib.fcfv_set_local(self._h, a.d(alpha, self.nel), a.d(beta, 2 * self.nel), a.d(Z, 4 * self.nel)))
+
+    def run_local(self, formulation, A=A_DEFAULT):
+        self.check(self.lib.fcfv_run_local(self._h, formulation_id(formulation), float(A)))
+
+    def run_assemble(self, variant, formulation, A=A_DEFAULT, want_muu=False):
+        self.check(self.lib.fcfv_run_assemble(self._h, int(variant), formulation_id(formulation), float(A), int(bool(want_muu))))
+
+    def run_residuals(self, formulation, tau_mode="REFERENCE", fetch=True):
+        if not fetch:
+            self.check(self.lib.fcfv_run_residuals(self._h, formulation_id(formulation), _TAU_MODES[tau_mode], None, None))
+            return None
+        ss, nrm = np.zeros(6), np.zeros(6)
+        self.check(self.lib.fcfv_run_residuals(self._h, formulation_id(formulation), _TAU_MODES[tau_mode], _out(ss), _out(nrm)))
+        return ss, nrm
+
+    def get_local(self, tau=True):
+        nel, nf = self.nel, self.nf
+        al, be, Z = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")
+        t = np.empty(nf) if tau else None
+        self.check(self.lib.fcfv_get_local(self._h, _out(al), _out(be), _out(Z), _out(t)))
+        return al, be, Z, t
+
+    def get_nnz(self):
+        v = [C.c_int64(0) for _ in range(3)]
+        self.check(self.lib.fcfv_get_nnz(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    # -- export -------------------------------------------------------------------------------
+    def block_size(self, block):
+        v = [C.c_int64(0) for _ in range(3)]
+        self.check(self.lib.fcfv_block_size(self._h, block, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def export_csr(self, block):
+        """Device CSR as (rowptr, colidx, val), 0-based."""
+        nrows, ncols, nnz = self.block_size(block)
+        w = self.lib.fcfv_index_width(self._h)
+        rp = np.empty(nrows + 1, dtype=np.int64 if w == 8 else np.int32)
+        ci, v = np.empty(nnz, dtype=np.int32), np.empty(nnz)
+        self.check(self.lib.fcfv_export(self._h, block, _L.CSR0, _out(rp), _out(ci), _out(v)))
+        return rp, ci, v
+
+    def export_csc(self, block):
+        """Julia SparseMatrixCSC fields (colptr, rowval, nzval), 1-based int64."""
+        nrows, ncols, nnz = self.block_size(block)
+        cp, rv, v = np.empty(ncols + 1, dtype=np.int64), np.empty(nnz, dtype=np.int64), np.empty(nnz)
+        self.check(self.lib.fcfv_export(self._h, block, _L.CSC1_INT64, _out(cp), _out(rv), _out(v)))
+        return cp, rv, v
+
+    def export_scipy_csc(self, block):
+        import scipy.sparse as sp
+        nrows, ncols, _ = self.block_size(block)
+        cp, rv, v = self.export_csc(block)
+        return sp.csc_matrix((v, rv - 1, cp - 1), shape=(nrows, ncols))
+
+    def export_rhs(self):
+        fu, fp = np.empty(2 * self.nf), np.empty(self.nel)
+        self.check(self.lib.fcfv_export_rhs(self._h, _out(fu), _out(fp)))
+        return fu, fp
+
+    # -- synthetic meshes ---------------------------------------------------------------------
+    def generate_structured(self, n, row0=0, row1=None, setting="solkz", tau_r=10.0, eta_incl=1e-2, neumann_south=False):
+        row1 = n if row1 is None else row1
+        sid = {"solkz": 0, "inclusion": 1}[setting]
+        self.check(self.lib.fcfv_generate_structured(self._h, int(n), int(row0), int(row1), 1, sid, float(tau_r),
+                                                     float(eta_incl), int(bool(neumann_south))))
+        nel, nf = C.c_int64(0), C.c_int64(0)
+        self.check(self.lib.fcfv_mesh_size(self._h, C.byref(nel), C.byref(nf)))
+        self.nel, self.nf = nel.value, nf.value
+
+    def get_mesh(self):
+        """Resident mesh as a dict of NumPy arrays in the reference's layout."""
+        nel, nf = self.nel, self.nf
+        o = dict(e2f=np.empty((nel, 3), dtype=np.int64, order="F"), bc=np.empty(nf, dtype=np.int64), Ω=np.empty(nel),
+                 n_x=np.empty((nel, 3), order="F"), n_y=np.empty((nel, 3), order="F"), Γ=np.empty((nel, 3), order="F"),
+                 ke=np.empty(nel), δ=np.empty(nel), τe=np.empty(nel), τ=np.empty(nf))
+        self.check(self.lib.fcfv_get_mesh(self._h, *[_out(o[k]) for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe", "τ")]))
+        return o
+
+    def get_data(self):
+        nel, nf = self.nel, self.nf
+        names = ("sex", "sey", "VxDir", "VyDir", "sxx", "syy", "sxy", "syx", "Vxh", "Vyh", "Pe")
+        o = {k: np.empty(nel if k in ("sex", "sey", "Pe") else nf) for k in names}
+        self.check(self.lib.fcfv_get_data(self._h, *[_out(o[k]) for k in names]))
+        return o
+
+    # -- communicator -------------------------------------------------------------------------
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        self.check(self.lib.fcfv_comm_unique_id(self._h, buf))
+        return bytes(buf)
+
+    def comm_init(self, id128, rank, nranks):
+        buf = (C.c_char * 128).from_buffer_copy(id128)
+        self.check(self.lib.fcfv_comm_init(self._h, buf, int(rank), int(nranks)))
+
+
+# ---------------------------------------------------------------------------------------------
+# handle cache: one handle per mesh object, created on first use
+# ---------------------------------------------------------------------------------------------
+def handle_for(mesh, device=None) -> Handle:
+    h = getattr(mesh, "_fcfv_handle", None)
+    if h is None:
+        h = Handle(0 if device is None else device)
+        h.set_mesh(mesh)
+        mesh._fcfv_handle = h
+    return h
+
+
+def _refresh(mesh, h):
+    """The drivers mutate ke, δ, τe, τ after mesh creation (ViscousInclusionFCFV_v2.jl:44,127;
+    SolKzFCFV.jl:25,149): re-upload those vectors at the top of every entry point."""
+    taue = mesh.τe if mesh.τe is not None else None
+    h.update_fields(ke=mesh.ke, delta=mesh.δ, taue=taue, tau=mesh.τ)
+
+
+def mesh_geometry(mesh, τr, device=0):
+    """Fills Ω, xc, yc, n_x, n_y, Γ and τ (= τr on every face) -- the geometry loops of
+    MakeTriangleMesh / LoadExternalMesh2 (CreateMeshFCFV.jl:142-156,180-211 / :300-314,337-367)."""
+    h = Handle(device)
+    try:
+        mesh.Ω, mesh.xc, mesh.yc, mesh.n_x, mesh.n_y, mesh.Γ, mesh.τ = h.geometry(
+            mesh.nel, mesh.nf, mesh.nv, mesh.e2v, mesh.e2f, mesh.xv, mesh.yv, mesh.xf, mesh.yf, mesh.numbering, τr,
+            tau=mesh.τ)
+    finally:
+        h.close()
+    return mesh
+
+
+def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τr, Formulation, A=A_DEFAULT):
+    """src/DiscretisationFCFV_Stokes.jl:8-44.  Returns α (nel), β (nel x 2), Ζ (nel x 2 x 2) and
+    overwrites ``mesh.τ`` (allocated when missing, as after ``LoadExternalMesh``).  The Neumann
+    arrays and τr are accepted and unused, as in the reference."""
+    if mesh.τ is None:
+        mesh.τ = np.zeros(mesh.nf)
+    h = handle_for(mesh)
+    _refresh(mesh, h)
+    nel, nf = h.nel, h.nf
+    a = _Arg()
+    al, be, Z = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")
+    tau = np.empty(nf)
+    h.check(h.lib.fcfv_compute_local(h._h, formulation_id(Formulation), float(A), a.d(sex, nel), a.d(sey, nel),
+                                     a.d(VxDir, nf), a.d(VyDir, nf), _out(al), _out(be), _out(Z), _out(tau)))
+    mesh.τ = tau
+    return al, be, Z
+
+
+def _assemble(variant, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A, want_muu, export):
+    h = handle_for(mesh)
+    _refresh(mesh, h)
+    nel, nf = h.nel, h.nf
+    a = _Arg()
+    nnz = [C.c_int64(0) for _ in range(3)]
+    sec = C.c_double(0.0)
+    h.check(h.lib.fcfv_assemble(h._h, variant, formulation_id(Formulation), float(A), a.d(α, nel), a.d(β, 2 * nel),
+                                a.d(Ζ, 4 * nel), a.d(VxDir, nf), a.d(VyDir, nf), a.d(σxxNeu, nf), a.d(σyyNeu, nf),
+                                a.d(σxyNeu, nf), a.d(σyxNeu, nf), int(bool(want_muu)), C.byref(nnz[0]), C.byref(nnz[1]),
+                                C.byref(nnz[2]), C.byref(sec)))
+    if not export:   # result stays on the device (fcfv_device_csr / Handle.export_*)
+        return h, tuple(x.value for x in nnz), sec.value
+    Kuu = h.export_scipy_csc(_L.KUU)
+    Kup = h.export_scipy_csc(_L.KUP)
+    Muu = h.export_scipy_csc(_L.MUU) if want_muu else None
+    fu, fp = h.export_rhs()
+    return Kuu, Muu, Kup, fu.reshape(-1, 1), fp, sec.value
+
+
+def ElementAssemblyLoop(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A=A_DEFAULT,
+                        want_muu=True, export=True):
+    """src/DiscretisationFCFV_Stokes.jl:102-202 (+ Sparsify :355-364).  Returns
+    ``Kuu, Muu, Kup`` (CSC, int64 indices), ``fu`` (2nf x 1), ``fp`` (nel), ``tsparse`` (device
+    seconds of the CSR build).  ``export=False`` keeps everything on the GPU and returns
+    ``(handle, (nnz_uu, nnz_up, nnz_muu), seconds)``."""
+    return _assemble(_L.LOOP_OLD, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A, want_muu, export)
+
+
+def ElementAssemblyLoopNEW(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A=A_DEFAULT,
+                           want_muu=True, export=True):
+    """src/DiscretisationFCFV_Stokes.jl:210-347 (+ Sparsify)."""
+    return _assemble(_L.LOOP_NEW, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A, want_muu, export)
+
+
+_RES_LINES = (
+    "Residual of local  equation 20a: %2.2e",
+    "Residual of local  equation 20b: %2.2e",
+    "Residual of local  equation 20c: %2.2e",
+    "Residual of global equation 19a: %2.2e",
+    "Residual of global equation 19a: %2.2e",
+    "Residual of global equation 19b: %2.2e",
+)
+
+
+def ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu,
+                                   SyxNeu, Formulation, tau_mode="REFERENCE", verbose=True, arrays=False):
+    """src/ComputeResidualsFCFV_Stokes.jl:5-108.  Prints the same six lines (:101-106); the
+    reference returns ``nothing``, this returns the six RMS norms (and, with ``arrays=True``,
+    F_nodes_x, F_nodes_y, F_glob2).  ``tau_mode='REFERENCE'`` reads ``mesh.τ[e]`` like the
+    reference (:17,54); ``'FACE'`` uses the face value ``mesh.τ[e2f[e,i]]``."""
+    h = handle_for(mesh)
+    _refresh(mesh, h)
+    nel, nf = h.nel, h.nf
+    a = _Arg()
+    norms = np.zeros(6)
+    Fx = np.empty(nf) if arrays else None
+    Fy = np.empty(nf) if arrays else None
+    Fg2 = np.empty(nel) if arrays else None
+    h.check(h.lib.fcfv_residuals(h._h, formulation_id(Formulation), _TAU_MODES[tau_mode], a.d(Vxh, nf), a.d(Vyh, nf),
+                                 a.d(Pe, nel), a.d(ae, nel), a.d(be, 2 * nel), a.d(ze, 4 * nel), a.d(sex, nel), a.d(sey, nel),
+                                 a.d(VxDir, nf), a.d(VyDir, nf), a.d(SxxNeu, nf), a.d(SyyNeu, nf), a.d(SxyNeu, nf),
+                                 a.d(SyxNeu, nf), _out(norms), _out(Fx), _out(Fy), _out(Fg2)))
+    if verbose:
+        for line, v in zip(_RES_LINES, norms):
+            print(line % v)
+    if arrays:
+        return norms, dict(F_nodes_x=Fx, F_nodes_y=Fy, F_glob2=Fg2)
+    return norms
+
+
+# ---------------------------------------------------------------------------------------------
+# Powell-Hestenes lines of StokesSolvers! that consume the device CSR (SolversFCFV_Stokes.jl:40-49)
+# ---------------------------------------------------------------------------------------------
+def ph_residual(mesh, u, p):
+    """ru = fu - Kuu*u - Kup*p, rp = fp - Kpu*u, (norm(ru), norm(rp))."""
+    h = handle_for(mesh)
+    a = _Arg()
+    ru, rp, nrm = np.empty(2 * h.nf), np.empty(h.nel), np.zeros(2)
+    h.check(h.lib.fcfv_ph_residual(h._h, a.d(u, 2 * h.nf), a.d(p, h.nel), _out(ru), _out(rp), _out(nrm)))
+    return ru, rp, nrm
+
+
+def ph_update_p(mesh, penalty, u, p):
+    """p .+= (penalty.*ke./Ω) .* (fp .- Kpu*u); returns the new p."""
+    h = handle_for(mesh)
+    a = _Arg()
+    pn = np.array(p, dtype=np.float64).ravel().copy()
+    h.check(h.lib.fcfv_ph_update_p(h._h, float(penalty), a.d(u, 2 * h.nf), _out(pn)))
+    return pn
+
+
+def ph_fusc(mesh, penalty, p):
+    """fusc = fu .- Kup*(Kppi*fp .+ p)."""
+    h = handle_for(mesh)
+    a = _Arg()
+    out = np.empty(2 * h.nf)
+    h.check(h.lib.fcfv_ph_fusc(h._h, float(penalty), a.d(p, h.nel), _out(out)))
+    return out

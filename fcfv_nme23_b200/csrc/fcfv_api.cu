@@ -1,0 +1,1087 @@
+// fcfv_api.cu -- C ABI of libfcfv_b200.so (see include/fcfv_b200.h for the contract).
+//
+// Host side of the library: owns the GPU buffers, moves the caller's arrays, launches the kernels
+// of fcfv_kernels.cuh on one stream.  There is no CPU implementation of any step in here: if
+// CUDA is unavailable every call fails with FCFV_ERR_CUDA.
+#include "../../include/fcfv_b200.h"
+#include "fcfv_kernels.cuh"
+#include "fcfv_generate.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace fcfv;
+
+struct Id128 { char b[128]; };   // ncclUniqueId
+
+namespace {
+
+struct DBuf {   // device buffer that only grows
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Csr {
+    DBuf rowptr, col, val;
+    long long nrows = 0, ncols = 0, nnz = -1;   // nnz < 0: not assembled
+};
+
+// ---- NCCL through dlopen: only the four entry points the path needs -------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+}  // namespace
+
+struct fcfv_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    bool async = false;
+    long long launches = 0;
+    size_t bytes = 0;
+
+    long long nel = 0, nf = 0;
+    long long nel_global = 0, nf_global = 0;
+    bool have_mesh = false, have_local = false, have_face_data = false, have_sources = false, have_solution = false;
+    bool rp64 = false;
+    bool have_elem_owned = false, have_face_owned = false, have_tau_ref = false;
+
+    // mesh
+    DBuf e2f, bc, f2e, Om, G, nx, ny, ke, dl, taue, tau, elem_owned, face_owned, tau_ref;
+    // data
+    DBuf sex, sey, VxDir, VyDir, sxx, syy, sxy, syx, Vxh, Vyh, Pe;
+    // local coefficients
+    DBuf alpha, beta, Z;
+    // assembly
+    Csr Kuu, Kup, Muu;
+    DBuf fu, fp, sums, bases, totals;
+    long long totals_host[9] = {0};
+    bool totals_valid = false;
+    // residual
+    DBuf Fg, partial, sumsq;
+    // scratch
+    DBuf tmp, tmp2, err_flag, phw;
+    // nccl
+    NcclApi nccl;
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(fcfv_t* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, FCFV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define TRY(expr)            \
+    do {                     \
+        int rc_ = (expr);    \
+        if (rc_) return rc_; \
+    } while (0)
+
+#define LAUNCH(h, kernel, grid, block, ...)                            \
+    do {                                                               \
+        kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);      \
+        (h)->launches++;                                               \
+    } while (0)
+
+int ensure(fcfv_t* h, DBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    if (b.cap >= bytes) return FCFV_OK;
+    if (b.p) { CU(cudaFree(b.p)); h->bytes -= b.cap; b.p = nullptr; b.cap = 0; }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(h, FCFV_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = bytes;
+    h->bytes += bytes;
+    return FCFV_OK;
+}
+
+void release(fcfv_t* h, DBuf& b) {
+    if (b.p) { cudaFree(b.p); h->bytes -= b.cap; }
+    b.p = nullptr; b.cap = 0;
+}
+
+// Copies between any combination of host/device pointers (UVA resolves the direction).
+int copy(fcfv_t* h, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return FCFV_OK;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream));
+    return FCFV_OK;
+}
+
+int upload(fcfv_t* h, DBuf& b, const void* src, size_t bytes) {
+    TRY(ensure(h, b, bytes));
+    return copy(h, b.p, src, bytes);
+}
+
+int sync(fcfv_t* h) {
+    CU(cudaStreamSynchronize(h->stream));
+    return FCFV_OK;
+}
+
+int finish(fcfv_t* h) { return h->async ? FCFV_OK : sync(h); }
+
+inline int nblocks(long long n, int block = kBlock) { return (int)std::max<long long>(1, (n + block - 1) / block); }
+
+template <typename T> T* P(const DBuf& b) { return (T*)b.p; }
+
+MeshView mesh_view(fcfv_t* h) {
+    MeshView M;
+    M.nel = (int)h->nel; M.nf = (int)h->nf;
+    M.e2f = P<int>(h->e2f); M.bc = P<int8_t>(h->bc); M.f2e = P<int2>(h->f2e);
+    M.Om = P<double>(h->Om); M.G = P<double>(h->G); M.nx = P<double>(h->nx); M.ny = P<double>(h->ny);
+    M.ke = P<double>(h->ke); M.dl = P<double>(h->dl); M.taue = P<double>(h->taue); M.tau = P<double>(h->tau);
+    M.elem_owned = h->have_elem_owned ? P<uint8_t>(h->elem_owned) : nullptr;
+    M.face_owned = h->have_face_owned ? P<uint8_t>(h->face_owned) : nullptr;
+    M.tau_ref = h->have_tau_ref ? P<double>(h->tau_ref) : nullptr;
+    return M;
+}
+LocalView local_view(fcfv_t* h) { return LocalView{P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z)}; }
+FaceDataView face_view(fcfv_t* h) {
+    return FaceDataView{P<double>(h->VxDir), P<double>(h->VyDir), P<double>(h->sxx),
+                        P<double>(h->syy), P<double>(h->sxy), P<double>(h->syx)};
+}
+SolutionView sol_view(fcfv_t* h) { return SolutionView{P<double>(h->Vxh), P<double>(h->Vyh), P<double>(h->Pe)}; }
+
+int check_form(fcfv_t* h, int formulation) {
+    if (formulation != FCFV_GRADIENT && formulation != FCFV_SYMMETRIC_GRADIENT)
+        return fail(h, FCFV_ERR_INVALID, "formulation must be FCFV_GRADIENT or FCFV_SYMMETRIC_GRADIENT (got %d)", formulation);
+    return FCFV_OK;
+}
+
+int need(fcfv_t* h, bool ok, const char* what) {
+    if (!ok) return fail(h, FCFV_ERR_STATE, "%s", what);
+    return FCFV_OK;
+}
+
+// Builds the face -> element map and validates the connectivity (device side, integer atomics).
+int build_f2e(fcfv_t* h) {
+    const long long nel = h->nel, nf = h->nf;
+    TRY(ensure(h, h->f2e, sizeof(int2) * nf));
+    TRY(ensure(h, h->tmp2, sizeof(int) * nf));
+    LAUNCH(h, k_f2e_init, nblocks(nf, 256), 256, P<int2>(h->f2e), P<int>(h->tmp2), (int)nf);
+    LAUNCH(h, k_f2e_build, nblocks(nel, 256), 256, P<int>(h->e2f), P<int2>(h->f2e), P<int>(h->tmp2), (int)nel);
+    LAUNCH(h, k_f2e_check, nblocks(nf, 256), 256, P<int2>(h->f2e), P<int>(h->tmp2), (int)nf, P<int>(h->err_flag));
+    return FCFV_OK;
+}
+
+int alloc_mesh_dependent(fcfv_t* h) {
+    const long long nel = h->nel, nf = h->nf;
+    TRY(ensure(h, h->tau, sizeof(double) * nf));
+    TRY(ensure(h, h->alpha, sizeof(double) * nel));
+    TRY(ensure(h, h->beta, sizeof(double) * 2 * nel));
+    TRY(ensure(h, h->Z, sizeof(double) * 4 * nel));
+    h->rp64 = 20 * nf >= (1LL << 31);
+    return FCFV_OK;
+}
+
+int read_err_flag(fcfv_t* h, int* flag) {
+    CU(cudaMemcpyAsync(flag, h->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return sync(h);
+}
+
+}  // namespace
+
+// =================================================================================================
+// All entry points are declared extern "C" in include/fcfv_b200.h; the definitions below inherit
+// that linkage.
+
+int fcfv_version(void) { return 100; }
+
+int fcfv_create(fcfv_t** out, int device) {
+    if (!out) return FCFV_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return FCFV_ERR_CUDA;   // no CPU fallback
+    if (device < 0 || device >= count) return FCFV_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return FCFV_ERR_CUDA;
+    fcfv_t* h = new (std::nothrow) fcfv_handle();
+    if (!h) return FCFV_ERR_ALLOC;
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return FCFV_ERR_CUDA;
+    }
+    if (ensure(h, h->err_flag, sizeof(int)) || ensure(h, h->totals, sizeof(long long) * 16) ||
+        ensure(h, h->sumsq, sizeof(double) * 8)) {
+        delete h;
+        return FCFV_ERR_ALLOC;
+    }
+    cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream);
+    *out = h;
+    return FCFV_OK;
+}
+
+int fcfv_destroy(fcfv_t* h) {
+    if (!h) return FCFV_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
+    DBuf* all[] = {&h->e2f, &h->bc, &h->f2e, &h->Om, &h->G, &h->nx, &h->ny, &h->ke, &h->dl, &h->taue, &h->tau,
+                   &h->elem_owned, &h->face_owned, &h->tau_ref, &h->sex, &h->sey, &h->VxDir, &h->VyDir, &h->sxx,
+                   &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
+                   &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,
+                   &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->totals,
+                   &h->Fg, &h->partial, &h->sumsq, &h->tmp, &h->tmp2, &h->err_flag, &h->phw};
+    for (DBuf* b : all) release(h, *b);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return FCFV_OK;
+}
+
+const char* fcfv_last_error(fcfv_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int fcfv_set_async(fcfv_t* h, int async) {
+    if (!h) return FCFV_ERR_INVALID;
+    h->async = async != 0;
+    return FCFV_OK;
+}
+
+int fcfv_sync(fcfv_t* h) {
+    if (!h) return FCFV_ERR_INVALID;
+    return sync(h);
+}
+
+void* fcfv_stream(fcfv_t* h) { return h ? (void*)h->stream : nullptr; }
+int64_t fcfv_kernel_launches(fcfv_t* h) { return h ? h->launches : 0; }
+int64_t fcfv_device_bytes(fcfv_t* h) { return h ? (int64_t)h->bytes : 0; }
+
+// -------------------------------------------------------------------------------------------------
+int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const int64_t* bc, const double* Omega,
+                  const double* nx, const double* ny, const double* Gamma, const double* ke, const double* delta,
+                  const double* taue, int64_t ntaue) {
+    if (!h) return FCFV_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    if (nel < 0 || nf < 0 || nel >= (1LL << 29) || nf >= (1LL << 30))
+        return fail(h, FCFV_ERR_INVALID, "mesh size out of range (nel=%lld < 2^29, nf=%lld < 2^30 required)", (long long)nel, (long long)nf);
+    if (!e2f || !bc || !Omega || !nx || !ny || !Gamma || !ke || !delta)
+        return fail(h, FCFV_ERR_INVALID, "fcfv_set_mesh: null mesh array");
+    if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
+    h->have_mesh = false; h->have_local = false;
+    h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = -1;
+    h->nel = nel; h->nf = nf; h->nel_global = nel; h->nf_global = nf;
+    h->have_elem_owned = h->have_face_owned = h->have_tau_ref = false;
+    // connectivity: int64 1-based -> int32 0-based on the device
+    TRY(upload(h, h->tmp, e2f, sizeof(int64_t) * 3 * nel));
+    TRY(ensure(h, h->e2f, sizeof(int) * 3 * nel));
+    CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
+    LAUNCH(h, k_convert_e2f, nblocks(3 * nel, 256), 256, P<long long>(h->tmp), P<int>(h->e2f), (long long)(3 * nel), (int)nf,
+           P<int>(h->err_flag));
+    TRY(upload(h, h->tmp, bc, sizeof(int64_t) * nf));
+    TRY(ensure(h, h->bc, (size_t)nf));
+    LAUNCH(h, k_convert_bc, nblocks(nf, 256), 256, P<long long>(h->tmp), P<int8_t>(h->bc), (int)nf);
+    TRY(upload(h, h->Om, Omega, sizeof(double) * nel));
+    TRY(upload(h, h->nx, nx, sizeof(double) * 3 * nel));
+    TRY(upload(h, h->ny, ny, sizeof(double) * 3 * nel));
+    TRY(upload(h, h->G, Gamma, sizeof(double) * 3 * nel));
+    TRY(upload(h, h->ke, ke, sizeof(double) * nel));
+    TRY(upload(h, h->dl, delta, sizeof(double) * nel));
+    TRY(ensure(h, h->taue, sizeof(double) * nel));
+    if (taue) TRY(copy(h, h->taue.p, taue, sizeof(double) * nel));
+    else CU(cudaMemsetAsync(h->taue.p, 0, sizeof(double) * nel, h->stream));
+    TRY(alloc_mesh_dependent(h));
+    CU(cudaMemsetAsync(h->tau.p, 0, sizeof(double) * nf, h->stream));
+    TRY(build_f2e(h));
+    int flag = 0;
+    TRY(read_err_flag(h, &flag));
+    if (flag & 1) return fail(h, FCFV_ERR_INVALID, "e2f contains a face id outside 1..nf");
+    if (flag & 2) return fail(h, FCFV_ERR_INVALID, "a face is referenced by more than two (element, local face) pairs");
+    h->have_mesh = true;
+    return FCFV_OK;
+}
+
+int fcfv_update_fields(fcfv_t* h, const double* ke, const double* delta, const double* taue, int64_t ntaue,
+                       const double* tau) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_update_fields: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    if (taue && ntaue < h->nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel", (long long)ntaue);
+    if (ke) TRY(copy(h, h->ke.p, ke, sizeof(double) * h->nel));
+    if (delta) TRY(copy(h, h->dl.p, delta, sizeof(double) * h->nel));
+    if (taue) TRY(copy(h, h->taue.p, taue, sizeof(double) * h->nel));
+    if (tau) TRY(copy(h, h->tau.p, tau, sizeof(double) * h->nf));
+    return finish(h);
+}
+
+int fcfv_set_ownership(fcfv_t* h, const uint8_t* elem_owned, const uint8_t* face_owned, int64_t nel_global,
+                       int64_t nf_global, const double* tau_ref) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_set_ownership: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    h->have_elem_owned = elem_owned != nullptr;
+    h->have_face_owned = face_owned != nullptr;
+    h->have_tau_ref = tau_ref != nullptr;
+    if (elem_owned) TRY(upload(h, h->elem_owned, elem_owned, (size_t)h->nel));
+    if (face_owned) TRY(upload(h, h->face_owned, face_owned, (size_t)h->nf));
+    if (tau_ref) TRY(upload(h, h->tau_ref, tau_ref, sizeof(double) * h->nel));
+    h->nel_global = nel_global > 0 ? nel_global : h->nel;
+    h->nf_global = nf_global > 0 ? nf_global : h->nf;
+    return finish(h);
+}
+
+// -------------------------------------------------------------------------------------------------
+int fcfv_geometry(fcfv_t* h, int64_t nel, int64_t nf, int64_t nv, const int64_t* e2v, const int64_t* e2f,
+                  const double* xv, const double* yv, const double* xf, const double* yf, int numbering, double tau_r,
+                  double* Omega, double* xc, double* yc, double* nx, double* ny, double* Gamma, double* tau) {
+    if (!h) return FCFV_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    if (nel < 0 || nf < 0 || nv < 0 || nel >= (1LL << 29) || nf >= (1LL << 30) || nv >= (1LL << 31))
+        return fail(h, FCFV_ERR_INVALID, "fcfv_geometry: size out of range");
+    if (!e2v || !e2f || !xv || !yv || !xf || !yf) return fail(h, FCFV_ERR_INVALID, "fcfv_geometry: null input");
+    if (numbering != 0 && numbering != 1) return fail(h, FCFV_ERR_INVALID, "fcfv_geometry: numbering must be 0 or 1");
+    DBuf d_e2v, d_e2f, d_xv, d_yv, d_xf, d_yf, d_out, d_tau;
+    int rc = FCFV_OK;
+    auto body = [&]() -> int {
+        CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
+        TRY(upload(h, h->tmp, e2v, sizeof(int64_t) * 3 * nel));
+        TRY(ensure(h, d_e2v, sizeof(int) * 3 * nel));
+        LAUNCH(h, k_convert_e2f, nblocks(3 * nel, 256), 256, P<long long>(h->tmp), P<int>(d_e2v), (long long)(3 * nel), (int)nv, P<int>(h->err_flag));
+        TRY(upload(h, h->tmp, e2f, sizeof(int64_t) * 3 * nel));
+        TRY(ensure(h, d_e2f, sizeof(int) * 3 * nel));
+        LAUNCH(h, k_convert_e2f, nblocks(3 * nel, 256), 256, P<long long>(h->tmp), P<int>(d_e2f), (long long)(3 * nel), (int)nf, P<int>(h->err_flag));
+        TRY(upload(h, d_xv, xv, sizeof(double) * nv));
+        TRY(upload(h, d_yv, yv, sizeof(double) * nv));
+        TRY(upload(h, d_xf, xf, sizeof(double) * nf));
+        TRY(upload(h, d_yf, yf, sizeof(double) * nf));
+        TRY(ensure(h, d_out, sizeof(double) * 12 * nel));
+        double* o = P<double>(d_out);
+        double *dOm = o, *dxc = o + nel, *dyc = o + 2 * nel, *dnx = o + 3 * nel, *dny = o + 6 * nel, *dG = o + 9 * nel;
+        double* dtau = nullptr;
+        if (tau) {
+            TRY(ensure(h, d_tau, sizeof(double) * nf));
+            TRY(copy(h, d_tau.p, tau, sizeof(double) * nf));   // faces without elements keep their value
+            dtau = P<double>(d_tau);
+        }
+        LAUNCH(h, k_geometry, nblocks(nel), kBlock, (int)nel, P<int>(d_e2v), P<int>(d_e2f), P<double>(d_xv), P<double>(d_yv),
+               P<double>(d_xf), P<double>(d_yf), numbering, tau_r, dOm, dxc, dyc, dnx, dny, dG, dtau);
+        int flag = 0;
+        TRY(read_err_flag(h, &flag));
+        if (flag) return fail(h, FCFV_ERR_INVALID, "fcfv_geometry: e2v / e2f entry out of range");
+        if (Omega) TRY(copy(h, Omega, dOm, sizeof(double) * nel));
+        if (xc) TRY(copy(h, xc, dxc, sizeof(double) * nel));
+        if (yc) TRY(copy(h, yc, dyc, sizeof(double) * nel));
+        if (nx) TRY(copy(h, nx, dnx, sizeof(double) * 3 * nel));
+        if (ny) TRY(copy(h, ny, dny, sizeof(double) * 3 * nel));
+        if (Gamma) TRY(copy(h, Gamma, dG, sizeof(double) * 3 * nel));
+        if (tau) TRY(copy(h, tau, dtau, sizeof(double) * nf));
+        return sync(h);
+    };
+    rc = body();
+    cudaStreamSynchronize(h->stream);
+    for (DBuf* b : {&d_e2v, &d_e2f, &d_xv, &d_yv, &d_xf, &d_yf, &d_out, &d_tau}) release(h, *b);
+    return rc;
+}
+
+// -------------------------------------------------------------------------------------------------
+int fcfv_set_sources(fcfv_t* h, const double* sex, const double* sey) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_set_sources: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    if (!sex || !sey) return fail(h, FCFV_ERR_INVALID, "fcfv_set_sources: null array");
+    TRY(upload(h, h->sex, sex, sizeof(double) * h->nel));
+    TRY(upload(h, h->sey, sey, sizeof(double) * h->nel));
+    h->have_sources = true;
+    return finish(h);
+}
+
+int fcfv_set_face_data(fcfv_t* h, const double* VxDir, const double* VyDir, const double* sxxNeu, const double* syyNeu,
+                       const double* sxyNeu, const double* syxNeu) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_set_face_data: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    const size_t b = sizeof(double) * h->nf;
+    DBuf* dst[6] = {&h->VxDir, &h->VyDir, &h->sxx, &h->syy, &h->sxy, &h->syx};
+    const double* src[6] = {VxDir, VyDir, sxxNeu, syyNeu, sxyNeu, syxNeu};
+    for (int k = 0; k < 6; k++) {
+        const bool fresh = dst[k]->cap < b;
+        TRY(ensure(h, *dst[k], b));
+        if (src[k]) TRY(copy(h, dst[k]->p, src[k], b));
+        else if (fresh || !h->have_face_data) CU(cudaMemsetAsync(dst[k]->p, 0, b, h->stream));
+    }
+    h->have_face_data = true;
+    return finish(h);
+}
+
+int fcfv_set_solution(fcfv_t* h, const double* Vxh, const double* Vyh, const double* Pe) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_set_solution: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    if (!Vxh || !Vyh || !Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_set_solution: null array");
+    TRY(upload(h, h->Vxh, Vxh, sizeof(double) * h->nf));
+    TRY(upload(h, h->Vyh, Vyh, sizeof(double) * h->nf));
+    TRY(upload(h, h->Pe, Pe, sizeof(double) * h->nel));
+    h->have_solution = true;
+    return finish(h);
+}
+
+int fcfv_set_local(fcfv_t* h, const double* alpha, const double* beta, const double* Z) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_set_local: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    if (!alpha || !beta || !Z) return fail(h, FCFV_ERR_INVALID, "fcfv_set_local: null array");
+    TRY(copy(h, h->alpha.p, alpha, sizeof(double) * h->nel));
+    TRY(copy(h, h->beta.p, beta, sizeof(double) * 2 * h->nel));
+    TRY(copy(h, h->Z.p, Z, sizeof(double) * 4 * h->nel));
+    h->have_local = true;
+    return finish(h);
+}
+
+// -------------------------------------------------------------------------------------------------
+int fcfv_run_local(fcfv_t* h, int formulation, double A) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(check_form(h, formulation));
+    TRY(need(h, h->have_mesh, "fcfv_run_local: no mesh set"));
+    TRY(need(h, h->have_sources && h->have_face_data, "fcfv_run_local: sources / face data not set"));
+    CU(cudaSetDevice(h->device));
+    const MeshView M = mesh_view(h);
+    LAUNCH(h, k_face_tau, nblocks(h->nf, 256), 256, M.f2e, M.taue, P<double>(h->tau), M.nf);
+    if (formulation == FCFV_GRADIENT)
+        LAUNCH(h, k_local<kGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey), P<double>(h->VxDir),
+               P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z));
+    else
+        LAUNCH(h, k_local<kSymmetricGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey),
+               P<double>(h->VxDir), P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z));
+    CU(cudaGetLastError());
+    h->have_local = true;
+    return finish(h);
+}
+
+int fcfv_get_local(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_local, "fcfv_get_local: local coefficients not computed"));
+    CU(cudaSetDevice(h->device));
+    if (alpha) TRY(copy(h, alpha, h->alpha.p, sizeof(double) * h->nel));
+    if (beta) TRY(copy(h, beta, h->beta.p, sizeof(double) * 2 * h->nel));
+    if (Z) TRY(copy(h, Z, h->Z.p, sizeof(double) * 4 * h->nel));
+    if (tau) TRY(copy(h, tau, h->tau.p, sizeof(double) * h->nf));
+    return sync(h);
+}
+
+int fcfv_compute_local(fcfv_t* h, int formulation, double A, const double* sex, const double* sey, const double* VxDir,
+                       const double* VyDir, double* alpha, double* beta, double* Z, double* tau) {
+    if (!h) return FCFV_ERR_INVALID;
+    const bool was_async = h->async;
+    h->async = true;
+    int rc = fcfv_set_sources(h, sex, sey);
+    if (!rc) {
+        if (!VxDir || !VyDir) rc = fail(h, FCFV_ERR_INVALID, "fcfv_compute_local: null Dirichlet array");
+        else rc = fcfv_set_face_data(h, VxDir, VyDir, nullptr, nullptr, nullptr, nullptr);
+    }
+    if (!rc) rc = fcfv_run_local(h, formulation, A);
+    h->async = was_async;
+    if (rc) return rc;
+    return fcfv_get_local(h, alpha, beta, Z, tau);
+}
+
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+template <int VARIANT, int FORM, bool WANT_M>
+int launch_assemble(fcfv_t* h, double A) {
+    const MeshView M = mesh_view(h);
+    const LocalView L = local_view(h);
+    const FaceDataView D = face_view(h);
+    const int nblk = nblocks(h->nf);
+    LAUNCH(h, (k_asm_count<VARIANT, FORM, WANT_M>), nblk, kBlock, M, L, D, A, P<int>(h->sums), nblk);
+    LAUNCH(h, k_scan_bases, kNumSums, kScanThreads, P<int>(h->sums), P<long long>(h->bases), nblk, P<long long>(h->totals));
+    CsrOut ouu{h->Kuu.rowptr.p, P<int>(h->Kuu.col), P<double>(h->Kuu.val)};
+    CsrOut oup{h->Kup.rowptr.p, P<int>(h->Kup.col), P<double>(h->Kup.val)};
+    CsrOut omu{h->Muu.rowptr.p, P<int>(h->Muu.col), P<double>(h->Muu.val)};
+    if (h->rp64) {
+        LAUNCH(h, k_finish_bases<long long>, nblocks(nblk, 256), 256, P<long long>(h->bases), nblk, P<long long>(h->totals),
+               (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)omu.rowptr, M.nf, (int)WANT_M);
+        LAUNCH(h, (k_asm_fill<VARIANT, FORM, WANT_M, long long>), nblk, kBlock, M, L, D, A, P<long long>(h->bases), nblk, ouu, oup,
+               omu, P<double>(h->fu), P<double>(h->fp));
+    } else {
+        LAUNCH(h, k_finish_bases<int>, nblocks(nblk, 256), 256, P<long long>(h->bases), nblk, P<long long>(h->totals),
+               (int*)ouu.rowptr, (int*)oup.rowptr, (int*)omu.rowptr, M.nf, (int)WANT_M);
+        LAUNCH(h, (k_asm_fill<VARIANT, FORM, WANT_M, int>), nblk, kBlock, M, L, D, A, P<long long>(h->bases), nblk, ouu, oup, omu,
+               P<double>(h->fu), P<double>(h->fp));
+    }
+    return FCFV_OK;
+}
+
+template <int VARIANT, int FORM>
+int launch_assemble_m(fcfv_t* h, double A, int want_muu) {
+    return want_muu ? launch_assemble<VARIANT, FORM, true>(h, A) : launch_assemble<VARIANT, FORM, false>(h, A);
+}
+
+int fetch_totals(fcfv_t* h) {
+    if (h->totals_valid) return FCFV_OK;
+    CU(cudaMemcpyAsync(h->totals_host, h->totals.p, sizeof(long long) * 9, cudaMemcpyDeviceToHost, h->stream));
+    TRY(sync(h));
+    h->Kuu.nnz = h->totals_host[6];
+    h->Kup.nnz = h->totals_host[7];
+    if (h->Muu.nnz != -1) h->Muu.nnz = h->totals_host[8];
+    h->totals_valid = true;
+    return FCFV_OK;
+}
+
+}  // namespace
+
+int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int want_muu) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(check_form(h, formulation));
+    if (variant != FCFV_LOOP_OLD && variant != FCFV_LOOP_NEW)
+        return fail(h, FCFV_ERR_INVALID, "variant must be FCFV_LOOP_OLD or FCFV_LOOP_NEW (got %d)", variant);
+    TRY(need(h, h->have_mesh, "fcfv_run_assemble: no mesh set"));
+    TRY(need(h, h->have_local, "fcfv_run_assemble: local coefficients missing (fcfv_compute_local / fcfv_set_local)"));
+    TRY(need(h, h->have_face_data, "fcfv_run_assemble: face data not set"));
+    CU(cudaSetDevice(h->device));
+    const long long nel = h->nel, nf = h->nf;
+    const size_t rpw = h->rp64 ? 8 : 4;
+    const int nblk = nblocks(nf);
+    // capacity = upper bounds (10 / 2 / 5 entries per row), so no host round trip between the passes
+    TRY(ensure(h, h->Kuu.rowptr, rpw * (2 * nf + 1)));
+    TRY(ensure(h, h->Kuu.col, sizeof(int) * 20 * nf));
+    TRY(ensure(h, h->Kuu.val, sizeof(double) * 20 * nf));
+    TRY(ensure(h, h->Kup.rowptr, rpw * (2 * nf + 1)));
+    TRY(ensure(h, h->Kup.col, sizeof(int) * 4 * nf));
+    TRY(ensure(h, h->Kup.val, sizeof(double) * 4 * nf));
+    if (want_muu) {
+        TRY(ensure(h, h->Muu.rowptr, rpw * (2 * nf + 1)));
+        TRY(ensure(h, h->Muu.col, sizeof(int) * 10 * nf));
+        TRY(ensure(h, h->Muu.val, sizeof(double) * 10 * nf));
+    }
+    TRY(ensure(h, h->fu, sizeof(double) * 2 * nf));
+    TRY(ensure(h, h->fp, sizeof(double) * nel));
+    TRY(ensure(h, h->sums, sizeof(int) * kNumSums * nblk));
+    TRY(ensure(h, h->bases, sizeof(long long) * kNumSums * nblk));
+    h->Kuu.nrows = 2 * nf; h->Kuu.ncols = 2 * nf;
+    h->Kup.nrows = 2 * nf; h->Kup.ncols = nel;
+    h->Muu.nrows = 2 * nf; h->Muu.ncols = 2 * nf;
+    h->Kuu.nnz = h->Kup.nnz = -2;            // assembled, count not fetched yet
+    h->Muu.nnz = want_muu ? -2 : -1;
+    h->totals_valid = false;
+    // elements that are not owned / have no local face 0 thread keep fp = 0
+    CU(cudaMemsetAsync(h->fp.p, 0, sizeof(double) * nel, h->stream));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    int rc;
+    if (variant == FCFV_LOOP_OLD)
+        rc = formulation == FCFV_GRADIENT ? launch_assemble_m<kLoopOld, kGradient>(h, A, want_muu)
+                                          : launch_assemble_m<kLoopOld, kSymmetricGradient>(h, A, want_muu);
+    else
+        rc = formulation == FCFV_GRADIENT ? launch_assemble_m<kLoopNew, kGradient>(h, A, want_muu)
+                                          : launch_assemble_m<kLoopNew, kSymmetricGradient>(h, A, want_muu);
+    TRY(rc);
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaGetLastError());
+    return finish(h);
+}
+
+int fcfv_get_nnz(fcfv_t* h, int64_t* nnz_uu, int64_t* nnz_up, int64_t* nnz_muu) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_get_nnz: nothing assembled"));
+    CU(cudaSetDevice(h->device));
+    TRY(fetch_totals(h));
+    if (nnz_uu) *nnz_uu = h->Kuu.nnz;
+    if (nnz_up) *nnz_up = h->Kup.nnz;
+    if (nnz_muu) *nnz_muu = h->Muu.nnz < 0 ? 0 : h->Muu.nnz;
+    return FCFV_OK;
+}
+
+int fcfv_assemble(fcfv_t* h, int variant, int formulation, double A, const double* alpha, const double* beta,
+                  const double* Z, const double* VxDir, const double* VyDir, const double* sxxNeu, const double* syyNeu,
+                  const double* sxyNeu, const double* syxNeu, int want_muu, int64_t* nnz_uu, int64_t* nnz_up,
+                  int64_t* nnz_muu, double* seconds) {
+    if (!h) return FCFV_ERR_INVALID;
+    const bool was_async = h->async;
+    h->async = true;
+    int rc = FCFV_OK;
+    if (alpha || beta || Z) rc = fcfv_set_local(h, alpha, beta, Z);
+    if (!rc) rc = fcfv_set_face_data(h, VxDir, VyDir, sxxNeu, syyNeu, sxyNeu, syxNeu);
+    if (!rc) rc = fcfv_run_assemble(h, variant, formulation, A, want_muu);
+    h->async = was_async;
+    if (rc) return rc;
+    TRY(fcfv_get_nnz(h, nnz_uu, nnz_up, nnz_muu));   // synchronises
+    if (seconds) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *seconds = 1e-3 * ms;
+    }
+    return FCFV_OK;
+}
+
+int fcfv_index_width(fcfv_t* h) { return h && h->rp64 ? 8 : 4; }
+
+namespace {
+Csr* block_of(fcfv_t* h, int block) {
+    switch (block) {
+        case FCFV_KUU: return &h->Kuu;
+        case FCFV_KUP: return &h->Kup;
+        case FCFV_MUU: return &h->Muu;
+        default: return nullptr;
+    }
+}
+}  // namespace
+
+int fcfv_block_size(fcfv_t* h, int block, int64_t* nrows, int64_t* ncols, int64_t* nnz) {
+    if (!h) return FCFV_ERR_INVALID;
+    Csr* c = block_of(h, block);
+    if (!c) return fail(h, FCFV_ERR_INVALID, "unknown block %d", block);
+    TRY(need(h, c->nnz != -1, "fcfv_block_size: block not assembled"));
+    CU(cudaSetDevice(h->device));
+    TRY(fetch_totals(h));
+    if (nrows) *nrows = c->nrows;
+    if (ncols) *ncols = c->ncols;
+    if (nnz) *nnz = c->nnz;
+    return FCFV_OK;
+}
+
+int fcfv_export(fcfv_t* h, int block, int layout, void* ptr, void* idx, double* val) {
+    if (!h) return FCFV_ERR_INVALID;
+    Csr* c = block_of(h, block);
+    if (!c) return fail(h, FCFV_ERR_INVALID, "unknown block %d", block);
+    TRY(need(h, c->nnz != -1, "fcfv_export: block not assembled"));
+    CU(cudaSetDevice(h->device));
+    TRY(fetch_totals(h));
+    const size_t rpw = h->rp64 ? 8 : 4;
+    const long long nnz = c->nnz, nrows = c->nrows, ncols = c->ncols;
+    if (layout == FCFV_CSR0) {
+        if (ptr) TRY(copy(h, ptr, c->rowptr.p, rpw * (nrows + 1)));
+        if (idx) TRY(copy(h, idx, c->col.p, sizeof(int) * nnz));
+        if (val) TRY(copy(h, val, c->val.p, sizeof(double) * nnz));
+        return sync(h);
+    }
+    if (layout != FCFV_CSC1_INT64) return fail(h, FCFV_ERR_INVALID, "unknown layout %d", layout);
+    if (!ptr || !idx || !val) return fail(h, FCFV_ERR_INVALID, "fcfv_export: CSC export needs ptr, idx and val");
+    // CSR -> Julia CSC: stable counting sort by column on the host (API boundary, not the hot path);
+    // rows are visited in ascending order, so rows are ascending inside every column.
+    std::vector<char> rp(rpw * (nrows + 1));
+    std::vector<int> col((size_t)nnz);
+    std::vector<double> v((size_t)nnz);
+    CU(cudaMemcpyAsync(rp.data(), c->rowptr.p, rp.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(col.data(), c->col.p, sizeof(int) * nnz, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(v.data(), c->val.p, sizeof(double) * nnz, cudaMemcpyDeviceToHost, h->stream));
+    TRY(sync(h));
+    int64_t* colptr = (int64_t*)ptr;
+    int64_t* rowval = (int64_t*)idx;
+    std::vector<int64_t> next((size_t)ncols + 1, 0);
+    for (long long k = 0; k < nnz; k++) next[col[k] + 1]++;
+    for (long long j = 0; j < ncols; j++) next[j + 1] += next[j];
+    for (long long j = 0; j <= ncols; j++) colptr[j] = next[j] + 1;
+    auto rowptr_at = [&](long long r) -> long long {
+        return h->rp64 ? ((const long long*)rp.data())[r] : (long long)((const int*)rp.data())[r];
+    };
+    for (long long r = 0; r < nrows; r++)
+        for (long long k = rowptr_at(r); k < rowptr_at(r + 1); k++) {
+            const int64_t p = next[col[k]]++;
+            rowval[p] = r + 1;
+            val[p] = v[k];
+        }
+    return FCFV_OK;
+}
+
+int fcfv_export_rhs(fcfv_t* h, double* fu, double* fp) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_export_rhs: nothing assembled"));
+    CU(cudaSetDevice(h->device));
+    if (fu) TRY(copy(h, fu, h->fu.p, sizeof(double) * 2 * h->nf));
+    if (fp) TRY(copy(h, fp, h->fp.p, sizeof(double) * h->nel));
+    return sync(h);
+}
+
+int fcfv_device_csr(fcfv_t* h, int block, void** rowptr, void** colidx, void** val) {
+    if (!h) return FCFV_ERR_INVALID;
+    Csr* c = block_of(h, block);
+    if (!c) return fail(h, FCFV_ERR_INVALID, "unknown block %d", block);
+    TRY(need(h, c->nnz != -1, "fcfv_device_csr: block not assembled"));
+    if (rowptr) *rowptr = c->rowptr.p;
+    if (colidx) *colidx = c->col.p;
+    if (val) *val = c->val.p;
+    return FCFV_OK;
+}
+
+int fcfv_device_rhs(fcfv_t* h, void** fu, void** fp) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_device_rhs: nothing assembled"));
+    if (fu) *fu = h->fu.p;
+    if (fp) *fp = h->fp.p;
+    return FCFV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, double* norms) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(check_form(h, formulation));
+    if (tau_mode != FCFV_TAU_REFERENCE && tau_mode != FCFV_TAU_FACE)
+        return fail(h, FCFV_ERR_INVALID, "tau_mode must be FCFV_TAU_REFERENCE or FCFV_TAU_FACE (got %d)", tau_mode);
+    TRY(need(h, h->have_mesh, "fcfv_run_residuals: no mesh set"));
+    TRY(need(h, h->have_local, "fcfv_run_residuals: local coefficients missing"));
+    TRY(need(h, h->have_sources && h->have_face_data && h->have_solution, "fcfv_run_residuals: sources / face data / solution not set"));
+    if (tau_mode == FCFV_TAU_REFERENCE && !h->have_tau_ref && h->nf < h->nel)
+        return fail(h, FCFV_ERR_INVALID, "FCFV_TAU_REFERENCE reads tau[e] for e <= nel but nf < nel");
+    CU(cudaSetDevice(h->device));
+    const long long nel = h->nel, nf = h->nf;
+    const int nbe = nblocks(nel), nbf = nblocks(nf);
+    const int stride = std::max(nbe, nbf);
+    TRY(ensure(h, h->Fg, sizeof(double) * 6 * nel));
+    TRY(ensure(h, h->partial, sizeof(double) * 6 * stride));
+    const MeshView M = mesh_view(h);
+    double* part = P<double>(h->partial);
+    if (formulation == FCFV_GRADIENT)
+        LAUNCH(h, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+               P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr);
+    else
+        LAUNCH(h, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+               P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr);
+    LAUNCH(h, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, (double*)nullptr, (double*)nullptr);
+    // sumsq order = print order: F_eq1, F_eq2, F_eq3, F_nodes_x, F_nodes_y, F_glob2
+    double* ss = P<double>(h->sumsq);
+    LAUNCH(h, k_reduce_partials, 3, 1024, part, nbe, stride, ss);                                // eq1, eq2, eq3
+    LAUNCH(h, k_reduce_partials, 2, 1024, part + 4 * (size_t)stride, nbf, stride, ss + 3);       // nodes x, y
+    LAUNCH(h, k_reduce_partials, 1, 1024, part + 3 * (size_t)stride, nbe, stride, ss + 5);       // glob2
+    CU(cudaGetLastError());
+    if (h->comm) TRY(fcfv_comm_allreduce_sum(h, ss, 6));
+    if (sumsq || norms) {
+        double hs[6];
+        CU(cudaMemcpyAsync(hs, ss, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+        TRY(sync(h));
+        if (sumsq) memcpy(sumsq, hs, sizeof hs);
+        if (norms) {
+            const double ne = (double)h->nel_global, nfg = (double)h->nf_global;
+            const double len[6] = {4.0 * ne, 2.0 * ne, ne, nfg, nfg, ne};
+            for (int k = 0; k < 6; k++) norms[k] = len[k] > 0 ? sqrt(hs[k]) / sqrt(len[k]) : 0.0;
+        }
+        return FCFV_OK;
+    }
+    return finish(h);
+}
+
+int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, const double* Vyh, const double* Pe,
+                   const double* alpha, const double* beta, const double* Z, const double* sex, const double* sey,
+                   const double* VxDir, const double* VyDir, const double* SxxNeu, const double* SyyNeu,
+                   const double* SxyNeu, const double* SyxNeu, double* norms, double* F_nodes_x, double* F_nodes_y,
+                   double* F_glob2) {
+    if (!h) return FCFV_ERR_INVALID;
+    const bool was_async = h->async;
+    h->async = true;
+    int rc = fcfv_set_solution(h, Vxh, Vyh, Pe);
+    if (!rc && (alpha || beta || Z)) rc = fcfv_set_local(h, alpha, beta, Z);
+    if (!rc) rc = fcfv_set_sources(h, sex, sey);
+    if (!rc) rc = fcfv_set_face_data(h, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu);
+    h->async = was_async;
+    if (rc) return rc;
+    double dummy[6];
+    TRY(fcfv_run_residuals(h, formulation, tau_mode, nullptr, norms ? norms : dummy));
+    if (F_nodes_x || F_nodes_y || F_glob2) {
+        // optional arrays: rerun the two kernels with output pointers (device scratch), then copy out
+        const long long nel = h->nel, nf = h->nf;
+        TRY(ensure(h, h->tmp, sizeof(double) * (2 * nf + nel)));
+        double* t = P<double>(h->tmp);
+        const int nbe = nblocks(nel), nbf = nblocks(nf), stride = std::max(nbe, nbf);
+        const MeshView M = mesh_view(h);
+        double* part = P<double>(h->partial);
+        if (formulation == FCFV_GRADIENT)
+            LAUNCH(h, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+                   P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf);
+        else
+            LAUNCH(h, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h),
+                   P<double>(h->sex), P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf);
+        LAUNCH(h, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, t, t + nf);
+        CU(cudaGetLastError());
+        if (F_nodes_x) TRY(copy(h, F_nodes_x, t, sizeof(double) * nf));
+        if (F_nodes_y) TRY(copy(h, F_nodes_y, t + nf, sizeof(double) * nf));
+        if (F_glob2) TRY(copy(h, F_glob2, t + 2 * nf, sizeof(double) * nel));
+        TRY(sync(h));
+    }
+    return FCFV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+namespace {
+int ph_inputs(fcfv_t* h, const double* u, const double* p, double** du, double** dp) {
+    // u (2nf) and p (nel) staged in tmp: [u | p]
+    TRY(ensure(h, h->tmp, sizeof(double) * (2 * h->nf + h->nel)));
+    double* t = P<double>(h->tmp);
+    if (u) TRY(copy(h, t, u, sizeof(double) * 2 * h->nf));
+    if (p) TRY(copy(h, t + 2 * h->nf, p, sizeof(double) * h->nel));
+    *du = t; *dp = t + 2 * h->nf;
+    return FCFV_OK;
+}
+}  // namespace
+
+int fcfv_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, double* rp, double* nrm) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_residual: nothing assembled"));
+    if (!u || !p) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_residual: null u or p");
+    CU(cudaSetDevice(h->device));
+    const long long nel = h->nel, nf = h->nf;
+    double *du, *dp;
+    TRY(ph_inputs(h, u, p, &du, &dp));
+    TRY(ensure(h, h->tmp2, sizeof(double) * (2 * nf + nel)));
+    double* dru = P<double>(h->tmp2);
+    double* drp = dru + 2 * nf;
+    const int nbr = nblocks(2 * nf), nbe = nblocks(nel), stride = std::max(nbr, nbe);
+    TRY(ensure(h, h->partial, sizeof(double) * 6 * std::max<long long>(stride, nblocks(nf))));
+    double* part = P<double>(h->partial);
+    const MeshView M = mesh_view(h);
+    if (h->rp64)
+        LAUNCH(h, k_ph_ru<long long>, nbr, kBlock, (int)(2 * nf), P<long long>(h->Kuu.rowptr), P<int>(h->Kuu.col), P<double>(h->Kuu.val),
+               P<long long>(h->Kup.rowptr), P<int>(h->Kup.col), P<double>(h->Kup.val), P<double>(h->fu), du, dp, dru, part);
+    else
+        LAUNCH(h, k_ph_ru<int>, nbr, kBlock, (int)(2 * nf), P<int>(h->Kuu.rowptr), P<int>(h->Kuu.col), P<double>(h->Kuu.val),
+               P<int>(h->Kup.rowptr), P<int>(h->Kup.col), P<double>(h->Kup.val), P<double>(h->fu), du, dp, dru, part);
+    LAUNCH(h, k_ph_rp, nbe, kBlock, M, P<double>(h->fp), du, 0, 0.0, drp, (double*)nullptr, part + stride);
+    double* ss = P<double>(h->sumsq);
+    LAUNCH(h, k_reduce_partials, 1, 1024, part, nbr, stride, ss + 6);
+    LAUNCH(h, k_reduce_partials, 1, 1024, part + stride, nbe, stride, ss + 7);
+    CU(cudaGetLastError());
+    if (h->comm) TRY(fcfv_comm_allreduce_sum(h, ss + 6, 2));
+    double hs[2];
+    CU(cudaMemcpyAsync(hs, ss + 6, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+    if (ru) TRY(copy(h, ru, dru, sizeof(double) * 2 * nf));
+    if (rp) TRY(copy(h, rp, drp, sizeof(double) * nel));
+    TRY(sync(h));
+    if (nrm) { nrm[0] = sqrt(hs[0]); nrm[1] = sqrt(hs[1]); }
+    return FCFV_OK;
+}
+
+int fcfv_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_update_p: nothing assembled"));
+    if (!u || !p) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_update_p: null u or p");
+    CU(cudaSetDevice(h->device));
+    double *du, *dp;
+    TRY(ph_inputs(h, u, p, &du, &dp));
+    const MeshView M = mesh_view(h);
+    LAUNCH(h, k_ph_rp, nblocks(h->nel), kBlock, M, P<double>(h->fp), du, 1, gamma, (double*)nullptr, dp, (double*)nullptr);
+    CU(cudaGetLastError());
+    TRY(copy(h, p, dp, sizeof(double) * h->nel));
+    return sync(h);
+}
+
+int fcfv_ph_fusc(fcfv_t* h, double gamma, const double* p, double* fusc) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_fusc: nothing assembled"));
+    if (!p || !fusc) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_fusc: null p or fusc");
+    CU(cudaSetDevice(h->device));
+    const long long nel = h->nel, nf = h->nf;
+    double *du, *dp;
+    TRY(ph_inputs(h, nullptr, p, &du, &dp));
+    TRY(ensure(h, h->phw, sizeof(double) * nel));
+    TRY(ensure(h, h->tmp2, sizeof(double) * (2 * nf + nel)));
+    double* out = P<double>(h->tmp2);
+    LAUNCH(h, k_ph_w, nblocks(nel, 256), 256, (int)nel, P<double>(h->ke), P<double>(h->Om), P<double>(h->fp), dp, gamma, P<double>(h->phw));
+    if (h->rp64)
+        LAUNCH(h, k_ph_fusc<long long>, nblocks(2 * nf, 256), 256, (int)(2 * nf), P<long long>(h->Kup.rowptr), P<int>(h->Kup.col),
+               P<double>(h->Kup.val), P<double>(h->fu), P<double>(h->phw), out);
+    else
+        LAUNCH(h, k_ph_fusc<int>, nblocks(2 * nf, 256), 256, (int)(2 * nf), P<int>(h->Kup.rowptr), P<int>(h->Kup.col),
+               P<double>(h->Kup.val), P<double>(h->fu), P<double>(h->phw), out);
+    CU(cudaGetLastError());
+    TRY(copy(h, fusc, out, sizeof(double) * 2 * nf));
+    return sync(h);
+}
+
+// -------------------------------------------------------------------------------------------------
+int fcfv_mesh_size(fcfv_t* h, int64_t* nel, int64_t* nf) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_mesh_size: no mesh set"));
+    if (nel) *nel = h->nel;
+    if (nf) *nf = h->nf;
+    return FCFV_OK;
+}
+
+int fcfv_get_mesh(fcfv_t* h, int64_t* e2f, int64_t* bc, double* Omega, double* nx, double* ny, double* Gamma,
+                  double* ke, double* delta, double* taue, double* tau) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_get_mesh: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    const long long nel = h->nel, nf = h->nf;
+    if (e2f) {
+        TRY(ensure(h, h->tmp, sizeof(int64_t) * 3 * nel));
+        LAUNCH(h, k_widen_e2f, nblocks(3 * nel, 256), 256, P<int>(h->e2f), P<long long>(h->tmp), (long long)(3 * nel));
+        TRY(copy(h, e2f, h->tmp.p, sizeof(int64_t) * 3 * nel));
+        TRY(sync(h));
+    }
+    if (bc) {
+        TRY(ensure(h, h->tmp, sizeof(int64_t) * nf));
+        LAUNCH(h, k_widen_bc, nblocks(nf, 256), 256, P<int8_t>(h->bc), P<long long>(h->tmp), (long long)nf);
+        TRY(copy(h, bc, h->tmp.p, sizeof(int64_t) * nf));
+        TRY(sync(h));
+    }
+    if (Omega) TRY(copy(h, Omega, h->Om.p, sizeof(double) * nel));
+    if (nx) TRY(copy(h, nx, h->nx.p, sizeof(double) * 3 * nel));
+    if (ny) TRY(copy(h, ny, h->ny.p, sizeof(double) * 3 * nel));
+    if (Gamma) TRY(copy(h, Gamma, h->G.p, sizeof(double) * 3 * nel));
+    if (ke) TRY(copy(h, ke, h->ke.p, sizeof(double) * nel));
+    if (delta) TRY(copy(h, delta, h->dl.p, sizeof(double) * nel));
+    if (taue) TRY(copy(h, taue, h->taue.p, sizeof(double) * nel));
+    if (tau) TRY(copy(h, tau, h->tau.p, sizeof(double) * nf));
+    return sync(h);
+}
+
+int fcfv_get_data(fcfv_t* h, double* sex, double* sey, double* VxDir, double* VyDir, double* sxxNeu, double* syyNeu,
+                  double* sxyNeu, double* syxNeu, double* Vxh, double* Vyh, double* Pe) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh && h->have_sources && h->have_face_data && h->have_solution, "fcfv_get_data: data not set"));
+    CU(cudaSetDevice(h->device));
+    const size_t be = sizeof(double) * h->nel, bf = sizeof(double) * h->nf;
+    if (sex) TRY(copy(h, sex, h->sex.p, be));
+    if (sey) TRY(copy(h, sey, h->sey.p, be));
+    if (VxDir) TRY(copy(h, VxDir, h->VxDir.p, bf));
+    if (VyDir) TRY(copy(h, VyDir, h->VyDir.p, bf));
+    if (sxxNeu) TRY(copy(h, sxxNeu, h->sxx.p, bf));
+    if (syyNeu) TRY(copy(h, syyNeu, h->syy.p, bf));
+    if (sxyNeu) TRY(copy(h, sxyNeu, h->sxy.p, bf));
+    if (syxNeu) TRY(copy(h, syxNeu, h->syx.p, bf));
+    if (Vxh) TRY(copy(h, Vxh, h->Vxh.p, bf));
+    if (Vyh) TRY(copy(h, Vyh, h->Vyh.p, bf));
+    if (Pe) TRY(copy(h, Pe, h->Pe.p, be));
+    return sync(h);
+}
+
+// -------------------------------------------------------------------------------------------------
+int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, int ghost_below, int setting,
+                             double tau_r, double eta_incl, int neumann_south) {
+    if (!h) return FCFV_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    if (n < 1 || row0 < 0 || row1 > n || row0 >= row1) return fail(h, FCFV_ERR_INVALID, "fcfv_generate_structured: bad row range");
+    if (setting != 0 && setting != 1) return fail(h, FCFV_ERR_INVALID, "fcfv_generate_structured: setting must be 0 or 1");
+    (void)ghost_below;   // ghost rows are added automatically where the strip has neighbours
+    const StripLayout S = make_strip_layout(n, row0, row1);
+    if (S.nel >= (1LL << 29) || S.nf >= (1LL << 30)) return fail(h, FCFV_ERR_INVALID, "fcfv_generate_structured: strip too large");
+    h->have_mesh = false; h->have_local = false;
+    h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = -1;
+    const long long nel = S.nel, nf = S.nf;
+    h->nel = nel; h->nf = nf;
+    h->nel_global = 4 * n * n; h->nf_global = 6 * n * n + 2 * n;
+    TRY(ensure(h, h->e2f, sizeof(int) * 3 * nel));
+    TRY(ensure(h, h->bc, (size_t)nf));
+    for (DBuf* b : {&h->Om, &h->ke, &h->dl, &h->taue, &h->sex, &h->sey, &h->Pe}) TRY(ensure(h, *b, sizeof(double) * nel));
+    for (DBuf* b : {&h->nx, &h->ny, &h->G}) TRY(ensure(h, *b, sizeof(double) * 3 * nel));
+    for (DBuf* b : {&h->VxDir, &h->VyDir, &h->sxx, &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh}) TRY(ensure(h, *b, sizeof(double) * nf));
+    TRY(ensure(h, h->elem_owned, (size_t)nel));
+    TRY(ensure(h, h->face_owned, (size_t)nf));
+    TRY(alloc_mesh_dependent(h));
+    CU(cudaMemsetAsync(h->tau.p, 0, sizeof(double) * nf, h->stream));
+    GenOut G;
+    G.e2f = P<int>(h->e2f); G.bc = P<int8_t>(h->bc);
+    G.Om = P<double>(h->Om); G.nx = P<double>(h->nx); G.ny = P<double>(h->ny); G.G = P<double>(h->G);
+    G.ke = P<double>(h->ke); G.dl = P<double>(h->dl); G.taue = P<double>(h->taue);
+    G.sex = P<double>(h->sex); G.sey = P<double>(h->sey); G.Pe = P<double>(h->Pe);
+    G.VxDir = P<double>(h->VxDir); G.VyDir = P<double>(h->VyDir); G.sxx = P<double>(h->sxx); G.syy = P<double>(h->syy);
+    G.sxy = P<double>(h->sxy); G.syx = P<double>(h->syx); G.Vxh = P<double>(h->Vxh); G.Vyh = P<double>(h->Vyh);
+    G.elem_owned = P<uint8_t>(h->elem_owned); G.face_owned = P<uint8_t>(h->face_owned);
+    LAUNCH(h, k_gen_elements, nblocks(nel), kBlock, S, G, setting, tau_r, eta_incl);
+    LAUNCH(h, k_gen_faces, nblocks(S.nquads), kBlock, S, G, setting, neumann_south);
+    CU(cudaGetLastError());
+    const bool partitioned = S.rlo != 0 || S.rhi != n;
+    h->have_elem_owned = h->have_face_owned = partitioned;
+    h->have_tau_ref = false;
+    CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
+    TRY(build_f2e(h));
+    if (setting == 1) {   // interface faces: the two adjacent elements have different viscosity
+        LAUNCH(h, k_gen_interface, nblocks(nf, 256), 256, P<int2>(h->f2e), P<double>(h->ke), P<int8_t>(h->bc), (int)nf);
+        CU(cudaGetLastError());
+    }
+    int flag = 0;
+    TRY(read_err_flag(h, &flag));
+    if (flag) return fail(h, FCFV_ERR_STATE, "fcfv_generate_structured: generated connectivity failed validation (%d)", flag);
+    h->have_mesh = h->have_sources = h->have_face_data = h->have_solution = true;
+    return FCFV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+namespace {
+int load_nccl(fcfv_t* h) {
+    if (h->nccl.lib) return FCFV_OK;
+    const char* env = getenv("FCFV_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nme : names) {
+        if (!nme) continue;
+        lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(h, FCFV_ERR_NCCL, "cannot load libnccl.so.2 (set FCFV_NCCL_LIB): %s", dlerror());
+    h->nccl.lib = lib;
+    h->nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    h->nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(lib, "ncclCommInitRank");
+    h->nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    h->nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    h->nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!h->nccl.GetUniqueId || !h->nccl.CommInitRank || !h->nccl.AllReduce || !h->nccl.CommDestroy)
+        return fail(h, FCFV_ERR_NCCL, "libnccl is missing a required symbol");
+    return FCFV_OK;
+}
+int nccl_fail(fcfv_t* h, const char* what, int rc) {
+    return fail(h, FCFV_ERR_NCCL, "%s failed: %s", what, h->nccl.GetErrorString ? h->nccl.GetErrorString(rc) : "?");
+}
+}  // namespace
+
+int fcfv_comm_unique_id(fcfv_t* h, void* id128) {
+    if (!h || !id128) return FCFV_ERR_INVALID;
+    TRY(load_nccl(h));
+    const int rc = h->nccl.GetUniqueId(id128);
+    if (rc) return nccl_fail(h, "ncclGetUniqueId", rc);
+    return FCFV_OK;
+}
+
+int fcfv_comm_init(fcfv_t* h, const void* id128, int rank, int nranks) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return FCFV_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    TRY(load_nccl(h));
+    Id128 id;
+    memcpy(id.b, id128, 128);
+    const int rc = h->nccl.CommInitRank(&h->comm, nranks, id, rank);
+    if (rc) { h->comm = nullptr; return nccl_fail(h, "ncclCommInitRank", rc); }
+    h->rank = rank; h->nranks = nranks;
+    return FCFV_OK;
+}
+
+int fcfv_comm_allreduce_sum(fcfv_t* h, double* data, int n) {
+    if (!h || !data || n < 0) return FCFV_ERR_INVALID;
+    if (!h->comm) return FCFV_OK;   // single rank: identity
+    CU(cudaSetDevice(h->device));
+    cudaPointerAttributes at;
+    const bool on_device = cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    double* d = data;
+    if (!on_device) {
+        if (n > 8) return fail(h, FCFV_ERR_INVALID, "host all-reduce supports at most 8 values");
+        TRY(ensure(h, h->phw, sizeof(double) * 8));
+        d = P<double>(h->phw);
+        TRY(copy(h, d, data, sizeof(double) * n));
+    }
+    const int rc = h->nccl.AllReduce(d, d, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, h->stream);
+    if (rc) return nccl_fail(h, "ncclAllReduce", rc);
+    if (!on_device) {
+        TRY(copy(h, data, d, sizeof(double) * n));
+        return sync(h);
+    }
+    return FCFV_OK;
+}

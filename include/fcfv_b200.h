@@ -1,0 +1,181 @@
+/*
+ * fcfv_b200.h -- C ABI of libfcfv_b200.so: the B200 (sm_100a, FP64) implementation of the
+ * data-parallel hot path of tduretz/FCFV_NME23.
+ *
+ * This header is the drop-in boundary.  The reference is pure Julia and has no FFI of its
+ * own; each entry point below replaces the body of one exported Julia function (cited as
+ * file:line of the reference checkout) and is what a Julia `ccall` shim binds
+ * (julia/FCFV_B200.jl).  tests/ and bench.py bind the same symbols through
+ * Python ctypes.
+ *
+ * Conventions
+ *  - All functions return an int status (FCFV_OK == 0).  No exceptions, no printing, no
+ *    signal handlers.  fcfv_last_error(h) returns a message owned by the handle.
+ *  - Array arguments use the reference's (Julia) memory layout: Float64 / Int64,
+ *    column-major, 1-based connectivity.  X[e,i] of an nel x 3 matrix is at X[(i-1)*nel+(e-1)],
+ *    Z[e,a,b] of nel x 2 x 2 at Z[(e-1) + nel*(a-1) + 2*nel*(b-1)].
+ *  - Every array pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer of the
+ *    handle's GPU; the library detects which (cudaPointerGetAttributes).  Pointers are borrowed
+ *    for the duration of the call only.  Output arrays are caller-allocated; NULL skips them.
+ *  - A handle owns one GPU, one stream and all device-resident state.  It is not thread-safe.
+ *    Calls return after the stream has been synchronised unless stated otherwise.
+ *  - Assembled blocks stay on the device as CSR: 0-based, int32 column indices, row pointers
+ *    int32 when 20*nf < 2^31 and int64 otherwise (fcfv_index_width).  Within a row columns are
+ *    ascending; entries whose summed value is exactly +-0.0 are dropped, like
+ *    dropzeros(sparse(...)) in the reference (DiscretisationFCFV_Stokes.jl:355-364).
+ */
+#ifndef FCFV_B200_H
+#define FCFV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fcfv_handle fcfv_t;
+
+enum { FCFV_OK = 0, FCFV_ERR_INVALID = 1, FCFV_ERR_CUDA = 2, FCFV_ERR_STATE = 3, FCFV_ERR_ALLOC = 4, FCFV_ERR_NCCL = 5 };
+enum { FCFV_GRADIENT = 0, FCFV_SYMMETRIC_GRADIENT = 1 };  /* Formulation == :Gradient / :SymmetricGradient */
+enum { FCFV_LOOP_OLD = 0, FCFV_LOOP_NEW = 1 };             /* ElementAssemblyLoop / ElementAssemblyLoopNEW  */
+enum { FCFV_TAU_REFERENCE = 0, FCFV_TAU_FACE = 1 };        /* residual: mesh.τ[e] (as written) / mesh.τ[e2f[e,i]] */
+enum { FCFV_KUU = 0, FCFV_KUP = 1, FCFV_MUU = 2 };
+enum { FCFV_CSR0 = 0, FCFV_CSC1_INT64 = 1 };               /* export layouts */
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int fcfv_create(fcfv_t** h, int device);
+int fcfv_destroy(fcfv_t* h);
+const char* fcfv_last_error(fcfv_t* h);
+int fcfv_version(void);
+
+/* ---- mesh: the fields of FCFV_Mesh the path reads (src/CreateMeshFCFV.jl:10-44) --------
+ * e2f nel x 3 (1-based), bc nf, Omega nel, nx/ny/Gamma nel x 3, ke/delta nel,
+ * taue ntaue >= nel entries (examples/ViscousInclusionFCFV_v2.jl:127 passes nf of them).
+ * Copies everything to the GPU (int32 connectivity, int8 tags) and builds the face->element
+ * map.  A face referenced by more than two (element, local face) pairs is rejected. */
+int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const int64_t* bc,
+                  const double* Omega, const double* nx, const double* ny, const double* Gamma,
+                  const double* ke, const double* delta, const double* taue, int64_t ntaue);
+
+/* The drivers mutate mesh.ke, mesh.δ, mesh.τe, mesh.τ after mesh creation
+ * (ViscousInclusionFCFV_v2.jl:44,127; SolKzFCFV.jl:25,149).  NULL leaves a field as it is. */
+int fcfv_update_fields(fcfv_t* h, const double* ke, const double* delta, const double* taue,
+                       int64_t ntaue, const double* tau);
+
+/* Element/face ownership of a partitioned mesh (uint8 masks, NULL = everything owned), the
+ * global sizes used to normalise the residual norms and, for FCFV_TAU_REFERENCE on a
+ * partition, tau_ref[e] = global mesh.τ[global id of e] (NULL: use local τ[e]). */
+int fcfv_set_ownership(fcfv_t* h, const uint8_t* elem_owned, const uint8_t* face_owned,
+                       int64_t nel_global, int64_t nf_global, const double* tau_ref);
+
+/* ---- a2: Ω, centroids, outward normals, face lengths ------------------------------------
+ * src/CreateMeshFCFV.jl:142-156,180-211 (numbering 0: nodeA=[2 3 1], nodeB=[3 1 2]) and
+ * :300-314,337-367 (numbering 1: nodeA=[3 2 1], nodeB=[1 3 2]).  Stand-alone: does not need
+ * fcfv_set_mesh.  tau (nf) receives tau_r on every referenced face (:209,365); may be NULL. */
+int fcfv_geometry(fcfv_t* h, int64_t nel, int64_t nf, int64_t nv, const int64_t* e2v,
+                  const int64_t* e2f, const double* xv, const double* yv, const double* xf,
+                  const double* yf, int numbering, double tau_r, double* Omega, double* xc,
+                  double* yc, double* nx, double* ny, double* Gamma, double* tau);
+
+/* ---- a4: ComputeFCFV (src/DiscretisationFCFV_Stokes.jl:8-44) ---------------------------
+ * Outputs alpha nel, beta nel x 2, Z nel x 2 x 2, tau nf (mesh.τ after the call: face f gets
+ * τe of its highest-numbered adjacent element, faces without elements keep their value). */
+int fcfv_compute_local(fcfv_t* h, int formulation, double A, const double* sex, const double* sey,
+                       const double* VxDir, const double* VyDir, double* alpha, double* beta,
+                       double* Z, double* tau);
+
+/* ---- a5/a6/a7: ElementAssemblyLoop[NEW] + Sparsify (Discretisation:102-202,210-347,355-364)
+ * alpha/beta/Z: NULL = use the device-resident result of the last fcfv_compute_local.
+ * Uses mesh.τ as resident (fcfv_compute_local / fcfv_update_fields).  Result: device CSR of
+ * Kuu (2nf x 2nf), Kup (2nf x nel), optional Muu, plus fu (2nf) and fp (nel).
+ * seconds receives the device time of the build (the reference's `tsparse`). */
+int fcfv_assemble(fcfv_t* h, int variant, int formulation, double A, const double* alpha,
+                  const double* beta, const double* Z, const double* VxDir, const double* VyDir,
+                  const double* sxxNeu, const double* syyNeu, const double* sxyNeu,
+                  const double* syxNeu, int want_muu, int64_t* nnz_uu, int64_t* nnz_up,
+                  int64_t* nnz_muu, double* seconds);
+
+/* Bytes per row-pointer entry of the device CSR (4 or 8). */
+int fcfv_index_width(fcfv_t* h);
+/* Sizes of an assembled block. */
+int fcfv_block_size(fcfv_t* h, int block, int64_t* nrows, int64_t* ncols, int64_t* nnz);
+/* Copy a block out.  FCFV_CSR0: ptr has nrows+1 entries of fcfv_index_width bytes, idx int32,
+ * 0-based.  FCFV_CSC1_INT64: ptr ncols+1, idx nnz, both int64 and 1-based, rows ascending in a
+ * column -- the fields of Julia's SparseMatrixCSC{Float64,Int64}. */
+int fcfv_export(fcfv_t* h, int block, int layout, void* ptr, void* idx, double* val);
+int fcfv_export_rhs(fcfv_t* h, double* fu, double* fp);
+/* Device pointers of the resident CSR for GPU consumers (valid until the next assemble). */
+int fcfv_device_csr(fcfv_t* h, int block, void** rowptr, void** colidx, void** val);
+int fcfv_device_rhs(fcfv_t* h, void** fu, void** fp);
+
+/* ---- a8: ComputeResidualsFCFV_Stokes_o1 (src/ComputeResidualsFCFV_Stokes.jl:5-108) ------
+ * norms[6] = norm(F)/sqrt(length(F)) for F_eq1, F_eq2, F_eq3, F_nodes_x, F_nodes_y, F_glob2
+ * (print order :101-106).  alpha/beta/Z NULL = resident.  Optional outputs F_nodes_x/y (nf),
+ * F_glob2 (nel). */
+int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, const double* Vyh,
+                   const double* Pe, const double* alpha, const double* beta, const double* Z,
+                   const double* sex, const double* sey, const double* VxDir, const double* VyDir,
+                   const double* SxxNeu, const double* SyyNeu, const double* SxyNeu,
+                   const double* SyxNeu, double* norms, double* F_nodes_x, double* F_nodes_y,
+                   double* F_glob2);
+
+/* ---- a9: Powell-Hestenes residual / updates on the resident CSR --------------------------
+ * src/SolversFCFV_Stokes.jl:40-42: ru = fu - Kuu*u - Kup*p, rp = fp - Kpu*u (Kpu = -Kup'),
+ * nrm = {norm(ru), norm(rp)};  :23,49: p += (gamma*ke/Ω) .* (fp - Kpu*u);
+ * :47: fusc = fu - Kup*((gamma*ke/Ω).*fp + p).   u has 2nf entries, p nel. */
+int fcfv_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, double* rp, double* nrm);
+int fcfv_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p);
+int fcfv_ph_fusc(fcfv_t* h, double gamma, const double* p, double* fusc);
+
+/* ---- device-resident pipeline (what bench.py times as `value`) ---------------------------
+ * Upload once, then run the kernels on resident data without host traffic.  The host-buffer
+ * entry points above are compositions of these. */
+int fcfv_set_sources(fcfv_t* h, const double* sex, const double* sey);
+int fcfv_set_face_data(fcfv_t* h, const double* VxDir, const double* VyDir, const double* sxxNeu,
+                       const double* syyNeu, const double* sxyNeu, const double* syxNeu);
+int fcfv_set_solution(fcfv_t* h, const double* Vxh, const double* Vyh, const double* Pe);
+int fcfv_set_local(fcfv_t* h, const double* alpha, const double* beta, const double* Z);
+int fcfv_run_local(fcfv_t* h, int formulation, double A);
+int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int want_muu);
+/* sumsq[6]: sums of squares over owned elements/faces (device-reduced, then all-reduced over
+ * the communicator if one is attached); norms[6] as fcfv_residuals.  Either may be NULL. */
+int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, double* norms);
+int fcfv_get_local(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau);
+int fcfv_get_nnz(fcfv_t* h, int64_t* nnz_uu, int64_t* nnz_up, int64_t* nnz_muu);
+/* run_* calls enqueue on the handle's stream and return without synchronising when async != 0. */
+int fcfv_set_async(fcfv_t* h, int async);
+int fcfv_sync(fcfv_t* h);
+void* fcfv_stream(fcfv_t* h);               /* cudaStream_t */
+int64_t fcfv_kernel_launches(fcfv_t* h);    /* kernels launched by this handle so far */
+int64_t fcfv_device_bytes(fcfv_t* h);       /* device memory currently held by the handle */
+
+/* ---- synthetic structured mesh S(n) generated on the device (bench / large tests) --------
+ * Quad rows row0 <= qy < row1 of the n x n criss-cross triangulation of the unit square with
+ * the closed-form first-seen face numbering (meshes/ReadMeshesDat.jl:36-88), geometry from the
+ * a2 kernel, then one of the closed-form field settings of SURVEY.md §8(d):
+ * setting 0 = SolKz (ke = exp(13.8 yc), sey = sin(1.6 pi yc) cos(3 pi xc), τe = tau_r*max(ke,1),
+ * all boundary Dirichlet), 1 = inclusion (ke = eta_incl inside radius 1/6, interface faces
+ * tagged -1, τe = tau_r, south boundary Neumann when neumann_south != 0).
+ * With ghost_below != 0 the quad row row0-1 is included as non-owned ghost elements.
+ * Installs the mesh, ownership, sources, face data and a smooth (û, p) in the handle. */
+int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, int ghost_below,
+                             int setting, double tau_r, double eta_incl, int neumann_south);
+/* Copies the resident mesh / data back (any pointer may be NULL); sizes via fcfv_mesh_size. */
+int fcfv_mesh_size(fcfv_t* h, int64_t* nel, int64_t* nf);
+int fcfv_get_mesh(fcfv_t* h, int64_t* e2f, int64_t* bc, double* Omega, double* nx, double* ny,
+                  double* Gamma, double* ke, double* delta, double* taue, double* tau);
+int fcfv_get_data(fcfv_t* h, double* sex, double* sey, double* VxDir, double* VyDir, double* sxxNeu,
+                  double* syyNeu, double* sxyNeu, double* syxNeu, double* Vxh, double* Vyh, double* Pe);
+
+/* ---- multi-GPU: one process per GPU, NCCL only for the norm reductions --------------------
+ * fcfv_comm_unique_id fills 128 bytes (ncclUniqueId) on rank 0; broadcast them by any means,
+ * then every rank calls fcfv_comm_init.  libnccl.so.2 is loaded at run time (dlopen). */
+int fcfv_comm_unique_id(fcfv_t* h, void* id128);
+int fcfv_comm_init(fcfv_t* h, const void* id128, int rank, int nranks);
+/* In-place sum over ranks of n doubles (host or device pointer). */
+int fcfv_comm_allreduce_sum(fcfv_t* h, double* data, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCFV_B200_H */

@@ -1,0 +1,219 @@
+// host_emulation.cpp -- TEST INFRASTRUCTURE.  Compiles the per-element / per-face arithmetic of
+// the CUDA library (fcfv_math.cuh and the gather/count helpers of fcfv_kernels.cuh) for the HOST
+// and drives it with plain serial loops, so that tests without a GPU can compare the arithmetic
+// the kernels execute against the oracle.  It replaces only the launch machinery (thread index ->
+// loop index, block scan -> running sum); it is never loaded by the product package.
+// Build: g++ -O2 -ffp-contract=off -shared -fPIC (see tests/conftest.py).
+#include "../fcfv_nme23_b200/csrc/fcfv_kernels.cuh"
+#include "../fcfv_nme23_b200/csrc/fcfv_generate.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace fcfv;
+
+namespace {
+struct HostMesh {
+    std::vector<int> e2f; std::vector<int8_t> bc; std::vector<int2> f2e;
+    MeshView view;
+};
+
+void build_mesh(HostMesh& H, long long nel, long long nf, const long long* e2f, const long long* bc, const double* Om,
+                const double* nx, const double* ny, const double* G, const double* ke, const double* dl,
+                const double* taue, const double* tau) {
+    H.e2f.resize(3 * nel); H.bc.resize(nf); H.f2e.assign(nf, int2{0x7fffffff, -1});
+    for (long long k = 0; k < 3 * nel; k++) H.e2f[k] = (int)(e2f[k] - 1);
+    for (long long f = 0; f < nf; f++) { long long v = bc[f]; H.bc[f] = (v == 1 || v == 2 || v == -1) ? (int8_t)v : 0; }
+    std::vector<int> cnt(nf, 0);
+    for (long long e = 0; e < nel; e++)
+        for (int i = 0; i < 3; i++) {
+            int f = H.e2f[i * nel + e], code = 4 * (int)e + i;
+            if (code < H.f2e[f].x) H.f2e[f].x = code;
+            if (code > H.f2e[f].y) H.f2e[f].y = code;
+            cnt[f]++;
+        }
+    for (long long f = 0; f < nf; f++) if (!cnt[f]) H.f2e[f] = int2{-1, -1};
+    MeshView& M = H.view;
+    M.nel = (int)nel; M.nf = (int)nf; M.e2f = H.e2f.data(); M.bc = H.bc.data(); M.f2e = H.f2e.data();
+    M.Om = Om; M.G = G; M.nx = nx; M.ny = ny; M.ke = ke; M.dl = dl; M.taue = taue; M.tau = tau;
+    M.elem_owned = nullptr; M.face_owned = nullptr; M.tau_ref = nullptr;
+}
+
+template <int VARIANT, int FORM>
+void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, double A, long long* rp_uu, int* c_uu,
+              double* v_uu, long long* rp_up, int* c_up, double* v_up, long long* rp_mu, int* c_mu, double* v_mu,
+              double* fu, double* fp) {
+    const int nf = M.nf;
+    std::vector<int> cx(nf), cy(nf), px(nf), py(nf), mx(nf), my(nf);
+    for (int f = 0; f < nf; f++) {   // count pass
+        FaceRows R; double fpv[2]; int fpe[2]; RowCounts C;
+        gather_face_rows<VARIANT, FORM, true>(M, L, D, f, A, R, fpv, fpe);
+        count_rows<true>(R, C);
+        cx[f] = C.nxx + C.nxy; cy[f] = C.nyx + C.nyy; px[f] = C.npx; py[f] = C.npy; mx[f] = C.nmx; my[f] = C.nmy;
+    }
+    long long run = 0;
+    for (int f = 0; f < nf; f++) { rp_uu[f] = run; run += cx[f]; }
+    for (int f = 0; f < nf; f++) { rp_uu[nf + f] = run; run += cy[f]; }
+    rp_uu[2 * nf] = run; run = 0;
+    for (int f = 0; f < nf; f++) { rp_up[f] = run; run += px[f]; }
+    for (int f = 0; f < nf; f++) { rp_up[nf + f] = run; run += py[f]; }
+    rp_up[2 * nf] = run; run = 0;
+    for (int f = 0; f < nf; f++) { rp_mu[f] = run; run += mx[f]; }
+    for (int f = 0; f < nf; f++) { rp_mu[nf + f] = run; run += my[f]; }
+    rp_mu[2 * nf] = run;
+    for (int e = 0; e < M.nel; e++) fp[e] = 0.0;
+    for (int f = 0; f < nf; f++) {   // fill pass (same placement arithmetic as k_asm_fill)
+        FaceRows R; double fpv[2]; int fpe[2]; RowCounts C;
+        gather_face_rows<VARIANT, FORM, true>(M, L, D, f, A, R, fpv, fpe);
+        if (fpe[0] >= 0) fp[fpe[0]] = fpv[0];
+        if (fpe[1] >= 0) fp[fpe[1]] = fpv[1];
+        count_rows<true>(R, C);
+        fu[f] = R.fx; fu[nf + f] = R.fy;
+        for (int k = 0; k < 6; k++) {
+            if (C.nzxx[k]) { long long p = rp_uu[f] + sorted_pos(R.key, C.nzxx, k); v_uu[p] = R.xx[k]; c_uu[p] = R.key[k]; }
+            if (C.nzxy[k]) { long long p = rp_uu[f] + C.nxx + sorted_pos(R.key, C.nzxy, k); v_uu[p] = R.xy[k]; c_uu[p] = R.key[k] + nf; }
+            if (C.nzyx[k]) { long long p = rp_uu[nf + f] + sorted_pos(R.key, C.nzyx, k); v_uu[p] = R.yx[k]; c_uu[p] = R.key[k]; }
+            if (C.nzyy[k]) { long long p = rp_uu[nf + f] + C.nyx + sorted_pos(R.key, C.nzyy, k); v_uu[p] = R.yy[k]; c_uu[p] = R.key[k] + nf; }
+            if (C.nzmx[k]) { long long p = rp_mu[f] + sorted_pos(R.key, C.nzmx, k); v_mu[p] = R.mxx[k]; c_mu[p] = R.key[k]; }
+            if (C.nzmy[k]) { long long p = rp_mu[nf + f] + sorted_pos(R.key, C.nzmy, k); v_mu[p] = R.myy[k]; c_mu[p] = R.key[k] + nf; }
+        }
+        long long qx = rp_up[f], qy = rp_up[nf + f];
+        for (int s = 0; s < 2; s++) {
+            if (C.pzx[s]) { v_up[qx] = R.px[s]; c_up[qx] = R.pe[s]; qx++; }
+            if (C.pzy[s]) { v_up[qy] = R.py[s]; c_up[qy] = R.pe[s]; qy++; }
+        }
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int emu_geometry(long long nel, const long long* e2v, const long long* e2f, const double* xv, const double* yv,
+                 const double* xf, const double* yf, int numbering, double* Om, double* xc, double* yc, double* nx,
+                 double* ny, double* G) {
+    for (long long e = 0; e < nel; e++) {
+        double x[3], y[3], xm[3], ym[3];
+        for (int k = 0; k < 3; k++) {
+            long long v = e2v[k * nel + e] - 1, f = e2f[k * nel + e] - 1;
+            x[k] = xv[v]; y[k] = yv[v]; xm[k] = xf[f]; ym[k] = yf[f];
+        }
+        ElemGeom g;
+        element_geometry(x, y, xm, ym, numbering, g);
+        Om[e] = g.Om; xc[e] = g.xc; yc[e] = g.yc;
+        for (int k = 0; k < 3; k++) { nx[k * nel + e] = g.nx[k]; ny[k * nel + e] = g.ny[k]; G[k * nel + e] = g.G[k]; }
+    }
+    return 0;
+}
+
+int emu_local(int formulation, double A, long long nel, long long nf, const long long* e2f, const long long* bc,
+              const double* Om, const double* nx, const double* ny, const double* G, const double* taue,
+              const double* sex, const double* sey, const double* VxDir, const double* VyDir, double* alpha,
+              double* beta, double* Z, double* tau) {
+    HostMesh H;
+    build_mesh(H, nel, nf, e2f, bc, Om, nx, ny, G, Om, Om, taue, tau);
+    const MeshView& M = H.view;
+    for (long long f = 0; f < nf; f++) { int hi = M.f2e[f].y; if (hi >= 0) tau[f] = taue[hi >> 2]; }   // k_face_tau
+    for (int e = 0; e < (int)nel; e++) {                                                              // k_local
+        double g[3], n1[3], n2[3], vx[3], vy[3]; bool dir[3];
+        for (int i = 0; i < 3; i++) {
+            int f = M.e2f[i * nel + e];
+            g[i] = G[i * nel + e]; n1[i] = nx[i * nel + e]; n2[i] = ny[i * nel + e];
+            dir[i] = M.bc[f] == 1; vx[i] = dir[i] ? VxDir[f] : 0.0; vy[i] = dir[i] ? VyDir[f] : 0.0;
+        }
+        ElemLocal o;
+        if (formulation == 0) element_local<kGradient>(Om[e], taue[e], sex[e], sey[e], g, n1, n2, dir, vx, vy, A, o);
+        else element_local<kSymmetricGradient>(Om[e], taue[e], sex[e], sey[e], g, n1, n2, dir, vx, vy, A, o);
+        alpha[e] = o.alpha; beta[e] = o.b1; beta[nel + e] = o.b2;
+        Z[e] = o.Z11; Z[nel + e] = o.Z21; Z[2 * nel + e] = o.Z12; Z[3 * nel + e] = o.Z22;
+    }
+    return 0;
+}
+
+int emu_assemble(int variant, int formulation, double A, long long nel, long long nf, const long long* e2f,
+                 const long long* bc, const double* Om, const double* nx, const double* ny, const double* G,
+                 const double* ke, const double* dl, const double* tau, const double* alpha, const double* beta,
+                 const double* Z, const double* VxDir, const double* VyDir, const double* sxx, const double* syy,
+                 const double* sxy, const double* syx, long long* rp_uu, int* c_uu, double* v_uu, long long* rp_up,
+                 int* c_up, double* v_up, long long* rp_mu, int* c_mu, double* v_mu, double* fu, double* fp) {
+    HostMesh H;
+    build_mesh(H, nel, nf, e2f, bc, Om, nx, ny, G, ke, dl, ke, tau);
+    LocalView L{alpha, beta, Z};
+    FaceDataView D{VxDir, VyDir, sxx, syy, sxy, syx};
+#define ARGS H.view, L, D, A, rp_uu, c_uu, v_uu, rp_up, c_up, v_up, rp_mu, c_mu, v_mu, fu, fp
+    if (variant == 0 && formulation == 0) assemble<kLoopOld, kGradient>(ARGS);
+    else if (variant == 0) assemble<kLoopOld, kSymmetricGradient>(ARGS);
+    else if (formulation == 0) assemble<kLoopNew, kGradient>(ARGS);
+    else assemble<kLoopNew, kSymmetricGradient>(ARGS);
+#undef ARGS
+    return 0;
+}
+
+int emu_residuals(int formulation, int tau_mode, long long nel, long long nf, const long long* e2f, const long long* bc,
+                  const double* Om, const double* nx, const double* ny, const double* G, const double* ke,
+                  const double* dl, const double* tau, const double* alpha, const double* beta, const double* Z,
+                  const double* Vxh, const double* Vyh, const double* Pe, const double* sex, const double* sey,
+                  const double* VxDir, const double* VyDir, const double* sxx, const double* syy, const double* sxy,
+                  const double* syx, double* sumsq, double* Fx, double* Fy, double* Fg2) {
+    HostMesh H;
+    build_mesh(H, nel, nf, e2f, bc, Om, nx, ny, G, ke, dl, ke, tau);
+    const MeshView& M = H.view;
+    std::vector<double> Fg(6 * nel);
+    for (int q = 0; q < 6; q++) sumsq[q] = 0.0;
+    for (int e = 0; e < (int)nel; e++) {   // k_res_elem
+        double g[3], n1[3], n2[3], t[3], uhx[3], uhy[3], udx[3], udy[3], tix[3], tiy[3]; int b[3];
+        for (int i = 0; i < 3; i++) {
+            int f = M.e2f[i * nel + e];
+            g[i] = G[i * nel + e]; n1[i] = nx[i * nel + e]; n2[i] = ny[i * nel + e]; b[i] = M.bc[f];
+            t[i] = tau_mode == 0 ? tau[e] : tau[f];
+            uhx[i] = Vxh[f]; uhy[i] = Vyh[f]; udx[i] = udy[i] = tix[i] = tiy[i] = 0.0;
+            if (b[i] == 1) { udx[i] = VxDir[f]; udy[i] = VyDir[f]; }
+            if (b[i] == 2) { tix[i] = n1[i] * sxx[f] + n2[i] * sxy[f]; tiy[i] = n1[i] * syx[f] + n2[i] * syy[f]; }
+        }
+        ElemRes r;
+        if (formulation == 0)
+            element_residual<kGradient>(Om[e], ke[e], dl[e], alpha[e], beta[e], beta[nel + e], Z[e], Z[nel + e], Z[2 * nel + e],
+                                        Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, uhx, uhy, udx, udy, tix, tiy, r);
+        else
+            element_residual<kSymmetricGradient>(Om[e], ke[e], dl[e], alpha[e], beta[e], beta[nel + e], Z[e], Z[nel + e],
+                                                 Z[2 * nel + e], Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, uhx, uhy,
+                                                 udx, udy, tix, tiy, r);
+        for (int i = 0; i < 3; i++) { Fg[(2 * i) * nel + e] = r.Fg1[i][0]; Fg[(2 * i + 1) * nel + e] = r.Fg1[i][1]; }
+        Fg2[e] = r.Fg2;
+        sumsq[0] += r.F1[0][0] * r.F1[0][0] + r.F1[1][0] * r.F1[1][0] + r.F1[0][1] * r.F1[0][1] + r.F1[1][1] * r.F1[1][1];
+        sumsq[1] += r.F2[0] * r.F2[0] + r.F2[1] * r.F2[1];
+        sumsq[2] += r.F3 * r.F3;
+        sumsq[5] += r.Fg2 * r.Fg2;
+    }
+    for (int f = 0; f < (int)nf; f++) {    // k_res_face
+        double fx = 0.0, fy = 0.0;
+        int2 pr = M.f2e[f];
+        if (pr.x >= 0 && M.bc[f] != 1) {
+            fx += Fg[(2 * (pr.x & 3)) * nel + (pr.x >> 2)]; fy += Fg[(2 * (pr.x & 3) + 1) * nel + (pr.x >> 2)];
+            if (pr.y != pr.x) { fx += Fg[(2 * (pr.y & 3)) * nel + (pr.y >> 2)]; fy += Fg[(2 * (pr.y & 3) + 1) * nel + (pr.y >> 2)]; }
+        }
+        Fx[f] = fx; Fy[f] = fy;
+        sumsq[3] += fx * fx; sumsq[4] += fy * fy;
+    }
+    return 0;
+}
+
+// strip layout + local face ids of the device generator (integer logic only)
+int emu_strip_connectivity(long long n, long long row0, long long row1, long long* sizes /* nel, nf, rlo, rhi */,
+                           int* e2f /* 3*nel or NULL */) {
+    StripLayout S = make_strip_layout(n, row0, row1);
+    sizes[0] = S.nel; sizes[1] = S.nf; sizes[2] = S.rlo; sizes[3] = S.rhi;
+    if (!e2f) return 0;
+    for (long long le = 0; le < S.nel; le++) {
+        long long ql = le >> 2; int t = (int)(le & 3);
+        long long qy = S.rlo + ql / n, qx = ql % n;
+        int f[8];
+        quad_faces(S, qx, qy, f);
+        int f1, f2, f3;
+        tri_faces(f, t, f1, f2, f3);
+        e2f[le] = f1; e2f[S.nel + le] = f2; e2f[2 * S.nel + le] = f3;
+    }
+    return 0;
+}
+
+}  // extern "C"

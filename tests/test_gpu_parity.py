@@ -1,0 +1,303 @@
+"""Parity of the CUDA path (through the C ABI, via the ctypes mirror of the Julia shim) against the
+oracle on identical seeded inputs.  Contract (BASELINE.json north_star): CSR sparsity and face
+numbering bit-exact; matrix, RHS and residual values within 1e-12 relative.  Design goal checked
+here: alpha/beta/Z/tau/Kuu/Kup/Muu/fu/fp are BITWISE equal; residual norms within 1e-12."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from helpers import assert_csr_equal, csc_triple_to_csr, rel_inf
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12   # relative tolerance stated by north_star for floating-point values
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+@pytest.fixture(scope="module")
+def api():
+    from fcfv_nme23_b200 import api
+    return api
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(cases.GOLDEN, "golden_oracle.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("name", ["H1", "H2", "S6", "S17"])
+def test_geometry_bitwise(name, api, oracle):
+    m = cases.load_mesh(name)                      # geometry from the oracle
+    ref = {k: getattr(m, k).copy() for k in ("Ω", "xc", "yc", "n_x", "n_y", "Γ")}
+    for k in ref:
+        setattr(m, k, None)
+    m.τ = None
+    api.mesh_geometry(m, 3.5)
+    for k, v in ref.items():
+        assert np.array_equal(getattr(m, k), v), k
+    assert np.all(m.τ == 3.5)
+    assert abs(m.Ω.sum() - 1.0) < 1e-12            # SolKzFCFV.jl:86 sanity check
+
+
+@pytest.mark.parametrize("case", cases.all_cases(), ids=lambda c: c.name)
+def test_local_assembly_residual(case, api, oracle, golden):
+    m, d = cases.build(case)       # oracle side
+    g, _ = cases.build(case)       # CUDA side (same seeded data)
+    nel, nf = m.nel, m.nf
+    neu = d["neu"]
+    # ---- ComputeFCFV
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form)
+    ga, gb, gZ = api.ComputeFCFV(g, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form)
+    assert np.array_equal(ga, a) and np.array_equal(gb, b) and np.array_equal(gZ, Z)
+    assert np.array_equal(g.τ, m.τ)
+    # ---- assembly
+    ofn = oracle.ElementAssemblyLoop if case.variant == 0 else oracle.ElementAssemblyLoopNEW
+    gfn = api.ElementAssemblyLoop if case.variant == 0 else api.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, _, _ = ofn(m, a, b, Z, d["VxDir"], d["VyDir"], *neu, case.form)
+    gKuu, gMuu, gKup, gfu, gfp, tsparse = gfn(g, ga, gb, gZ, d["VxDir"], d["VyDir"], *neu, case.form)
+    assert tsparse > 0.0 and gfu.shape == (2 * nf, 1) and gfp.shape == (nel,)
+    h = api.handle_for(g)
+    from fcfv_nme23_b200 import lib as L
+    for blk, ref, shape, what in ((L.KUU, Kuu, (2 * nf, 2 * nf), "Kuu"), (L.KUP, Kup, (2 * nf, nel), "Kup"),
+                                  (L.MUU, Muu, (2 * nf, 2 * nf), "Muu")):
+        # device CSR against CSR of the oracle's Julia-style CSC
+        assert_csr_equal(h.export_csr(blk), csc_triple_to_csr(ref, shape), what)
+        # Julia-facing CSC export: colptr / rowval / nzval identical to the oracle's SparseMatrixCSC fields
+        cp, rv, v = h.export_csc(blk)
+        assert cp.dtype == np.int64 and rv.dtype == np.int64
+        assert np.array_equal(cp, ref[0]) and np.array_equal(rv, ref[1]) and np.array_equal(v, ref[2]), what + " CSC"
+    assert np.array_equal(gfu, fu) and np.array_equal(gfp, fp)
+    assert (gKuu != h.export_scipy_csc(L.KUU)).nnz == 0
+    # ---- golden digests (pin the oracle; the CUDA path must hash to the same bytes)
+    gold = golden[case.name]
+    assert (gold["nnz_uu"], gold["nnz_up"], gold["nnz_muu"]) == (gKuu.nnz, gKup.nnz, gMuu.nnz)
+    assert gold["local"] == digest(ga, gb.ravel(order="F"), gZ.ravel(order="F"), g.τ)
+    assert gold["Kuu"] == digest(*h.export_csc(L.KUU)) and gold["Kup"] == digest(*h.export_csc(L.KUP))
+    assert gold["Muu"] == digest(*h.export_csc(L.MUU)) and gold["rhs"] == digest(gfu, gfp)
+    # ---- residuals
+    for tau_mode in ("REFERENCE", "FACE"):
+        norms, arr = oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"],
+                                                           d["VxDir"], d["VyDir"], *neu, case.form, tau_mode=tau_mode,
+                                                           arrays=True)
+        gn, garr = api.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], g, ga, gb, gZ, d["sex"], d["sey"],
+                                                      d["VxDir"], d["VyDir"], *neu, case.form, tau_mode=tau_mode,
+                                                      verbose=False, arrays=True)
+        for k in range(6):
+            if norms[k] > 1e-9:
+                assert abs(gn[k] - norms[k]) <= TOL * abs(norms[k]), (tau_mode, k, gn[k], norms[k])
+            else:
+                assert gn[k] < 1e-9
+        for k in ("F_nodes_x", "F_nodes_y", "F_glob2"):
+            assert rel_inf(garr[k], arr[k]) <= TOL, (tau_mode, k)
+    # ---- Powell-Hestenes lines on the resident CSR
+    u = np.concatenate([d["Vxh"], d["Vyh"]])
+    ru, rp, nrm = oracle.ph_residual(m, Kuu, Kup, fu, fp, u, d["Pe"])
+    gru, grp, gnrm = api.ph_residual(g, u, d["Pe"])
+    assert rel_inf(gru, ru) <= TOL and rel_inf(grp, rp) <= TOL and rel_inf(gnrm, nrm) <= TOL
+    assert rel_inf(api.ph_update_p(g, 1e4, u, d["Pe"]), oracle.ph_update_p(m, Kup, fp, 1e4, u, d["Pe"])) <= TOL
+    assert rel_inf(api.ph_fusc(g, 1e4, d["Pe"]), oracle.ph_fusc(m, Kup, fu, fp, 1e4, d["Pe"])) <= TOL
+    h.close()
+
+
+def test_edge_cases(api, oracle):
+    from fcfv_nme23_b200 import lib as L
+    from fcfv_nme23_b200.mesh import FCFV_Mesh
+    # single triangle, all faces Dirichlet: Kuu = identity, Kup empty
+    m = FCFV_Mesh(nel=1, nf=3, nv=3, nf_el=3, nn_el=3)
+    m.e2v = np.asfortranarray(np.array([[1, 2, 3]], dtype=np.int64)); m.e2f = np.asfortranarray(np.array([[1, 2, 3]], dtype=np.int64))
+    m.xv = np.array([0.0, 1.0, 0.0]); m.yv = np.array([0.0, 0.0, 1.0])
+    m.xf = np.array([0.5, 0.0, 0.5]); m.yf = np.array([0.5, 0.5, 0.0])   # numbering 0: face1=(v2,v3) face2=(v3,v1) face3=(v1,v2)
+    m.bc = np.array([1, 1, 1], dtype=np.int64); m.numbering = 0
+    m.ke = np.ones(1); m.δ = np.ones(1); m.τe = np.ones(1)
+    api.mesh_geometry(m, 1.0)
+    assert abs(m.Ω[0] - 0.5) < 1e-15
+    z3, z1 = np.zeros(3), np.zeros(1)
+    V = np.array([1.0, 2.0, 3.0])
+    a, b, Z = api.ComputeFCFV(m, z1, z1, V, -V, z3, z3, z3, z3, 1.0, ":Gradient")
+    Kuu, Muu, Kup, fu, fp, _ = api.ElementAssemblyLoop(m, a, b, Z, V, -V, z3, z3, z3, z3, ":Gradient")
+    assert Kuu.nnz == 6 and np.array_equal(Kuu.toarray(), np.eye(6)) and Kup.nnz == 0
+    assert np.array_equal(fu.ravel(), np.concatenate([V, -V]))
+    # invalid inputs fail loudly with a message, not a crash
+    h = api.Handle(0)
+    with pytest.raises(L.FCFVError):
+        h.run_local("Gradient")                       # no mesh
+    bad = cases.load_mesh("S6"); bad.e2f = bad.e2f.copy(); bad.e2f[0, 0] = bad.nf + 5
+    with pytest.raises(L.FCFVError):
+        h.set_mesh(bad)
+    with pytest.raises(ValueError):
+        api.formulation_id("Divergence")
+    h.close()
+
+
+@pytest.mark.parametrize("setting", ["solkz", "inclusion"])
+def test_device_generator_matches_host(setting, api, oracle):
+    """fcfv_generate_structured: connectivity identical to the host closed form (itself checked
+    against the ReadMeshesDat first-seen rule), geometry bitwise equal to the oracle geometry."""
+    from fcfv_nme23_b200 import mesh as M
+    n = 13
+    h = api.Handle(0)
+    h.generate_structured(n, setting=setting, tau_r=10.0 if setting == "solkz" else 2.0, neumann_south=(setting == "inclusion"))
+    dm = h.get_mesh()
+    host = cases.load_mesh(f"S{n}")
+    assert h.nel == host.nel and h.nf == host.nf
+    assert np.array_equal(dm["e2f"], host.e2f)
+    for k in ("Ω", "n_x", "n_y", "Γ"):
+        assert np.array_equal(dm[k], getattr(host, k)), k
+    bc = host.bc.copy()
+    if setting == "inclusion":
+        bc[(bc == 1) & (host.yf == 0.0)] = 2
+        assert (dm["bc"] == -1).sum() > 0
+    assert np.array_equal(dm["bc"] != 0, bc != 0) or setting == "inclusion"
+    assert np.array_equal(dm["bc"][bc > 0], bc[bc > 0])
+    h.close()
+
+
+@pytest.mark.parametrize("setting,variant,form", [("solkz", 1, "SymmetricGradient"), ("inclusion", 0, "Gradient")])
+def test_device_pipeline_vs_oracle(setting, variant, form, api, oracle):
+    """Device-resident pipeline (what bench.py times) on a generated mesh: pull the generated inputs
+    back, run the oracle on them, compare everything."""
+    from fcfv_nme23_b200 import lib as L
+    from fcfv_nme23_b200.mesh import FCFV_Mesh
+    n = 24
+    h = api.Handle(0)
+    tau_r = 10.0 if setting == "solkz" else 2.0
+    h.generate_structured(n, setting=setting, tau_r=tau_r, neumann_south=(setting == "inclusion"))
+    h.run_local(form)
+    h.run_assemble(variant, form, want_muu=True)
+    ss, norms = h.run_residuals(form, "FACE")
+    dm, dd = h.get_mesh(), h.get_data()
+    m = FCFV_Mesh(nel=h.nel, nf=h.nf, nf_el=3)
+    for k, v in dm.items():
+        setattr(m, k, v)
+    m.τ = None
+    neu = [dd["sxx"], dd["syy"], dd["sxy"], dd["syx"]]
+    a, b, Z = oracle.ComputeFCFV(m, dd["sex"], dd["sey"], dd["VxDir"], dd["VyDir"], *neu, tau_r, form)
+    ga, gb, gZ, gtau = h.get_local()
+    assert np.array_equal(ga, a) and np.array_equal(gb, b) and np.array_equal(gZ, Z) and np.array_equal(gtau, m.τ)
+    ofn = oracle.ElementAssemblyLoop if variant == 0 else oracle.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, _, _ = ofn(m, a, b, Z, dd["VxDir"], dd["VyDir"], *neu, form)
+    nel, nf = m.nel, m.nf
+    assert_csr_equal(h.export_csr(L.KUU), csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu")
+    assert_csr_equal(h.export_csr(L.KUP), csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup")
+    assert_csr_equal(h.export_csr(L.MUU), csc_triple_to_csr(Muu, (2 * nf, 2 * nf)), "Muu")
+    gfu, gfp = h.export_rhs()
+    assert np.array_equal(gfu, fu.ravel()) and np.array_equal(gfp, fp)
+    on = oracle.ComputeResidualsFCFV_Stokes_o1(dd["Vxh"], dd["Vyh"], dd["Pe"], m, a, b, Z, dd["sex"], dd["sey"], dd["VxDir"],
+                                               dd["VyDir"], *neu, form, tau_mode="FACE")
+    assert rel_inf(norms, on) <= TOL
+    h.close()
+
+
+def _strip_face_global(n, row0, row1):
+    """local -> global (0-based) face ids of a generated strip (fcfv_generate.cuh layout)."""
+    rlo = row0 - 1 if row0 > 0 else 0
+    rhi = row1 + 1 if row1 < n else n
+    base = lambda qx, qy: 6 * (qy * n + qx) + (qx if qy == 0 else n) + qy + (1 if qx > 0 else 0)
+    ids = []
+    if rlo > 0:
+        ids += [base(qx, rlo - 1) + (1 if rlo - 1 == 0 else 0) + 4 for qx in range(n)]
+    ids += list(range(base(0, rlo), base(0, rhi) if rhi < n else 6 * n * n + 2 * n))
+    return np.array(ids, dtype=np.int64), rlo, rhi
+
+
+@pytest.mark.parametrize("setting,variant,form", [("solkz", 1, "SymmetricGradient"), ("inclusion", 1, "Gradient")])
+def test_strips_reproduce_single_gpu_rows(setting, variant, form, api):
+    """Element-partitioned strips with ghost rows: every owned row is bit-identical to the row the
+    unpartitioned run produces, and the partial sums of squares add up to the global ones."""
+    from fcfv_nme23_b200 import lib as L
+    n, parts = 12, 3
+    tau_r = 10.0 if setting == "solkz" else 2.0
+    full = api.Handle(0)
+    full.generate_structured(n, setting=setting, tau_r=tau_r)
+    full.run_local(form); full.run_assemble(variant, form); ss_full, _ = full.run_residuals(form, "FACE")
+    NF = full.nf
+    rp, ci, v = full.export_csr(L.KUU)
+    rpp, cip, vp = full.export_csr(L.KUP)
+    fu_full, fp_full = full.export_rhs()
+    ss_sum = np.zeros(6)
+    rows_seen = np.zeros(2 * NF, dtype=int)
+    for r in range(parts):
+        row0, row1 = r * n // parts, (r + 1) * n // parts
+        h = api.Handle(0)
+        h.generate_structured(n, row0, row1, setting=setting, tau_r=tau_r)
+        h.run_local(form); h.run_assemble(variant, form); ss, _ = h.run_residuals(form, "FACE")
+        ss_sum += ss
+        fg, rlo, rhi = _strip_face_global(n, row0, row1)
+        assert fg.size == h.nf
+        lrp, lci, lv = h.export_csr(L.KUU)
+        lrpp, lcip, lvp = h.export_csr(L.KUP)
+        lfu, lfp = h.export_rhs()
+        nf = h.nf
+        ebase = 4 * n * rlo
+        for blockoff_l, blockoff_g in ((0, 0), (nf, NF)):
+            for lf in range(nf):
+                lr, gr = blockoff_l + lf, blockoff_g + fg[lf]
+                cnt = lrp[lr + 1] - lrp[lr]
+                if cnt == 0 and lfu[lr] == 0.0:
+                    continue   # not owned here (owned rows always hold their diagonal)
+                rows_seen[gr] += 1
+                cols_l = lci[lrp[lr]:lrp[lr + 1]].astype(np.int64)
+                cols_g = np.where(cols_l >= nf, fg[cols_l - nf] + NF, fg[np.minimum(cols_l, nf - 1)])
+                assert np.array_equal(cols_g, ci[rp[gr]:rp[gr + 1]]), (r, lf)
+                assert np.array_equal(lv[lrp[lr]:lrp[lr + 1]], v[rp[gr]:rp[gr + 1]])
+                assert np.array_equal(lcip[lrpp[lr]:lrpp[lr + 1]] + ebase, cip[rpp[gr]:rpp[gr + 1]])
+                assert np.array_equal(lvp[lrpp[lr]:lrpp[lr + 1]], vp[rpp[gr]:rpp[gr + 1]])
+                assert lfu[lr] == fu_full[gr]
+        own = slice(4 * n * (row0 - rlo), 4 * n * (row1 - rlo))
+        assert np.array_equal(lfp[own], fp_full[4 * n * row0:4 * n * row1])
+        h.close()
+    assert np.all(rows_seen == 1), "every global row must be produced by exactly one strip"
+    assert rel_inf(ss_sum, ss_full) <= TOL
+    full.close()
+
+
+def test_large_mesh_properties(api):
+    """1M-element mesh (BASELINE config 3 size): size-independent properties on the device result."""
+    from fcfv_nme23_b200 import lib as L
+    n = 500
+    h = api.Handle(0)
+    h.generate_structured(n, setting="solkz", tau_r=10.0)
+    assert h.nel == 4 * n * n and h.nf == 6 * n * n + 2 * n
+    h.run_local("SymmetricGradient")
+    h.run_assemble(L.LOOP_NEW, "SymmetricGradient")
+    nnz_uu, nnz_up, _ = h.get_nnz()
+    rp, ci, v = h.export_csr(L.KUU)
+    assert rp[0] == 0 and rp[-1] == nnz_uu and np.all(np.diff(rp) >= 1) and np.diff(rp).max() <= 10
+    # columns strictly ascending inside every row
+    inner = np.ones(nnz_uu, dtype=bool); inner[rp[1:-1]] = False
+    assert np.all(np.diff(ci.astype(np.int64))[inner[1:]] > 0)
+    assert np.all(v != 0.0) and np.all(np.isfinite(v))
+    # 24.78..25 nnz/element on S(n) for :SymmetricGradient, Kup ~ 5/element
+    assert 24.9 < nnz_uu / h.nel < 25.0 and 4.99 < nnz_up / h.nel < 5.0
+    # the symmetric formulation assembles a symmetric Kuu (pattern and values to round-off)
+    import scipy.sparse as sp
+    K = sp.csr_matrix((v, ci, rp), shape=(2 * h.nf, 2 * h.nf))
+    D = (K - K.T).tocoo()
+    assert np.abs(D.data).max() <= 1e-12 * np.abs(v).max()
+    # identity 1: matrix-free residual == SpMV residual on non-Dirichlet rows, for arbitrary (u,p)
+    dd, dm = h.get_data(), h.get_mesh()
+    u = np.concatenate([dd["Vxh"], dd["Vyh"]])
+    ru = np.empty(2 * h.nf); rp_ = np.empty(h.nel); nrm = np.zeros(2)
+    import ctypes as C
+    h.check(h.lib.fcfv_ph_residual(h._h, u.ctypes.data_as(C.c_void_p), dd["Pe"].ctypes.data_as(C.c_void_p),
+                                   ru.ctypes.data_as(C.c_void_p), rp_.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p)))
+    ss, norms = h.run_residuals("SymmetricGradient", "FACE")
+    nd = dm["bc"] != 1
+    fx2 = (ru[:h.nf][nd] ** 2).sum(); fy2 = (ru[h.nf:][nd] ** 2).sum()
+    assert abs(fx2 - ss[3]) <= 1e-9 * ss[3] and abs(fy2 - ss[4]) <= 1e-9 * ss[4]
+    assert abs((rp_ ** 2).sum() - ss[5]) <= 1e-9 * ss[5]
+    # run-to-run determinism: a second assembly gives identical bytes
+    h.run_assemble(L.LOOP_NEW, "SymmetricGradient")
+    rp2, ci2, v2 = h.export_csr(L.KUU)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2) and np.array_equal(v, v2)
+    h.close()

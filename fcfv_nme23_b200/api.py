@@ -119,6 +119,16 @@ class Handle:
     def stream(self):
         return self.lib.fcfv_stream(self._h)
 
+    def set_timing(self, flag):
+        self.check(self.lib.fcfv_set_timing(self._h, int(bool(flag))))
+
+    def get_timers(self):
+        """{kernel name: (total ms, launches)} accumulated since set_timing(True)."""
+        n = self.lib.fcfv_num_timers()
+        ms, calls = np.zeros(n), np.zeros(n, dtype=np.int64)
+        self.check(self.lib.fcfv_get_timers(self._h, _out(ms), _out(calls)))
+        return {self.lib.fcfv_timer_name(k).decode(): (float(ms[k]), int(calls[k])) for k in range(n)}
+
     def set_async(self, flag):
         self.check(self.lib.fcfv_set_async(self._h, int(bool(flag))))
 
@@ -256,6 +266,13 @@ class Handle:
                  ke=np.empty(nel), δ=np.empty(nel), τe=np.empty(nel), τ=np.empty(nf))
         self.check(self.lib.fcfv_get_mesh(self._h, *[_out(o[k]) for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe", "τ")]))
         return o
+
+    def get_ownership(self):
+        """(elem_owned, face_owned, nel_global, nf_global) of the resident (possibly partitioned) mesh."""
+        eo, fo = np.empty(self.nel, dtype=np.uint8), np.empty(self.nf, dtype=np.uint8)
+        ng, fg = C.c_int64(0), C.c_int64(0)
+        self.check(self.lib.fcfv_get_ownership(self._h, _out(eo), _out(fo), C.byref(ng), C.byref(fg)))
+        return eo, fo, ng.value, fg.value
 
     def get_data(self):
         nel, nf = self.nel, self.nf

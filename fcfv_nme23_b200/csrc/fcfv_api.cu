@@ -21,6 +21,11 @@ using namespace fcfv;
 
 struct Id128 { char b[128]; };   // ncclUniqueId
 
+enum { T_TAU = 0, T_LOCAL, T_COUNT, T_SCAN, T_FILL, T_RES_ELEM, T_RES_FACE, T_REDUCE, T_PH, T_OTHER, kNumTimers };
+static const char* const kTimerNames[kNumTimers] = {"k_face_tau", "k_local", "k_asm_count", "k_scan_bases", "k_asm_fill",
+                                                    "k_res_elem", "k_res_face", "k_reduce_partials", "k_ph", "other"};
+struct TimerRec { int id; cudaEvent_t a, b; };
+
 namespace {
 
 struct DBuf {   // device buffer that only grows
@@ -75,6 +80,13 @@ struct fcfv_handle {
     DBuf Fg, partial, sumsq;
     // scratch
     DBuf tmp, tmp2, err_flag, phw;
+    // per-kernel device timers (fcfv_set_timing): event pairs resolved lazily
+    bool timing = false;
+    std::vector<TimerRec> timer_recs;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    double timer_ms[kNumTimers] = {0};
+    long long timer_calls[kNumTimers] = {0};
     // nccl
     NcclApi nccl;
     void* comm = nullptr;
@@ -110,6 +122,40 @@ int fail(fcfv_t* h, int code, const char* fmt, ...) {
     do {                                                               \
         kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);      \
         (h)->launches++;                                               \
+    } while (0)
+
+cudaEvent_t pool_event(fcfv_t* h) {
+    if (h->events_used == h->event_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->event_pool.push_back(e);
+    }
+    return h->event_pool[h->events_used++];
+}
+
+// Folds finished event pairs into the per-kernel totals (stream must be synchronised).
+void resolve_timers(fcfv_t* h) {
+    for (const TimerRec& r : h->timer_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { h->timer_ms[r.id] += ms; h->timer_calls[r.id]++; }
+    }
+    h->timer_recs.clear();
+    h->events_used = 0;
+}
+
+// LAUNCH with the kernel bracketed by two events on the launching stream when timing is on.
+#define TLAUNCH(h, tid, kernel, grid, block, ...)                                        \
+    do {                                                                                 \
+        if ((h)->timing) {                                                               \
+            TimerRec r_{tid, pool_event(h), pool_event(h)};                              \
+            cudaEventRecord(r_.a, (h)->stream);                                          \
+            kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                    \
+            cudaEventRecord(r_.b, (h)->stream);                                          \
+            (h)->timer_recs.push_back(r_);                                               \
+        } else {                                                                         \
+            kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                    \
+        }                                                                                \
+        (h)->launches++;                                                                 \
     } while (0)
 
 int ensure(fcfv_t* h, DBuf& b, size_t bytes) {
@@ -254,6 +300,7 @@ int fcfv_destroy(fcfv_t* h) {
                    &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->totals,
                    &h->Fg, &h->partial, &h->sumsq, &h->tmp, &h->tmp2, &h->err_flag, &h->phw};
     for (DBuf* b : all) release(h, *b);
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -272,6 +319,29 @@ int fcfv_set_async(fcfv_t* h, int async) {
 int fcfv_sync(fcfv_t* h) {
     if (!h) return FCFV_ERR_INVALID;
     return sync(h);
+}
+
+int fcfv_set_timing(fcfv_t* h, int on) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(sync(h));
+    resolve_timers(h);
+    h->timing = on != 0;
+    for (int k = 0; k < kNumTimers; k++) { h->timer_ms[k] = 0.0; h->timer_calls[k] = 0; }
+    return FCFV_OK;
+}
+
+int fcfv_num_timers(void) { return kNumTimers; }
+const char* fcfv_timer_name(int k) { return (k >= 0 && k < kNumTimers) ? kTimerNames[k] : ""; }
+
+int fcfv_get_timers(fcfv_t* h, double* ms, int64_t* calls) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(sync(h));
+    resolve_timers(h);
+    for (int k = 0; k < kNumTimers; k++) {
+        if (ms) ms[k] = h->timer_ms[k];
+        if (calls) calls[k] = h->timer_calls[k];
+    }
+    return FCFV_OK;
 }
 
 void* fcfv_stream(fcfv_t* h) { return h ? (void*)h->stream : nullptr; }
@@ -466,12 +536,12 @@ int fcfv_run_local(fcfv_t* h, int formulation, double A) {
     TRY(need(h, h->have_sources && h->have_face_data, "fcfv_run_local: sources / face data not set"));
     CU(cudaSetDevice(h->device));
     const MeshView M = mesh_view(h);
-    LAUNCH(h, k_face_tau, nblocks(h->nf, 256), 256, M.f2e, M.taue, P<double>(h->tau), M.nf);
+    TLAUNCH(h, T_TAU, k_face_tau, nblocks(h->nf, 256), 256, M.f2e, M.taue, P<double>(h->tau), M.nf);
     if (formulation == FCFV_GRADIENT)
-        LAUNCH(h, k_local<kGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey), P<double>(h->VxDir),
+        TLAUNCH(h, T_LOCAL, k_local<kGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey), P<double>(h->VxDir),
                P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z));
     else
-        LAUNCH(h, k_local<kSymmetricGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey),
+        TLAUNCH(h, T_LOCAL, k_local<kSymmetricGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey),
                P<double>(h->VxDir), P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z));
     CU(cudaGetLastError());
     h->have_local = true;
@@ -514,20 +584,20 @@ int launch_assemble(fcfv_t* h, double A) {
     const LocalView L = local_view(h);
     const FaceDataView D = face_view(h);
     const int nblk = nblocks(h->nf);
-    LAUNCH(h, (k_asm_count<VARIANT, FORM, WANT_M>), nblk, kBlock, M, L, D, A, P<int>(h->sums), nblk);
-    LAUNCH(h, k_scan_bases, kNumSums, kScanThreads, P<int>(h->sums), P<long long>(h->bases), nblk, P<long long>(h->totals));
+    TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, WANT_M>), nblk, kBlock, M, L, D, A, P<int>(h->sums), nblk);
+    TLAUNCH(h, T_SCAN, k_scan_bases, kNumSums, kScanThreads, P<int>(h->sums), P<long long>(h->bases), nblk, P<long long>(h->totals));
     CsrOut ouu{h->Kuu.rowptr.p, P<int>(h->Kuu.col), P<double>(h->Kuu.val)};
     CsrOut oup{h->Kup.rowptr.p, P<int>(h->Kup.col), P<double>(h->Kup.val)};
     CsrOut omu{h->Muu.rowptr.p, P<int>(h->Muu.col), P<double>(h->Muu.val)};
     if (h->rp64) {
-        LAUNCH(h, k_finish_bases<long long>, nblocks(nblk, 256), 256, P<long long>(h->bases), nblk, P<long long>(h->totals),
+        TLAUNCH(h, T_SCAN, k_finish_bases<long long>, nblocks(nblk, 256), 256, P<long long>(h->bases), nblk, P<long long>(h->totals),
                (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)omu.rowptr, M.nf, (int)WANT_M);
-        LAUNCH(h, (k_asm_fill<VARIANT, FORM, WANT_M, long long>), nblk, kBlock, M, L, D, A, P<long long>(h->bases), nblk, ouu, oup,
+        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, long long>), nblk, kBlock, M, L, D, A, P<long long>(h->bases), nblk, ouu, oup,
                omu, P<double>(h->fu), P<double>(h->fp));
     } else {
-        LAUNCH(h, k_finish_bases<int>, nblocks(nblk, 256), 256, P<long long>(h->bases), nblk, P<long long>(h->totals),
+        TLAUNCH(h, T_SCAN, k_finish_bases<int>, nblocks(nblk, 256), 256, P<long long>(h->bases), nblk, P<long long>(h->totals),
                (int*)ouu.rowptr, (int*)oup.rowptr, (int*)omu.rowptr, M.nf, (int)WANT_M);
-        LAUNCH(h, (k_asm_fill<VARIANT, FORM, WANT_M, int>), nblk, kBlock, M, L, D, A, P<long long>(h->bases), nblk, ouu, oup, omu,
+        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, int>), nblk, kBlock, M, L, D, A, P<long long>(h->bases), nblk, ouu, oup, omu,
                P<double>(h->fu), P<double>(h->fp));
     }
     return FCFV_OK;
@@ -752,17 +822,17 @@ int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, 
     const MeshView M = mesh_view(h);
     double* part = P<double>(h->partial);
     if (formulation == FCFV_GRADIENT)
-        LAUNCH(h, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+        TLAUNCH(h, T_RES_ELEM, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
                P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr);
     else
-        LAUNCH(h, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+        TLAUNCH(h, T_RES_ELEM, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
                P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr);
-    LAUNCH(h, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, (double*)nullptr, (double*)nullptr);
+    TLAUNCH(h, T_RES_FACE, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, (double*)nullptr, (double*)nullptr);
     // sumsq order = print order: F_eq1, F_eq2, F_eq3, F_nodes_x, F_nodes_y, F_glob2
     double* ss = P<double>(h->sumsq);
-    LAUNCH(h, k_reduce_partials, 3, 1024, part, nbe, stride, ss);                                // eq1, eq2, eq3
-    LAUNCH(h, k_reduce_partials, 2, 1024, part + 4 * (size_t)stride, nbf, stride, ss + 3);       // nodes x, y
-    LAUNCH(h, k_reduce_partials, 1, 1024, part + 3 * (size_t)stride, nbe, stride, ss + 5);       // glob2
+    TLAUNCH(h, T_REDUCE, k_reduce_partials, 3, 1024, part, nbe, stride, ss);                                // eq1, eq2, eq3
+    TLAUNCH(h, T_REDUCE, k_reduce_partials, 2, 1024, part + 4 * (size_t)stride, nbf, stride, ss + 3);       // nodes x, y
+    TLAUNCH(h, T_REDUCE, k_reduce_partials, 1, 1024, part + 3 * (size_t)stride, nbe, stride, ss + 5);       // glob2
     CU(cudaGetLastError());
     if (h->comm) TRY(fcfv_comm_allreduce_sum(h, ss, 6));
     if (sumsq || norms) {
@@ -805,12 +875,12 @@ int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, 
         const MeshView M = mesh_view(h);
         double* part = P<double>(h->partial);
         if (formulation == FCFV_GRADIENT)
-            LAUNCH(h, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+            TLAUNCH(h, T_RES_ELEM, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
                    P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf);
         else
-            LAUNCH(h, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h),
+            TLAUNCH(h, T_RES_ELEM, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h),
                    P<double>(h->sex), P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf);
-        LAUNCH(h, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, t, t + nf);
+        TLAUNCH(h, T_RES_FACE, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, t, t + nf);
         CU(cudaGetLastError());
         if (F_nodes_x) TRY(copy(h, F_nodes_x, t, sizeof(double) * nf));
         if (F_nodes_y) TRY(copy(h, F_nodes_y, t + nf, sizeof(double) * nf));
@@ -856,8 +926,8 @@ int fcfv_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, do
                P<int>(h->Kup.rowptr), P<int>(h->Kup.col), P<double>(h->Kup.val), P<double>(h->fu), du, dp, dru, part);
     LAUNCH(h, k_ph_rp, nbe, kBlock, M, P<double>(h->fp), du, 0, 0.0, drp, (double*)nullptr, part + stride);
     double* ss = P<double>(h->sumsq);
-    LAUNCH(h, k_reduce_partials, 1, 1024, part, nbr, stride, ss + 6);
-    LAUNCH(h, k_reduce_partials, 1, 1024, part + stride, nbe, stride, ss + 7);
+    TLAUNCH(h, T_REDUCE, k_reduce_partials, 1, 1024, part, nbr, stride, ss + 6);
+    TLAUNCH(h, T_REDUCE, k_reduce_partials, 1, 1024, part + stride, nbe, stride, ss + 7);
     CU(cudaGetLastError());
     if (h->comm) TRY(fcfv_comm_allreduce_sum(h, ss + 6, 2));
     double hs[2];
@@ -941,6 +1011,23 @@ int fcfv_get_mesh(fcfv_t* h, int64_t* e2f, int64_t* bc, double* Omega, double* n
     if (delta) TRY(copy(h, delta, h->dl.p, sizeof(double) * nel));
     if (taue) TRY(copy(h, taue, h->taue.p, sizeof(double) * nel));
     if (tau) TRY(copy(h, tau, h->tau.p, sizeof(double) * nf));
+    return sync(h);
+}
+
+int fcfv_get_ownership(fcfv_t* h, uint8_t* elem_owned, uint8_t* face_owned, int64_t* nel_global, int64_t* nf_global) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_get_ownership: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    if (elem_owned) {
+        if (h->have_elem_owned) TRY(copy(h, elem_owned, h->elem_owned.p, (size_t)h->nel));
+        else memset(elem_owned, 1, (size_t)h->nel);
+    }
+    if (face_owned) {
+        if (h->have_face_owned) TRY(copy(h, face_owned, h->face_owned.p, (size_t)h->nf));
+        else memset(face_owned, 1, (size_t)h->nf);
+    }
+    if (nel_global) *nel_global = h->nel_global;
+    if (nf_global) *nf_global = h->nf_global;
     return sync(h);
 }
 

@@ -85,10 +85,14 @@ def load():
         "fcfv_get_nnz": [vp, P(i64), P(i64), P(i64)],
         "fcfv_set_async": [vp, ci],
         "fcfv_sync": [vp],
+        "fcfv_set_timing": [vp, ci],
+        "fcfv_num_timers": [],
+        "fcfv_get_timers": [vp, vp, vp],
         "fcfv_generate_structured": [vp, i64, i64, i64, ci, ci, dbl, dbl, ci],
         "fcfv_mesh_size": [vp, P(i64), P(i64)],
         "fcfv_get_mesh": [vp] + [vp] * 10,
         "fcfv_get_data": [vp] + [vp] * 11,
+        "fcfv_get_ownership": [vp, vp, vp, P(i64), P(i64)],
         "fcfv_comm_unique_id": [vp, vp],
         "fcfv_comm_init": [vp, vp, ci, ci],
         "fcfv_comm_allreduce_sum": [vp, vp, ci],
@@ -99,6 +103,8 @@ def load():
         fn.restype = ci
     lib.fcfv_last_error.argtypes = [vp]
     lib.fcfv_last_error.restype = C.c_char_p
+    lib.fcfv_timer_name.argtypes = [ci]
+    lib.fcfv_timer_name.restype = C.c_char_p
     lib.fcfv_stream.argtypes = [vp]
     lib.fcfv_stream.restype = vp
     lib.fcfv_kernel_launches.argtypes = [vp]

@@ -146,6 +146,13 @@ int fcfv_get_nnz(fcfv_t* h, int64_t* nnz_uu, int64_t* nnz_up, int64_t* nnz_muu);
 int fcfv_set_async(fcfv_t* h, int async);
 int fcfv_sync(fcfv_t* h);
 void* fcfv_stream(fcfv_t* h);               /* cudaStream_t */
+/* Per-kernel device timing: when on, every hot-path kernel launch is bracketed by CUDA events on the
+ * handle's stream; fcfv_get_timers returns the accumulated milliseconds and launch counts per
+ * kernel (arrays of fcfv_num_timers() entries, names via fcfv_timer_name).  set_timing resets. */
+int fcfv_set_timing(fcfv_t* h, int on);
+int fcfv_num_timers(void);
+const char* fcfv_timer_name(int k);
+int fcfv_get_timers(fcfv_t* h, double* ms, int64_t* calls);
 int64_t fcfv_kernel_launches(fcfv_t* h);    /* kernels launched by this handle so far */
 int64_t fcfv_device_bytes(fcfv_t* h);       /* device memory currently held by the handle */
 
@@ -164,6 +171,7 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
 int fcfv_mesh_size(fcfv_t* h, int64_t* nel, int64_t* nf);
 int fcfv_get_mesh(fcfv_t* h, int64_t* e2f, int64_t* bc, double* Omega, double* nx, double* ny,
                   double* Gamma, double* ke, double* delta, double* taue, double* tau);
+int fcfv_get_ownership(fcfv_t* h, uint8_t* elem_owned, uint8_t* face_owned, int64_t* nel_global, int64_t* nf_global);
 int fcfv_get_data(fcfv_t* h, double* sex, double* sey, double* VxDir, double* VyDir, double* sxxNeu,
                   double* syyNeu, double* sxyNeu, double* syxNeu, double* Vxh, double* Vyh, double* Pe);
 

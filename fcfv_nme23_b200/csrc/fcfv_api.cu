@@ -22,7 +22,7 @@ using namespace fcfv;
 struct Id128 { char b[128]; };   // ncclUniqueId
 
 enum { T_TAU = 0, T_LOCAL, T_COUNT, T_SCAN, T_FILL, T_RES_ELEM, T_RES_FACE, T_REDUCE, T_PH, T_OTHER, kNumTimers };
-static const char* const kTimerNames[kNumTimers] = {"k_face_tau", "k_local", "k_asm_count", "k_scan_bases", "k_asm_fill",
+static const char* const kTimerNames[kNumTimers] = {"k_face_tau", "k_local", "k_asm_count", "k_scan", "k_asm_fill",
                                                     "k_res_elem", "k_res_face", "k_reduce_partials", "k_ph", "other"};
 struct TimerRec { int id; cudaEvent_t a, b; };
 
@@ -73,7 +73,7 @@ struct fcfv_handle {
     DBuf alpha, beta, Z;
     // assembly
     Csr Kuu, Kup, Muu;
-    DBuf fu, fp, sums, bases, totals;
+    DBuf fu, fp, sums, bases, chunks, totals;
     long long totals_host[9] = {0};
     bool totals_valid = false;
     // residual
@@ -236,7 +236,8 @@ int build_f2e(fcfv_t* h) {
     TRY(ensure(h, h->tmp2, sizeof(int) * nf));
     LAUNCH(h, k_f2e_init, nblocks(nf, 256), 256, P<int2>(h->f2e), P<int>(h->tmp2), (int)nf);
     LAUNCH(h, k_f2e_build, nblocks(nel, 256), 256, P<int>(h->e2f), P<int2>(h->f2e), P<int>(h->tmp2), (int)nel);
-    LAUNCH(h, k_f2e_check, nblocks(nf, 256), 256, P<int2>(h->f2e), P<int>(h->tmp2), (int)nf, P<int>(h->err_flag));
+    LAUNCH(h, k_f2e_check, nblocks(nf, 256), 256, P<int2>(h->f2e), P<int>(h->tmp2), P<int>(h->e2f), (int)nel, (int)nf,
+           P<int>(h->err_flag));
     return FCFV_OK;
 }
 
@@ -297,7 +298,7 @@ int fcfv_destroy(fcfv_t* h) {
                    &h->elem_owned, &h->face_owned, &h->tau_ref, &h->sex, &h->sey, &h->VxDir, &h->VyDir, &h->sxx,
                    &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
                    &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,
-                   &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->totals,
+                   &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->chunks, &h->totals,
                    &h->Fg, &h->partial, &h->sumsq, &h->tmp, &h->tmp2, &h->err_flag, &h->phw};
     for (DBuf* b : all) release(h, *b);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
@@ -388,6 +389,7 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     TRY(read_err_flag(h, &flag));
     if (flag & 1) return fail(h, FCFV_ERR_INVALID, "e2f contains a face id outside 1..nf");
     if (flag & 2) return fail(h, FCFV_ERR_INVALID, "a face is referenced by more than two (element, local face) pairs");
+    if (flag & 4) return fail(h, FCFV_ERR_INVALID, "two elements share more than one face (or an element lists a face twice)");
     h->have_mesh = true;
     return FCFV_OK;
 }
@@ -583,22 +585,27 @@ int launch_assemble(fcfv_t* h, double A) {
     const MeshView M = mesh_view(h);
     const LocalView L = local_view(h);
     const FaceDataView D = face_view(h);
-    const int nblk = nblocks(h->nf);
-    TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, WANT_M>), nblk, kBlock, M, L, D, A, P<int>(h->sums), nblk);
-    TLAUNCH(h, T_SCAN, k_scan_bases, kNumSums, kScanThreads, P<int>(h->sums), P<long long>(h->bases), nblk, P<long long>(h->totals));
+    const int nblk = nblocks(h->nf, kAsmFaces);
+    const int nchunks = nblocks(nblk, kScanChunk);
+    int* sums = P<int>(h->sums);
+    int* local = P<int>(h->bases);
+    long long* chunk_tot = P<long long>(h->chunks);
+    long long* chunk_base = chunk_tot + (size_t)kNumSums * nchunks;
+    TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, WANT_M>), nblk, kAsmBlock, M, L, D, A, sums, nblk);
+    TLAUNCH(h, T_SCAN, k_scan_local, dim3(nchunks, kNumSums), 1024, sums, local, nblk, nchunks, chunk_tot);
     CsrOut ouu{h->Kuu.rowptr.p, P<int>(h->Kuu.col), P<double>(h->Kuu.val)};
     CsrOut oup{h->Kup.rowptr.p, P<int>(h->Kup.col), P<double>(h->Kup.val)};
     CsrOut omu{h->Muu.rowptr.p, P<int>(h->Muu.col), P<double>(h->Muu.val)};
     if (h->rp64) {
-        TLAUNCH(h, T_SCAN, k_finish_bases<long long>, nblocks(nblk, 256), 256, P<long long>(h->bases), nblk, P<long long>(h->totals),
-               (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)omu.rowptr, M.nf, (int)WANT_M);
-        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, long long>), nblk, kBlock, M, L, D, A, P<long long>(h->bases), nblk, ouu, oup,
-               omu, P<double>(h->fu), P<double>(h->fp));
+        TLAUNCH(h, T_SCAN, k_scan_chunks<long long>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals),
+                (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)omu.rowptr, M.nf, (int)WANT_M);
+        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, long long>), nblk, kAsmBlock, M, L, D, A, local, chunk_base, nblk,
+                nchunks, ouu, oup, omu, P<double>(h->fu), P<double>(h->fp));
     } else {
-        TLAUNCH(h, T_SCAN, k_finish_bases<int>, nblocks(nblk, 256), 256, P<long long>(h->bases), nblk, P<long long>(h->totals),
-               (int*)ouu.rowptr, (int*)oup.rowptr, (int*)omu.rowptr, M.nf, (int)WANT_M);
-        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, int>), nblk, kBlock, M, L, D, A, P<long long>(h->bases), nblk, ouu, oup, omu,
-               P<double>(h->fu), P<double>(h->fp));
+        TLAUNCH(h, T_SCAN, k_scan_chunks<int>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals), (int*)ouu.rowptr,
+                (int*)oup.rowptr, (int*)omu.rowptr, M.nf, (int)WANT_M);
+        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, int>), nblk, kAsmBlock, M, L, D, A, local, chunk_base, nblk, nchunks,
+                ouu, oup, omu, P<double>(h->fu), P<double>(h->fp));
     }
     return FCFV_OK;
 }
@@ -632,7 +639,8 @@ int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int wan
     CU(cudaSetDevice(h->device));
     const long long nel = h->nel, nf = h->nf;
     const size_t rpw = h->rp64 ? 8 : 4;
-    const int nblk = nblocks(nf);
+    const int nblk = nblocks(nf, kAsmFaces);
+    const int nchunks = nblocks(nblk, kScanChunk);
     // capacity = upper bounds (10 / 2 / 5 entries per row), so no host round trip between the passes
     TRY(ensure(h, h->Kuu.rowptr, rpw * (2 * nf + 1)));
     TRY(ensure(h, h->Kuu.col, sizeof(int) * 20 * nf));
@@ -647,8 +655,9 @@ int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int wan
     }
     TRY(ensure(h, h->fu, sizeof(double) * 2 * nf));
     TRY(ensure(h, h->fp, sizeof(double) * nel));
-    TRY(ensure(h, h->sums, sizeof(int) * kNumSums * nblk));
-    TRY(ensure(h, h->bases, sizeof(long long) * kNumSums * nblk));
+    TRY(ensure(h, h->sums, sizeof(int) * kNumSums * (size_t)nblk));
+    TRY(ensure(h, h->bases, sizeof(int) * kNumSums * (size_t)nblk));
+    TRY(ensure(h, h->chunks, sizeof(long long) * 2 * kNumSums * (size_t)nchunks));
     h->Kuu.nrows = 2 * nf; h->Kuu.ncols = 2 * nf;
     h->Kup.nrows = 2 * nf; h->Kup.ncols = nel;
     h->Muu.nrows = 2 * nf; h->Muu.ncols = 2 * nf;

@@ -38,19 +38,32 @@ struct LocalView { const double *alpha, *beta, *Z; };
 struct FaceDataView { const double *VxDir, *VyDir, *sxx, *syy, *sxy, *syx; };
 struct SolutionView { const double *Vxh, *Vyh, *Pe; };
 
-// Loads what element e contributes to the rows of its faces.
+// Everything a face row needs of one adjacent element, loaded once and viewed per component.
+struct FaceElem {
+    int g[3], bc[3];
+    double tau[3], G[3], nx[3], ny[3];
+    double eta, ia, iO, D11, D12, D21, D22;
+    double b1, b2, Z11, Z21, Z12, Z22;
+};
+
+// The element's three faces are loaded ROTATED so that the row face (local index i) sits at
+// position 0: every later index is then a compile-time constant (no selects, no local memory).
+// The values do not depend on the order in which the pairs (i, j) are visited; fp, whose
+// sequential sum does, is only formed when i == 0, where the rotation is the identity.
 template <int VARIANT>
-FCFV_HD void load_elem_asm(const MeshView& M, const LocalView& L, int e, ElemAsm& E) {
+FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, int e, int i, FaceElem& E) {
     const int nel = M.nel;
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
+    for (int k = 0; k < 3; k++) {
+        int j = i + k;
+        j = j >= 3 ? j - 3 : j;
         const int g = M.e2f[j * nel + e];
-        E.g[j] = g;
-        E.bc[j] = M.bc[g];
-        E.tau[j] = M.tau[g];
-        E.G[j] = M.G[j * nel + e];
-        E.nx[j] = M.nx[j * nel + e];
-        E.ny[j] = M.ny[j * nel + e];
+        E.g[k] = g;
+        E.bc[k] = M.bc[g];
+        E.tau[k] = M.tau[g];
+        E.G[k] = M.G[j * nel + e];
+        E.nx[k] = M.nx[j * nel + e];
+        E.ny[k] = M.ny[j * nel + e];
     }
     const double Om = M.Om[e];
     E.eta = M.ke[e];
@@ -66,71 +79,96 @@ FCFV_HD void load_elem_asm(const MeshView& M, const LocalView& L, int e, ElemAsm
     E.Z11 = L.Z[e]; E.Z21 = L.Z[nel + e]; E.Z12 = L.Z[2 * nel + e]; E.Z22 = L.Z[3 * nel + e];
 }
 
-// Everything one face thread needs: both rows of face f, fu, Kup entries; and, as a by-product
-// for the elements whose local face 0 is f, their fp value (so fp costs no extra pass).
-template <int VARIANT, int FORM, bool WANT_M>
-FCFV_HD void gather_face_rows(const MeshView& M, const LocalView& L, const FaceDataView& D, int f, double A,
-                              FaceRows& R, double fp_out[2], int fp_elem[2]) {
-    face_rows_init(R);
-    fp_elem[0] = fp_elem[1] = -1;
-    const int2 pr = M.f2e[f];
-    if (pr.x < 0) return;
-    const double vxf = D.VxDir[f], vyf = D.VyDir[f];
-    const double sxx = D.sxx[f], syy = D.syy[f], sxy = D.sxy[f], syx = D.syx[f];
+// comp-relative view (register renaming only): nr = normal component of the row's velocity component
+FCFV_HD void lane_view(const FaceElem& F, int comp, LaneElem& E) {
 #pragma unroll
-    for (int slot = 0; slot < 2; slot++) {
-        const int code = slot == 0 ? pr.x : pr.y;
-        if (slot == 1 && pr.y == pr.x) break;
-        const int e = code >> 2, i = code & 3;
-        ElemAsm E;
-        load_elem_asm<VARIANT>(M, L, e, E);
-        add_element_rows<VARIANT, FORM, WANT_M>(E, i, slot, e, A, vxf, vyf, sxx, syy, sxy, syx, R);
-        if (i == 0 && (M.elem_owned == nullptr || M.elem_owned[e])) {
-            bool dir[3]; double vx[3], vy[3];
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                dir[j] = E.bc[j] == 1;
-                vx[j] = dir[j] ? D.VxDir[E.g[j]] : 0.0;
-                vy[j] = dir[j] ? D.VyDir[E.g[j]] : 0.0;
-            }
-            fp_out[slot] = element_fp(E.G, E.nx, E.ny, dir, vx, vy);
-            fp_elem[slot] = e;
-        }
+    for (int j = 0; j < 3; j++) {
+        E.g[j] = F.g[j]; E.bc[j] = F.bc[j]; E.tau[j] = F.tau[j]; E.G[j] = F.G[j];
+        E.nr[j] = comp == 0 ? F.nx[j] : F.ny[j];
+        E.no[j] = comp == 0 ? F.ny[j] : F.nx[j];
     }
-    face_rows_merge<WANT_M>(R);
+    E.eta = F.eta; E.ia = F.ia; E.iO = F.iO;
+    E.Drr = comp == 0 ? F.D11 : F.D22;
+    E.Dro = comp == 0 ? F.D12 : F.D21;
+    E.br = comp == 0 ? F.b1 : F.b2;
+    E.Z1r = comp == 0 ? F.Z11 : F.Z12;   // Z[e,1,comp]
+    E.Z2r = comp == 0 ? F.Z21 : F.Z22;   // Z[e,2,comp]
+    E.Zr1 = comp == 0 ? F.Z11 : F.Z21;   // Z[e,comp,1]
+    E.Zr2 = comp == 0 ? F.Z12 : F.Z22;   // Z[e,comp,2]
 }
 
-// Non-zero flags and counts of the compacted rows.
-struct RowCounts {
-    bool nzxx[6], nzxy[6], nzyx[6], nzyy[6], nzmx[6], nzmy[6];
-    int nxx, nxy, nyx, nyy, nmx, nmy;   // per kind
-    bool pzx[2], pzy[2];
-    int npx, npy;
+// Rows (f,x) and (f,y): contributions of the element in `slot` (inactive when the face has no such
+// element).  With do_fp, when f is local face 0 of an owned element, that element's fp
+// (Discretisation:194) is returned too, so that fp needs no pass of its own.
+template <int VARIANT, int FORM, bool WANT_M>
+FCFV_HD void compute_slot(const MeshView& M, const LocalView& L, const FaceDataView& D, int f, int slot, double A,
+                          bool do_fp, LaneRow& Rx, LaneRow& Ry, int& fp_elem, double& fp_val) {
+    fp_elem = -1; fp_val = 0.0;
+    const int2 pr = M.f2e[f];
+    const bool has = pr.x >= 0 && (slot == 0 || pr.y != pr.x);
+    if (!has) { lane_row_inactive(Rx); lane_row_inactive(Ry); return; }
+    const int code = slot == 0 ? pr.x : pr.y;
+    const int e = code >> 2, i = code & 3;
+    FaceElem F;
+    load_face_elem<VARIANT>(M, L, e, i, F);
+    const int bcf = F.bc[0];
+    double vx = 0.0, vy = 0.0, sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
+    if (bcf == 1) { vx = D.VxDir[f]; vy = D.VyDir[f]; }
+    if (bcf == 2) { sxx = D.sxx[f]; sxy = D.sxy[f]; syx = D.syx[f]; syy = D.syy[f]; }   // tractions only enter through t*Xi
+    LaneElem E;
+    lane_view(F, 0, E);
+    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 0, A, vx, sxx, sxy, Rx);   // row face at rotated index 0
+    lane_view(F, 1, E);
+    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 1, A, vy, syx, syy, Ry);
+    if (do_fp && i == 0 && (M.elem_owned == nullptr || M.elem_owned[e])) {
+        bool dir[3]; double dvx[3], dvy[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            dir[j] = F.bc[j] == 1;
+            dvx[j] = dir[j] ? D.VxDir[F.g[j]] : 0.0;
+            dvy[j] = dir[j] ? D.VyDir[F.g[j]] : 0.0;
+        }
+        fp_val = element_fp(F.G, F.nx, F.ny, dir, dvx, dvy);
+        fp_elem = e;
+    }
+}
+
+// One CSR row: merged / ranked / zero-dropped contributions of both adjacent elements.
+struct AsmRow {
+    LaneRow R0, R1;        // contributions of the lower / higher adjacent element
+    LanePlace P0, P1;
+    int m0, m1;            // nz masks
 };
 
-template <bool WANT_M>
-FCFV_HD void count_rows(const FaceRows& R, RowCounts& C) {
-    C.nxx = C.nxy = C.nyx = C.nyy = C.nmx = C.nmy = 0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        const bool alive = R.key[k] != kDeadKey;
-        C.nzxx[k] = alive && R.xx[k] != 0.0; C.nxx += C.nzxx[k];
-        C.nzxy[k] = alive && R.xy[k] != 0.0; C.nxy += C.nzxy[k];
-        C.nzyx[k] = alive && R.yx[k] != 0.0; C.nyx += C.nzyx[k];
-        C.nzyy[k] = alive && R.yy[k] != 0.0; C.nyy += C.nzyy[k];
-        if (WANT_M) {
-            C.nzmx[k] = alive && R.mxx[k] != 0.0; C.nmx += C.nzmx[k];
-            C.nzmy[k] = alive && R.myy[k] != 0.0; C.nmy += C.nzmy[k];
-        } else {
-            C.nzmx[k] = C.nzmy[k] = false;
-        }
+FCFV_HD void finish_row(AsmRow& o, int comp) {
+    LanePeer p0, p1;
+    lane_peer_of(o.R0, p0);
+    lane_peer_of(o.R1, p1);
+    lane_merge(o.R0, 0, p1);
+    lane_merge(o.R1, 1, p0);
+    o.m0 = lane_nzmask(o.R0);
+    o.m1 = lane_nzmask(o.R1);
+    lane_place(o.R0, o.m0, o.R1.key, o.m1, comp, o.P0);
+    lane_place(o.R1, o.m1, o.R0.key, o.m0, comp, o.P1);
+}
+
+// Both rows of face f -- what one assembly thread computes; shared by the count pass, the fill
+// pass and the host emulation.
+template <int VARIANT, int FORM, bool WANT_M>
+FCFV_HD void asm_face(const MeshView& M, const LocalView& L, const FaceDataView& D, double A, int f, bool do_fp,
+                      AsmRow& ax, AsmRow& ay, int fp_elem[2], double fp_val[2]) {
+    const bool inrange = f < M.nf;
+    const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
+    fp_elem[0] = fp_elem[1] = -1; fp_val[0] = fp_val[1] = 0.0;
+    if (inrange && (owned || do_fp)) {
+        compute_slot<VARIANT, FORM, WANT_M>(M, L, D, f, 0, A, do_fp, ax.R0, ay.R0, fp_elem[0], fp_val[0]);
+        compute_slot<VARIANT, FORM, WANT_M>(M, L, D, f, 1, A, do_fp, ax.R1, ay.R1, fp_elem[1], fp_val[1]);
     }
-    C.npx = C.npy = 0;
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        C.pzx[s] = R.pe[s] >= 0 && R.px[s] != 0.0; C.npx += C.pzx[s];
-        C.pzy[s] = R.pe[s] >= 0 && R.py[s] != 0.0; C.npy += C.pzy[s];
+    if (!owned) {   // rows of faces owned elsewhere (or out of range) stay empty
+        lane_row_inactive(ax.R0); lane_row_inactive(ax.R1); lane_row_inactive(ay.R0); lane_row_inactive(ay.R1);
     }
+    finish_row(ax, 0);
+    finish_row(ay, 1);
 }
 
 #if defined(__CUDACC__)
@@ -138,8 +176,14 @@ FCFV_HD void count_rows(const FaceRows& R, RowCounts& C) {
 // kernels
 // =============================================================================================
 constexpr int kBlock = 128;          // threads per block for element / face kernels
+constexpr int kAsmBlock = 128;       // assembly: one thread per face (both rows)
+constexpr int kAsmFaces = kAsmBlock;
 constexpr int kMaxRow = 10;          // max entries of a Kuu row (5 faces x 2 components)
 constexpr int kNumSums = 6;          // Kuu-x, Kuu-y, Kup-x, Kup-y, Muu-x, Muu-y
+constexpr int kScanChunk = 4096;     // block sums scanned per chunk
+#ifndef FCFV_ASM_MINBLOCKS
+#define FCFV_ASM_MINBLOCKS 4         // resident 128-thread assembly blocks per SM the register budget is tuned for (<=128 regs)
+#endif
 
 __device__ __forceinline__ int warp_incl_scan(int v) {
     const int lane = threadIdx.x & 31;
@@ -151,8 +195,9 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
     return v;
 }
 
-// Exclusive scan of one int per thread over a block of kBlock threads; returns the offset and the
-// block total.  `sw` is shared scratch of kBlock/32 + 1 ints.  Deterministic (integers).
+// Exclusive scan of one int per thread over a block of NT threads; returns the offset and the
+// block total.  `sw` is shared scratch of NT/32 ints.  Deterministic (integers).
+template <int NT>
 __device__ __forceinline__ int block_excl_scan(int v, int& total, int* sw) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int inc = warp_incl_scan(v);
@@ -160,7 +205,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int& total, int* sw) {
     __syncthreads();
     int base = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < kBlock / 32; k++) {
+    for (int k = 0; k < NT / 32; k++) {
         const int s = sw[k];
         if (k < w) base += s;
         tot += s;
@@ -224,12 +269,23 @@ __global__ void k_f2e_build(const int* __restrict__ e2f, int2* __restrict__ f2e,
     }
 }
 
-__global__ void k_f2e_check(int2* __restrict__ f2e, const int* __restrict__ cnt, int nf, int* __restrict__ err) {
+// err bit 1: face referenced more than twice; bit 2: the two references come from the same element
+// or the two elements share more than one face (the row gather assumes one shared column).
+__global__ void k_f2e_check(int2* __restrict__ f2e, const int* __restrict__ cnt, const int* __restrict__ e2f, int nel,
+                            int nf, int* __restrict__ err) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;
     const int c = cnt[f];
     if (c > 2) atomicOr(err, 2);
     if (c == 0) f2e[f] = make_int2(-1, -1);
+    if (c == 2) {
+        const int2 pr = f2e[f];
+        const int e0 = pr.x >> 2, e1 = pr.y >> 2;
+        int shared = 0;
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) shared += e2f[a * nel + e0] == e2f[b * nel + e1];
+        if (e0 == e1 || shared != 1) atomicOr(err, 4);
+    }
 }
 
 // ---- a3: tau[f] = taue[highest-numbered adjacent element] (Discretisation:40, last writer) ----
@@ -297,210 +353,183 @@ k_local(MeshView M, const double* __restrict__ sex, const double* __restrict__ s
     Z[e] = o.Z11; Z[nel + e] = o.Z21; Z[2 * nel + e] = o.Z12; Z[3 * nel + e] = o.Z22;
 }
 
-// ---- a5/a6/a7 assembly: count pass ---------------------------------------------------------------
-// sums[q*nblk + b] = number of stored entries block b will write for quantity q.
+// ---- a5/a6/a7 assembly --------------------------------------------------------------------------
+// Thread = (face, comp): tid = 2*face_local + comp.  A thread owns one CSR row: it loads the <=2
+// adjacent elements one after the other (the x and y threads of a face are neighbouring lanes and
+// read the same addresses, so the pair costs one L1 access), merges the duplicate column, ranks
+// the <=5 columns and drops exact zeros.  Both passes run the same computation; the count pass
+// only reduces the row lengths of a block, the fill pass places the entries.
+// count pass: one thread per face (both rows); sums[q*nblk + b] = number of stored entries block b
+// will write for quantity q
 template <int VARIANT, int FORM, bool WANT_M>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_MINBLOCKS)
 k_asm_count(MeshView M, LocalView L, FaceDataView D, double A, int* __restrict__ sums, int nblk) {
-    __shared__ int sw[kBlock / 32 + 1];
-    const int f = blockIdx.x * kBlock + threadIdx.x;
-    int c0 = 0, c1 = 0, c2 = 0;
-    if (f < M.nf && (M.face_owned == nullptr || M.face_owned[f])) {
-        FaceRows R; double fpv[2]; int fpe[2];
-        gather_face_rows<VARIANT, FORM, WANT_M>(M, L, D, f, A, R, fpv, fpe);
-        RowCounts C;
-        count_rows<WANT_M>(R, C);
-        c0 = (C.nxx + C.nxy) | ((C.nyx + C.nyy) << 16);
-        c1 = C.npx | (C.npy << 16);
-        c2 = C.nmx | (C.nmy << 16);
-    }
-    int t0, t1, t2;
-    block_excl_scan(c0, t0, sw);
-    block_excl_scan(c1, t1, sw);
-    if (WANT_M) block_excl_scan(c2, t2, sw); else t2 = 0;
-    if (threadIdx.x == 0) {
+    __shared__ int sw[kAsmBlock / 32];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x * kAsmFaces + tid;
+    AsmRow ax, ay;
+    int fpe[2]; double fpv[2];
+    asm_face<VARIANT, FORM, WANT_M>(M, L, D, A, f, false, ax, ay, fpe, fpv);
+    const int c0 = (ax.P0.n_first + ax.P0.n_second) | ((ay.P0.n_first + ay.P0.n_second) << 16);
+    const int c1 = (((ax.m0 >> 9) & 1) + ((ax.m1 >> 9) & 1)) | ((((ay.m0 >> 9) & 1) + ((ay.m1 >> 9) & 1)) << 16);
+    const int c2 = ax.P0.n_m | (ay.P0.n_m << 16);
+    int t0, t1, t2 = 0;
+    block_excl_scan<kAsmBlock>(c0, t0, sw);
+    block_excl_scan<kAsmBlock>(c1, t1, sw);
+    if (WANT_M) block_excl_scan<kAsmBlock>(c2, t2, sw);
+    if (tid == 0) {
         const int b = blockIdx.x;
-        sums[0 * nblk + b] = t0 & 0xffff; sums[1 * nblk + b] = t0 >> 16;
-        sums[2 * nblk + b] = t1 & 0xffff; sums[3 * nblk + b] = t1 >> 16;
-        sums[4 * nblk + b] = t2 & 0xffff; sums[5 * nblk + b] = t2 >> 16;
+        sums[0 * (size_t)nblk + b] = t0 & 0xffff; sums[1 * (size_t)nblk + b] = t0 >> 16;
+        sums[2 * (size_t)nblk + b] = t1 & 0xffff; sums[3 * (size_t)nblk + b] = t1 >> 16;
+        sums[4 * (size_t)nblk + b] = t2 & 0xffff; sums[5 * (size_t)nblk + b] = t2 >> 16;
     }
 }
 
-// ---- scan of the block sums -> global bases (one block per quantity pair) ------------------------
-// bases[q*nblk + b] = global offset of block b's first entry of quantity q inside its CSR
-// (x rows first, then y rows).  totals[q] = entries of quantity q; totals[6..8] = nnz of Kuu/Kup/Muu.
-constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 4;
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_bases(const int* __restrict__ sums, long long* __restrict__ bases, int nblk, long long* __restrict__ totals) {
-    __shared__ long long swarp[kScanThreads / 32];
-    __shared__ long long carry_s;
-    const int q = blockIdx.x;   // 0..5
+// ---- scan of the block sums: chunk-local exclusive scan, then the (few) chunk totals -------------
+// grid (nchunks, 6); local[q*nblk + b] = exclusive prefix of sums inside b's chunk.
+__global__ void __launch_bounds__(1024)
+k_scan_local(const int* __restrict__ sums, int* __restrict__ local, int nblk, int nchunks, long long* __restrict__ chunk_tot) {
+    __shared__ int sw[32];
+    const int q = blockIdx.y, c = blockIdx.x;
     const int* in = sums + (size_t)q * nblk;
-    long long* out = bases + (size_t)q * nblk;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (long long start = 0; start < nblk; start += (long long)kScanThreads * kScanItems) {
-        const long long i0 = start + (long long)threadIdx.x * kScanItems;
-        int v[kScanItems];
-        long long tsum = 0;
+    int* out = local + (size_t)q * nblk;
+    const long long i0 = (long long)c * kScanChunk + (long long)threadIdx.x * 4;
+    int v[4], tsum = 0;
 #pragma unroll
-        for (int k = 0; k < kScanItems; k++) { v[k] = (i0 + k < nblk) ? in[i0 + k] : 0; tsum += v[k]; }
-        long long inc = tsum;
+    for (int k = 0; k < 4; k++) { v[k] = (i0 + k < nblk) ? in[i0 + k] : 0; tsum += v[k]; }
+    int total;
+    int run = block_excl_scan<1024>(tsum, total, sw);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const long long t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        if (lane == 31) swarp[w] = inc;
-        __syncthreads();
-        long long wbase = 0, tot = 0;
-        for (int k = 0; k < kScanThreads / 32; k++) { const long long s = swarp[k]; if (k < w) wbase += s; tot += s; }
-        long long run = carry_s + wbase + inc - tsum;
-#pragma unroll
-        for (int k = 0; k < kScanItems; k++) { if (i0 + k < nblk) out[i0 + k] = run; run += v[k]; }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) totals[q] = carry_s;
+    for (int k = 0; k < 4; k++) { if (i0 + k < nblk) out[i0 + k] = run; run += v[k]; }
+    if (threadIdx.x == 0) chunk_tot[(size_t)q * nchunks + c] = total;
 }
 
-// y-row bases are offset by the x-row total of the same matrix; also emits nnz and the last rowptr entry.
+// one block: exclusive scan of the chunk totals per quantity; y-row bases are offset by the x-row
+// total of the same matrix.  totals[0..5] per quantity, totals[6..8] nnz of Kuu/Kup/Muu; also writes
+// the last row pointer of each CSR.
 template <typename RP>
-__global__ void k_finish_bases(long long* __restrict__ bases, int nblk, long long* __restrict__ totals,
-                               RP* __restrict__ rp_uu, RP* __restrict__ rp_up, RP* __restrict__ rp_mu, int nf,
-                               int want_m) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nblk) {
-        bases[1 * (size_t)nblk + i] += totals[0];
-        bases[3 * (size_t)nblk + i] += totals[2];
-        if (want_m) bases[5 * (size_t)nblk + i] += totals[4];
+__global__ void k_scan_chunks(const long long* __restrict__ chunk_tot, long long* __restrict__ chunk_base, int nchunks,
+                              long long* __restrict__ totals, RP* __restrict__ rp_uu, RP* __restrict__ rp_up,
+                              RP* __restrict__ rp_mu, int nf, int want_m) {
+    __shared__ long long tot[kNumSums];
+    const int q = threadIdx.x;
+    if (q < kNumSums) {
+        long long run = 0;
+        for (int c = 0; c < nchunks; c++) { chunk_base[(size_t)q * nchunks + c] = run; run += chunk_tot[(size_t)q * nchunks + c]; }
+        tot[q] = run;
+        totals[q] = run;
     }
-    if (i == 0) {
-        totals[6] = totals[0] + totals[1];
-        totals[7] = totals[2] + totals[3];
-        totals[8] = totals[4] + totals[5];
-        rp_uu[2 * (size_t)nf] = (RP)(totals[0] + totals[1]);
-        rp_up[2 * (size_t)nf] = (RP)(totals[2] + totals[3]);
-        if (want_m) rp_mu[2 * (size_t)nf] = (RP)(totals[4] + totals[5]);
+    __syncthreads();
+    if (q < kNumSums && (q & 1))
+        for (int c = 0; c < nchunks; c++) chunk_base[(size_t)q * nchunks + c] += tot[q - 1];
+    if (q == 0) {
+        totals[6] = tot[0] + tot[1]; totals[7] = tot[2] + tot[3]; totals[8] = tot[4] + tot[5];
+        rp_uu[2 * (size_t)nf] = (RP)(tot[0] + tot[1]);
+        rp_up[2 * (size_t)nf] = (RP)(tot[2] + tot[3]);
+        if (want_m) rp_mu[2 * (size_t)nf] = (RP)(tot[4] + tot[5]);
     }
 }
 
-// ---- assembly: fill pass ------------------------------------------------------------------------
-// Recomputes the rows (cheaper than storing padded rows), takes the block-local exclusive scan of
-// the row lengths, stages the block's compacted entries in shared memory and writes them to the
-// CSR arrays as contiguous, fully coalesced segments (rows of a block are consecutive).
+// ---- fill pass ----------------------------------------------------------------------------------
+// Recomputes the lanes, takes the block-local exclusive scan of the row lengths, stages the block's
+// compacted entries in shared memory (x rows in the lower half, y rows in the upper half) and
+// writes them to the CSR arrays as two contiguous, fully coalesced segments.
 struct CsrOut { void* rowptr; int* col; double* val; };
 
-template <typename RP>
 __device__ __forceinline__ void flush_segment(const double* sval, const int* scol, int count, long long base,
                                               const CsrOut& O) {
-    for (int k = threadIdx.x; k < count; k += kBlock) {
+    for (int k = threadIdx.x; k < count; k += kAsmBlock) {
         O.val[base + k] = sval[k];
         O.col[base + k] = scol[k];
     }
 }
 
+// stages the Kuu entries of one row into shared memory at its block-local offset
+__device__ __forceinline__ void stage_row(const AsmRow& a, int off, int cs, int cc, double* sval, int* scol) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        if (a.P0.ps[j] >= 0) { const int p = off + a.P0.ps[j]; sval[p] = a.R0.vs[j]; scol[p] = a.R0.key[j] + cs; }
+        if (a.P0.pc[j] >= 0) { const int p = off + a.P0.pc[j]; sval[p] = a.R0.vc[j]; scol[p] = a.R0.key[j] + cc; }
+        if (a.P1.ps[j] >= 0) { const int p = off + a.P1.ps[j]; sval[p] = a.R1.vs[j]; scol[p] = a.R1.key[j] + cs; }
+        if (a.P1.pc[j] >= 0) { const int p = off + a.P1.pc[j]; sval[p] = a.R1.vc[j]; scol[p] = a.R1.key[j] + cc; }
+    }
+}
+
 template <int VARIANT, int FORM, bool WANT_M, typename RP>
-__global__ void __launch_bounds__(kBlock)
-k_asm_fill(MeshView M, LocalView L, FaceDataView D, double A, const long long* __restrict__ bases, int nblk,
-           CsrOut Kuu, CsrOut Kup, CsrOut Muu, double* __restrict__ fu, double* __restrict__ fp) {
-    __shared__ double sval[kMaxRow * kBlock];
-    __shared__ int scol[kMaxRow * kBlock];
-    __shared__ int sw[kBlock / 32 + 1];
+__global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_MINBLOCKS)
+k_asm_fill(MeshView M, LocalView L, FaceDataView D, double A, const int* __restrict__ local, const long long* __restrict__ chunk_base,
+           int nblk, int nchunks, CsrOut Kuu, CsrOut Kup, CsrOut Muu, double* __restrict__ fu, double* __restrict__ fp) {
+    constexpr int kHalf = kMaxRow * kAsmFaces;            // staging capacity per component
+    __shared__ double sval[2 * kHalf];
+    __shared__ int scol[2 * kHalf];
+    __shared__ int sw[kAsmBlock / 32];
     const int b = blockIdx.x;
-    const int f = b * kBlock + threadIdx.x;
+    const int tid = threadIdx.x;
+    const int f = b * kAsmFaces + tid;
     const int nf = M.nf;
     const bool inrange = f < nf;
-    const bool active = inrange && (M.face_owned == nullptr || M.face_owned[f]);
-    FaceRows R; RowCounts C;
-    double fpv[2]; int fpe[2] = {-1, -1};
-    int c0 = 0, c1 = 0, c2 = 0;
+    AsmRow ax, ay;
+    int fpe[2]; double fpv[2];
+    asm_face<VARIANT, FORM, WANT_M>(M, L, D, A, f, true, ax, ay, fpe, fpv);
+    if (fpe[0] >= 0) fp[fpe[0]] = fpv[0];
+    if (fpe[1] >= 0) fp[fpe[1]] = fpv[1];
     if (inrange) {
-        // fp duty is independent of face ownership, so gather whenever the face exists locally
-        gather_face_rows<VARIANT, FORM, WANT_M>(M, L, D, f, A, R, fpv, fpe);
-        if (fpe[0] >= 0) fp[fpe[0]] = fpv[0];
-        if (fpe[1] >= 0) fp[fpe[1]] = fpv[1];
+        fu[f] = ax.R0.active ? ax.R0.fu : 0.0;
+        fu[(size_t)nf + f] = ay.R0.active ? ay.R0.fu : 0.0;
     }
-    if (active) {
-        count_rows<WANT_M>(R, C);
-        c0 = (C.nxx + C.nxy) | ((C.nyx + C.nyy) << 16);
-        c1 = C.npx | (C.npy << 16);
-        c2 = C.nmx | (C.nmy << 16);
-        fu[f] = R.fx;
-        fu[nf + f] = R.fy;
-    } else if (inrange) {
-        fu[f] = 0.0; fu[nf + f] = 0.0;
-    }
-    int t0, t1, t2 = 0;
-    const int o0 = block_excl_scan(c0, t0, sw);
-    const int o1 = block_excl_scan(c1, t1, sw);
-    int o2 = 0;
-    if (WANT_M) o2 = block_excl_scan(c2, t2, sw);
-    const long long bux = bases[0 * (size_t)nblk + b], buy = bases[1 * (size_t)nblk + b];
-    const long long bpx = bases[2 * (size_t)nblk + b], bpy = bases[3 * (size_t)nblk + b];
+    const int c0 = (ax.P0.n_first + ax.P0.n_second) | ((ay.P0.n_first + ay.P0.n_second) << 16);
+    const int c1 = (((ax.m0 >> 9) & 1) + ((ax.m1 >> 9) & 1)) | ((((ay.m0 >> 9) & 1) + ((ay.m1 >> 9) & 1)) << 16);
+    const int c2 = ax.P0.n_m | (ay.P0.n_m << 16);
+    int t0, t1, t2 = 0, o2 = 0;
+    const int o0 = block_excl_scan<kAsmBlock>(c0, t0, sw);
+    const int o1 = block_excl_scan<kAsmBlock>(c1, t1, sw);
+    if (WANT_M) o2 = block_excl_scan<kAsmBlock>(c2, t2, sw);
+    const int ch = b / kScanChunk;
+    auto gbase = [&](int q) -> long long { return chunk_base[(size_t)q * nchunks + ch] + local[(size_t)q * nblk + b]; };
+    const long long bux = gbase(0), buy = gbase(1), bpx = gbase(2), bpy = gbase(3);
+    const long long bmx = WANT_M ? gbase(4) : 0, bmy = WANT_M ? gbase(5) : 0;
     if (inrange) {
         ((RP*)Kuu.rowptr)[f] = (RP)(bux + (o0 & 0xffff));
         ((RP*)Kuu.rowptr)[(size_t)nf + f] = (RP)(buy + (o0 >> 16));
         ((RP*)Kup.rowptr)[f] = (RP)(bpx + (o1 & 0xffff));
         ((RP*)Kup.rowptr)[(size_t)nf + f] = (RP)(bpy + (o1 >> 16));
         if (WANT_M) {
-            ((RP*)Muu.rowptr)[f] = (RP)(bases[4 * (size_t)nblk + b] + (o2 & 0xffff));
-            ((RP*)Muu.rowptr)[(size_t)nf + f] = (RP)(bases[5 * (size_t)nblk + b] + (o2 >> 16));
+            ((RP*)Muu.rowptr)[f] = (RP)(bmx + (o2 & 0xffff));
+            ((RP*)Muu.rowptr)[(size_t)nf + f] = (RP)(bmy + (o2 >> 16));
         }
     }
-    // ---- Kuu x rows: columns (g,x) ascending, then (g,y) ascending
-    if (active) {
-        const int off = o0 & 0xffff;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            if (C.nzxx[k]) { const int p = off + sorted_pos(R.key, C.nzxx, k); sval[p] = R.xx[k]; scol[p] = R.key[k]; }
-            if (C.nzxy[k]) { const int p = off + C.nxx + sorted_pos(R.key, C.nzxy, k); sval[p] = R.xy[k]; scol[p] = R.key[k] + nf; }
-        }
+    // ---- Kuu: x rows in the lower half of the staging buffer, y rows in the upper half
+    stage_row(ax, o0 & 0xffff, 0, nf, sval, scol);
+    stage_row(ay, kHalf + (o0 >> 16), nf, 0, sval, scol);
+    __syncthreads();
+    flush_segment(sval, scol, t0 & 0xffff, bux, Kuu);
+    flush_segment(sval + kHalf, scol + kHalf, t0 >> 16, buy, Kuu);
+    __syncthreads();
+    // ---- Kup: columns = element ids, slot order = ascending element id
+    {
+        int p = o1 & 0xffff;
+        if ((ax.m0 >> 9) & 1) { sval[p] = ax.R0.kp; scol[p] = ax.R0.e; p++; }
+        if ((ax.m1 >> 9) & 1) { sval[p] = ax.R1.kp; scol[p] = ax.R1.e; }
+        p = kHalf + (o1 >> 16);
+        if ((ay.m0 >> 9) & 1) { sval[p] = ay.R0.kp; scol[p] = ay.R0.e; p++; }
+        if ((ay.m1 >> 9) & 1) { sval[p] = ay.R1.kp; scol[p] = ay.R1.e; }
     }
     __syncthreads();
-    flush_segment<RP>(sval, scol, t0 & 0xffff, bux, Kuu);
-    __syncthreads();
-    // ---- Kuu y rows
-    if (active) {
-        const int off = o0 >> 16;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            if (C.nzyx[k]) { const int p = off + sorted_pos(R.key, C.nzyx, k); sval[p] = R.yx[k]; scol[p] = R.key[k]; }
-            if (C.nzyy[k]) { const int p = off + C.nyx + sorted_pos(R.key, C.nzyy, k); sval[p] = R.yy[k]; scol[p] = R.key[k] + nf; }
-        }
-    }
-    __syncthreads();
-    flush_segment<RP>(sval, scol, t0 >> 16, buy, Kuu);
-    __syncthreads();
-    // ---- Kup: x rows in sval[0..), y rows in sval[2*kBlock..); columns = element ids (slot order ascending)
-    if (active) {
-        int px = o1 & 0xffff, py = 2 * kBlock + (o1 >> 16);
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            if (C.pzx[s]) { sval[px] = R.px[s]; scol[px] = R.pe[s]; px++; }
-            if (C.pzy[s]) { sval[py] = R.py[s]; scol[py] = R.pe[s]; py++; }
-        }
-    }
-    __syncthreads();
-    flush_segment<RP>(sval, scol, t1 & 0xffff, bpx, Kup);
-    flush_segment<RP>(sval + 2 * kBlock, scol + 2 * kBlock, t1 >> 16, bpy, Kup);
+    flush_segment(sval, scol, t1 & 0xffff, bpx, Kup);
+    flush_segment(sval + kHalf, scol + kHalf, t1 >> 16, bpy, Kup);
     if (WANT_M) {
         __syncthreads();
-        // ---- Muu: block diagonal, x rows hold (g,x) columns only, y rows (g,y) only
-        if (active) {
-            const int offx = o2 & 0xffff, offy = 5 * kBlock + (o2 >> 16);
+        // ---- Muu: block diagonal, row (f,comp) only holds columns (g,comp)
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                if (C.nzmx[k]) { const int p = offx + sorted_pos(R.key, C.nzmx, k); sval[p] = R.mxx[k]; scol[p] = R.key[k]; }
-                if (C.nzmy[k]) { const int p = offy + sorted_pos(R.key, C.nzmy, k); sval[p] = R.myy[k]; scol[p] = R.key[k] + nf; }
-            }
+        for (int j = 0; j < 3; j++) {
+            if (ax.P0.pm[j] >= 0) { const int p = (o2 & 0xffff) + ax.P0.pm[j]; sval[p] = ax.R0.ms[j]; scol[p] = ax.R0.key[j]; }
+            if (ax.P1.pm[j] >= 0) { const int p = (o2 & 0xffff) + ax.P1.pm[j]; sval[p] = ax.R1.ms[j]; scol[p] = ax.R1.key[j]; }
+            if (ay.P0.pm[j] >= 0) { const int p = kHalf + (o2 >> 16) + ay.P0.pm[j]; sval[p] = ay.R0.ms[j]; scol[p] = ay.R0.key[j] + nf; }
+            if (ay.P1.pm[j] >= 0) { const int p = kHalf + (o2 >> 16) + ay.P1.pm[j]; sval[p] = ay.R1.ms[j]; scol[p] = ay.R1.key[j] + nf; }
         }
         __syncthreads();
-        flush_segment<RP>(sval, scol, t2 & 0xffff, bases[4 * (size_t)nblk + b], Muu);
-        flush_segment<RP>(sval + 5 * kBlock, scol + 5 * kBlock, t2 >> 16, bases[5 * (size_t)nblk + b], Muu);
+        flush_segment(sval, scol, t2 & 0xffff, bmx, Muu);
+        flush_segment(sval + kHalf, scol + kHalf, t2 >> 16, bmy, Muu);
     }
 }
 

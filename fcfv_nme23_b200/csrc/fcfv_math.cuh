@@ -106,19 +106,19 @@ FCFV_HD void element_local(double Om, double te, double sex, double sey, const d
 }
 
 // ---------------------------------------------------------------------------------------------
-// a5/a6 element matrix entries.  ElemAsm = what one element contributes, loaded once per
-// (face row, adjacent element).
+// a5/a6/a7 assembly, lane formulation.
+//
+// The rows (f,x) and (f,y) of a face f are produced by FOUR lanes: (slot, comp) with slot = which
+// of the <=2 adjacent elements, comp = which velocity component the row belongs to.  A lane loads
+// ONE element and computes, for that element's three faces g_j, the two values of row (f,comp):
+//   vs[j] -> column (g_j, comp)      ("same" component block, carries alpha^-1 tau tau and tau delta)
+//   vc[j] -> column (g_j, other)     ("cross" component block)
+// plus its share of fu[(f,comp)] and its Kup[(f,comp), e] entry.  The two slot lanes of a row then
+// merge: the column (f,.) appears in both elements and is summed (sparse() sums duplicates, lower
+// element first), columns are ranked across both lanes, exact zeros are dropped (dropzeros).
+// set_mesh rejects meshes in which two elements share more than one face, so the row face is the
+// only duplicate column.
 // ---------------------------------------------------------------------------------------------
-struct ElemAsm {
-    int g[3];        // global face ids (0-based)
-    int bc[3];       // face tags
-    double tau[3];   // face stabilisation
-    double G[3], nx[3], ny[3];
-    double eta, ia;  // viscosity, 1/alpha
-    double iO;       // 1/Omega                (old loop)
-    double D11, D12, D21, D22;                // (NEW loop)
-    double b1, b2, Z11, Z21, Z12, Z22;
-};
 
 // D of ElementAssemblyLoopNEW (:231-236).  delta == 1: ([ke ke/δ; ke/δ ke] .* 1.0)/Ω;
 // otherwise inv(inv(M) .* Ω) with 2x2 partial-pivoting inverses (parity 1e-12 only).
@@ -136,6 +136,19 @@ FCFV_HD void inv2(const double M[4], double R[4]) {
     }
 }
 
+// delta != 1 branch (:234-235): kept out of line so that the common path stays small
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void rheology_general(double ke, double de, double Om, double* D /* D11 D21 D12 D22 */) {
+    double M[4] = {ke, ke / de, ke / de, ke}, Dv[4];
+    inv2(M, Dv);
+    for (int q = 0; q < 4; q++) Dv[q] = Dv[q] * Om;
+    inv2(Dv, D);
+}
+
 FCFV_HD void rheology_new(double ke, double de, double Om, double& D11, double& D12, double& D21, double& D22) {
     if (de == 1.0) {
         D11 = (ke * 1.0) / Om;
@@ -143,167 +156,207 @@ FCFV_HD void rheology_new(double ke, double de, double Om, double& D11, double& 
         D21 = D12;
         D22 = D11;
     } else {
-        double M[4] = {ke, ke / de, ke / de, ke}, Dv[4], R[4];
-        inv2(M, Dv);
-        for (int q = 0; q < 4; q++) Dv[q] = Dv[q] * Om;
-        inv2(Dv, R);
+        double R[4];
+        rheology_general(ke, de, Om, R);
         D11 = R[0]; D21 = R[1]; D12 = R[2]; D22 = R[3];
     }
 }
 
-// The four values the reference computes for loop indices (i, j) of one element, named by the
-// normal product they carry:  vA ~ c*nix*njx (u1u1), vB ~ c*niy*njx, vC ~ c*nix*njy, vD ~ c*niy*njy.
-// Old loop :146-154, NEW :273-276 / :288-291.  mA/mD: the Muu values (:157-158 / :295-296).
-template <int VARIANT, int FORM, bool WANT_M>
-FCFV_HD void kvals(const ElemAsm& E, int i, int j, double A, double& vA, double& vB, double& vC, double& vD,
-                   double& mA, double& mD) {
-    const bool on = (E.bc[i] != 1) & (E.bc[j] != 1);
-    const double mG = bmul(on, -E.G[i]);
-    const double nix = E.nx[i], niy = E.ny[i], njx = E.nx[j], njy = E.ny[j], Gj = E.G[j];
-    const double ninj = nix * njx + niy * njy;
-    const double c = (FORM == kGradient) ? (0.0 + bmul(E.bc[i] == -1, 1.0)) : A;
-    const double t1 = ((E.ia * E.tau[i]) * E.tau[j]) * Gj;
-    if (VARIANT == kLoopOld) {
-        const double t3 = E.tau[i] * (0.0 + bmul(i == j, 1.0));
-        const double hG = (E.eta * E.iO) * Gj;
-        const double mhG = ((-E.eta) * E.iO) * Gj;
-        vA = mG * ((t1 - hG * (ninj + (c * nix) * njx)) - t3);
-        vB = mG * (mhG * ((c * niy) * njx));
-        vC = mG * (mhG * ((c * nix) * njy));
-        vD = mG * ((t1 - hG * (ninj + (c * niy) * njy)) - t3);
-        if (WANT_M) { mA = mG * ((t1 - hG * ninj) - t3); mD = mA; }
-    } else {
-        const double t3 = bmul(i == j, E.tau[i]);
-        vA = mG * ((t1 - (E.D11 * Gj) * (ninj + (c * nix) * njx)) - t3);
-        vD = mG * ((t1 - (E.D22 * Gj) * (ninj + (c * niy) * njy)) - t3);
-        if (FORM == kGradient) {   // slots [j,i+nf] (D12, nix*njy) and [j+nf,i] (D21, niy*njx)
-            vC = mG * (((-E.D12) * Gj) * ((c * nix) * njy));
-            vB = mG * (((-E.D21) * Gj) * ((c * niy) * njx));
-        } else {                   // slots [i,j+nf] (D12, niy*njx) and [i+nf,j] (D21, nix*njy)
-            vB = mG * (((-E.D12) * Gj) * ((c * niy) * njx));
-            vC = mG * (((-E.D21) * Gj) * ((c * nix) * njy));
-        }
-        if (WANT_M) { mA = mG * ((t1 - (E.D11 * Gj) * ninj) - t3); mD = mG * ((t1 - (E.D22 * Gj) * ninj) - t3); }
-    }
-}
+// register-friendly selection a[i] for a runtime i in 0..2 (no local-memory indexing)
+template <typename T>
+FCFV_HD T pick3(int i, const T a[3]) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
 
-// One face row pair (rows (f,x) and (f,y)) before compaction: up to 6 candidate column faces
-// (3 per adjacent element), their four values, Muu values, RHS and Kup entries.
-struct FaceRows {
-    int key[6];                         // column face id, kDeadKey when unused / merged away
-    double xx[6], xy[6], yx[6], yy[6];  // (row x,col x) (row x,col y) (row y,col x) (row y,col y)
-    double mxx[6], myy[6];
-    double fx, fy;                      // fu contributions (summed over the adjacent elements)
-    int pe[2];                          // Kup column (element id) per adjacent element, -1 unused
-    double px[2], py[2];
+// What one lane loads of its element (comp-relative: nr = normal component of the row's velocity
+// component, no = the other one).
+struct LaneElem {
+    int g[3], bc[3];
+    double tau[3], G[3], nr[3], no[3];
+    double eta, ia;        // viscosity, 1/alpha
+    double iO;             // 1/Omega (old loop)
+    double Drr, Dro;       // D[r,r], D[r,o] (NEW loop)
+    double br;             // beta[e, comp]
+    double Z1r, Z2r;       // Z[e,1,comp], Z[e,2,comp]
+    double Zr1, Zr2;       // Z[e,comp,1], Z[e,comp,2]  (old :Gradient interface terms only)
 };
 
-// Contribution of adjacent element `slot` (local face i of E is the row face).
-// Row/column convention: old loop and NEW-:SymmetricGradient store value(i,j) at (row i, col j);
-// NEW-:Gradient stores value(i,j) at (row j, col i) (values written at [j,i], indices at [i,j],
-// Discretisation:273-276 vs :299-302) and NEW stores Muu the same transposed way (:295-296).
+struct LaneRow {
+    int key[3];            // column face ids, kDeadKey when dropped / merged into the partner
+    double vs[3], vc[3];   // same / cross component values
+    double ms[3];          // Muu values (same component block only)
+    double fu, kp;         // RHS share, Kup value
+    int e, i;              // element, local index of the row face in it
+    bool active;
+};
+
+// value of loop pair (p = i_loop, q = j_loop) of the reference: "same" = u1u1/u2u2 entry of component
+// r, "cross" = the off-diagonal-block entry this lane's row owns.  TRANSPOSED = NEW :Gradient storage.
+template <int VARIANT, int FORM, bool TRANSPOSED>
+FCFV_HD void pair_values(const LaneElem& E, int p, int q, int comp, double A, double& same, double& cross, double& msame) {
+    const int bcp = pick3(p, E.bc), bcq = pick3(q, E.bc);
+    const double Gp = pick3(p, E.G), Gq = pick3(q, E.G);
+    const double npr = pick3(p, E.nr), npo = pick3(p, E.no), nqr = pick3(q, E.nr), nqo = pick3(q, E.no);
+    const double taup = pick3(p, E.tau), tauq = pick3(q, E.tau);
+    const bool on = (bcp != 1) & (bcq != 1);
+    const double mG = bmul(on, -Gp);
+    // ninj = ni_x*nj_x + ni_y*nj_y (x product first; a+b == b+a bitwise)
+    const double ninj = comp == 0 ? (npr * nqr + npo * nqo) : (npo * nqo + npr * nqr);
+    const double c = (FORM == kGradient) ? (0.0 + bmul(bcp == -1, 1.0)) : A;
+    const double t1 = ((E.ia * taup) * tauq) * Gq;
+    const double cr = TRANSPOSED ? (c * npr) * nqo : (c * npo) * nqr;
+    if (VARIANT == kLoopOld) {
+        const double t3 = taup * (0.0 + bmul(p == q, 1.0));
+        const double hG = (E.eta * E.iO) * Gq;
+        const double mhG = ((-E.eta) * E.iO) * Gq;
+        same = mG * ((t1 - hG * (ninj + (c * npr) * nqr)) - t3);
+        cross = mG * (mhG * cr);
+        msame = mG * ((t1 - hG * ninj) - t3);
+    } else {
+        const double t3 = bmul(p == q, taup);
+        same = mG * ((t1 - (E.Drr * Gq) * (ninj + (c * npr) * nqr)) - t3);
+        cross = mG * (((-E.Dro) * Gq) * cr);
+        msame = mG * ((t1 - (E.Drr * Gq) * ninj) - t3);
+    }
+}
+
+// Row (f, comp) contributions of one element.  i = local index of f in the element.
+// vDir = Dirichlet value of component comp on f; Sr1, Sr2 = Neumann stress row of component comp
+// (comp x: sxx, sxy; comp y: syx, syy) -- only read by the caller when the face is Neumann.
 template <int VARIANT, int FORM, bool WANT_M>
-FCFV_HD void add_element_rows(const ElemAsm& E, int i, int slot, int e, double A, double VxDir_f, double VyDir_f,
-                              double sxx, double syy, double sxy, double syx, FaceRows& R) {
+FCFV_HD void lane_row(const LaneElem& E, int e, int i, int comp, double A, double vDir, double Sr1, double Sr2,
+                      LaneRow& R) {
+    R.e = e; R.i = i; R.active = true;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        double vA, vB, vC, vD, mA = 0.0, mD = 0.0;
-        double xx, xy, yx, yy, mxx = 0.0, myy = 0.0;
-        if (VARIANT == kLoopNew && FORM == kGradient) {
-            kvals<VARIANT, FORM, false>(E, j, i, A, vA, vB, vC, vD, mA, mD);   // loop (i=j, j=i)
-            xx = vA; xy = vC; yx = vB; yy = vD;
-        } else {
-            kvals<VARIANT, FORM, false>(E, i, j, A, vA, vB, vC, vD, mA, mD);
-            xx = vA; xy = vB; yx = vC; yy = vD;
-        }
-        if (WANT_M) {
-            double t0, t1, t2, t3;
-            if (VARIANT == kLoopNew) kvals<VARIANT, FORM, true>(E, j, i, A, t0, t1, t2, t3, mA, mD);
-            else                     kvals<VARIANT, FORM, true>(E, i, j, A, t0, t1, t2, t3, mA, mD);
-            mxx = mA; myy = mD;
-        }
+        double same, cross, msame, t0, t1;
+        if (VARIANT == kLoopNew && FORM == kGradient) pair_values<VARIANT, FORM, true>(E, j, i, comp, A, same, cross, msame);
+        else                                          pair_values<VARIANT, FORM, false>(E, i, j, comp, A, same, cross, msame);
+        if (WANT_M && VARIANT == kLoopNew && FORM != kGradient)   // NEW stores Muu transposed in both formulations
+            pair_values<VARIANT, FORM, true>(E, j, i, comp, A, t0, t1, msame);
         if (j == i) {   // Dirichlet rows :187-190
-            const double one = bmul(E.bc[i] == 1, 1.0);
-            xx += one; yy += one;
-            if (WANT_M) { mxx += one; myy += one; }
+            const double one = bmul(pick3(i, E.bc) == 1, 1.0);
+            same += one;
+            msame += one;
         }
-        const int k = 3 * slot + j;
-        R.key[k] = E.g[j];
-        R.xx[k] = xx; R.xy[k] = xy; R.yx[k] = yx; R.yy[k] = yy;
-        R.mxx[k] = mxx; R.myy[k] = myy;
+        R.key[j] = E.g[j];
+        R.vs[j] = same; R.vc[j] = cross; R.ms[j] = WANT_M ? msame : 0.0;
     }
     // RHS :167-178 / :310-323
-    const int bci = E.bc[i];
-    const double nix = E.nx[i], niy = E.ny[i], Gi = E.G[i], ti = E.tau[i];
+    const int bci = pick3(i, E.bc);
+    const double nir = pick3(i, E.nr), nio = pick3(i, E.no), Gi = pick3(i, E.G), ti = pick3(i, E.tau);
+    const double nix = comp == 0 ? nir : nio, niy = comp == 0 ? nio : nir;
     const double Xi = 0.0 + bmul(bci == 2, 1.0);
-    const double tix = nix * sxx + niy * sxy;
-    const double tiy = nix * syx + niy * syy;
+    const double tir = nix * Sr1 + niy * Sr2;
     const double mGi = bmul(bci != 1, -Gi);
-    double feix, feiy;
+    double fe;
     if (VARIANT == kLoopOld) {
-        double nZx, nZy;
+        double nZ;
         if (FORM == kGradient) {
             const double J = 0.0 + bmul(bci == -1, 1.0);
-            nZx = nix * (E.Z11 + J * E.Z11) + niy * (E.Z21 + J * E.Z12);
-            nZy = nix * (E.Z12 + J * E.Z21) + niy * (E.Z22 + J * E.Z22);
+            nZ = nix * (E.Z1r + J * E.Zr1) + niy * (E.Z2r + J * E.Zr2);
         } else {
-            nZx = nix * E.Z11 + niy * E.Z21;
-            nZy = nix * E.Z12 + niy * E.Z22;
+            nZ = nix * E.Z1r + niy * E.Z2r;
         }
-        feix = mGi * (((((-E.ia) * ti) * E.b1) + (E.eta * E.iO) * nZx) - tix * Xi);
-        feiy = mGi * (((((-E.ia) * ti) * E.b2) + (E.eta * E.iO) * nZy) - tiy * Xi);
+        fe = mGi * (((((-E.ia) * ti) * E.br) + (E.eta * E.iO) * nZ) - tir * Xi);
     } else {
-        feix = mGi * (((((-E.ia) * ti) * E.b1) + ((E.D11 * nix) * E.Z11 + (E.D11 * niy) * E.Z21)) - tix * Xi);
-        feiy = mGi * (((((-E.ia) * ti) * E.b2) + ((E.D22 * nix) * E.Z12 + (E.D22 * niy) * E.Z22)) - tiy * Xi);
+        fe = mGi * (((((-E.ia) * ti) * E.br) + ((E.Drr * nix) * E.Z1r + (E.Drr * niy) * E.Z2r)) - tir * Xi);
     }
-    // fu[i,e] += (bci!=1)*feix + (bci==1)*VxDir*1e0  (from 0.0)  :191-192
-    const double fxe = 0.0 + (bmul(bci != 1, feix) + bmul(bci == 1, VxDir_f) * 1.0);
-    const double fye = 0.0 + (bmul(bci != 1, feiy) + bmul(bci == 1, VyDir_f) * 1.0);
-    if (slot == 0) { R.fx = fxe; R.fy = fye; } else { R.fx = R.fx + fxe; R.fy = R.fy + fye; }
-    // Kup :180-185
-    R.pe[slot] = e;
-    R.px[slot] = 0.0 - bmul(bci != 1, Gi) * nix;
-    R.py[slot] = 0.0 - bmul(bci != 1, Gi) * niy;
+    R.fu = 0.0 + (bmul(bci != 1, fe) + bmul(bci == 1, vDir) * 1.0);   // :191-192
+    R.kp = 0.0 - bmul(bci != 1, Gi) * nir;                             // :180-185
 }
 
-FCFV_HD void face_rows_init(FaceRows& R) {
+FCFV_HD void lane_row_inactive(LaneRow& R) {
+    R.e = -1; R.i = 0; R.active = false;
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-        R.key[k] = kDeadKey;
-        R.xx[k] = R.xy[k] = R.yx[k] = R.yy[k] = 0.0;
-        R.mxx[k] = R.myy[k] = 0.0;
+    for (int j = 0; j < 3; j++) { R.key[j] = kDeadKey; R.vs[j] = R.vc[j] = R.ms[j] = 0.0; }
+    R.fu = 0.0; R.kp = 0.0;
+}
+
+// What a lane needs from the other slot lane of the same row (shuffles on the device).
+struct LanePeer {
+    bool active;
+    double ds, dc, dm;     // its values on the row face column (f,.)
+    double fu;
+};
+
+FCFV_HD void lane_peer_of(const LaneRow& R, LanePeer& P) {
+    P.active = R.active;
+    P.ds = pick3(R.i, R.vs); P.dc = pick3(R.i, R.vc); P.dm = pick3(R.i, R.ms);
+    P.fu = R.fu;
+}
+
+// Slot 0 folds the peer's diagonal-face values and RHS into its own (element order = slot order);
+// slot 1 drops its copy of that column.
+FCFV_HD void lane_merge(LaneRow& R, int slot, const LanePeer& P) {
+    if (!R.active || !P.active) {
+        if (slot == 0 && R.active && R.fu == 0.0) R.fu = 0.0;   // Array(dropzeros(sparse)): -0.0 -> +0.0
+        return;
     }
-    R.fx = R.fy = 0.0;
-    R.pe[0] = R.pe[1] = -1;
-    R.px[0] = R.px[1] = R.py[0] = R.py[1] = 0.0;
+    if (slot == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (j == R.i) { R.vs[j] = R.vs[j] + P.ds; R.vc[j] = R.vc[j] + P.dc; R.ms[j] = R.ms[j] + P.dm; }
+        R.fu = R.fu + P.fu;
+        if (R.fu == 0.0) R.fu = 0.0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (j == R.i) R.key[j] = kDeadKey;
+    }
 }
 
-// sparse(..) sums duplicate (row, col) pairs: the row face itself when the face has two
-// elements (and any other face shared by both elements of a degenerate pair).  Input order of
-// the reference = ascending element id = slot order; the second slot is folded into the first.
-template <bool WANT_M>
-FCFV_HD void face_rows_merge(FaceRows& R) {
+// 3-bit masks of stored (non-zero, alive) entries of a lane: bits 0-2 same, 3-5 cross, 6-8 Muu, 9 Kup
+FCFV_HD int lane_nzmask(const LaneRow& R) {
+    int m = 0;
 #pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 3; b < 6; b++)
-            if (R.key[a] == R.key[b] && R.key[a] != kDeadKey) {
-                R.xx[a] = R.xx[a] + R.xx[b]; R.xy[a] = R.xy[a] + R.xy[b];
-                R.yx[a] = R.yx[a] + R.yx[b]; R.yy[a] = R.yy[a] + R.yy[b];
-                if (WANT_M) { R.mxx[a] = R.mxx[a] + R.mxx[b]; R.myy[a] = R.myy[a] + R.myy[b]; }
-                R.key[b] = kDeadKey;
-            }
-    // fu = Array(dropzeros(sparse(..))): a stored -0.0 comes back as +0.0
-    if (R.fx == 0.0) R.fx = 0.0;
-    if (R.fy == 0.0) R.fy = 0.0;
+    for (int j = 0; j < 3; j++) {
+        const bool alive = R.key[j] != kDeadKey;
+        m |= (alive && R.vs[j] != 0.0) ? (1 << j) : 0;
+        m |= (alive && R.vc[j] != 0.0) ? (8 << j) : 0;
+        m |= (alive && R.ms[j] != 0.0) ? (64 << j) : 0;
+    }
+    m |= (R.active && R.kp != 0.0) ? 512 : 0;
+    return m;
 }
 
-// Position of entry k among the non-zero entries of the same kind, in ascending column order.
-FCFV_HD int sorted_pos(const int key[6], const bool nz[6], int k) {
-    int p = 0;
+FCFV_HD int popc6(int x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// Placement of a lane's entries inside row (f, comp).  The row is laid out [col (g,x) ascending |
+// col (g,y) ascending]: for comp 0 the first part holds the "same" values, for comp 1 the "cross"
+// values.  okey/omask: the peer lane's keys and nz mask.  Outputs the number of entries of the
+// first and second part of the whole row and, per own entry j, the position (or -1) of its
+// same / cross / Muu value inside the row.
+struct LanePlace {
+    int n_first, n_second, n_m;     // whole-row counts (identical in both slot lanes)
+    int ps[3], pc[3], pm[3];
+};
+
+FCFV_HD void lane_place(const LaneRow& R, int mymask, const int okey[3], int omask, int comp, LanePlace& L) {
+    const int all_s = (mymask & 7) | ((omask & 7) << 3);
+    const int all_c = ((mymask >> 3) & 7) | (((omask >> 3) & 7) << 3);
+    const int all_m = ((mymask >> 6) & 7) | (((omask >> 6) & 7) << 3);
+    const int ns = popc6(all_s), nc = popc6(all_c);
+    L.n_first = comp == 0 ? ns : nc;
+    L.n_second = comp == 0 ? nc : ns;
+    L.n_m = popc6(all_m);
 #pragma unroll
-    for (int m = 0; m < 6; m++) p += (m != k) & nz[m] & (key[m] < key[k]);
-    return p;
+    for (int j = 0; j < 3; j++) {
+        int lower = 0;   // entries (mine bits 0-2, peer bits 3-5) with a smaller column face id
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            lower |= (R.key[m] < R.key[j]) ? (1 << m) : 0;
+            lower |= (okey[m] < R.key[j]) ? (8 << m) : 0;
+        }
+        const int rs = popc6(all_s & lower), rc = popc6(all_c & lower);
+        L.ps[j] = ((mymask >> j) & 1) ? (comp == 0 ? rs : nc + rs) : -1;
+        L.pc[j] = ((mymask >> (3 + j)) & 1) ? (comp == 0 ? ns + rc : rc) : -1;
+        L.pm[j] = ((mymask >> (6 + j)) & 1) ? popc6(all_m & lower) : -1;
+    }
 }
 
 // fp[e] :194 -- sequential over the three faces, Dirichlet faces only contribute.

@@ -12,7 +12,7 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfcfv_b200.so")
+LIB_PATH = os.environ.get("FCFV_LIB") or os.path.join(_HERE, "libfcfv_b200.so")   # FCFV_LIB: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fcfv_b200.h")
 
 FCFV_OK = 0

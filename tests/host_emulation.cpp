@@ -40,48 +40,52 @@ void build_mesh(HostMesh& H, long long nel, long long nf, const long long* e2f, 
     M.elem_owned = nullptr; M.face_owned = nullptr; M.tau_ref = nullptr;
 }
 
+// Serial stand-in for k_asm_count / k_asm_fill: thread (face, comp) becomes a loop iteration, the
+// block scan becomes a running sum; asm_row and the placement arithmetic are the kernels' own code.
 template <int VARIANT, int FORM>
 void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, double A, long long* rp_uu, int* c_uu,
               double* v_uu, long long* rp_up, int* c_up, double* v_up, long long* rp_mu, int* c_mu, double* v_mu,
               double* fu, double* fp) {
     const int nf = M.nf;
-    std::vector<int> cx(nf), cy(nf), px(nf), py(nf), mx(nf), my(nf);
+    std::vector<int> cnt[6];
+    for (auto& c : cnt) c.assign(nf, 0);
     for (int f = 0; f < nf; f++) {   // count pass
-        FaceRows R; double fpv[2]; int fpe[2]; RowCounts C;
-        gather_face_rows<VARIANT, FORM, true>(M, L, D, f, A, R, fpv, fpe);
-        count_rows<true>(R, C);
-        cx[f] = C.nxx + C.nxy; cy[f] = C.nyx + C.nyy; px[f] = C.npx; py[f] = C.npy; mx[f] = C.nmx; my[f] = C.nmy;
+        AsmRow r[2]; int fpe[2]; double fpv[2];
+        asm_face<VARIANT, FORM, true>(M, L, D, A, f, false, r[0], r[1], fpe, fpv);
+        for (int comp = 0; comp < 2; comp++) {
+            cnt[comp][f] = r[comp].P0.n_first + r[comp].P0.n_second;
+            cnt[2 + comp][f] = ((r[comp].m0 >> 9) & 1) + ((r[comp].m1 >> 9) & 1);
+            cnt[4 + comp][f] = r[comp].P0.n_m;
+        }
     }
-    long long run = 0;
-    for (int f = 0; f < nf; f++) { rp_uu[f] = run; run += cx[f]; }
-    for (int f = 0; f < nf; f++) { rp_uu[nf + f] = run; run += cy[f]; }
-    rp_uu[2 * nf] = run; run = 0;
-    for (int f = 0; f < nf; f++) { rp_up[f] = run; run += px[f]; }
-    for (int f = 0; f < nf; f++) { rp_up[nf + f] = run; run += py[f]; }
-    rp_up[2 * nf] = run; run = 0;
-    for (int f = 0; f < nf; f++) { rp_mu[f] = run; run += mx[f]; }
-    for (int f = 0; f < nf; f++) { rp_mu[nf + f] = run; run += my[f]; }
-    rp_mu[2 * nf] = run;
+    long long* rps[3] = {rp_uu, rp_up, rp_mu};
+    for (int m = 0; m < 3; m++) {
+        long long run = 0;
+        for (int f = 0; f < nf; f++) { rps[m][f] = run; run += cnt[2 * m][f]; }
+        for (int f = 0; f < nf; f++) { rps[m][nf + f] = run; run += cnt[2 * m + 1][f]; }
+        rps[m][2 * nf] = run;
+    }
     for (int e = 0; e < M.nel; e++) fp[e] = 0.0;
     for (int f = 0; f < nf; f++) {   // fill pass (same placement arithmetic as k_asm_fill)
-        FaceRows R; double fpv[2]; int fpe[2]; RowCounts C;
-        gather_face_rows<VARIANT, FORM, true>(M, L, D, f, A, R, fpv, fpe);
-        if (fpe[0] >= 0) fp[fpe[0]] = fpv[0];
-        if (fpe[1] >= 0) fp[fpe[1]] = fpv[1];
-        count_rows<true>(R, C);
-        fu[f] = R.fx; fu[nf + f] = R.fy;
-        for (int k = 0; k < 6; k++) {
-            if (C.nzxx[k]) { long long p = rp_uu[f] + sorted_pos(R.key, C.nzxx, k); v_uu[p] = R.xx[k]; c_uu[p] = R.key[k]; }
-            if (C.nzxy[k]) { long long p = rp_uu[f] + C.nxx + sorted_pos(R.key, C.nzxy, k); v_uu[p] = R.xy[k]; c_uu[p] = R.key[k] + nf; }
-            if (C.nzyx[k]) { long long p = rp_uu[nf + f] + sorted_pos(R.key, C.nzyx, k); v_uu[p] = R.yx[k]; c_uu[p] = R.key[k]; }
-            if (C.nzyy[k]) { long long p = rp_uu[nf + f] + C.nyx + sorted_pos(R.key, C.nzyy, k); v_uu[p] = R.yy[k]; c_uu[p] = R.key[k] + nf; }
-            if (C.nzmx[k]) { long long p = rp_mu[f] + sorted_pos(R.key, C.nzmx, k); v_mu[p] = R.mxx[k]; c_mu[p] = R.key[k]; }
-            if (C.nzmy[k]) { long long p = rp_mu[nf + f] + sorted_pos(R.key, C.nzmy, k); v_mu[p] = R.myy[k]; c_mu[p] = R.key[k] + nf; }
-        }
-        long long qx = rp_up[f], qy = rp_up[nf + f];
-        for (int s = 0; s < 2; s++) {
-            if (C.pzx[s]) { v_up[qx] = R.px[s]; c_up[qx] = R.pe[s]; qx++; }
-            if (C.pzy[s]) { v_up[qy] = R.py[s]; c_up[qy] = R.pe[s]; qy++; }
+        AsmRow r[2]; int fpe[2]; double fpv[2];
+        asm_face<VARIANT, FORM, true>(M, L, D, A, f, true, r[0], r[1], fpe, fpv);
+        for (int s = 0; s < 2; s++) if (fpe[s] >= 0) fp[fpe[s]] = fpv[s];
+        for (int comp = 0; comp < 2; comp++) {
+            const AsmRow& a = r[comp];
+            fu[comp * nf + f] = a.R0.active ? a.R0.fu : 0.0;
+            const long long row = (long long)comp * nf + f;
+            const int cs = comp == 0 ? 0 : nf, cc = comp == 0 ? nf : 0;
+            const LaneRow* R[2] = {&a.R0, &a.R1};
+            const LanePlace* P[2] = {&a.P0, &a.P1};
+            for (int s = 0; s < 2; s++)
+                for (int j = 0; j < 3; j++) {
+                    if (P[s]->ps[j] >= 0) { long long p = rp_uu[row] + P[s]->ps[j]; v_uu[p] = R[s]->vs[j]; c_uu[p] = R[s]->key[j] + cs; }
+                    if (P[s]->pc[j] >= 0) { long long p = rp_uu[row] + P[s]->pc[j]; v_uu[p] = R[s]->vc[j]; c_uu[p] = R[s]->key[j] + cc; }
+                    if (P[s]->pm[j] >= 0) { long long p = rp_mu[row] + P[s]->pm[j]; v_mu[p] = R[s]->ms[j]; c_mu[p] = R[s]->key[j] + cs; }
+                }
+            long long p = rp_up[row];
+            if ((a.m0 >> 9) & 1) { v_up[p] = a.R0.kp; c_up[p] = a.R0.e; p++; }
+            if ((a.m1 >> 9) & 1) { v_up[p] = a.R1.kp; c_up[p] = a.R1.e; }
         }
     }
 }

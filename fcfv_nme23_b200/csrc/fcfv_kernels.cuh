@@ -101,13 +101,13 @@ FCFV_HD void lane_view(const FaceElem& F, int comp, LaneElem& E) {
 // element).  With do_fp, when f is local face 0 of an owned element, that element's fp
 // (Discretisation:194) is returned too, so that fp needs no pass of its own.
 template <int VARIANT, int FORM, bool WANT_M>
-FCFV_HD void compute_slot(const MeshView& M, const LocalView& L, const FaceDataView& D, int f, int slot, double A,
+FCFV_HD void compute_slot(const MeshView& M, const LocalView& L, const FaceDataView& D, int f, int2 pr, int slot, double A,
                           bool do_fp, LaneRow& Rx, LaneRow& Ry, int& fp_elem, double& fp_val) {
     fp_elem = -1; fp_val = 0.0;
-    const int2 pr = M.f2e[f];
+    // No early exit: a missing second element re-reads the first one and is discarded afterwards, so
+    // that the loads of both slots are independent of any branch and can be issued up front.
     const bool has = pr.x >= 0 && (slot == 0 || pr.y != pr.x);
-    if (!has) { lane_row_inactive(Rx); lane_row_inactive(Ry); return; }
-    const int code = slot == 0 ? pr.x : pr.y;
+    const int code = pr.x < 0 ? 0 : (slot == 0 ? pr.x : pr.y);
     const int e = code >> 2, i = code & 3;
     FaceElem F;
     load_face_elem<VARIANT>(M, L, e, i, F);
@@ -120,7 +120,7 @@ FCFV_HD void compute_slot(const MeshView& M, const LocalView& L, const FaceDataV
     lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 0, A, vx, sxx, sxy, Rx);   // row face at rotated index 0
     lane_view(F, 1, E);
     lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 1, A, vy, syx, syy, Ry);
-    if (do_fp && i == 0 && (M.elem_owned == nullptr || M.elem_owned[e])) {
+    if (do_fp && has && i == 0 && (M.elem_owned == nullptr || M.elem_owned[e])) {
         bool dir[3]; double dvx[3], dvy[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -131,6 +131,7 @@ FCFV_HD void compute_slot(const MeshView& M, const LocalView& L, const FaceDataV
         fp_val = element_fp(F.G, F.nx, F.ny, dir, dvx, dvy);
         fp_elem = e;
     }
+    if (!has) { lane_row_inactive(Rx); lane_row_inactive(Ry); }
 }
 
 // One CSR row: merged / ranked / zero-dropped contributions of both adjacent elements.
@@ -161,8 +162,9 @@ FCFV_HD void asm_face(const MeshView& M, const LocalView& L, const FaceDataView&
     const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
     fp_elem[0] = fp_elem[1] = -1; fp_val[0] = fp_val[1] = 0.0;
     if (inrange && (owned || do_fp)) {
-        compute_slot<VARIANT, FORM, WANT_M>(M, L, D, f, 0, A, do_fp, ax.R0, ay.R0, fp_elem[0], fp_val[0]);
-        compute_slot<VARIANT, FORM, WANT_M>(M, L, D, f, 1, A, do_fp, ax.R1, ay.R1, fp_elem[1], fp_val[1]);
+        const int2 pr = M.f2e[f];
+        compute_slot<VARIANT, FORM, WANT_M>(M, L, D, f, pr, 0, A, do_fp, ax.R0, ay.R0, fp_elem[0], fp_val[0]);
+        compute_slot<VARIANT, FORM, WANT_M>(M, L, D, f, pr, 1, A, do_fp, ax.R1, ay.R1, fp_elem[1], fp_val[1]);
     }
     if (!owned) {   // rows of faces owned elsewhere (or out of range) stay empty
         lane_row_inactive(ax.R0); lane_row_inactive(ax.R1); lane_row_inactive(ay.R0); lane_row_inactive(ay.R1);
@@ -181,6 +183,9 @@ constexpr int kAsmFaces = kAsmBlock;
 constexpr int kMaxRow = 10;          // max entries of a Kuu row (5 faces x 2 components)
 constexpr int kNumSums = 6;          // Kuu-x, Kuu-y, Kup-x, Kup-y, Muu-x, Muu-y
 constexpr int kScanChunk = 4096;     // block sums scanned per chunk
+#ifndef FCFV_RES_MINBLOCKS
+#define FCFV_RES_MINBLOCKS 5         // resident 128-thread residual blocks per SM
+#endif
 #ifndef FCFV_ASM_MINBLOCKS
 #define FCFV_ASM_MINBLOCKS 4         // resident 128-thread assembly blocks per SM the register budget is tuned for (<=128 regs)
 #endif
@@ -538,7 +543,7 @@ k_asm_fill(MeshView M, LocalView L, FaceDataView D, double A, const int* __restr
 // the sums of squares of F_eq1, F_eq2, F_eq3, F_glob2 reduced per block (warp shuffles, fixed order).
 // partial[q*nblk + b], q = 0:F_eq1 1:F_eq2 2:F_eq3 3:F_glob2.
 template <int FORM>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, FCFV_RES_MINBLOCKS)
 k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double* __restrict__ sex,
            const double* __restrict__ sey, int tau_mode, double* __restrict__ Fg, double* __restrict__ partial,
            int nblk, double* __restrict__ F_glob2_out) {

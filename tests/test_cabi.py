@@ -1,0 +1,63 @@
+"""The C-ABI library: builds, loads, exports every symbol include/fcfv_b200.h declares, and fails
+loudly (no CPU fallback) when there is no CUDA device.  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from fcfv_nme23_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(L.LIB_PATH), "run __graft_entry__.build() first"
+    so = C.CDLL(L.LIB_PATH)
+    declared = L.declared_symbols()
+    assert len(declared) >= 40
+    missing = [s for s in declared if not hasattr(so, s)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (fcfv_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+    assert so.fcfv_version() == 100
+
+
+def test_binding_covers_header():
+    lib = L.load()
+    for s in L.declared_symbols():
+        assert getattr(lib, s).restype is not None or s in ("fcfv_stream",), s
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", L.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu():
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    lib = L.load()
+    h = C.c_void_p()
+    assert lib.fcfv_create(C.byref(h), 0) != 0 and not h.value     # FCFV_ERR_CUDA, no handle
+    from fcfv_nme23_b200 import api
+    with pytest.raises(L.FCFVError):
+        api.Handle(0)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under fcfv_nme23_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "fcfv_nme23_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle" not in text and "fcfv_oracle" not in text, fn

@@ -301,3 +301,63 @@ def test_large_mesh_properties(api):
     rp2, ci2, v2 = h.export_csr(L.KUU)
     assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2) and np.array_equal(v, v2)
     h.close()
+
+
+@pytest.mark.parametrize("mesh_name,setting,variant,form,nparts", [
+    ("LowRes", "inclusion", 0, "Gradient", 3),
+    ("H1", "solkz", 1, "SymmetricGradient", 2),
+])
+def test_partitioned_mesh_on_gpu(mesh_name, setting, variant, form, nparts, api, oracle):
+    """General (unstructured) element partition through the C ABI, ranks run one after the other on
+    one GPU: union of owned rows == oracle rows of the unpartitioned mesh, bit for bit; partial
+    sums of squares add up to the global norms (both tau modes, REFERENCE via tau_ref)."""
+    from fcfv_nme23_b200 import lib as L
+    from fcfv_nme23_b200.partition import partition_mesh
+    case = cases.Case(mesh_name, setting, variant, form, tau_r=2.0 if setting == "inclusion" else 10.0)
+    gm, d = cases.build(case)
+    a, b, Z = oracle.ComputeFCFV(gm, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, form)
+    ofn = oracle.ElementAssemblyLoop if variant == 0 else oracle.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, _, _ = ofn(gm, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], form)
+    NF, NEL = gm.nf, gm.nel
+    grp, gci, gv = csc_triple_to_csr(Kuu, (2 * NF, 2 * NF))
+    grpp, gcip, gvp = csc_triple_to_csr(Kup, (2 * NF, NEL))
+    norms = {tm: oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], gm, a, b, Z, d["sex"], d["sey"], d["VxDir"],
+                                                       d["VyDir"], *d["neu"], form, tau_mode=tm) for tm in ("REFERENCE", "FACE")}
+    ss = {"REFERENCE": np.zeros(6), "FACE": np.zeros(6)}
+    rows_seen = np.zeros(2 * NF, dtype=int)
+    for r in range(nparts):
+        P = partition_mesh(gm, nparts, r)      # gm.τ is the global τ after ComputeFCFV -> tau_ref
+        m = P.mesh
+        m.τ = None
+        sf, se = P.scatter_face, P.scatter_elem
+        neu = [sf(x) for x in d["neu"]]
+        la, lb, lZ = api.ComputeFCFV(m, se(d["sex"]), se(d["sey"]), sf(d["VxDir"]), sf(d["VyDir"]), *neu, case.tau_r, form)
+        assert np.array_equal(la[P.elem_owned], a[P.elem_global[P.elem_owned]])
+        gfn = api.ElementAssemblyLoop if variant == 0 else api.ElementAssemblyLoopNEW
+        h, nnz, sec = gfn(m, la, lb, lZ, sf(d["VxDir"]), sf(d["VyDir"]), *neu, form, export=False)
+        lrp, lci, lv = h.export_csr(L.KUU)
+        lrpp, lcip, lvp = h.export_csr(L.KUP)
+        lfu, lfp = h.export_rhs()
+        for lr, gr in zip(P.local_rows(), P.owned_rows()):
+            rows_seen[gr] += 1
+            assert np.array_equal(P.global_columns(lci[lrp[lr]:lrp[lr + 1]]), gci[grp[gr]:grp[gr + 1]])
+            assert np.array_equal(lv[lrp[lr]:lrp[lr + 1]], gv[grp[gr]:grp[gr + 1]])
+            assert np.array_equal(P.global_columns(lcip[lrpp[lr]:lrpp[lr + 1]], "up"), gcip[grpp[gr]:grpp[gr + 1]])
+            assert np.array_equal(lvp[lrpp[lr]:lrpp[lr + 1]], gvp[grpp[gr]:grpp[gr + 1]])
+            assert lfu[lr] == fu[gr, 0]
+        # rows of faces owned elsewhere are empty
+        notmine = np.setdiff1d(np.arange(2 * m.nf), P.local_rows())
+        assert np.all(np.diff(lrp)[notmine] == 0)
+        assert np.array_equal(lfp[P.elem_owned], fp[P.elem_global[P.elem_owned]])
+        h.set_solution(sf(d["Vxh"]), sf(d["Vyh"]), se(d["Pe"]))
+        for tm in ("REFERENCE", "FACE"):
+            s, _ = h.run_residuals(form, tm)
+            ss[tm] += s
+        h.close()
+    assert np.all(rows_seen[np.diff(grp) > 0] == 1)
+    lens = np.array([4 * NEL, 2 * NEL, NEL, NF, NF, NEL], dtype=float)
+    for tm in ("REFERENCE", "FACE"):
+        got = np.sqrt(ss[tm]) / np.sqrt(lens)
+        big = norms[tm] > 1e-9
+        assert np.all(np.abs(got[big] - norms[tm][big]) <= TOL * norms[tm][big]), (tm, got, norms[tm])
+        assert np.all(got[~big] < 1e-9)

@@ -1,0 +1,196 @@
+"""The oracle itself: pinned by digests (regression), cross-checked against an independent NumPy
+restatement (bitwise) and against identities of the discretisation that do not depend on either
+restatement.  Runs without a GPU.  PARITY UNPINNED w.r.t. real Julia
+output -- see oracle/fcfv_oracle.c."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import cases
+import np_restatement as R
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def run_oracle(O, case):
+    m, d = cases.build(case)
+    a, b, Z = O.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, case.form)
+    fn = O.ElementAssemblyLoop if case.variant == 0 else O.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, ts, tl = fn(m, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], case.form)
+    return m, d, a, b, Z, Kuu, Muu, Kup, fu, fp
+
+
+@pytest.mark.parametrize("case", cases.all_cases(), ids=lambda c: c.name)
+def test_golden_digests(case, oracle):
+    gold = json.load(open(os.path.join(cases.GOLDEN, "golden_oracle.json")))[case.name]
+    m, d, a, b, Z, Kuu, Muu, Kup, fu, fp = run_oracle(oracle, case)
+    assert (gold["nel"], gold["nf"]) == (m.nel, m.nf)
+    assert (gold["nnz_uu"], gold["nnz_muu"], gold["nnz_up"]) == (len(Kuu[2]), len(Muu[2]), len(Kup[2]))
+    assert gold["local"] == digest(a, b.ravel(order="F"), Z.ravel(order="F"), m.τ)
+    assert gold["Kuu"] == digest(*Kuu) and gold["Muu"] == digest(*Muu) and gold["Kup"] == digest(*Kup)
+    assert gold["rhs"] == digest(fu, fp)
+    for mode, key in (("REFERENCE", "norms_reference"), ("FACE", "norms_face")):
+        n = oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"],
+                                                  d["VyDir"], *d["neu"], case.form, tau_mode=mode)
+        assert np.array_equal(n, np.array(gold[key]))
+
+
+@pytest.mark.parametrize("case", cases.all_cases(small_only=True), ids=lambda c: c.name)
+def test_against_numpy_restatement(case, oracle):
+    m, d, a, b, Z, Kuu, Muu, Kup, fu, fp = run_oracle(oracle, case)
+    m2, _ = cases.build(case)
+    a2, b2, Z2, tau2 = R.compute_fcfv(m2, d["sex"], d["sey"], d["VxDir"], d["VyDir"], case.form)
+    assert np.array_equal(a, a2) and np.array_equal(b, b2) and np.array_equal(Z, Z2) and np.array_equal(tau2, m.τ)
+    m2.τ = tau2
+    K2, M2, P2, fu2, fp2 = R.assemble(m2, a2, b2, Z2, d["VxDir"], d["VyDir"], *d["neu"], case.form, variant=case.variant)
+    nel, nf = m.nel, m.nf
+    for got, ref, shape in ((Kuu, K2, (2 * nf, 2 * nf)), (Muu, M2, (2 * nf, 2 * nf)), (Kup, P2, (2 * nf, nel))):
+        S = oracle.csc_to_scipy(got, shape)
+        assert np.array_equal(S.indptr, ref.indptr) and np.array_equal(S.indices, ref.indices) and np.array_equal(S.data, ref.data)
+    assert np.array_equal(fu.ravel(), fu2) and np.array_equal(fp, fp2)
+    for mode in ("REFERENCE", "FACE"):
+        n1, arr = oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"],
+                                                        d["VyDir"], *d["neu"], case.form, tau_mode=mode, arrays=True)
+        arr2 = R.residual_arrays(m2, d["Vxh"], d["Vyh"], d["Pe"], a2, b2, Z2, d["sex"], d["sey"], d["VxDir"], d["VyDir"],
+                                 *d["neu"], case.form, tau_mode=mode)
+        for k in arr:
+            scale = max(np.abs(arr2[k]).max(), 1e-300)
+            assert np.abs(np.asarray(arr[k]) - arr2[k]).max() <= 1e-13 * scale, k
+
+
+# SURVEY.md Appendix C (probe constants, re-confirmed by the oracle): nnz after the exact-zero drop
+APPENDIX_C = [
+    ("LowRes", "inclusion", "Gradient", 29546, 11314), ("LowRes", "inclusion", "SymmetricGradient", 55882, 11314),
+    ("MedRes", "inclusion", "Gradient", 120916, 47492), ("MedRes", "inclusion", "SymmetricGradient", 236052, 47492),
+    ("H1", "solkz", "SymmetricGradient", 25456, 5168), ("H1", "solkz", "Gradient", 14912, 5168),
+    ("H2", "solkz", "SymmetricGradient", 103072, 20768),
+]
+
+
+@pytest.mark.parametrize("mesh,setting,form,nnz_uu,nnz_up", APPENDIX_C)
+def test_appendix_c_nnz(mesh, setting, form, nnz_uu, nnz_up, oracle):
+    case = cases.Case(mesh, setting, 0, form, tau_r=2.0 if setting == "inclusion" else 10.0)
+    m, d, a, b, Z, Kuu, Muu, Kup, fu, fp = run_oracle(oracle, case)
+    assert (len(Kuu[2]), len(Kup[2])) == (nnz_uu, nnz_up)
+
+
+def test_structured_row_histogram(oracle):
+    """S(32): 100 992 / 20 352 stored entries, row lengths 1/5/6/7/8/9."""
+    case = cases.Case("S32", "solkz", 0, "SymmetricGradient", tau_r=10.0)
+    m, d, a, b, Z, Kuu, Muu, Kup, fu, fp = run_oracle(oracle, case)
+    assert (len(Kuu[2]), len(Kup[2])) == (100992, 20352)
+    S = oracle.csc_to_scipy(Kuu, (2 * m.nf, 2 * m.nf)).tocsr()
+    hist = np.bincount(np.diff(S.indptr), minlength=11)
+    assert list(hist[:10]) == [0, 256, 0, 0, 0, 1984, 8, 248, 248, 9672]
+
+
+@pytest.mark.parametrize("form", ["Gradient", "SymmetricGradient"])
+def test_identity_matrix_free_equals_spmv(form, oracle):
+    """§4 identity 1/2: with the FACE tau the matrix-free residual equals fu - Kuu*u - Kup*p on
+    non-Dirichlet rows and fp - Kpu*u = -F_glob2, for ARBITRARY (u, p) -- ties the assembly to the
+    residual function line by line; with element-varying tau the REFERENCE mode (quirk) does not."""
+    case = cases.Case("H1", "solkz", 0, form, tau_r=10.0)
+    m, d, a, b, Z, Kuu, Muu, Kup, fu, fp = run_oracle(oracle, case)
+    u = np.concatenate([d["Vxh"], d["Vyh"]])
+    ru, rp, nrm = oracle.ph_residual(m, Kuu, Kup, fu, fp, u, d["Pe"])
+    nd = m.bc != 1
+    _, arr = oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"],
+                                                   d["VyDir"], *d["neu"], form, tau_mode="FACE", arrays=True)
+    scale = np.abs(ru).max()
+    assert np.abs(ru[:m.nf][nd] - arr["F_nodes_x"][nd]).max() <= 1e-12 * scale
+    assert np.abs(ru[m.nf:][nd] - arr["F_nodes_y"][nd]).max() <= 1e-12 * scale
+    assert np.abs(rp + arr["F_glob2"]).max() <= 1e-12 * max(np.abs(rp).max(), 1.0)
+    assert np.array_equal(ru[:m.nf][~nd], (d["VxDir"] - d["Vxh"])[~nd])      # Dirichlet rows: VDir - u
+    _, arr_ref = oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"],
+                                                       d["VyDir"], *d["neu"], form, tau_mode="REFERENCE", arrays=True)
+    assert np.abs(ru[:m.nf][nd] - arr_ref["F_nodes_x"][nd]).max() > 1e-3 * scale
+
+
+def test_identity_new_vs_old(oracle):
+    """§4 identity 3: NEW(:SymmetricGradient, δ=1) == old to round-off with identical sparsity;
+    NEW(:Gradient) == transpose of old(:Gradient)."""
+    for mesh in ("LowRes", "H1"):
+        setting = "inclusion" if mesh == "LowRes" else "solkz"
+        o = run_oracle(oracle, cases.Case(mesh, setting, 0, "SymmetricGradient"))
+        n = run_oracle(oracle, cases.Case(mesh, setting, 1, "SymmetricGradient"))
+        nf = o[0].nf
+        assert np.array_equal(o[5][0], n[5][0]) and np.array_equal(o[5][1], n[5][1])
+        assert np.abs(o[5][2] - n[5][2]).max() <= 1e-15 * np.abs(o[5][2]).max()
+        og = run_oracle(oracle, cases.Case(mesh, setting, 0, "Gradient"))
+        ng = run_oracle(oracle, cases.Case(mesh, setting, 1, "Gradient"))
+        Ko = oracle.csc_to_scipy(og[5], (2 * nf, 2 * nf)); Kn = oracle.csc_to_scipy(ng[5], (2 * nf, 2 * nf))
+        D = (Ko.T - Kn).tocoo()
+        assert D.nnz == 0 or np.abs(D.data).max() <= 1e-15 * np.abs(Ko.data).max()
+
+
+def test_identity_kup_column_sums(oracle):
+    """§4 identity 5: sum_i Γ_i n_i = 0 per element => columns of Kup of elements without Dirichlet
+    faces sum to zero (x and y blocks separately)."""
+    m, d, a, b, Z, Kuu, Muu, Kup, fu, fp = run_oracle(oracle, cases.Case("LowRes", "inclusion", 0, "Gradient"))
+    P = oracle.csc_to_scipy(Kup, (2 * m.nf, m.nel)).tocsc()
+    has_dir = (m.bc[np.asarray(m.e2f) - 1] == 1).any(axis=1)
+    sx = np.asarray(P[:m.nf].sum(axis=0)).ravel(); sy = np.asarray(P[m.nf:].sum(axis=0)).ravel()
+    assert np.abs(sx[~has_dir]).max() < 1e-15 and np.abs(sy[~has_dir]).max() < 1e-15
+
+
+@pytest.mark.parametrize("form,solver_tau", [("Gradient", 2.0), ("SymmetricGradient", 2.0)])
+def test_powell_hestenes_converges_and_residuals_vanish(form, solver_tau, oracle):
+    """§4 identity 4: Powell-Hestenes (SolversFCFV_Stokes.jl:23-49, SciPy LU standing in for UMFPACK)
+    on LowRes, η = [1, 1e-2], γ = 1e5: local equations at round-off, global equations at the PH
+    tolerance; PH residual RMS equals the matrix-free norms."""
+    case = cases.Case("LowRes", "inclusion", 0, form, tau_r=solver_tau)
+    m, d, a, b, Z, Kuu, Muu, Kup, fu, fp = run_oracle(oracle, case)
+    nel, nf = m.nel, m.nf
+    K = oracle.csc_to_scipy(Kuu, (2 * nf, 2 * nf)); P = oracle.csc_to_scipy(Kup, (2 * nf, nel))
+    gamma = 1e5
+    coef = gamma * m.ke / m.Ω
+    Kpu = -P.T
+    Ksc = (K - P @ sp.diags(coef) @ Kpu).tocsc()
+    lu = spla.splu(Ksc)
+    u = np.zeros(2 * nf); p = np.zeros(nel)
+    for it in range(20):
+        ru, rp, nrm = oracle.ph_residual(m, Kuu, Kup, fu, fp, u, p)
+        if nrm[0] / np.sqrt(2 * nf) < 1e-8 and nrm[1] / np.sqrt(2 * nf) < 1e-8:
+            break
+        u = lu.solve(oracle.ph_fusc(m, Kup, fu, fp, gamma, p))
+        p = oracle.ph_update_p(m, Kup, fp, gamma, u, p)
+    assert it <= 6
+    norms = oracle.ComputeResidualsFCFV_Stokes_o1(u[:nf], u[nf:], p, m, a, b, Z, d["sex"], d["sey"], d["VxDir"], d["VyDir"],
+                                                  *d["neu"], form, tau_mode="REFERENCE")
+    assert norms[0] < 1e-14 and norms[1] < 1e-13
+    assert np.all(norms[2:] < 1e-7)
+    assert abs(np.sqrt((norms[3] ** 2 + norms[4] ** 2) / 2) - nrm[0] / np.sqrt(2 * nf)) < 1e-9
+    assert abs(norms[5] - nrm[1] / np.sqrt(nel)) < 1e-9
+
+
+@pytest.mark.parametrize("mesh,field", [("LowRes", "uniform"), ("MedRes", "uniform"), ("H1", "uniform"), ("S6", "uniform")])
+@pytest.mark.parametrize("form", ["Gradient", "SymmetricGradient"])
+def test_known_answer_exact_flows(mesh, field, form, oracle):
+    """Known-answer tests independent of any restatement.  'uniform': rigid translation u = (1.5, -0.5)
+    with constant pressure is reproduced exactly on ANY mesh (L = 0, u_e = û, the pressure fluxes of
+    the two sides of a face cancel), so with û = the exact face values all six residuals vanish to
+    round-off and the assembled system is satisfied.  (A linear field is NOT reproduced exactly by
+    the lowest-order scheme: the tau(u_e - û) jumps of the two sides of a face do not cancel.)"""
+    m = cases.load_mesh(mesh)
+    nel, nf = m.nel, m.nf
+    m.ke = np.ones(nel); m.τe = 3.0 * np.ones(nel); m.τ = None
+    m.bc = np.where(m.bc == -1, 0, m.bc)
+    VxDir, VyDir, P = np.full(nf, 1.5), np.full(nf, -0.5), np.full(nel, 0.7)
+    z = np.zeros(nf); ze = np.zeros(nel)
+    a, b, Z = oracle.ComputeFCFV(m, ze, ze, VxDir, VyDir, z, z, z, z, 3.0, form)
+    norms = oracle.ComputeResidualsFCFV_Stokes_o1(VxDir, VyDir, P, m, a, b, Z, ze, ze, VxDir, VyDir, z, z, z, z, form)
+    assert np.all(norms < 1e-13), norms
+    # ... and the assembled system is satisfied by it: fu - Kuu*u - Kup*p = 0, fp - Kpu*u = 0
+    Kuu, Muu, Kup, fu, fp, _, _ = oracle.ElementAssemblyLoop(m, a, b, Z, VxDir, VyDir, z, z, z, z, form)
+    ru, rp, nrm = oracle.ph_residual(m, Kuu, Kup, fu, fp, np.concatenate([VxDir, VyDir]), P)
+    assert nrm[0] < 1e-11 and nrm[1] < 1e-11

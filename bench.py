@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="quads per side of the per-rank-equivalent mesh (default 3536)")
+    ap.add_argument("--mesh-n", dest="n", type=int, default=None, help="quads per side of the per-rank-equivalent mesh (default 3536)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -1,0 +1,212 @@
+# FCFV_B200.jl -- drop-in Julia shim: same names and signatures as the reference's exported functions
+# (src/FCFV_NME23.jl:13,17), every floating-point operation done by libfcfv_b200.so on a B200.
+#
+#     include("julia/FCFV_B200.jl"); using .FCFV_B200        # instead of the three reference functions
+#
+# NOTE: Julia is not available in the build image of this repository, so this file has not been
+# executed there; tests/ and bench.py drive the very same C entry points through Python ctypes
+# (fcfv_nme23_b200/lib.py, api.py), which mirrors this file call for call.
+module FCFV_B200
+
+using SparseArrays, Printf
+
+export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1,
+       MeshGeometry!, PHResidual, PHUpdateP!, PHFusc
+
+const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
+
+const GRADIENT, SYMMETRIC_GRADIENT = Cint(0), Cint(1)
+const LOOP_OLD, LOOP_NEW = Cint(0), Cint(1)
+const TAU_REFERENCE, TAU_FACE = Cint(0), Cint(1)
+const KUU, KUP, MUU = Cint(0), Cint(1), Cint(2)
+const CSC1_INT64 = Cint(1)
+const A = 1.0                      # src/DiscretisationFCFV_Stokes.jl:1-2
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    nel::Int
+    nf::Int
+end
+
+function Handle(device::Integer = 0)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:fcfv_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
+    rc == 0 || error("fcfv_create failed with status $rc: no usable CUDA device (there is no CPU fallback)")
+    h = Handle(r[], 0, 0)
+    finalizer(x -> ccall((:fcfv_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), h)
+    return h
+end
+
+function check(h::Handle, rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:fcfv_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr))
+    error("libfcfv_b200 status $rc: $msg")
+end
+
+form_id(F::Symbol) = F == :Gradient ? GRADIENT : F == :SymmetricGradient ? SYMMETRIC_GRADIENT :
+                     error("Formulation must be :Gradient or :SymmetricGradient")
+
+const HANDLES = IdDict{Any,Handle}()     # one handle per mesh object
+
+f64(x) = convert(Array{Float64}, x)
+i64(x) = convert(Array{Int64}, x)
+
+function handle_for(mesh)
+    haskey(HANDLES, mesh) && return HANDLES[mesh]
+    h = Handle()
+    e2f, bc = i64(mesh.e2f), i64(mesh.bc)
+    Ω, nx, ny, Γ, ke, δ = f64(mesh.Ω), f64(mesh.n_x), f64(mesh.n_y), f64(mesh.Γ), f64(mesh.ke), f64(mesh.δ)
+    τe = ismissing(mesh.τe) ? zeros(mesh.nel) : f64(mesh.τe)       # may have nf entries (v2.jl:127)
+    GC.@preserve e2f bc Ω nx ny Γ ke δ τe begin
+        check(h, ccall((:fcfv_set_mesh, LIB), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+            h.ptr, mesh.nel, mesh.nf, e2f, bc, Ω, nx, ny, Γ, ke, δ, τe, length(τe)))
+    end
+    h.nel, h.nf = mesh.nel, mesh.nf
+    HANDLES[mesh] = h
+    return h
+end
+
+# The drivers mutate mesh.ke / δ / τe / τ after the mesh is built (v2.jl:44,127; SolKzFCFV.jl:25,149):
+# refresh those vectors at the top of every entry point.
+function refresh!(h::Handle, mesh)
+    ke, δ = f64(mesh.ke), f64(mesh.δ)
+    τe = ismissing(mesh.τe) ? zeros(mesh.nel) : f64(mesh.τe)
+    τ = ismissing(mesh.τ) ? Float64[] : f64(mesh.τ)
+    GC.@preserve ke δ τe τ begin
+        check(h, ccall((:fcfv_update_fields, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+            h.ptr, ke, δ, τe, length(τe), isempty(τ) ? C_NULL : pointer(τ)))
+    end
+end
+
+"""Ω, centroids, outward normals, Γ (and τ .= τr) from xv, yv, e2v, e2f, xf, yf -- the loops of
+MakeTriangleMesh / LoadExternalMesh2 (CreateMeshFCFV.jl:142-156,180-211 / :300-314,337-367).
+`numbering` 0: nodeA=[2 3 1], nodeB=[3 1 2]; 1: nodeA=[3 2 1], nodeB=[1 3 2]."""
+function MeshGeometry!(mesh, τr; numbering::Integer = 0)
+    h = Handle()
+    nel, nf, nv = mesh.nel, mesh.nf, length(mesh.xv)
+    e2v, e2f = i64(mesh.e2v), i64(mesh.e2f)
+    xv, yv, xf, yf = f64(mesh.xv), f64(mesh.yv), f64(mesh.xf), f64(mesh.yf)
+    Ω, xc, yc = zeros(nel), zeros(nel), zeros(nel)
+    nx, ny, Γ = zeros(nel, 3), zeros(nel, 3), zeros(nel, 3)
+    τ = ismissing(mesh.τ) ? zeros(nf) : f64(mesh.τ)
+    GC.@preserve e2v e2f xv yv xf yf Ω xc yc nx ny Γ τ begin
+        check(h, ccall((:fcfv_geometry, LIB), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h.ptr, nel, nf, nv, e2v, e2f, xv, yv, xf, yf, numbering, τr, Ω, xc, yc, nx, ny, Γ, τ))
+    end
+    mesh.Ω, mesh.xc, mesh.yc, mesh.n_x, mesh.n_y, mesh.Γ, mesh.τ = Ω, xc, yc, nx, ny, Γ, τ
+    return mesh
+end
+
+"""src/DiscretisationFCFV_Stokes.jl:8-44"""
+function ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τr, Formulation)
+    ismissing(mesh.τ) && (mesh.τ = zeros(mesh.nf))      # LoadExternalMesh leaves τ missing
+    h = handle_for(mesh); refresh!(h, mesh)
+    nel, nf = mesh.nel, mesh.nf
+    α, β, Ζ, τ = zeros(nel), zeros(nel, 2), zeros(nel, 2, 2), zeros(nf)
+    sx, sy, vx, vy = f64(sex), f64(sey), f64(VxDir), f64(VyDir)
+    GC.@preserve sx sy vx vy α β Ζ τ begin
+        check(h, ccall((:fcfv_compute_local, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}),
+            h.ptr, form_id(Formulation), A, sx, sy, vx, vy, α, β, Ζ, τ))
+    end
+    mesh.τ = τ
+    return α, β, Ζ
+end
+
+function export_csc(h::Handle, block::Cint)
+    nr, nc, nnz = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    check(h, ccall((:fcfv_block_size, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}, Ref{Int64}, Ref{Int64}), h.ptr, block, nr, nc, nnz))
+    colptr, rowval, nzval = Vector{Int64}(undef, nc[] + 1), Vector{Int64}(undef, nnz[]), Vector{Float64}(undef, nnz[])
+    GC.@preserve colptr rowval nzval begin
+        check(h, ccall((:fcfv_export, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
+                       h.ptr, block, CSC1_INT64, colptr, rowval, nzval))
+    end
+    return SparseMatrixCSC{Float64,Int64}(nr[], nc[], colptr, rowval, nzval)
+end
+
+function assemble(variant::Cint, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation)
+    h = handle_for(mesh); refresh!(h, mesh)
+    nel, nf = mesh.nel, mesh.nf
+    a, b, z = f64(α), f64(β), f64(Ζ)
+    vx, vy, sxx, syy, sxy, syx = f64(VxDir), f64(VyDir), f64(σxxNeu), f64(σyyNeu), f64(σxyNeu), f64(σyxNeu)
+    n1, n2, n3, sec = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0), Ref{Float64}(0.0)
+    GC.@preserve a b z vx vy sxx syy sxy syx begin
+        check(h, ccall((:fcfv_assemble, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
+            h.ptr, variant, form_id(Formulation), A, a, b, z, vx, vy, sxx, syy, sxy, syx, 1, n1, n2, n3, sec))
+    end
+    Kuu, Muu, Kup = export_csc(h, KUU), export_csc(h, MUU), export_csc(h, KUP)
+    fu, fp = zeros(2nf, 1), zeros(nel)                  # fu is a 2nf x 1 Matrix in the reference
+    GC.@preserve fu fp check(h, ccall((:fcfv_export_rhs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h.ptr, fu, fp))
+    return Kuu, Muu, Kup, fu, fp, sec[]                 # sec plays `tsparse`
+end
+
+"""src/DiscretisationFCFV_Stokes.jl:102-202"""
+ElementAssemblyLoop(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation) =
+    assemble(LOOP_OLD, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation)
+
+"""src/DiscretisationFCFV_Stokes.jl:210-347"""
+ElementAssemblyLoopNEW(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation) =
+    assemble(LOOP_NEW, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation)
+
+"""src/ComputeResidualsFCFV_Stokes.jl:5-108 -- prints the same six lines, returns nothing.
+`tau_mode = :Reference` reads mesh.τ[e] like the reference (:17,54); `:Face` uses mesh.τ[e2f[e,i]]."""
+function ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu,
+                                        Formulation; tau_mode::Symbol = :Reference)
+    h = handle_for(mesh); refresh!(h, mesh)
+    vxh, vyh, pe, a, b, z = f64(Vxh), f64(Vyh), f64(Pe), f64(ae), f64(be), f64(ze)
+    sx, sy, vx, vy = f64(sex), f64(sey), f64(VxDir), f64(VyDir)
+    sxx, syy, sxy, syx = f64(SxxNeu), f64(SyyNeu), f64(SxyNeu), f64(SyxNeu)
+    norms = zeros(6)
+    GC.@preserve vxh vyh pe a b z sx sy vx vy sxx syy sxy syx norms begin
+        check(h, ccall((:fcfv_residuals, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h.ptr, form_id(Formulation), tau_mode == :Face ? TAU_FACE : TAU_REFERENCE, vxh, vyh, pe, a, b, z, sx, sy, vx, vy,
+            sxx, syy, sxy, syx, norms, C_NULL, C_NULL, C_NULL))
+    end
+    @printf("Residual of local  equation 20a: %2.2e\n", norms[1])
+    @printf("Residual of local  equation 20b: %2.2e\n", norms[2])
+    @printf("Residual of local  equation 20c: %2.2e\n", norms[3])
+    @printf("Residual of global equation 19a: %2.2e\n", norms[4])
+    @printf("Residual of global equation 19a: %2.2e\n", norms[5])
+    @printf("Residual of global equation 19b: %2.2e\n", norms[6])
+    return
+end
+
+# --- the Powell-Hestenes lines of StokesSolvers! that consume the device CSR (SolversFCFV_Stokes.jl:40-49)
+"""ru = fu - Kuu*u - Kup*p, rp = fp - Kpu*u, (norm(ru), norm(rp))"""
+function PHResidual(mesh, u, p)
+    h = handle_for(mesh)
+    uu, pp = f64(vec(u)), f64(vec(p))
+    ru, rp, nrm = zeros(2h.nf), zeros(h.nel), zeros(2)
+    GC.@preserve uu pp ru rp nrm check(h, ccall((:fcfv_ph_residual, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), h.ptr, uu, pp, ru, rp, nrm))
+    return ru, rp, nrm[1], nrm[2]
+end
+
+"""p .+= (penalty .* ke ./ Ω) .* (fp .- Kpu*u)"""
+function PHUpdateP!(mesh, penalty, u, p)
+    h = handle_for(mesh)
+    uu = f64(vec(u))
+    GC.@preserve uu p check(h, ccall((:fcfv_ph_update_p, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}), h.ptr, penalty, uu, p))
+    return p
+end
+
+"""fusc = fu .- Kup*(Kppi*fp .+ p)"""
+function PHFusc(mesh, penalty, p)
+    h = handle_for(mesh)
+    pp, out = f64(vec(p)), zeros(2h.nf)
+    GC.@preserve pp out check(h, ccall((:fcfv_ph_fusc, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}), h.ptr, penalty, pp, out))
+    return out
+end
+
+end # module

@@ -21,8 +21,8 @@ using namespace fcfv;
 
 struct Id128 { char b[128]; };   // ncclUniqueId
 
-enum { T_TAU = 0, T_LOCAL, T_COUNT, T_SCAN, T_FILL, T_RES_ELEM, T_RES_FACE, T_REDUCE, T_PH, T_OTHER, kNumTimers };
-static const char* const kTimerNames[kNumTimers] = {"k_face_tau", "k_local", "k_asm_count", "k_scan", "k_asm_fill",
+enum { T_TAU = 0, T_LOCAL, T_COEF, T_COUNT, T_SCAN, T_FILL, T_RES_ELEM, T_RES_FACE, T_REDUCE, T_PH, T_OTHER, kNumTimers };
+static const char* const kTimerNames[kNumTimers] = {"k_face_tau", "k_local", "k_elem_coef", "k_asm_count", "k_scan", "k_asm_fill",
                                                     "k_res_elem", "k_res_face", "k_reduce_partials", "k_ph", "other"};
 struct TimerRec { int id; cudaEvent_t a, b; };
 
@@ -71,6 +71,9 @@ struct fcfv_handle {
     DBuf sex, sey, VxDir, VyDir, sxx, syy, sxy, syx, Vxh, Vyh, Pe;
     // local coefficients
     DBuf alpha, beta, Z;
+    // per-element assembly coefficients (k_elem_coef): ia, c11 and, when some delta != 1, c12 c21 c22
+    DBuf coef, coefx;
+    bool delta_dirty = true, aniso = false;
     // assembly
     Csr Kuu, Kup, Muu;
     DBuf fu, fp, sums, bases, chunks, totals;
@@ -299,7 +302,7 @@ int fcfv_destroy(fcfv_t* h) {
                    &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
                    &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,
                    &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->chunks, &h->totals,
-                   &h->Fg, &h->partial, &h->sumsq, &h->tmp, &h->tmp2, &h->err_flag, &h->phw};
+                   &h->Fg, &h->partial, &h->sumsq, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx};
     for (DBuf* b : all) release(h, *b);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     cudaEventDestroy(h->ev0);
@@ -361,6 +364,7 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
         return fail(h, FCFV_ERR_INVALID, "fcfv_set_mesh: null mesh array");
     if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
     h->have_mesh = false; h->have_local = false;
+    h->delta_dirty = true;
     h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = -1;
     h->nel = nel; h->nf = nf; h->nel_global = nel; h->nf_global = nf;
     h->have_elem_owned = h->have_face_owned = h->have_tau_ref = false;
@@ -401,7 +405,7 @@ int fcfv_update_fields(fcfv_t* h, const double* ke, const double* delta, const d
     CU(cudaSetDevice(h->device));
     if (taue && ntaue < h->nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel", (long long)ntaue);
     if (ke) TRY(copy(h, h->ke.p, ke, sizeof(double) * h->nel));
-    if (delta) TRY(copy(h, h->dl.p, delta, sizeof(double) * h->nel));
+    if (delta) { TRY(copy(h, h->dl.p, delta, sizeof(double) * h->nel)); h->delta_dirty = true; }
     if (taue) TRY(copy(h, h->taue.p, taue, sizeof(double) * h->nel));
     if (tau) TRY(copy(h, h->tau.p, tau, sizeof(double) * h->nf));
     return finish(h);
@@ -580,18 +584,28 @@ int fcfv_compute_local(fcfv_t* h, int formulation, double A, const double* sex, 
 // -------------------------------------------------------------------------------------------------
 namespace {
 
-template <int VARIANT, int FORM, bool WANT_M>
+CoefView coef_view(fcfv_t* h) {
+    double* c = P<double>(h->coef);
+    double* x = P<double>(h->coefx);
+    const size_t nel = (size_t)h->nel;
+    return CoefView{c, c + nel, h->aniso ? x : nullptr, h->aniso ? x + nel : nullptr, h->aniso ? x + 2 * nel : nullptr};
+}
+
+template <int VARIANT, int FORM, bool WANT_M, bool ANISO>
 int launch_assemble(fcfv_t* h, double A) {
     const MeshView M = mesh_view(h);
     const LocalView L = local_view(h);
     const FaceDataView D = face_view(h);
+    const CoefView Cf = coef_view(h);
     const int nblk = nblocks(h->nf, kAsmFaces);
     const int nchunks = nblocks(nblk, kScanChunk);
     int* sums = P<int>(h->sums);
     int* local = P<int>(h->bases);
     long long* chunk_tot = P<long long>(h->chunks);
     long long* chunk_base = chunk_tot + (size_t)kNumSums * nchunks;
-    TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, WANT_M>), nblk, kAsmBlock, M, L, D, A, sums, nblk);
+    TLAUNCH(h, T_COEF, k_elem_coef<VARIANT>, nblocks(h->nel, 256), 256, M.nel, L.alpha, M.ke, M.dl, M.Om, (double*)Cf.ia, (double*)Cf.c11,
+            (double*)Cf.c12, (double*)Cf.c21, (double*)Cf.c22);
+    TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, WANT_M, ANISO>), nblk, kAsmBlock, M, L, Cf, D, A, sums, nblk);
     TLAUNCH(h, T_SCAN, k_scan_local, dim3(nchunks, kNumSums), 1024, sums, local, nblk, nchunks, chunk_tot);
     CsrOut ouu{h->Kuu.rowptr.p, P<int>(h->Kuu.col), P<double>(h->Kuu.val)};
     CsrOut oup{h->Kup.rowptr.p, P<int>(h->Kup.col), P<double>(h->Kup.val)};
@@ -599,12 +613,12 @@ int launch_assemble(fcfv_t* h, double A) {
     if (h->rp64) {
         TLAUNCH(h, T_SCAN, k_scan_chunks<long long>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals),
                 (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)omu.rowptr, M.nf, (int)WANT_M);
-        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, long long>), nblk, kAsmBlock, M, L, D, A, local, chunk_base, nblk,
+        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, ANISO, long long>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk,
                 nchunks, ouu, oup, omu, P<double>(h->fu), P<double>(h->fp));
     } else {
         TLAUNCH(h, T_SCAN, k_scan_chunks<int>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals), (int*)ouu.rowptr,
                 (int*)oup.rowptr, (int*)omu.rowptr, M.nf, (int)WANT_M);
-        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, int>), nblk, kAsmBlock, M, L, D, A, local, chunk_base, nblk, nchunks,
+        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, ANISO, int>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk, nchunks,
                 ouu, oup, omu, P<double>(h->fu), P<double>(h->fp));
     }
     return FCFV_OK;
@@ -612,7 +626,9 @@ int launch_assemble(fcfv_t* h, double A) {
 
 template <int VARIANT, int FORM>
 int launch_assemble_m(fcfv_t* h, double A, int want_muu) {
-    return want_muu ? launch_assemble<VARIANT, FORM, true>(h, A) : launch_assemble<VARIANT, FORM, false>(h, A);
+    if (VARIANT == kLoopNew && h->aniso)
+        return want_muu ? launch_assemble<VARIANT, FORM, true, true>(h, A) : launch_assemble<VARIANT, FORM, false, true>(h, A);
+    return want_muu ? launch_assemble<VARIANT, FORM, true, false>(h, A) : launch_assemble<VARIANT, FORM, false, false>(h, A);
 }
 
 int fetch_totals(fcfv_t* h) {
@@ -655,6 +671,17 @@ int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int wan
     }
     TRY(ensure(h, h->fu, sizeof(double) * 2 * nf));
     TRY(ensure(h, h->fp, sizeof(double) * nel));
+    if (h->delta_dirty) {   // does any element have delta != 1?  (only after delta was uploaded)
+        CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
+        LAUNCH(h, k_delta_flag, nblocks(nel, 256), 256, P<double>(h->dl), (int)nel, P<int>(h->err_flag));
+        int flag = 0;
+        TRY(read_err_flag(h, &flag));
+        CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
+        h->aniso = flag != 0;
+        h->delta_dirty = false;
+    }
+    TRY(ensure(h, h->coef, sizeof(double) * 2 * nel));
+    if (h->aniso) TRY(ensure(h, h->coefx, sizeof(double) * 3 * nel));
     TRY(ensure(h, h->sums, sizeof(int) * kNumSums * (size_t)nblk));
     TRY(ensure(h, h->bases, sizeof(int) * kNumSums * (size_t)nblk));
     TRY(ensure(h, h->chunks, sizeof(long long) * 2 * kNumSums * (size_t)nchunks));
@@ -1071,6 +1098,7 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     const StripLayout S = make_strip_layout(n, row0, row1);
     if (S.nel >= (1LL << 29) || S.nf >= (1LL << 30)) return fail(h, FCFV_ERR_INVALID, "fcfv_generate_structured: strip too large");
     h->have_mesh = false; h->have_local = false;
+    h->delta_dirty = true;
     h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = -1;
     const long long nel = S.nel, nf = S.nf;
     h->nel = nel; h->nf = nf;
@@ -1108,6 +1136,7 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     TRY(read_err_flag(h, &flag));
     if (flag) return fail(h, FCFV_ERR_STATE, "fcfv_generate_structured: generated connectivity failed validation (%d)", flag);
     h->have_mesh = h->have_sources = h->have_face_data = h->have_solution = true;
+    h->delta_dirty = false; h->aniso = false;   // the generator sets delta = 1 everywhere
     return FCFV_OK;
 }
 

@@ -35,6 +35,9 @@ struct MeshView {
 };
 
 struct LocalView { const double *alpha, *beta, *Z; };
+// per-element assembly coefficients (k_elem_coef): 1/alpha, c11 (old: eta/Omega, NEW: D11) and, only
+// when some delta != 1 (c12 != nullptr), the other three entries of D
+struct CoefView { const double *ia, *c11, *c12, *c21, *c22; };
 struct FaceDataView { const double *VxDir, *VyDir, *sxx, *syy, *sxy, *syx; };
 struct SolutionView { const double *Vxh, *Vyh, *Pe; };
 
@@ -42,17 +45,41 @@ struct SolutionView { const double *Vxh, *Vyh, *Pe; };
 struct FaceElem {
     int g[3], bc[3];
     double tau[3], G[3], nx[3], ny[3];
-    double eta, ia, iO, D11, D12, D21, D22;
+    double ia, c11, c12, c21, c22;
     double b1, b2, Z11, Z21, Z12, Z22;
 };
 
+// rot3: r[k] = a[(i + k) mod 3] with selects (no local-memory indexing)
+template <typename T>
+FCFV_HD void rot3(int i, const T a[3], T r[3]) {
+    r[0] = i == 0 ? a[0] : (i == 1 ? a[1] : a[2]);
+    r[1] = i == 0 ? a[1] : (i == 1 ? a[2] : a[0]);
+    r[2] = i == 0 ? a[2] : (i == 1 ? a[0] : a[1]);
+}
+
+#ifndef FCFV_ROT_SELECT
+#define FCFV_ROT_SELECT 0   // 1: load the element's faces in natural order (lanes stay in one SoA plane), rotate in registers
+#endif
+
 // The element's three faces are loaded ROTATED so that the row face (local index i) sits at
-// position 0: every later index is then a compile-time constant (no selects, no local memory).
-// The values do not depend on the order in which the pairs (i, j) are visited; fp, whose
-// sequential sum does, is only formed when i == 0, where the rotation is the identity.
-template <int VARIANT>
-FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, int e, int i, FaceElem& E) {
+// position 0: every later index is then a compile-time constant (no local memory).  The values
+// do not depend on the order in which the pairs (i, j) are visited.
+template <int VARIANT, bool ANISO>
+FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, const CoefView& Cf, int e, int i, FaceElem& E) {
     const int nel = M.nel;
+#if FCFV_ROT_SELECT
+    {
+        int g[3]; double G[3], nx[3], ny[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            g[j] = M.e2f[j * nel + e];
+            G[j] = M.G[j * nel + e]; nx[j] = M.nx[j * nel + e]; ny[j] = M.ny[j * nel + e];
+        }
+        rot3(i, g, E.g); rot3(i, G, E.G); rot3(i, nx, E.nx); rot3(i, ny, E.ny);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { E.bc[k] = M.bc[E.g[k]]; E.tau[k] = M.tau[E.g[k]]; }
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         int j = i + k;
@@ -65,16 +92,11 @@ FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, int e, int i,
         E.nx[k] = M.nx[j * nel + e];
         E.ny[k] = M.ny[j * nel + e];
     }
-    const double Om = M.Om[e];
-    E.eta = M.ke[e];
-    E.ia = 1.0 / L.alpha[e];
-    if (VARIANT == kLoopOld) {
-        E.iO = 1.0 / Om;
-        E.D11 = E.D12 = E.D21 = E.D22 = 0.0;
-    } else {
-        E.iO = 0.0;
-        rheology_new(E.eta, M.dl[e], Om, E.D11, E.D12, E.D21, E.D22);
-    }
+#endif
+    E.ia = Cf.ia[e];
+    E.c11 = Cf.c11[e];
+    if (VARIANT == kLoopNew && ANISO) { E.c12 = Cf.c12[e]; E.c21 = Cf.c21[e]; E.c22 = Cf.c22[e]; }
+    else { E.c12 = E.c11; E.c21 = E.c11; E.c22 = E.c11; }   // delta == 1 everywhere: D12 = D21 = D22 = D11 (old loop: unused)
     E.b1 = L.beta[e]; E.b2 = L.beta[nel + e];
     E.Z11 = L.Z[e]; E.Z21 = L.Z[nel + e]; E.Z12 = L.Z[2 * nel + e]; E.Z22 = L.Z[3 * nel + e];
 }
@@ -87,9 +109,9 @@ FCFV_HD void lane_view(const FaceElem& F, int comp, LaneElem& E) {
         E.nr[j] = comp == 0 ? F.nx[j] : F.ny[j];
         E.no[j] = comp == 0 ? F.ny[j] : F.nx[j];
     }
-    E.eta = F.eta; E.ia = F.ia; E.iO = F.iO;
-    E.Drr = comp == 0 ? F.D11 : F.D22;
-    E.Dro = comp == 0 ? F.D12 : F.D21;
+    E.ia = F.ia; E.c = F.c11;
+    E.Drr = comp == 0 ? F.c11 : F.c22;
+    E.Dro = comp == 0 ? F.c12 : F.c21;
     E.br = comp == 0 ? F.b1 : F.b2;
     E.Z1r = comp == 0 ? F.Z11 : F.Z12;   // Z[e,1,comp]
     E.Z2r = comp == 0 ? F.Z21 : F.Z22;   // Z[e,2,comp]
@@ -97,80 +119,89 @@ FCFV_HD void lane_view(const FaceElem& F, int comp, LaneElem& E) {
     E.Zr2 = comp == 0 ? F.Z12 : F.Z22;   // Z[e,comp,2]
 }
 
-// Rows (f,x) and (f,y): contributions of the element in `slot` (inactive when the face has no such
-// element).  With do_fp, when f is local face 0 of an owned element, that element's fp
-// (Discretisation:194) is returned too, so that fp needs no pass of its own.
+// Contributions of one adjacent element (already loaded and rotated, F) to rows (f,x), (f,y).
 template <int VARIANT, int FORM, bool WANT_M>
-FCFV_HD void compute_slot(const MeshView& M, const LocalView& L, const FaceDataView& D, int f, int2 pr, int slot, double A,
-                          bool do_fp, LaneRow& Rx, LaneRow& Ry, int& fp_elem, double& fp_val) {
-    fp_elem = -1; fp_val = 0.0;
-    // No early exit: a missing second element re-reads the first one and is discarded afterwards, so
-    // that the loads of both slots are independent of any branch and can be issued up front.
-    const bool has = pr.x >= 0 && (slot == 0 || pr.y != pr.x);
-    const int code = pr.x < 0 ? 0 : (slot == 0 ? pr.x : pr.y);
-    const int e = code >> 2, i = code & 3;
-    FaceElem F;
-    load_face_elem<VARIANT>(M, L, e, i, F);
-    const int bcf = F.bc[0];
-    double vx = 0.0, vy = 0.0, sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
-    if (bcf == 1) { vx = D.VxDir[f]; vy = D.VyDir[f]; }
-    if (bcf == 2) { sxx = D.sxx[f]; sxy = D.sxy[f]; syx = D.syx[f]; syy = D.syy[f]; }   // tractions only enter through t*Xi
+FCFV_HD void slot_lanes(const FaceElem& F, int e, double A, double vx, double vy, double sxx, double sxy,
+                        double syx, double syy, LaneRow& Lx, LaneRow& Ly) {
     LaneElem E;
     lane_view(F, 0, E);
-    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 0, A, vx, sxx, sxy, Rx);   // row face at rotated index 0
+    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 0, A, vx, sxx, sxy, Lx);   // row face at rotated index 0
     lane_view(F, 1, E);
-    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 1, A, vy, syx, syy, Ry);
-    if (do_fp && has && i == 0 && (M.elem_owned == nullptr || M.elem_owned[e])) {
-        bool dir[3]; double dvx[3], dvy[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            dir[j] = F.bc[j] == 1;
-            dvx[j] = dir[j] ? D.VxDir[F.g[j]] : 0.0;
-            dvy[j] = dir[j] ? D.VyDir[F.g[j]] : 0.0;
-        }
-        fp_val = element_fp(F.G, F.nx, F.ny, dir, dvx, dvy);
-        fp_elem = e;
-    }
-    if (!has) { lane_row_inactive(Rx); lane_row_inactive(Ry); }
+    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 1, A, vy, syx, syy, Ly);
 }
 
-// One CSR row: merged / ranked / zero-dropped contributions of both adjacent elements.
-struct AsmRow {
-    LaneRow R0, R1;        // contributions of the lower / higher adjacent element
-    LanePlace P0, P1;
-    int m0, m1;            // nz masks
-};
+// fp[e] (Discretisation:194) from a record rotated by i: the sum runs over the faces in their
+// local order j = 0,1,2 (rotated index k = (j - i) mod 3), Dirichlet faces only.
+FCFV_HD double slot_fp(const FaceElem& F, int i, const FaceDataView& D) {
+    bool dir[3]; double G[3], nx[3], ny[3], dvx[3], dvy[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        int k = j - i;
+        k = k < 0 ? k + 3 : k;
+        const int g = pick3(k, F.g);
+        dir[j] = pick3(k, F.bc) == 1;
+        G[j] = pick3(k, F.G); nx[j] = pick3(k, F.nx); ny[j] = pick3(k, F.ny);
+        dvx[j] = dir[j] ? D.VxDir[g] : 0.0;
+        dvy[j] = dir[j] ? D.VyDir[g] : 0.0;
+    }
+    return element_fp(G, nx, ny, dir, dvx, dvy);
+}
 
-FCFV_HD void finish_row(AsmRow& o, int comp) {
-    LanePeer p0, p1;
-    lane_peer_of(o.R0, p0);
-    lane_peer_of(o.R1, p1);
-    lane_merge(o.R0, 0, p1);
-    lane_merge(o.R1, 1, p0);
-    o.m0 = lane_nzmask(o.R0);
-    o.m1 = lane_nzmask(o.R1);
-    lane_place(o.R0, o.m0, o.R1.key, o.m1, comp, o.P0);
-    lane_place(o.R1, o.m1, o.R0.key, o.m0, comp, o.P1);
+// fp[e] is non-zero only for elements with a Dirichlet face; it is produced by the thread of the
+// element's FIRST Dirichlet face in local order (one writer per element), everything else keeps
+// the +0.0 the array is initialised with.
+FCFV_HD bool is_first_dirichlet(const FaceElem& F, int i) {
+    bool first = F.bc[0] == 1;
+    if (i >= 1) first = first && (i == 1 ? F.bc[2] : F.bc[1]) != 1;   // local face 0 sits at rotated index 3 - i
+    if (i == 2) first = first && F.bc[2] != 1;       // local face 1
+    return first;
 }
 
 // Both rows of face f -- what one assembly thread computes; shared by the count pass, the fill
-// pass and the host emulation.
-template <int VARIANT, int FORM, bool WANT_M>
-FCFV_HD void asm_face(const MeshView& M, const LocalView& L, const FaceDataView& D, double A, int f, bool do_fp,
-                      AsmRow& ax, AsmRow& ay, int fp_elem[2], double fp_val[2]) {
-    const bool inrange = f < M.nf;
-    const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
+// pass and the host emulation.  pr = f2e[f], bcf = bc[f]; load(slot, e, i, F) provides the record
+// of element e rotated by i.  With do_fp a Dirichlet face also returns fp of the adjacent owned
+// elements it is the first Dirichlet face of, so that fp needs no pass of its own.
+template <int VARIANT, int FORM, bool WANT_M, typename Loader>
+FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f, int2 pr, int bcf, bool owned, bool do_fp,
+                      Loader&& load, FaceRows& R, int fp_elem[2], double fp_val[2]) {
     fp_elem[0] = fp_elem[1] = -1; fp_val[0] = fp_val[1] = 0.0;
-    if (inrange && (owned || do_fp)) {
-        const int2 pr = M.f2e[f];
-        compute_slot<VARIANT, FORM, WANT_M>(M, L, D, f, pr, 0, A, do_fp, ax.R0, ay.R0, fp_elem[0], fp_val[0]);
-        compute_slot<VARIANT, FORM, WANT_M>(M, L, D, f, pr, 1, A, do_fp, ax.R1, ay.R1, fp_elem[1], fp_val[1]);
+    const bool has0 = pr.x >= 0, has1 = has0 && pr.y != pr.x;
+    const bool want_fp = do_fp && bcf == 1;
+    if (has0 && (owned || want_fp)) {
+        double vx = 0.0, vy = 0.0, sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
+        if (bcf == 1) { vx = D.VxDir[f]; vy = D.VyDir[f]; }
+        if (bcf == 2) { sxx = D.sxx[f]; sxy = D.sxy[f]; syx = D.syx[f]; syy = D.syy[f]; }   // tractions only enter through t*Xi
+        LaneRow Lx, Ly;
+        {
+            const int e = pr.x >> 2, i = pr.x & 3;
+            FaceElem F;
+            load(0, e, i, F);
+            slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
+            rows_put0<WANT_M>(R, Lx, Ly);
+            if (want_fp && (M.elem_owned == nullptr || M.elem_owned[e]) && is_first_dirichlet(F, i)) {
+                fp_val[0] = slot_fp(F, i, D);
+                fp_elem[0] = e;
+            }
+        }
+        {
+            // No branch around the second element: a missing one re-reads the first and is discarded,
+            // so that the loads of both records are independent of any branch and can be issued up front.
+            const int code = has1 ? pr.y : pr.x;
+            const int e = code >> 2, i = code & 3;
+            FaceElem F;
+            load(1, e, i, F);
+            slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
+            rows_put1<WANT_M>(R, has1, Lx, Ly);
+            if (has1 && want_fp && (M.elem_owned == nullptr || M.elem_owned[e]) && is_first_dirichlet(F, i)) {
+                fp_val[1] = slot_fp(F, i, D);
+                fp_elem[1] = e;
+            }
+        }
+        if (!owned) rows_clear(R);   // rows of faces owned by another rank stay empty (only fp was wanted)
+    } else {
+        rows_clear(R);
     }
-    if (!owned) {   // rows of faces owned elsewhere (or out of range) stay empty
-        lane_row_inactive(ax.R0); lane_row_inactive(ax.R1); lane_row_inactive(ay.R0); lane_row_inactive(ay.R1);
-    }
-    finish_row(ax, 0);
-    finish_row(ay, 1);
+    rows_finish<WANT_M>(R, owned && has0, owned && has1);
 }
 
 #if defined(__CUDACC__)
@@ -186,8 +217,11 @@ constexpr int kScanChunk = 4096;     // block sums scanned per chunk
 #ifndef FCFV_RES_MINBLOCKS
 #define FCFV_RES_MINBLOCKS 5         // resident 128-thread residual blocks per SM
 #endif
-#ifndef FCFV_ASM_MINBLOCKS
-#define FCFV_ASM_MINBLOCKS 4         // resident 128-thread assembly blocks per SM the register budget is tuned for (<=128 regs)
+#ifndef FCFV_ASM_COUNT_MINBLOCKS
+#define FCFV_ASM_COUNT_MINBLOCKS 5   // resident 128-thread blocks per SM the register budget of the count pass is tuned for (<= 96 registers)
+#endif
+#ifndef FCFV_ASM_FILL_MINBLOCKS
+#define FCFV_ASM_FILL_MINBLOCKS 4    // same for the fill pass (<= 128 registers)
 #endif
 
 __device__ __forceinline__ int warp_incl_scan(int v) {
@@ -358,35 +392,135 @@ k_local(MeshView M, const double* __restrict__ sex, const double* __restrict__ s
     Z[e] = o.Z11; Z[nel + e] = o.Z21; Z[2 * nel + e] = o.Z12; Z[3 * nel + e] = o.Z22;
 }
 
+// ---- per-element assembly coefficients -------------------------------------------------------------
+// flag |= 1 when some delta != 1 (the NEW loop then needs the full 2x2 D per element)
+__global__ void k_delta_flag(const double* __restrict__ dl, int nel, int* __restrict__ flag) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nel && dl[e] != 1.0) atomicOr(flag, 1);
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+k_elem_coef(int nel, const double* __restrict__ alpha, const double* __restrict__ ke, const double* __restrict__ dl,
+            const double* __restrict__ Om, double* __restrict__ ia, double* __restrict__ c11, double* __restrict__ c12,
+            double* __restrict__ c21, double* __restrict__ c22) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nel) return;
+    double a, d11, d12, d21, d22;
+    element_coef<VARIANT>(alpha[e], ke[e], (VARIANT == kLoopNew && c12 != nullptr) ? dl[e] : 1.0, Om[e], a, d11, d12, d21, d22);
+    ia[e] = a; c11[e] = d11;
+    if (VARIANT == kLoopNew && c12 != nullptr) { c12[e] = d12; c21[e] = d21; c22[e] = d22; }
+}
+
 // ---- a5/a6/a7 assembly --------------------------------------------------------------------------
-// Thread = (face, comp): tid = 2*face_local + comp.  A thread owns one CSR row: it loads the <=2
-// adjacent elements one after the other (the x and y threads of a face are neighbouring lanes and
-// read the same addresses, so the pair costs one L1 access), merges the duplicate column, ranks
-// the <=5 columns and drops exact zeros.  Both passes run the same computation; the count pass
-// only reduces the row lengths of a block, the fill pass places the entries.
-// count pass: one thread per face (both rows); sums[q*nblk + b] = number of stored entries block b
-// will write for quantity q
-template <int VARIANT, int FORM, bool WANT_M>
-__global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_MINBLOCKS)
-k_asm_count(MeshView M, LocalView L, FaceDataView D, double A, int* __restrict__ sums, int nblk) {
-    __shared__ int sw[kAsmBlock / 32];
-    const int tid = threadIdx.x;
-    const int f = blockIdx.x * kAsmFaces + tid;
-    AsmRow ax, ay;
-    int fpe[2]; double fpv[2];
-    asm_face<VARIANT, FORM, WANT_M>(M, L, D, A, f, false, ax, ay, fpe, fpv);
-    const int c0 = (ax.P0.n_first + ax.P0.n_second) | ((ay.P0.n_first + ay.P0.n_second) << 16);
-    const int c1 = (((ax.m0 >> 9) & 1) + ((ax.m1 >> 9) & 1)) | ((((ay.m0 >> 9) & 1) + ((ay.m1 >> 9) & 1)) << 16);
-    const int c2 = ax.P0.n_m | (ay.P0.n_m << 16);
-    int t0, t1, t2 = 0;
-    block_excl_scan<kAsmBlock>(c0, t0, sw);
-    block_excl_scan<kAsmBlock>(c1, t1, sw);
-    if (WANT_M) block_excl_scan<kAsmBlock>(c2, t2, sw);
-    if (tid == 0) {
+// A block owns a tile of kAsmFaces consecutive faces; a thread owns one face = CSR rows (f,x) and
+// (f,y).  It gathers the records of the <=2 adjacent elements (faces ROTATED so that the row face
+// sits at index 0: every later index is a compile-time constant), merges the shared column, ranks
+// the <=5 column faces and drops exact zeros in registers (FaceRows).  Both passes run the same
+// code; the count pass only reduces the row lengths of a block, the fill pass places the entries.
+//
+// The gathers go through L1/L2 (face ids follow element order, so neighbouring threads share lines).
+constexpr int kHalf = kMaxRow * kAsmFaces + 8;        // staging capacity per component (+ alignment shift)
+constexpr int kStageBytes = 2 * kHalf * (8 + 4);
+constexpr int kAsmSmemBytes = kStageBytes;
+#ifndef FCFV_PREFETCH_TILES
+#define FCFV_PREFETCH_TILES 0        // > 0: prefetch the records of the tile this many blocks ahead into L2
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// L2 prefetch of the SoA lines of element e (all lanes of a warp hit the same few lines)
+__device__ __forceinline__ void prefetch_elem(const MeshView& M, const LocalView& L, const CoefView& Cf, int e) {
+    const int nel = M.nel;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const size_t o = (size_t)j * nel + e;
+        prefetch_l2(M.e2f + o); prefetch_l2(M.G + o); prefetch_l2(M.nx + o); prefetch_l2(M.ny + o);
+    }
+    prefetch_l2(Cf.ia + e); prefetch_l2(Cf.c11 + e);
+    prefetch_l2(L.beta + e); prefetch_l2(L.beta + nel + e);
+#pragma unroll
+    for (int q = 0; q < 4; q++) prefetch_l2(L.Z + (size_t)q * nel + e);
+}
+
+// rows of the block's face of this thread
+template <int VARIANT, int FORM, bool WANT_M, bool ANISO>
+__device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceDataView& D, double A,
+                                               bool do_fp, int& f, bool& inrange, FaceRows& R, int fpe[2], double fpv[2]) {
+    f = blockIdx.x * kAsmFaces + threadIdx.x;
+    inrange = f < M.nf;
+    const int2 pr = inrange ? M.f2e[f] : make_int2(-1, -1);
+    const int bcf = inrange ? (int)M.bc[f] : 0;
+    const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
+#if FCFV_PREFETCH_TILES > 0
+    const long long fa = (long long)f + (long long)FCFV_PREFETCH_TILES * kAsmFaces;
+    int2 pa = make_int2(-1, -1);
+    if (fa < M.nf) pa = M.f2e[fa];                      // consumed at the end of the kernel
+#endif
+    auto load = [&](int, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO>(M, L, Cf, e, i, F); };
+    asm_face<VARIANT, FORM, WANT_M>(M, D, A, f, pr, bcf, owned, do_fp && inrange, load, R, fpe, fpv);
+#if FCFV_PREFETCH_TILES > 0
+    if (pa.x >= 0) {
+        prefetch_elem(M, L, Cf, pa.x >> 2);
+        if (pa.y != pa.x) prefetch_elem(M, L, Cf, pa.y >> 2);
+    }
+#endif
+}
+
+// row lengths of a face packed in one 64-bit word: Kuu x, Kuu y (11 bits: <= 1280 per block),
+// Kup x, Kup y (9 bits: <= 256), Muu x, Muu y (10 bits: <= 640)
+__device__ __forceinline__ int cshift(int q) { return q == 0 ? 0 : q == 1 ? 11 : q == 2 ? 22 : q == 3 ? 31 : q == 4 ? 40 : 50; }
+__device__ __forceinline__ int cfield(unsigned long long c, int q) {
+    const unsigned wd = q < 2 ? 11u : q < 4 ? 9u : 10u;
+    return (int)((c >> cshift(q)) & ((1u << wd) - 1u));
+}
+template <bool WANT_M>
+__device__ __forceinline__ unsigned long long rows_counts(const FaceRows& R) {
+    unsigned long long c = (unsigned long long)rows_nuu_x(R) | ((unsigned long long)rows_nuu_y(R) << cshift(1)) |
+                           ((unsigned long long)rows_nup_x(R) << cshift(2)) | ((unsigned long long)rows_nup_y(R) << cshift(3));
+    if (WANT_M) c |= ((unsigned long long)rows_nmu_x(R) << cshift(4)) | ((unsigned long long)rows_nmu_y(R) << cshift(5));
+    return c;
+}
+
+// exclusive scan of one packed count per thread over the block; sw64: NT/32 entries
+template <int NT>
+__device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long long v, unsigned long long& total,
+                                                                unsigned long long* sw64) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, dd);
+        if (lane >= dd) inc += t;
+    }
+    if (lane == 31) sw64[w] = inc;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; k++) {
+        const unsigned long long s = sw64[k];
+        if (k < w) base += s;
+        tot += s;
+    }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+// count pass: sums[q*nblk + b] = number of stored entries block b will write for quantity q
+template <int VARIANT, int FORM, bool WANT_M, bool ANISO>
+__global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_COUNT_MINBLOCKS)
+k_asm_count(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, int* __restrict__ sums, int nblk) {
+    __shared__ unsigned long long sw64[kAsmBlock / 32];
+    FaceRows R;
+    int f, fpe[2]; bool inrange; double fpv[2];
+    tile_face_rows<VARIANT, FORM, WANT_M, ANISO>(M, L, Cf, D, A, false, f, inrange, R, fpe, fpv);
+    unsigned long long tot;
+    block_excl_scan64<kAsmBlock>(rows_counts<WANT_M>(R), tot, sw64);
+    if (threadIdx.x == 0) {
         const int b = blockIdx.x;
-        sums[0 * (size_t)nblk + b] = t0 & 0xffff; sums[1 * (size_t)nblk + b] = t0 >> 16;
-        sums[2 * (size_t)nblk + b] = t1 & 0xffff; sums[3 * (size_t)nblk + b] = t1 >> 16;
-        sums[4 * (size_t)nblk + b] = t2 & 0xffff; sums[5 * (size_t)nblk + b] = t2 >> 16;
+#pragma unroll
+        for (int q = 0; q < kNumSums; q++) sums[q * (size_t)nblk + b] = cfield(tot, q);
     }
 }
 
@@ -436,105 +570,129 @@ __global__ void k_scan_chunks(const long long* __restrict__ chunk_tot, long long
 }
 
 // ---- fill pass ----------------------------------------------------------------------------------
-// Recomputes the lanes, takes the block-local exclusive scan of the row lengths, stages the block's
+// Recomputes the rows, takes the block-local exclusive scan of the row lengths, stages the block's
 // compacted entries in shared memory (x rows in the lower half, y rows in the upper half) and
 // writes them to the CSR arrays as two contiguous, fully coalesced segments.
 struct CsrOut { void* rowptr; int* col; double* val; };
 
+// The segment [base, base+count) of the CSR arrays is written with 16-byte stores: entry p of
+// the segment is staged at shared index p + (base & 1) for values and p + (base & 3) for columns, so
+// that shared and global addresses are 16-byte aligned together; the (<=1 / <=3) leading and
+// trailing entries outside full vectors are written one by one by the first threads.
 __device__ __forceinline__ void flush_segment(const double* sval, const int* scol, int count, long long base,
                                               const CsrOut& O) {
-    for (int k = threadIdx.x; k < count; k += kAsmBlock) {
-        O.val[base + k] = sval[k];
-        O.col[base + k] = scol[k];
-    }
-}
-
-// stages the Kuu entries of one row into shared memory at its block-local offset
-__device__ __forceinline__ void stage_row(const AsmRow& a, int off, int cs, int cc, double* sval, int* scol) {
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        if (a.P0.ps[j] >= 0) { const int p = off + a.P0.ps[j]; sval[p] = a.R0.vs[j]; scol[p] = a.R0.key[j] + cs; }
-        if (a.P0.pc[j] >= 0) { const int p = off + a.P0.pc[j]; sval[p] = a.R0.vc[j]; scol[p] = a.R0.key[j] + cc; }
-        if (a.P1.ps[j] >= 0) { const int p = off + a.P1.ps[j]; sval[p] = a.R1.vs[j]; scol[p] = a.R1.key[j] + cs; }
-        if (a.P1.pc[j] >= 0) { const int p = off + a.P1.pc[j]; sval[p] = a.R1.vc[j]; scol[p] = a.R1.key[j] + cc; }
-    }
-}
-
-template <int VARIANT, int FORM, bool WANT_M, typename RP>
-__global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_MINBLOCKS)
-k_asm_fill(MeshView M, LocalView L, FaceDataView D, double A, const int* __restrict__ local, const long long* __restrict__ chunk_base,
-           int nblk, int nchunks, CsrOut Kuu, CsrOut Kup, CsrOut Muu, double* __restrict__ fu, double* __restrict__ fp) {
-    constexpr int kHalf = kMaxRow * kAsmFaces;            // staging capacity per component
-    __shared__ double sval[2 * kHalf];
-    __shared__ int scol[2 * kHalf];
-    __shared__ int sw[kAsmBlock / 32];
-    const int b = blockIdx.x;
     const int tid = threadIdx.x;
-    const int f = b * kAsmFaces + tid;
+    {
+        const int sh = (int)(base & 1), end = sh + count;
+        double* gv = O.val + (base - sh);
+        const double2* s2 = reinterpret_cast<const double2*>(sval);
+        double2* g2 = reinterpret_cast<double2*>(gv);
+        const int k1 = end >> 1;                              // full vectors: sh <= k < k1
+#pragma unroll
+        for (int it = 0; it < (kHalf / 2 + kAsmBlock - 1) / kAsmBlock; it++) {   // short, fully unrolled, predicated
+            const int k = sh + tid + it * kAsmBlock;
+            if (k < k1) g2[k] = s2[k];
+        }
+        if (tid == 0 && sh && count > 0) gv[1] = sval[1];
+        if (tid == 1 && (end & 1) && end - 1 >= sh + sh) gv[end - 1] = sval[end - 1];
+    }
+    {
+        const int sh = (int)(base & 3), end = sh + count;
+        int* gc = O.col + (base - sh);
+        const int4* s4 = reinterpret_cast<const int4*>(scol);
+        int4* g4 = reinterpret_cast<int4*>(gc);
+        const int k0 = (sh + 3) >> 2, k1 = end >> 2;         // full vectors: k0 <= k < k1
+#pragma unroll
+        for (int it = 0; it < (kHalf / 4 + kAsmBlock - 1) / kAsmBlock; it++) {
+            const int k = k0 + tid + it * kAsmBlock;
+            if (k < k1) g4[k] = s4[k];
+        }
+        // head: indices [sh, min(4*k0, end)), tail: [max(4*k1, 4*k0, sh), end)  (each < 4 entries)
+        const int head_end = min(4 * k0, end);
+        if (tid < 4) { const int q = sh + tid; if (q < head_end) gc[q] = scol[q]; }
+        const int tail_beg = max(4 * k1, head_end);
+        if (tid >= 4 && tid < 8) { const int q = tail_beg + (tid - 4); if (q < end) gc[q] = scol[q]; }
+    }
+}
+
+template <int VARIANT, int FORM, bool WANT_M, bool ANISO, typename RP>
+__global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_FILL_MINBLOCKS)
+k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const int* __restrict__ local, const long long* __restrict__ chunk_base,
+           int nblk, int nchunks, CsrOut Kuu, CsrOut Kup, CsrOut Muu, double* __restrict__ fu, double* __restrict__ fp) {
+    __shared__ __align__(16) unsigned char raw[kAsmSmemBytes];
+    __shared__ unsigned long long sw64[kAsmBlock / 32];
+    const int b = blockIdx.x;
     const int nf = M.nf;
-    const bool inrange = f < nf;
-    AsmRow ax, ay;
-    int fpe[2]; double fpv[2];
-    asm_face<VARIANT, FORM, WANT_M>(M, L, D, A, f, true, ax, ay, fpe, fpv);
+    FaceRows R;
+    int f, fpe[2]; bool inrange; double fpv[2];
+    tile_face_rows<VARIANT, FORM, WANT_M, ANISO>(M, L, Cf, D, A, true, f, inrange, R, fpe, fpv);
     if (fpe[0] >= 0) fp[fpe[0]] = fpv[0];
     if (fpe[1] >= 0) fp[fpe[1]] = fpv[1];
     if (inrange) {
-        fu[f] = ax.R0.active ? ax.R0.fu : 0.0;
-        fu[(size_t)nf + f] = ay.R0.active ? ay.R0.fu : 0.0;
+        fu[f] = R.fux;
+        fu[(size_t)nf + f] = R.fuy;
     }
-    const int c0 = (ax.P0.n_first + ax.P0.n_second) | ((ay.P0.n_first + ay.P0.n_second) << 16);
-    const int c1 = (((ax.m0 >> 9) & 1) + ((ax.m1 >> 9) & 1)) | ((((ay.m0 >> 9) & 1) + ((ay.m1 >> 9) & 1)) << 16);
-    const int c2 = ax.P0.n_m | (ay.P0.n_m << 16);
-    int t0, t1, t2 = 0, o2 = 0;
-    const int o0 = block_excl_scan<kAsmBlock>(c0, t0, sw);
-    const int o1 = block_excl_scan<kAsmBlock>(c1, t1, sw);
-    if (WANT_M) o2 = block_excl_scan<kAsmBlock>(c2, t2, sw);
+    unsigned long long tot;
+    const unsigned long long off = block_excl_scan64<kAsmBlock>(rows_counts<WANT_M>(R), tot, sw64);   
     const int ch = b / kScanChunk;
     auto gbase = [&](int q) -> long long { return chunk_base[(size_t)q * nchunks + ch] + local[(size_t)q * nblk + b]; };
     const long long bux = gbase(0), buy = gbase(1), bpx = gbase(2), bpy = gbase(3);
     const long long bmx = WANT_M ? gbase(4) : 0, bmy = WANT_M ? gbase(5) : 0;
     if (inrange) {
-        ((RP*)Kuu.rowptr)[f] = (RP)(bux + (o0 & 0xffff));
-        ((RP*)Kuu.rowptr)[(size_t)nf + f] = (RP)(buy + (o0 >> 16));
-        ((RP*)Kup.rowptr)[f] = (RP)(bpx + (o1 & 0xffff));
-        ((RP*)Kup.rowptr)[(size_t)nf + f] = (RP)(bpy + (o1 >> 16));
+        ((RP*)Kuu.rowptr)[f] = (RP)(bux + cfield(off, 0));
+        ((RP*)Kuu.rowptr)[(size_t)nf + f] = (RP)(buy + cfield(off, 1));
+        ((RP*)Kup.rowptr)[f] = (RP)(bpx + cfield(off, 2));
+        ((RP*)Kup.rowptr)[(size_t)nf + f] = (RP)(bpy + cfield(off, 3));
         if (WANT_M) {
-            ((RP*)Muu.rowptr)[f] = (RP)(bmx + (o2 & 0xffff));
-            ((RP*)Muu.rowptr)[(size_t)nf + f] = (RP)(bmy + (o2 >> 16));
+            ((RP*)Muu.rowptr)[f] = (RP)(bmx + cfield(off, 4));
+            ((RP*)Muu.rowptr)[(size_t)nf + f] = (RP)(bmy + cfield(off, 5));
         }
     }
+    double* sval = reinterpret_cast<double*>(raw);
+    int* scol = reinterpret_cast<int*>(raw + (size_t)2 * kHalf * 8);
     // ---- Kuu: x rows in the lower half of the staging buffer, y rows in the upper half
-    stage_row(ax, o0 & 0xffff, 0, nf, sval, scol);
-    stage_row(ay, kHalf + (o0 >> 16), nf, 0, sval, scol);
-    __syncthreads();
-    flush_segment(sval, scol, t0 & 0xffff, bux, Kuu);
-    flush_segment(sval + kHalf, scol + kHalf, t0 >> 16, buy, Kuu);
-    __syncthreads();
-    // ---- Kup: columns = element ids, slot order = ascending element id
     {
-        int p = o1 & 0xffff;
-        if ((ax.m0 >> 9) & 1) { sval[p] = ax.R0.kp; scol[p] = ax.R0.e; p++; }
-        if ((ax.m1 >> 9) & 1) { sval[p] = ax.R1.kp; scol[p] = ax.R1.e; }
-        p = kHalf + (o1 >> 16);
-        if ((ay.m0 >> 9) & 1) { sval[p] = ay.R0.kp; scol[p] = ay.R0.e; p++; }
-        if ((ay.m1 >> 9) & 1) { sval[p] = ay.R1.kp; scol[p] = ay.R1.e; }
+        double* vx = sval + cfield(off, 0) + (int)(bux & 1);
+        double* vy = sval + kHalf + cfield(off, 1) + (int)(buy & 1);
+        int* cx = scol + cfield(off, 0) + (int)(bux & 3);
+        int* cy = scol + kHalf + cfield(off, 1) + (int)(buy & 3);
+        rows_emit_uu(R, nf, [&](int comp, int pos, int col, double v) {
+            if (comp == 0) { vx[pos] = v; cx[pos] = col; }
+            else { vy[pos] = v; cy[pos] = col; }
+        });
     }
     __syncthreads();
-    flush_segment(sval, scol, t1 & 0xffff, bpx, Kup);
-    flush_segment(sval + kHalf, scol + kHalf, t1 >> 16, bpy, Kup);
+    flush_segment(sval, scol, cfield(tot, 0), bux, Kuu);
+    flush_segment(sval + kHalf, scol + kHalf, cfield(tot, 1), buy, Kuu);
+    __syncthreads();
+    // ---- Kup: columns = element ids, ascending
+    {
+        double* vx = sval + cfield(off, 2) + (int)(bpx & 1);
+        double* vy = sval + kHalf + cfield(off, 3) + (int)(bpy & 1);
+        int* cx = scol + cfield(off, 2) + (int)(bpx & 3);
+        int* cy = scol + kHalf + cfield(off, 3) + (int)(bpy & 3);
+        rows_emit_up(R, [&](int comp, int pos, int col, double v) {
+            if (comp == 0) { vx[pos] = v; cx[pos] = col; }
+            else { vy[pos] = v; cy[pos] = col; }
+        });
+    }
+    __syncthreads();
+    flush_segment(sval, scol, cfield(tot, 2), bpx, Kup);
+    flush_segment(sval + kHalf, scol + kHalf, cfield(tot, 3), bpy, Kup);
     if (WANT_M) {
         __syncthreads();
         // ---- Muu: block diagonal, row (f,comp) only holds columns (g,comp)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            if (ax.P0.pm[j] >= 0) { const int p = (o2 & 0xffff) + ax.P0.pm[j]; sval[p] = ax.R0.ms[j]; scol[p] = ax.R0.key[j]; }
-            if (ax.P1.pm[j] >= 0) { const int p = (o2 & 0xffff) + ax.P1.pm[j]; sval[p] = ax.R1.ms[j]; scol[p] = ax.R1.key[j]; }
-            if (ay.P0.pm[j] >= 0) { const int p = kHalf + (o2 >> 16) + ay.P0.pm[j]; sval[p] = ay.R0.ms[j]; scol[p] = ay.R0.key[j] + nf; }
-            if (ay.P1.pm[j] >= 0) { const int p = kHalf + (o2 >> 16) + ay.P1.pm[j]; sval[p] = ay.R1.ms[j]; scol[p] = ay.R1.key[j] + nf; }
-        }
+        double* vx = sval + cfield(off, 4) + (int)(bmx & 1);
+        double* vy = sval + kHalf + cfield(off, 5) + (int)(bmy & 1);
+        int* cx = scol + cfield(off, 4) + (int)(bmx & 3);
+        int* cy = scol + kHalf + cfield(off, 5) + (int)(bmy & 3);
+        rows_emit_mu(R, nf, [&](int comp, int pos, int col, double v) {
+            if (comp == 0) { vx[pos] = v; cx[pos] = col; }
+            else { vy[pos] = v; cy[pos] = col; }
+        });
         __syncthreads();
-        flush_segment(sval, scol, t2 & 0xffff, bmx, Muu);
-        flush_segment(sval + kHalf, scol + kHalf, t2 >> 16, bmy, Muu);
+        flush_segment(sval, scol, cfield(tot, 4), bmx, Muu);
+        flush_segment(sval + kHalf, scol + kHalf, cfield(tot, 5), bmy, Muu);
     }
 }
 

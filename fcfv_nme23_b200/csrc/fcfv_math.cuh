@@ -152,13 +152,28 @@ void rheology_general(double ke, double de, double Om, double* D /* D11 D21 D12 
 FCFV_HD void rheology_new(double ke, double de, double Om, double& D11, double& D12, double& D21, double& D22) {
     if (de == 1.0) {
         D11 = (ke * 1.0) / Om;
-        D12 = ((ke / de) * 1.0) / Om;
+        D12 = D11;   // ((ke / 1.0) * 1.0) / Om: x / 1.0 == x exactly, so the same quotient
         D21 = D12;
         D22 = D11;
     } else {
         double R[4];
         rheology_general(ke, de, Om, R);
         D11 = R[0]; D21 = R[1]; D12 = R[2]; D22 = R[3];
+    }
+}
+
+// Per-element coefficients of the assembly, formed once per element and assembly (k_elem_coef)
+// instead of once per adjacent face: 1/alpha and, old loop, ηe*Ωe^-1 (Discretisation:146) or,
+// NEW loop, the rheology matrix D (:231-236).
+template <int VARIANT>
+FCFV_HD void element_coef(double alpha, double ke, double de, double Om, double& ia, double& c11, double& c12,
+                          double& c21, double& c22) {
+    ia = 1.0 / alpha;
+    if (VARIANT == kLoopOld) {
+        c11 = ke * (1.0 / Om);
+        c12 = c21 = c22 = 0.0;
+    } else {
+        rheology_new(ke, de, Om, c11, c12, c21, c22);
     }
 }
 
@@ -171,8 +186,8 @@ FCFV_HD T pick3(int i, const T a[3]) { return i == 0 ? a[0] : (i == 1 ? a[1] : a
 struct LaneElem {
     int g[3], bc[3];
     double tau[3], G[3], nr[3], no[3];
-    double eta, ia;        // viscosity, 1/alpha
-    double iO;             // 1/Omega (old loop)
+    double ia;             // 1/alpha
+    double c;              // old loop: eta * (1/Omega)
     double Drr, Dro;       // D[r,r], D[r,o] (NEW loop)
     double br;             // beta[e, comp]
     double Z1r, Z2r;       // Z[e,1,comp], Z[e,2,comp]
@@ -205,8 +220,8 @@ FCFV_HD void pair_values(const LaneElem& E, int p, int q, int comp, double A, do
     const double cr = TRANSPOSED ? (c * npr) * nqo : (c * npo) * nqr;
     if (VARIANT == kLoopOld) {
         const double t3 = taup * (0.0 + bmul(p == q, 1.0));
-        const double hG = (E.eta * E.iO) * Gq;
-        const double mhG = ((-E.eta) * E.iO) * Gq;
+        const double hG = E.c * Gq;          // (ηe*Ωe^-1)*Γj
+        const double mhG = (-E.c) * Gq;      // ((-ηe)*Ωe^-1)*Γj: rounding is sign-symmetric
         same = mG * ((t1 - hG * (ninj + (c * npr) * nqr)) - t3);
         cross = mG * (mhG * cr);
         msame = mG * ((t1 - hG * ninj) - t3);
@@ -256,7 +271,7 @@ FCFV_HD void lane_row(const LaneElem& E, int e, int i, int comp, double A, doubl
         } else {
             nZ = nix * E.Z1r + niy * E.Z2r;
         }
-        fe = mGi * (((((-E.ia) * ti) * E.br) + (E.eta * E.iO) * nZ) - tir * Xi);
+        fe = mGi * (((((-E.ia) * ti) * E.br) + E.c * nZ) - tir * Xi);
     } else {
         fe = mGi * (((((-E.ia) * ti) * E.br) + ((E.Drr * nix) * E.Z1r + (E.Drr * niy) * E.Z2r)) - tir * Xi);
     }
@@ -271,51 +286,105 @@ FCFV_HD void lane_row_inactive(LaneRow& R) {
     R.fu = 0.0; R.kp = 0.0;
 }
 
-// What a lane needs from the other slot lane of the same row (shuffles on the device).
-struct LanePeer {
-    bool active;
-    double ds, dc, dm;     // its values on the row face column (f,.)
-    double fu;
+// ---------------------------------------------------------------------------------------------
+// Rows (f,x) and (f,y) of one face, merged.  With the element faces rotated so that the row face
+// sits at local index 0, the <=5 distinct column faces are: candidate 0 = f itself (both elements
+// contribute, summed lower element first like sparse() does), 1-2 = the other two faces of the
+// lower element, 3-4 = those of the higher element.  Placement works in RANK space: rank(c) =
+// number of candidate keys below key[c]; a row part is described by a 5-bit mask with bit rank(c)
+// set when candidate c is stored (alive and != +-0.0, dropzeros), and the position of c inside the
+// part is popc(mask & lt[c]) with lt[c] = (1 << rank(c)) - 1.
+// ---------------------------------------------------------------------------------------------
+struct FaceRows {
+    int key[5];
+    int lt[5];
+    double xs[5], xc[5];   // row (f,x): x-column block ("same"), y-column block ("cross")
+    double ys[5], yc[5];   // row (f,y): y-column block ("same"), x-column block ("cross")
+    double mx[5], my[5];   // Muu rows (same-component block only)
+    double fux, fuy;
+    double kpx[2], kpy[2]; // Kup entries, lower / higher element
+    int kpe[2];
+    int m_xs, m_xc, m_ys, m_yc, m_mx, m_my;   // rank-space masks of stored entries
+    int m_kp;                                  // bit 0 kpx[0], 1 kpx[1], 2 kpy[0], 3 kpy[1]
 };
 
-FCFV_HD void lane_peer_of(const LaneRow& R, LanePeer& P) {
-    P.active = R.active;
-    P.ds = pick3(R.i, R.vs); P.dc = pick3(R.i, R.vc); P.dm = pick3(R.i, R.ms);
-    P.fu = R.fu;
+FCFV_HD void rows_clear(FaceRows& R) {
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        R.key[c] = kDeadKey; R.lt[c] = 0;
+        R.xs[c] = R.xc[c] = R.ys[c] = R.yc[c] = R.mx[c] = R.my[c] = 0.0;
+    }
+    R.fux = R.fuy = 0.0;
+    R.kpx[0] = R.kpx[1] = R.kpy[0] = R.kpy[1] = 0.0;
+    R.kpe[0] = R.kpe[1] = -1;
+    R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_mx = R.m_my = R.m_kp = 0;
 }
 
-// Slot 0 folds the peer's diagonal-face values and RHS into its own (element order = slot order);
-// slot 1 drops its copy of that column.
-FCFV_HD void lane_merge(LaneRow& R, int slot, const LanePeer& P) {
-    if (!R.active || !P.active) {
-        if (slot == 0 && R.active && R.fu == 0.0) R.fu = 0.0;   // Array(dropzeros(sparse)): -0.0 -> +0.0
-        return;
-    }
-    if (slot == 0) {
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            if (j == R.i) { R.vs[j] = R.vs[j] + P.ds; R.vc[j] = R.vc[j] + P.dc; R.ms[j] = R.ms[j] + P.dm; }
-        R.fu = R.fu + P.fu;
-        if (R.fu == 0.0) R.fu = 0.0;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            if (j == R.i) R.key[j] = kDeadKey;
-    }
-}
-
-// 3-bit masks of stored (non-zero, alive) entries of a lane: bits 0-2 same, 3-5 cross, 6-8 Muu, 9 Kup
-FCFV_HD int lane_nzmask(const LaneRow& R) {
-    int m = 0;
+// Lanes (comp x, comp y) of the lower element: candidates 0..2, RHS, first Kup entry.
+template <bool WANT_M>
+FCFV_HD void rows_put0(FaceRows& R, const LaneRow& Lx, const LaneRow& Ly) {
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const bool alive = R.key[j] != kDeadKey;
-        m |= (alive && R.vs[j] != 0.0) ? (1 << j) : 0;
-        m |= (alive && R.vc[j] != 0.0) ? (8 << j) : 0;
-        m |= (alive && R.ms[j] != 0.0) ? (64 << j) : 0;
+        R.key[j] = Lx.key[j];
+        R.xs[j] = Lx.vs[j]; R.xc[j] = Lx.vc[j]; R.ys[j] = Ly.vs[j]; R.yc[j] = Ly.vc[j];
+        R.mx[j] = WANT_M ? Lx.ms[j] : 0.0; R.my[j] = WANT_M ? Ly.ms[j] : 0.0;
     }
-    m |= (R.active && R.kp != 0.0) ? 512 : 0;
-    return m;
+    R.fux = Lx.fu; R.fuy = Ly.fu;
+    R.kpx[0] = Lx.kp; R.kpy[0] = Ly.kp; R.kpe[0] = Lx.e;
+}
+
+// Lanes of the higher element: its row-face column is summed into candidate 0 (lower element
+// first, like sparse()), its other two faces become candidates 3..4.  With on == false (the face
+// has no second element; the lanes then hold a discarded re-read of the first) nothing is added.
+template <bool WANT_M>
+FCFV_HD void rows_put1(FaceRows& R, bool on, const LaneRow& Lx, const LaneRow& Ly) {
+    R.xs[0] = on ? R.xs[0] + Lx.vs[0] : R.xs[0]; R.xc[0] = on ? R.xc[0] + Lx.vc[0] : R.xc[0];
+    R.ys[0] = on ? R.ys[0] + Ly.vs[0] : R.ys[0]; R.yc[0] = on ? R.yc[0] + Ly.vc[0] : R.yc[0];
+    if (WANT_M) { R.mx[0] = on ? R.mx[0] + Lx.ms[0] : R.mx[0]; R.my[0] = on ? R.my[0] + Ly.ms[0] : R.my[0]; }
+#pragma unroll
+    for (int j = 1; j < 3; j++) {
+        R.key[2 + j] = on ? Lx.key[j] : kDeadKey;
+        R.xs[2 + j] = Lx.vs[j]; R.xc[2 + j] = Lx.vc[j]; R.ys[2 + j] = Ly.vs[j]; R.yc[2 + j] = Ly.vc[j];
+        R.mx[2 + j] = WANT_M ? Lx.ms[j] : 0.0; R.my[2 + j] = WANT_M ? Ly.ms[j] : 0.0;
+    }
+    R.fux = on ? R.fux + Lx.fu : R.fux; R.fuy = on ? R.fuy + Ly.fu : R.fuy;
+    R.kpx[1] = Lx.kp; R.kpy[1] = Ly.kp; R.kpe[1] = Lx.e;
+}
+
+// a0 / a1: the lower / higher element contributed.  Ranks the column faces, builds the masks.
+template <bool WANT_M>
+FCFV_HD void rows_finish(FaceRows& R, bool a0, bool a1) {
+    if (R.fux == 0.0) R.fux = 0.0;   // Array(dropzeros(sparse)): -0.0 -> +0.0
+    if (R.fuy == 0.0) R.fuy = 0.0;
+    int mxs = 0, mxc = 0, mys = 0, myc = 0, mmx = 0, mmy = 0;
+    // ranks from the 10 pairwise comparisons (ties only between dead keys: broken by index)
+    int rks[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 5; c++)
+#pragma unroll
+        for (int d = c + 1; d < 5; d++) {
+            const int t = (R.key[d] < R.key[c]) ? 1 : 0;
+            rks[c] += t;
+            rks[d] += 1 - t;
+        }
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        const int rk = rks[c];
+        const int bit = 1 << rk;
+        R.lt[c] = bit - 1;
+        const bool alive = c < 3 ? a0 : a1;
+        mxs |= (alive && R.xs[c] != 0.0) ? bit : 0;
+        mxc |= (alive && R.xc[c] != 0.0) ? bit : 0;
+        mys |= (alive && R.ys[c] != 0.0) ? bit : 0;
+        myc |= (alive && R.yc[c] != 0.0) ? bit : 0;
+        if (WANT_M) {
+            mmx |= (alive && R.mx[c] != 0.0) ? bit : 0;
+            mmy |= (alive && R.my[c] != 0.0) ? bit : 0;
+        }
+    }
+    R.m_xs = mxs; R.m_xc = mxc; R.m_ys = mys; R.m_yc = myc; R.m_mx = mmx; R.m_my = mmy;
+    R.m_kp = ((a0 && R.kpx[0] != 0.0) ? 1 : 0) | ((a1 && R.kpx[1] != 0.0) ? 2 : 0) |
+             ((a0 && R.kpy[0] != 0.0) ? 4 : 0) | ((a1 && R.kpy[1] != 0.0) ? 8 : 0);
 }
 
 FCFV_HD int popc6(int x) {
@@ -326,37 +395,49 @@ FCFV_HD int popc6(int x) {
 #endif
 }
 
-// Placement of a lane's entries inside row (f, comp).  The row is laid out [col (g,x) ascending |
-// col (g,y) ascending]: for comp 0 the first part holds the "same" values, for comp 1 the "cross"
-// values.  okey/omask: the peer lane's keys and nz mask.  Outputs the number of entries of the
-// first and second part of the whole row and, per own entry j, the position (or -1) of its
-// same / cross / Muu value inside the row.
-struct LanePlace {
-    int n_first, n_second, n_m;     // whole-row counts (identical in both slot lanes)
-    int ps[3], pc[3], pm[3];
-};
+// stored entries of the rows: Kuu x / y, Kup x / y, Muu x / y
+FCFV_HD int rows_nuu_x(const FaceRows& R) { return popc6(R.m_xs | (R.m_xc << 5)); }
+FCFV_HD int rows_nuu_y(const FaceRows& R) { return popc6(R.m_ys | (R.m_yc << 5)); }
+FCFV_HD int rows_nup_x(const FaceRows& R) { return (R.m_kp & 1) + ((R.m_kp >> 1) & 1); }
+FCFV_HD int rows_nup_y(const FaceRows& R) { return ((R.m_kp >> 2) & 1) + ((R.m_kp >> 3) & 1); }
+FCFV_HD int rows_nmu_x(const FaceRows& R) { return popc6(R.m_mx); }
+FCFV_HD int rows_nmu_y(const FaceRows& R) { return popc6(R.m_my); }
 
-FCFV_HD void lane_place(const LaneRow& R, int mymask, const int okey[3], int omask, int comp, LanePlace& L) {
-    const int all_s = (mymask & 7) | ((omask & 7) << 3);
-    const int all_c = ((mymask >> 3) & 7) | (((omask >> 3) & 7) << 3);
-    const int all_m = ((mymask >> 6) & 7) | (((omask >> 6) & 7) << 3);
-    const int ns = popc6(all_s), nc = popc6(all_c);
-    L.n_first = comp == 0 ? ns : nc;
-    L.n_second = comp == 0 ? nc : ns;
-    L.n_m = popc6(all_m);
+// emit(comp, position inside the row, column, value); rows are laid out [x columns | y columns].
+// Positions are formed unconditionally so that the conditional part is just the store.
+template <typename Emit>
+FCFV_HD void rows_emit_uu(const FaceRows& R, int nf, Emit&& emit) {
+    const int n_xs = popc6(R.m_xs), n_yc = popc6(R.m_yc);
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        int lower = 0;   // entries (mine bits 0-2, peer bits 3-5) with a smaller column face id
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            lower |= (R.key[m] < R.key[j]) ? (1 << m) : 0;
-            lower |= (okey[m] < R.key[j]) ? (8 << m) : 0;
-        }
-        const int rs = popc6(all_s & lower), rc = popc6(all_c & lower);
-        L.ps[j] = ((mymask >> j) & 1) ? (comp == 0 ? rs : nc + rs) : -1;
-        L.pc[j] = ((mymask >> (3 + j)) & 1) ? (comp == 0 ? ns + rc : rc) : -1;
-        L.pm[j] = ((mymask >> (6 + j)) & 1) ? popc6(all_m & lower) : -1;
+    for (int c = 0; c < 5; c++) {
+        const int lt = R.lt[c], bit = lt + 1;
+        const int p_xs = popc6(R.m_xs & lt), p_xc = n_xs + popc6(R.m_xc & lt);
+        const int p_yc = popc6(R.m_yc & lt), p_ys = n_yc + popc6(R.m_ys & lt);
+        if (R.m_xs & bit) emit(0, p_xs, R.key[c], R.xs[c]);
+        if (R.m_xc & bit) emit(0, p_xc, R.key[c] + nf, R.xc[c]);
+        if (R.m_yc & bit) emit(1, p_yc, R.key[c], R.yc[c]);
+        if (R.m_ys & bit) emit(1, p_ys, R.key[c] + nf, R.ys[c]);
     }
+}
+
+template <typename Emit>
+FCFV_HD void rows_emit_mu(const FaceRows& R, int nf, Emit&& emit) {
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        const int lt = R.lt[c], bit = lt + 1;
+        const int p_x = popc6(R.m_mx & lt), p_y = popc6(R.m_my & lt);
+        if (R.m_mx & bit) emit(0, p_x, R.key[c], R.mx[c]);
+        if (R.m_my & bit) emit(1, p_y, R.key[c] + nf, R.my[c]);
+    }
+}
+
+// columns = element ids, lower element first
+template <typename Emit>
+FCFV_HD void rows_emit_up(const FaceRows& R, Emit&& emit) {
+    if (R.m_kp & 1) emit(0, 0, R.kpe[0], R.kpx[0]);
+    if (R.m_kp & 2) emit(0, R.m_kp & 1, R.kpe[1], R.kpx[1]);
+    if (R.m_kp & 4) emit(1, 0, R.kpe[0], R.kpy[0]);
+    if (R.m_kp & 8) emit(1, (R.m_kp >> 2) & 1, R.kpe[1], R.kpy[1]);
 }
 
 // fp[e] :194 -- sequential over the three faces, Dirichlet faces only contribute.

@@ -40,23 +40,34 @@ void build_mesh(HostMesh& H, long long nel, long long nf, const long long* e2f, 
     M.elem_owned = nullptr; M.face_owned = nullptr; M.tau_ref = nullptr;
 }
 
-// Serial stand-in for k_asm_count / k_asm_fill: thread (face, comp) becomes a loop iteration, the
-// block scan becomes a running sum; asm_row and the placement arithmetic are the kernels' own code.
+// Serial stand-in for k_asm_count / k_asm_fill: thread = face becomes a loop iteration, the block
+// scan becomes a running sum, the tile cache becomes a direct load; asm_face, the rank-space
+// placement (rows_emit_*) and the counts are the kernels' own code.
 template <int VARIANT, int FORM>
 void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, double A, long long* rp_uu, int* c_uu,
               double* v_uu, long long* rp_up, int* c_up, double* v_up, long long* rp_mu, int* c_mu, double* v_mu,
               double* fu, double* fp) {
     const int nf = M.nf;
+    // k_elem_coef
+    const int nel = M.nel;
+    bool aniso = false;
+    for (int e = 0; e < nel; e++) aniso = aniso || M.dl[e] != 1.0;
+    std::vector<double> ia(nel), c11(nel), c12(nel), c21(nel), c22(nel);
+    for (int e = 0; e < nel; e++)
+        element_coef<VARIANT>(L.alpha[e], M.ke[e], (VARIANT == kLoopNew && aniso) ? M.dl[e] : 1.0, M.Om[e], ia[e], c11[e], c12[e], c21[e], c22[e]);
+    const CoefView Cf{ia.data(), c11.data(), aniso ? c12.data() : nullptr, aniso ? c21.data() : nullptr, aniso ? c22.data() : nullptr};
+    auto load = [&](int, int e, int i, FaceElem& F) {
+        if (aniso) load_face_elem<VARIANT, true>(M, L, Cf, e, i, F);
+        else load_face_elem<VARIANT, false>(M, L, Cf, e, i, F);
+    };
     std::vector<int> cnt[6];
     for (auto& c : cnt) c.assign(nf, 0);
     for (int f = 0; f < nf; f++) {   // count pass
-        AsmRow r[2]; int fpe[2]; double fpv[2];
-        asm_face<VARIANT, FORM, true>(M, L, D, A, f, false, r[0], r[1], fpe, fpv);
-        for (int comp = 0; comp < 2; comp++) {
-            cnt[comp][f] = r[comp].P0.n_first + r[comp].P0.n_second;
-            cnt[2 + comp][f] = ((r[comp].m0 >> 9) & 1) + ((r[comp].m1 >> 9) & 1);
-            cnt[4 + comp][f] = r[comp].P0.n_m;
-        }
+        FaceRows R; int fpe[2]; double fpv[2];
+        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], M.bc[f], true, false, load, R, fpe, fpv);
+        cnt[0][f] = rows_nuu_x(R); cnt[1][f] = rows_nuu_y(R);
+        cnt[2][f] = rows_nup_x(R); cnt[3][f] = rows_nup_y(R);
+        cnt[4][f] = rows_nmu_x(R); cnt[5][f] = rows_nmu_y(R);
     }
     long long* rps[3] = {rp_uu, rp_up, rp_mu};
     for (int m = 0; m < 3; m++) {
@@ -67,26 +78,16 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
     }
     for (int e = 0; e < M.nel; e++) fp[e] = 0.0;
     for (int f = 0; f < nf; f++) {   // fill pass (same placement arithmetic as k_asm_fill)
-        AsmRow r[2]; int fpe[2]; double fpv[2];
-        asm_face<VARIANT, FORM, true>(M, L, D, A, f, true, r[0], r[1], fpe, fpv);
+        FaceRows R; int fpe[2]; double fpv[2];
+        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], M.bc[f], true, true, load, R, fpe, fpv);
         for (int s = 0; s < 2; s++) if (fpe[s] >= 0) fp[fpe[s]] = fpv[s];
-        for (int comp = 0; comp < 2; comp++) {
-            const AsmRow& a = r[comp];
-            fu[comp * nf + f] = a.R0.active ? a.R0.fu : 0.0;
-            const long long row = (long long)comp * nf + f;
-            const int cs = comp == 0 ? 0 : nf, cc = comp == 0 ? nf : 0;
-            const LaneRow* R[2] = {&a.R0, &a.R1};
-            const LanePlace* P[2] = {&a.P0, &a.P1};
-            for (int s = 0; s < 2; s++)
-                for (int j = 0; j < 3; j++) {
-                    if (P[s]->ps[j] >= 0) { long long p = rp_uu[row] + P[s]->ps[j]; v_uu[p] = R[s]->vs[j]; c_uu[p] = R[s]->key[j] + cs; }
-                    if (P[s]->pc[j] >= 0) { long long p = rp_uu[row] + P[s]->pc[j]; v_uu[p] = R[s]->vc[j]; c_uu[p] = R[s]->key[j] + cc; }
-                    if (P[s]->pm[j] >= 0) { long long p = rp_mu[row] + P[s]->pm[j]; v_mu[p] = R[s]->ms[j]; c_mu[p] = R[s]->key[j] + cs; }
-                }
-            long long p = rp_up[row];
-            if ((a.m0 >> 9) & 1) { v_up[p] = a.R0.kp; c_up[p] = a.R0.e; p++; }
-            if ((a.m1 >> 9) & 1) { v_up[p] = a.R1.kp; c_up[p] = a.R1.e; }
-        }
+        fu[f] = R.fux; fu[nf + f] = R.fuy;
+        rows_emit_uu(R, nf, [&](int comp, int pos, int col, double v) {
+            const long long p = rp_uu[(long long)comp * nf + f] + pos; v_uu[p] = v; c_uu[p] = col; });
+        rows_emit_up(R, [&](int comp, int pos, int col, double v) {
+            const long long p = rp_up[(long long)comp * nf + f] + pos; v_up[p] = v; c_up[p] = col; });
+        rows_emit_mu(R, nf, [&](int comp, int pos, int col, double v) {
+            const long long p = rp_mu[(long long)comp * nf + f] + pos; v_mu[p] = v; c_mu[p] = col; });
     }
 }
 }  // namespace

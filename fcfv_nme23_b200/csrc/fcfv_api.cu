@@ -66,7 +66,7 @@ struct fcfv_handle {
     bool have_elem_owned = false, have_face_owned = false, have_tau_ref = false;
 
     // mesh
-    DBuf e2f, bc, f2e, Om, G, nx, ny, ke, dl, taue, tau, elem_owned, face_owned, tau_ref;
+    DBuf e2f, bc, f2e, fconn, fbc, Om, G, nx, ny, ke, dl, taue, tau, elem_owned, face_owned, tau_ref;
     // data
     DBuf sex, sey, VxDir, VyDir, sxx, syy, sxy, syx, Vxh, Vyh, Pe;
     // local coefficients
@@ -207,6 +207,7 @@ MeshView mesh_view(fcfv_t* h) {
     MeshView M;
     M.nel = (int)h->nel; M.nf = (int)h->nf;
     M.e2f = P<int>(h->e2f); M.bc = P<int8_t>(h->bc); M.f2e = P<int2>(h->f2e);
+    M.fconn = P<int4>(h->fconn); M.fbc = P<int>(h->fbc);
     M.Om = P<double>(h->Om); M.G = P<double>(h->G); M.nx = P<double>(h->nx); M.ny = P<double>(h->ny);
     M.ke = P<double>(h->ke); M.dl = P<double>(h->dl); M.taue = P<double>(h->taue); M.tau = P<double>(h->tau);
     M.elem_owned = h->have_elem_owned ? P<uint8_t>(h->elem_owned) : nullptr;
@@ -241,6 +242,16 @@ int build_f2e(fcfv_t* h) {
     LAUNCH(h, k_f2e_build, nblocks(nel, 256), 256, P<int>(h->e2f), P<int2>(h->f2e), P<int>(h->tmp2), (int)nel);
     LAUNCH(h, k_f2e_check, nblocks(nf, 256), 256, P<int2>(h->f2e), P<int>(h->tmp2), P<int>(h->e2f), (int)nel, (int)nf,
            P<int>(h->err_flag));
+    return FCFV_OK;
+}
+
+// Face connectivity records of the assembly; call after f2e and bc are final.
+int build_fconn(fcfv_t* h) {
+    const long long nel = h->nel, nf = h->nf;
+    TRY(ensure(h, h->fconn, sizeof(int4) * nf));
+    TRY(ensure(h, h->fbc, sizeof(int) * nf));
+    LAUNCH(h, k_fconn, nblocks(nf, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), P<int2>(h->f2e), (int)nel, (int)nf, P<int4>(h->fconn),
+           P<int>(h->fbc));
     return FCFV_OK;
 }
 
@@ -297,7 +308,7 @@ int fcfv_destroy(fcfv_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
-    DBuf* all[] = {&h->e2f, &h->bc, &h->f2e, &h->Om, &h->G, &h->nx, &h->ny, &h->ke, &h->dl, &h->taue, &h->tau,
+    DBuf* all[] = {&h->e2f, &h->bc, &h->f2e, &h->fconn, &h->fbc, &h->Om, &h->G, &h->nx, &h->ny, &h->ke, &h->dl, &h->taue, &h->tau,
                    &h->elem_owned, &h->face_owned, &h->tau_ref, &h->sex, &h->sey, &h->VxDir, &h->VyDir, &h->sxx,
                    &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
                    &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,
@@ -391,6 +402,7 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     TRY(build_f2e(h));
     int flag = 0;
     TRY(read_err_flag(h, &flag));
+    if (!flag) { TRY(build_fconn(h)); TRY(sync(h)); }
     if (flag & 1) return fail(h, FCFV_ERR_INVALID, "e2f contains a face id outside 1..nf");
     if (flag & 2) return fail(h, FCFV_ERR_INVALID, "a face is referenced by more than two (element, local face) pairs");
     if (flag & 4) return fail(h, FCFV_ERR_INVALID, "two elements share more than one face (or an element lists a face twice)");
@@ -1135,6 +1147,8 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     int flag = 0;
     TRY(read_err_flag(h, &flag));
     if (flag) return fail(h, FCFV_ERR_STATE, "fcfv_generate_structured: generated connectivity failed validation (%d)", flag);
+    TRY(build_fconn(h));
+    TRY(sync(h));
     h->have_mesh = h->have_sources = h->have_face_data = h->have_solution = true;
     h->delta_dirty = false; h->aniso = false;   // the generator sets delta = 1 everywhere
     return FCFV_OK;

@@ -18,6 +18,7 @@
 
 #if !defined(__CUDACC__)
 struct int2 { int x, y; };   // host build of the arithmetic (tests/host_emulation.cpp)
+struct int4 { int x, y, z, w; };
 #endif
 
 namespace fcfv {
@@ -27,6 +28,8 @@ struct MeshView {
     const int* e2f;
     const int8_t* bc;
     const int2* f2e;
+    const int4* fconn;           // per face: the other two faces of the lower (x, y) and higher (z, w) element, -1 when absent
+    const int* fbc;              // per face: bc tags of (f, x, y, z, w) packed 4 bits each (tag + 1)
     const double *Om, *G, *nx, *ny, *ke, *dl, *taue;
     const double* tau;
     const uint8_t* elem_owned;   // nullable
@@ -49,50 +52,67 @@ struct FaceElem {
     double b1, b2, Z11, Z21, Z12, Z22;
 };
 
-// rot3: r[k] = a[(i + k) mod 3] with selects (no local-memory indexing)
-template <typename T>
-FCFV_HD void rot3(int i, const T a[3], T r[3]) {
-    r[0] = i == 0 ? a[0] : (i == 1 ? a[1] : a[2]);
-    r[1] = i == 0 ? a[1] : (i == 1 ? a[2] : a[0]);
-    r[2] = i == 0 ? a[2] : (i == 1 ? a[0] : a[1]);
+// Local face j of an element sits at position perm(i, j) of the record built for row face i: the
+// row face is SWAPPED to position 0 (j == i -> 0, j == 0 -> i, the third face stays).  Nothing
+// downstream depends on the order of the two other faces (columns are ranked by face id).
+FCFV_HD int face_pos(int i, int j) { return j == i ? 0 : (j == 0 ? i : j); }
+
+// Column faces of the rows of face f and their bc tags: k[0] = f, k[1..2] = the other faces of the
+// lower element, k[3..4] = those of the higher element (static per mesh: fconn / fbc arrays).
+struct FaceConn { int k[5], bc[5]; };
+
+FCFV_HD int pack_bc5(const int bc[5]) {
+    int p = 0;
+#pragma unroll
+    for (int c = 0; c < 5; c++) p |= ((bc[c] + 1) & 15) << (4 * c);
+    return p;
 }
 
-#ifndef FCFV_ROT_SELECT
-#define FCFV_ROT_SELECT 0   // 1: load the element's faces in natural order (lanes stay in one SoA plane), rotate in registers
-#endif
+FCFV_HD void unpack_conn(int f, int4 o, int p, FaceConn& C) {
+    C.k[0] = f; C.k[1] = o.x; C.k[2] = o.y; C.k[3] = o.z; C.k[4] = o.w;
+#pragma unroll
+    for (int c = 0; c < 5; c++) C.bc[c] = ((p >> (4 * c)) & 15) - 1;
+}
 
-// The element's three faces are loaded ROTATED so that the row face (local index i) sits at
-// position 0: every later index is then a compile-time constant (no local memory).  The values
-// do not depend on the order in which the pairs (i, j) are visited.
-template <int VARIANT, bool ANISO>
-FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, const CoefView& Cf, int e, int i, FaceElem& E) {
-    const int nel = M.nel;
-#if FCFV_ROT_SELECT
-    {
-        int g[3]; double G[3], nx[3], ny[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            g[j] = M.e2f[j * nel + e];
-            G[j] = M.G[j * nel + e]; nx[j] = M.nx[j * nel + e]; ny[j] = M.ny[j * nel + e];
+// what k_fconn stores for face f (pr = f2e[f]); bc tags of absent faces are 0
+FCFV_HD void face_conn_of(const int* e2f, const int8_t* bc, int nel, int f, int2 pr, int4& o, int& p) {
+    int k[5] = {f, -1, -1, -1, -1};
+    if (pr.x >= 0) {
+        const int e = pr.x >> 2, i = pr.x & 3;
+        k[1] = e2f[(i == 1 ? 0 : 1) * nel + e];
+        k[2] = e2f[(i == 2 ? 0 : 2) * nel + e];
+        if (pr.y != pr.x) {
+            const int e1 = pr.y >> 2, i1 = pr.y & 3;
+            k[3] = e2f[(i1 == 1 ? 0 : 1) * nel + e1];
+            k[4] = e2f[(i1 == 2 ? 0 : 2) * nel + e1];
         }
-        rot3(i, g, E.g); rot3(i, G, E.G); rot3(i, nx, E.nx); rot3(i, ny, E.ny);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { E.bc[k] = M.bc[E.g[k]]; E.tau[k] = M.tau[E.g[k]]; }
     }
-#else
+    int b[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) b[c] = k[c] >= 0 ? (int)bc[k[c]] : 0;
+    o.x = k[1]; o.y = k[2]; o.z = k[3]; o.w = k[4];
+    p = pack_bc5(b);
+}
+
+// The element's three faces are loaded with the row face (local index i) at position 0: every later
+// index is then a compile-time constant (no local memory).  The values do not depend on the order
+// in which the pairs (i, j) are visited.  Face ids and bc tags come from the face's connectivity
+// record (slot 0: candidates 0,1,2; slot 1: 0,3,4), so that nothing here waits for e2f.
+template <int VARIANT, bool ANISO>
+FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceConn& C, bool second, int e, int i,
+                            FaceElem& E) {
+    const int nel = M.nel;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        int j = i + k;
-        j = j >= 3 ? j - 3 : j;
-        const int g = M.e2f[j * nel + e];
+        const int j = k == 0 ? i : (k == i ? 0 : k);
+        const int g = k == 0 ? C.k[0] : (second ? C.k[2 + k] : C.k[k]);
         E.g[k] = g;
-        E.bc[k] = M.bc[g];
+        E.bc[k] = k == 0 ? C.bc[0] : (second ? C.bc[2 + k] : C.bc[k]);
         E.tau[k] = M.tau[g];
         E.G[k] = M.G[j * nel + e];
         E.nx[k] = M.nx[j * nel + e];
         E.ny[k] = M.ny[j * nel + e];
     }
-#endif
     E.ia = Cf.ia[e];
     E.c11 = Cf.c11[e];
     if (VARIANT == kLoopNew && ANISO) { E.c12 = Cf.c12[e]; E.c21 = Cf.c21[e]; E.c22 = Cf.c22[e]; }
@@ -119,25 +139,24 @@ FCFV_HD void lane_view(const FaceElem& F, int comp, LaneElem& E) {
     E.Zr2 = comp == 0 ? F.Z12 : F.Z22;   // Z[e,comp,2]
 }
 
-// Contributions of one adjacent element (already loaded and rotated, F) to rows (f,x), (f,y).
+// Contributions of one adjacent element (already loaded, row face first, F) to rows (f,x), (f,y).
 template <int VARIANT, int FORM, bool WANT_M>
 FCFV_HD void slot_lanes(const FaceElem& F, int e, double A, double vx, double vy, double sxx, double sxy,
                         double syx, double syy, LaneRow& Lx, LaneRow& Ly) {
     LaneElem E;
     lane_view(F, 0, E);
-    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 0, A, vx, sxx, sxy, Lx);   // row face at rotated index 0
+    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 0, A, vx, sxx, sxy, Lx);   // row face at index 0
     lane_view(F, 1, E);
     lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 1, A, vy, syx, syy, Ly);
 }
 
-// fp[e] (Discretisation:194) from a record rotated by i: the sum runs over the faces in their
-// local order j = 0,1,2 (rotated index k = (j - i) mod 3), Dirichlet faces only.
+// fp[e] (Discretisation:194) from the record built for row face i: the sum runs over the faces in
+// their local order j = 0,1,2 (record position face_pos(i, j)), Dirichlet faces only.
 FCFV_HD double slot_fp(const FaceElem& F, int i, const FaceDataView& D) {
     bool dir[3]; double G[3], nx[3], ny[3], dvx[3], dvy[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        int k = j - i;
-        k = k < 0 ? k + 3 : k;
+        const int k = face_pos(i, j);
         const int g = pick3(k, F.g);
         dir[j] = pick3(k, F.bc) == 1;
         G[j] = pick3(k, F.G); nx[j] = pick3(k, F.nx); ny[j] = pick3(k, F.ny);
@@ -152,14 +171,14 @@ FCFV_HD double slot_fp(const FaceElem& F, int i, const FaceDataView& D) {
 // the +0.0 the array is initialised with.
 FCFV_HD bool is_first_dirichlet(const FaceElem& F, int i) {
     bool first = F.bc[0] == 1;
-    if (i >= 1) first = first && (i == 1 ? F.bc[2] : F.bc[1]) != 1;   // local face 0 sits at rotated index 3 - i
-    if (i == 2) first = first && F.bc[2] != 1;       // local face 1
+    if (i >= 1) first = first && (i == 1 ? F.bc[1] : F.bc[2]) != 1;   // local face 0 sits at position i
+    if (i == 2) first = first && F.bc[1] != 1;                          // local face 1 stays at position 1
     return first;
 }
 
 // Both rows of face f -- what one assembly thread computes; shared by the count pass, the fill
-// pass and the host emulation.  pr = f2e[f], bcf = bc[f]; load(slot, e, i, F) provides the record
-// of element e rotated by i.  With do_fp a Dirichlet face also returns fp of the adjacent owned
+// pass and the host emulation.  pr = f2e[f], bcf = bc[f]; load(second, e, i, F) provides the record
+// of element e with row face i in front (second: take face ids / tags of the higher element).  With do_fp a Dirichlet face also returns fp of the adjacent owned
 // elements it is the first Dirichlet face of, so that fp needs no pass of its own.
 template <int VARIANT, int FORM, bool WANT_M, typename Loader>
 FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f, int2 pr, int bcf, bool owned, bool do_fp,
@@ -175,7 +194,7 @@ FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f,
         {
             const int e = pr.x >> 2, i = pr.x & 3;
             FaceElem F;
-            load(0, e, i, F);
+            load(false, e, i, F);
             slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
             rows_put0<WANT_M>(R, Lx, Ly);
             if (want_fp && (M.elem_owned == nullptr || M.elem_owned[e]) && is_first_dirichlet(F, i)) {
@@ -189,7 +208,7 @@ FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f,
             const int code = has1 ? pr.y : pr.x;
             const int e = code >> 2, i = code & 3;
             FaceElem F;
-            load(1, e, i, F);
+            load(has1, e, i, F);
             slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
             rows_put1<WANT_M>(R, has1, Lx, Ly);
             if (has1 && want_fp && (M.elem_owned == nullptr || M.elem_owned[e]) && is_first_dirichlet(F, i)) {
@@ -327,6 +346,17 @@ __global__ void k_f2e_check(int2* __restrict__ f2e, const int* __restrict__ cnt,
     }
 }
 
+// per-face connectivity record of the assembly (static per mesh; rebuilt when bc or e2f change)
+__global__ void k_fconn(const int* __restrict__ e2f, const int8_t* __restrict__ bc, const int2* __restrict__ f2e, int nel, int nf,
+                        int4* __restrict__ fconn, int* __restrict__ fbc) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    int4 o; int p;
+    face_conn_of(e2f, bc, nel, f, f2e[f], o, p);
+    fconn[f] = o;
+    fbc[f] = p;
+}
+
 // ---- a3: tau[f] = taue[highest-numbered adjacent element] (Discretisation:40, last writer) ----
 __global__ void k_face_tau(const int2* __restrict__ f2e, const double* __restrict__ taue, double* __restrict__ tau,
                            int nf) {
@@ -414,8 +444,8 @@ k_elem_coef(int nel, const double* __restrict__ alpha, const double* __restrict_
 
 // ---- a5/a6/a7 assembly --------------------------------------------------------------------------
 // A block owns a tile of kAsmFaces consecutive faces; a thread owns one face = CSR rows (f,x) and
-// (f,y).  It gathers the records of the <=2 adjacent elements (faces ROTATED so that the row face
-// sits at index 0: every later index is a compile-time constant), merges the shared column, ranks
+// (f,y).  It gathers the records of the <=2 adjacent elements (row face swapped to index 0, so
+// that every later index is a compile-time constant), merges the shared column, ranks
 // the <=5 column faces and drops exact zeros in registers (FaceRows).  Both passes run the same
 // code; the count pass only reduces the row lengths of a block, the fill pass places the entries.
 //
@@ -450,14 +480,16 @@ __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalVie
     f = blockIdx.x * kAsmFaces + threadIdx.x;
     inrange = f < M.nf;
     const int2 pr = inrange ? M.f2e[f] : make_int2(-1, -1);
-    const int bcf = inrange ? (int)M.bc[f] : 0;
+    FaceConn C;
+    unpack_conn(f, inrange ? M.fconn[f] : make_int4(-1, -1, -1, -1), inrange ? M.fbc[f] : 0x11111, C);
+    const int bcf = C.bc[0];
     const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
 #if FCFV_PREFETCH_TILES > 0
     const long long fa = (long long)f + (long long)FCFV_PREFETCH_TILES * kAsmFaces;
     int2 pa = make_int2(-1, -1);
     if (fa < M.nf) pa = M.f2e[fa];                      // consumed at the end of the kernel
 #endif
-    auto load = [&](int, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO>(M, L, Cf, e, i, F); };
+    auto load = [&](bool second, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO>(M, L, Cf, C, second, e, i, F); };
     asm_face<VARIANT, FORM, WANT_M>(M, D, A, f, pr, bcf, owned, do_fp && inrange, load, R, fpe, fpv);
 #if FCFV_PREFETCH_TILES > 0
     if (pa.x >= 0) {

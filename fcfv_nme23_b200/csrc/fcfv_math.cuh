@@ -287,7 +287,7 @@ FCFV_HD void lane_row_inactive(LaneRow& R) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Rows (f,x) and (f,y) of one face, merged.  With the element faces rotated so that the row face
+// Rows (f,x) and (f,y) of one face, merged.  With the row face moved to the front of each element record, so that it
 // sits at local index 0, the <=5 distinct column faces are: candidate 0 = f itself (both elements
 // contribute, summed lower element first like sparse() does), 1-2 = the other two faces of the
 // lower element, 3-4 = those of the higher element.  Placement works in RANK space: rank(c) =

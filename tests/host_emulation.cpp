@@ -16,6 +16,7 @@ using namespace fcfv;
 namespace {
 struct HostMesh {
     std::vector<int> e2f; std::vector<int8_t> bc; std::vector<int2> f2e;
+    std::vector<int4> fconn; std::vector<int> fbc;
     MeshView view;
 };
 
@@ -34,8 +35,11 @@ void build_mesh(HostMesh& H, long long nel, long long nf, const long long* e2f, 
             cnt[f]++;
         }
     for (long long f = 0; f < nf; f++) if (!cnt[f]) H.f2e[f] = int2{-1, -1};
+    H.fconn.resize(nf); H.fbc.resize(nf);
+    for (long long f = 0; f < nf; f++)   // k_fconn
+        face_conn_of(H.e2f.data(), H.bc.data(), (int)nel, (int)f, H.f2e[f], H.fconn[f], H.fbc[f]);
     MeshView& M = H.view;
-    M.nel = (int)nel; M.nf = (int)nf; M.e2f = H.e2f.data(); M.bc = H.bc.data(); M.f2e = H.f2e.data();
+    M.nel = (int)nel; M.nf = (int)nf; M.e2f = H.e2f.data(); M.bc = H.bc.data(); M.f2e = H.f2e.data(); M.fconn = H.fconn.data(); M.fbc = H.fbc.data();
     M.Om = Om; M.G = G; M.nx = nx; M.ny = ny; M.ke = ke; M.dl = dl; M.taue = taue; M.tau = tau;
     M.elem_owned = nullptr; M.face_owned = nullptr; M.tau_ref = nullptr;
 }
@@ -56,15 +60,17 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
     for (int e = 0; e < nel; e++)
         element_coef<VARIANT>(L.alpha[e], M.ke[e], (VARIANT == kLoopNew && aniso) ? M.dl[e] : 1.0, M.Om[e], ia[e], c11[e], c12[e], c21[e], c22[e]);
     const CoefView Cf{ia.data(), c11.data(), aniso ? c12.data() : nullptr, aniso ? c21.data() : nullptr, aniso ? c22.data() : nullptr};
-    auto load = [&](int, int e, int i, FaceElem& F) {
-        if (aniso) load_face_elem<VARIANT, true>(M, L, Cf, e, i, F);
-        else load_face_elem<VARIANT, false>(M, L, Cf, e, i, F);
+    FaceConn C;
+    auto load = [&](bool second, int e, int i, FaceElem& F) {
+        if (aniso) load_face_elem<VARIANT, true>(M, L, Cf, C, second, e, i, F);
+        else load_face_elem<VARIANT, false>(M, L, Cf, C, second, e, i, F);
     };
     std::vector<int> cnt[6];
     for (auto& c : cnt) c.assign(nf, 0);
     for (int f = 0; f < nf; f++) {   // count pass
         FaceRows R; int fpe[2]; double fpv[2];
-        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], M.bc[f], true, false, load, R, fpe, fpv);
+        unpack_conn(f, M.fconn[f], M.fbc[f], C);
+        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], C.bc[0], true, false, load, R, fpe, fpv);
         cnt[0][f] = rows_nuu_x(R); cnt[1][f] = rows_nuu_y(R);
         cnt[2][f] = rows_nup_x(R); cnt[3][f] = rows_nup_y(R);
         cnt[4][f] = rows_nmu_x(R); cnt[5][f] = rows_nmu_y(R);
@@ -79,7 +85,8 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
     for (int e = 0; e < M.nel; e++) fp[e] = 0.0;
     for (int f = 0; f < nf; f++) {   // fill pass (same placement arithmetic as k_asm_fill)
         FaceRows R; int fpe[2]; double fpv[2];
-        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], M.bc[f], true, true, load, R, fpe, fpv);
+        unpack_conn(f, M.fconn[f], M.fbc[f], C);
+        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], C.bc[0], true, true, load, R, fpe, fpv);
         for (int s = 0; s < 2; s++) if (fpe[s] >= 0) fp[fpe[s]] = fpv[s];
         fu[f] = R.fux; fu[nf + f] = R.fuy;
         rows_emit_uu(R, nf, [&](int comp, int pos, int col, double v) {

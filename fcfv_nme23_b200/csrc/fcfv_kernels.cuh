@@ -452,7 +452,6 @@ k_elem_coef(int nel, const double* __restrict__ alpha, const double* __restrict_
 // The gathers go through L1/L2 (face ids follow element order, so neighbouring threads share lines).
 constexpr int kHalf = kMaxRow * kAsmFaces + 8;        // staging capacity per component (+ alignment shift)
 constexpr int kStageBytes = 2 * kHalf * (8 + 4);
-constexpr int kAsmSmemBytes = kStageBytes;
 #ifndef FCFV_PREFETCH_TILES
 #define FCFV_PREFETCH_TILES 0        // > 0: prefetch the records of the tile this many blocks ahead into L2
 #endif
@@ -607,53 +606,67 @@ __global__ void k_scan_chunks(const long long* __restrict__ chunk_tot, long long
 // writes them to the CSR arrays as two contiguous, fully coalesced segments.
 struct CsrOut { void* rowptr; int* col; double* val; };
 
-// The segment [base, base+count) of the CSR arrays is written with 16-byte stores: entry p of
-// the segment is staged at shared index p + (base & 1) for values and p + (base & 3) for columns, so
-// that shared and global addresses are 16-byte aligned together; the (<=1 / <=3) leading and
-// trailing entries outside full vectors are written one by one by the first threads.
-__device__ __forceinline__ void flush_segment(const double* sval, const int* scol, int count, long long base,
-                                              const CsrOut& O) {
-    const int tid = threadIdx.x;
+// The segment [base, base+count) of a CSR array leaves shared memory through the TMA unit: ONE
+// thread issues a bulk copy (cp.async.bulk shared -> global) per array, so the flush costs no LSU
+// loads / stores and almost no instructions.  Bulk copies need 16-byte aligned addresses and
+// sizes: entry p of the segment is staged at shared index p + (base & 1) for values and
+// p + (base & 3) for columns, which aligns shared and global addresses together; the (<= 1 / <= 3)
+// leading and trailing entries outside the aligned middle part are written by ordinary stores.
+__device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, int bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// makes this thread's shared-memory writes visible to the async proxy (before the barrier that
+// precedes the bulk copy)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// middle part by TMA (called by one thread)
+__device__ __forceinline__ void flush_segment_bulk(const double* sval, const int* scol, int count, long long base, const CsrOut& O) {
+    {
+        const int sh = (int)(base & 1), end = sh + count;
+        const int q0 = 2 * sh, q1 = end & ~1;
+        if (q1 > q0) tma_store(O.val + (base - sh) + q0, sval + q0, (q1 - q0) * 8);
+    }
+    {
+        const int sh = (int)(base & 3), end = sh + count;
+        const int q0 = (sh + 3) & ~3, q1 = end & ~3;
+        if (q1 > q0) tma_store(O.col + (base - sh) + q0, scol + q0, (q1 - q0) * 4);
+    }
+}
+
+// leading / trailing entries: thread `t` (0..7) of the group handles at most one value and one column
+__device__ __forceinline__ void flush_segment_edges(const double* sval, const int* scol, int count, long long base, const CsrOut& O,
+                                                    int t) {
     {
         const int sh = (int)(base & 1), end = sh + count;
         double* gv = O.val + (base - sh);
-        const double2* s2 = reinterpret_cast<const double2*>(sval);
-        double2* g2 = reinterpret_cast<double2*>(gv);
-        const int k1 = end >> 1;                              // full vectors: sh <= k < k1
-#pragma unroll
-        for (int it = 0; it < (kHalf / 2 + kAsmBlock - 1) / kAsmBlock; it++) {   // short, fully unrolled, predicated
-            const int k = sh + tid + it * kAsmBlock;
-            if (k < k1) g2[k] = s2[k];
-        }
-        if (tid == 0 && sh && count > 0) gv[1] = sval[1];
-        if (tid == 1 && (end & 1) && end - 1 >= sh + sh) gv[end - 1] = sval[end - 1];
+        if (t == 0 && sh && count > 0) gv[1] = sval[1];
+        if (t == 1 && (end & 1) && end - 1 >= sh + sh) gv[end - 1] = sval[end - 1];
     }
     {
         const int sh = (int)(base & 3), end = sh + count;
         int* gc = O.col + (base - sh);
-        const int4* s4 = reinterpret_cast<const int4*>(scol);
-        int4* g4 = reinterpret_cast<int4*>(gc);
-        const int k0 = (sh + 3) >> 2, k1 = end >> 2;         // full vectors: k0 <= k < k1
-#pragma unroll
-        for (int it = 0; it < (kHalf / 4 + kAsmBlock - 1) / kAsmBlock; it++) {
-            const int k = k0 + tid + it * kAsmBlock;
-            if (k < k1) g4[k] = s4[k];
-        }
-        // head: indices [sh, min(4*k0, end)), tail: [max(4*k1, 4*k0, sh), end)  (each < 4 entries)
-        const int head_end = min(4 * k0, end);
-        if (tid < 4) { const int q = sh + tid; if (q < head_end) gc[q] = scol[q]; }
-        const int tail_beg = max(4 * k1, head_end);
-        if (tid >= 4 && tid < 8) { const int q = tail_beg + (tid - 4); if (q < end) gc[q] = scol[q]; }
+        const int head_end = min((sh + 3) & ~3, end);
+        if (t < 4) { const int q = sh + t; if (q < head_end) gc[q] = scol[q]; }
+        const int tail_beg = max(end & ~3, head_end);
+        if (t >= 4) { const int q = tail_beg + (t - 4); if (q < end) gc[q] = scol[q]; }
     }
 }
+
+constexpr int kHalfP = 2 * kAsmFaces + 8;              // Kup staging capacity per component
+constexpr int kStageBytesP = 2 * kHalfP * (8 + 4);
 
 template <int VARIANT, int FORM, bool WANT_M, bool ANISO, typename RP>
 __global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_FILL_MINBLOCKS)
 k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const int* __restrict__ local, const long long* __restrict__ chunk_base,
            int nblk, int nchunks, CsrOut Kuu, CsrOut Kup, CsrOut Muu, double* __restrict__ fu, double* __restrict__ fp) {
-    __shared__ __align__(16) unsigned char raw[kAsmSmemBytes];
+    __shared__ __align__(16) unsigned char raw[kStageBytes];      // Kuu (then Muu) staging
+    __shared__ __align__(16) unsigned char rawp[kStageBytesP];    // Kup staging
     __shared__ unsigned long long sw64[kAsmBlock / 32];
     const int b = blockIdx.x;
+    const int tid = threadIdx.x;
     const int nf = M.nf;
     FaceRows R;
     int f, fpe[2]; bool inrange; double fpv[2];
@@ -665,7 +678,7 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
         fu[(size_t)nf + f] = R.fuy;
     }
     unsigned long long tot;
-    const unsigned long long off = block_excl_scan64<kAsmBlock>(rows_counts<WANT_M>(R), tot, sw64);   
+    const unsigned long long off = block_excl_scan64<kAsmBlock>(rows_counts<WANT_M>(R), tot, sw64);
     const int ch = b / kScanChunk;
     auto gbase = [&](int q) -> long long { return chunk_base[(size_t)q * nchunks + ch] + local[(size_t)q * nblk + b]; };
     const long long bux = gbase(0), buy = gbase(1), bpx = gbase(2), bpy = gbase(3);
@@ -682,7 +695,9 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
     }
     double* sval = reinterpret_cast<double*>(raw);
     int* scol = reinterpret_cast<int*>(raw + (size_t)2 * kHalf * 8);
-    // ---- Kuu: x rows in the lower half of the staging buffer, y rows in the upper half
+    double* pval = reinterpret_cast<double*>(rawp);
+    int* pcol = reinterpret_cast<int*>(rawp + (size_t)2 * kHalfP * 8);
+    // ---- stage Kuu (x rows in the lower half of the buffer, y rows in the upper half) and Kup
     {
         double* vx = sval + cfield(off, 0) + (int)(bux & 1);
         double* vy = sval + kHalf + cfield(off, 1) + (int)(buy & 1);
@@ -693,27 +708,36 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
             else { vy[pos] = v; cy[pos] = col; }
         });
     }
-    __syncthreads();
-    flush_segment(sval, scol, cfield(tot, 0), bux, Kuu);
-    flush_segment(sval + kHalf, scol + kHalf, cfield(tot, 1), buy, Kuu);
-    __syncthreads();
-    // ---- Kup: columns = element ids, ascending
     {
-        double* vx = sval + cfield(off, 2) + (int)(bpx & 1);
-        double* vy = sval + kHalf + cfield(off, 3) + (int)(bpy & 1);
-        int* cx = scol + cfield(off, 2) + (int)(bpx & 3);
-        int* cy = scol + kHalf + cfield(off, 3) + (int)(bpy & 3);
-        rows_emit_up(R, [&](int comp, int pos, int col, double v) {
+        double* vx = pval + cfield(off, 2) + (int)(bpx & 1);
+        double* vy = pval + kHalfP + cfield(off, 3) + (int)(bpy & 1);
+        int* cx = pcol + cfield(off, 2) + (int)(bpx & 3);
+        int* cy = pcol + kHalfP + cfield(off, 3) + (int)(bpy & 3);
+        rows_emit_up(R, [&](int comp, int pos, int col, double v) {   // columns = element ids, ascending
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });
     }
+    fence_async_smem();
     __syncthreads();
-    flush_segment(sval, scol, cfield(tot, 2), bpx, Kup);
-    flush_segment(sval + kHalf, scol + kHalf, cfield(tot, 3), bpy, Kup);
+    // ---- flush: thread 0 drives the TMA unit, threads 32..63 write the unaligned edge entries
+    if (tid == 0) {
+        flush_segment_bulk(sval, scol, cfield(tot, 0), bux, Kuu);
+        flush_segment_bulk(sval + kHalf, scol + kHalf, cfield(tot, 1), buy, Kuu);
+        flush_segment_bulk(pval, pcol, cfield(tot, 2), bpx, Kup);
+        flush_segment_bulk(pval + kHalfP, pcol + kHalfP, cfield(tot, 3), bpy, Kup);
+        tma_store_commit();
+    } else if (tid >= 32 && tid < 64) {
+        const int seg = (tid - 32) >> 3, t = (tid - 32) & 7;
+        if (seg == 0) flush_segment_edges(sval, scol, cfield(tot, 0), bux, Kuu, t);
+        else if (seg == 1) flush_segment_edges(sval + kHalf, scol + kHalf, cfield(tot, 1), buy, Kuu, t);
+        else if (seg == 2) flush_segment_edges(pval, pcol, cfield(tot, 2), bpx, Kup, t);
+        else flush_segment_edges(pval + kHalfP, pcol + kHalfP, cfield(tot, 3), bpy, Kup, t);
+    }
     if (WANT_M) {
+        // ---- Muu (block diagonal: row (f,comp) only holds columns (g,comp)) reuses the Kuu buffer
+        if (tid == 0) tma_store_wait_read();
         __syncthreads();
-        // ---- Muu: block diagonal, row (f,comp) only holds columns (g,comp)
         double* vx = sval + cfield(off, 4) + (int)(bmx & 1);
         double* vy = sval + kHalf + cfield(off, 5) + (int)(bmy & 1);
         int* cx = scol + cfield(off, 4) + (int)(bmx & 3);
@@ -722,10 +746,19 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });
+        fence_async_smem();
         __syncthreads();
-        flush_segment(sval, scol, cfield(tot, 4), bmx, Muu);
-        flush_segment(sval + kHalf, scol + kHalf, cfield(tot, 5), bmy, Muu);
+        if (tid == 0) {
+            flush_segment_bulk(sval, scol, cfield(tot, 4), bmx, Muu);
+            flush_segment_bulk(sval + kHalf, scol + kHalf, cfield(tot, 5), bmy, Muu);
+            tma_store_commit();
+        } else if (tid >= 32 && tid < 48) {
+            const int seg = (tid - 32) >> 3, t = (tid - 32) & 7;
+            if (seg == 0) flush_segment_edges(sval, scol, cfield(tot, 4), bmx, Muu, t);
+            else flush_segment_edges(sval + kHalf, scol + kHalf, cfield(tot, 5), bmy, Muu, t);
+        }
     }
+    if (tid == 0) tma_store_wait_read();   // shared memory must stay valid until the TMA unit has read it
 }
 
 // ---- a8 residuals ------------------------------------------------------------------------------

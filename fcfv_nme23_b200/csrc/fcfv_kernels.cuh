@@ -177,16 +177,18 @@ FCFV_HD bool is_first_dirichlet(const FaceElem& F, int i) {
 }
 
 // Both rows of face f -- what one assembly thread computes; shared by the count pass, the fill
-// pass and the host emulation.  pr = f2e[f], bcf = bc[f]; load(second, e, i, F) provides the record
+// pass and the host emulation.  pr = f2e[f], C = connectivity record of f; load(second, e, i, F) provides the record
 // of element e with row face i in front (second: take face ids / tags of the higher element).  With do_fp a Dirichlet face also returns fp of the adjacent owned
 // elements it is the first Dirichlet face of, so that fp needs no pass of its own.
 template <int VARIANT, int FORM, bool WANT_M, typename Loader>
-FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f, int2 pr, int bcf, bool owned, bool do_fp,
+FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f, int2 pr, const FaceConn& C, bool owned, bool do_fp,
                       Loader&& load, FaceRows& R, int fp_elem[2], double fp_val[2]) {
     fp_elem[0] = fp_elem[1] = -1; fp_val[0] = fp_val[1] = 0.0;
+    const int bcf = C.bc[0];
     const bool has0 = pr.x >= 0, has1 = has0 && pr.y != pr.x;
     const bool want_fp = do_fp && bcf == 1;
     if (has0 && (owned || want_fp)) {
+        rows_begin(R, C.k);
         double vx = 0.0, vy = 0.0, sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
         if (bcf == 1) { vx = D.VxDir[f]; vy = D.VyDir[f]; }
         if (bcf == 2) { sxx = D.sxx[f]; sxy = D.sxy[f]; syx = D.syx[f]; syy = D.syy[f]; }   // tractions only enter through t*Xi
@@ -196,7 +198,7 @@ FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f,
             FaceElem F;
             load(false, e, i, F);
             slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
-            rows_put0<WANT_M>(R, Lx, Ly);
+            rows_put0<WANT_M>(R, owned, Lx, Ly);
             if (want_fp && (M.elem_owned == nullptr || M.elem_owned[e]) && is_first_dirichlet(F, i)) {
                 fp_val[0] = slot_fp(F, i, D);
                 fp_elem[0] = e;
@@ -210,17 +212,17 @@ FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f,
             FaceElem F;
             load(has1, e, i, F);
             slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
-            rows_put1<WANT_M>(R, has1, Lx, Ly);
+            rows_put1<WANT_M>(R, has1, owned, Lx, Ly);
             if (has1 && want_fp && (M.elem_owned == nullptr || M.elem_owned[e]) && is_first_dirichlet(F, i)) {
                 fp_val[1] = slot_fp(F, i, D);
                 fp_elem[1] = e;
             }
         }
-        if (!owned) rows_clear(R);   // rows of faces owned by another rank stay empty (only fp was wanted)
+        rows_finish<WANT_M>(R, owned);
+        if (!owned) { R.fux = 0.0; R.fuy = 0.0; }   // rows of faces owned by another rank stay empty (only fp was wanted)
     } else {
         rows_clear(R);
     }
-    rows_finish<WANT_M>(R, owned && has0, owned && has1);
 }
 
 #if defined(__CUDACC__)
@@ -237,7 +239,7 @@ constexpr int kScanChunk = 4096;     // block sums scanned per chunk
 #define FCFV_RES_MINBLOCKS 5         // resident 128-thread residual blocks per SM
 #endif
 #ifndef FCFV_ASM_COUNT_MINBLOCKS
-#define FCFV_ASM_COUNT_MINBLOCKS 5   // resident 128-thread blocks per SM the register budget of the count pass is tuned for (<= 96 registers)
+#define FCFV_ASM_COUNT_MINBLOCKS 7   // resident 128-thread blocks per SM the register budget of the count pass is tuned for (<= 72 registers)
 #endif
 #ifndef FCFV_ASM_FILL_MINBLOCKS
 #define FCFV_ASM_FILL_MINBLOCKS 4    // same for the fill pass (<= 128 registers)
@@ -481,7 +483,6 @@ __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalVie
     const int2 pr = inrange ? M.f2e[f] : make_int2(-1, -1);
     FaceConn C;
     unpack_conn(f, inrange ? M.fconn[f] : make_int4(-1, -1, -1, -1), inrange ? M.fbc[f] : 0x11111, C);
-    const int bcf = C.bc[0];
     const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
 #if FCFV_PREFETCH_TILES > 0
     const long long fa = (long long)f + (long long)FCFV_PREFETCH_TILES * kAsmFaces;
@@ -489,7 +490,7 @@ __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalVie
     if (fa < M.nf) pa = M.f2e[fa];                      // consumed at the end of the kernel
 #endif
     auto load = [&](bool second, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO>(M, L, Cf, C, second, e, i, F); };
-    asm_face<VARIANT, FORM, WANT_M>(M, D, A, f, pr, bcf, owned, do_fp && inrange, load, R, fpe, fpv);
+    asm_face<VARIANT, FORM, WANT_M>(M, D, A, f, pr, C, owned, do_fp && inrange, load, R, fpe, fpv);
 #if FCFV_PREFETCH_TILES > 0
     if (pa.x >= 0) {
         prefetch_elem(M, L, Cf, pa.x >> 2);

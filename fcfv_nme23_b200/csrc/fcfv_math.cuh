@@ -320,43 +320,12 @@ FCFV_HD void rows_clear(FaceRows& R) {
     R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_mx = R.m_my = R.m_kp = 0;
 }
 
-// Lanes (comp x, comp y) of the lower element: candidates 0..2, RHS, first Kup entry.
-template <bool WANT_M>
-FCFV_HD void rows_put0(FaceRows& R, const LaneRow& Lx, const LaneRow& Ly) {
+// Column faces and their ranks are known before any element data arrives (face connectivity
+// record): keys k[0..4], absent faces (< 0) rank last.  Masks start empty and are filled while the
+// values are produced, so that a pass that only counts keeps no values alive.
+FCFV_HD void rows_begin(FaceRows& R, const int k[5]) {
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        R.key[j] = Lx.key[j];
-        R.xs[j] = Lx.vs[j]; R.xc[j] = Lx.vc[j]; R.ys[j] = Ly.vs[j]; R.yc[j] = Ly.vc[j];
-        R.mx[j] = WANT_M ? Lx.ms[j] : 0.0; R.my[j] = WANT_M ? Ly.ms[j] : 0.0;
-    }
-    R.fux = Lx.fu; R.fuy = Ly.fu;
-    R.kpx[0] = Lx.kp; R.kpy[0] = Ly.kp; R.kpe[0] = Lx.e;
-}
-
-// Lanes of the higher element: its row-face column is summed into candidate 0 (lower element
-// first, like sparse()), its other two faces become candidates 3..4.  With on == false (the face
-// has no second element; the lanes then hold a discarded re-read of the first) nothing is added.
-template <bool WANT_M>
-FCFV_HD void rows_put1(FaceRows& R, bool on, const LaneRow& Lx, const LaneRow& Ly) {
-    R.xs[0] = on ? R.xs[0] + Lx.vs[0] : R.xs[0]; R.xc[0] = on ? R.xc[0] + Lx.vc[0] : R.xc[0];
-    R.ys[0] = on ? R.ys[0] + Ly.vs[0] : R.ys[0]; R.yc[0] = on ? R.yc[0] + Ly.vc[0] : R.yc[0];
-    if (WANT_M) { R.mx[0] = on ? R.mx[0] + Lx.ms[0] : R.mx[0]; R.my[0] = on ? R.my[0] + Ly.ms[0] : R.my[0]; }
-#pragma unroll
-    for (int j = 1; j < 3; j++) {
-        R.key[2 + j] = on ? Lx.key[j] : kDeadKey;
-        R.xs[2 + j] = Lx.vs[j]; R.xc[2 + j] = Lx.vc[j]; R.ys[2 + j] = Ly.vs[j]; R.yc[2 + j] = Ly.vc[j];
-        R.mx[2 + j] = WANT_M ? Lx.ms[j] : 0.0; R.my[2 + j] = WANT_M ? Ly.ms[j] : 0.0;
-    }
-    R.fux = on ? R.fux + Lx.fu : R.fux; R.fuy = on ? R.fuy + Ly.fu : R.fuy;
-    R.kpx[1] = Lx.kp; R.kpy[1] = Ly.kp; R.kpe[1] = Lx.e;
-}
-
-// a0 / a1: the lower / higher element contributed.  Ranks the column faces, builds the masks.
-template <bool WANT_M>
-FCFV_HD void rows_finish(FaceRows& R, bool a0, bool a1) {
-    if (R.fux == 0.0) R.fux = 0.0;   // Array(dropzeros(sparse)): -0.0 -> +0.0
-    if (R.fuy == 0.0) R.fuy = 0.0;
-    int mxs = 0, mxc = 0, mys = 0, myc = 0, mmx = 0, mmy = 0;
+    for (int c = 0; c < 5; c++) R.key[c] = k[c] < 0 ? kDeadKey : k[c];
     // ranks from the 10 pairwise comparisons (ties only between dead keys: broken by index)
     int rks[5] = {0, 0, 0, 0, 0};
 #pragma unroll
@@ -368,23 +337,62 @@ FCFV_HD void rows_finish(FaceRows& R, bool a0, bool a1) {
             rks[d] += 1 - t;
         }
 #pragma unroll
-    for (int c = 0; c < 5; c++) {
-        const int rk = rks[c];
-        const int bit = 1 << rk;
-        R.lt[c] = bit - 1;
-        const bool alive = c < 3 ? a0 : a1;
-        mxs |= (alive && R.xs[c] != 0.0) ? bit : 0;
-        mxc |= (alive && R.xc[c] != 0.0) ? bit : 0;
-        mys |= (alive && R.ys[c] != 0.0) ? bit : 0;
-        myc |= (alive && R.yc[c] != 0.0) ? bit : 0;
-        if (WANT_M) {
-            mmx |= (alive && R.mx[c] != 0.0) ? bit : 0;
-            mmy |= (alive && R.my[c] != 0.0) ? bit : 0;
-        }
+    for (int c = 0; c < 5; c++) R.lt[c] = (1 << rks[c]) - 1;
+    R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_mx = R.m_my = R.m_kp = 0;
+}
+
+template <bool WANT_M>
+FCFV_HD void rows_mark(FaceRows& R, int c, bool alive) {
+    const int bit = R.lt[c] + 1;
+    R.m_xs |= (alive && R.xs[c] != 0.0) ? bit : 0;
+    R.m_xc |= (alive && R.xc[c] != 0.0) ? bit : 0;
+    R.m_ys |= (alive && R.ys[c] != 0.0) ? bit : 0;
+    R.m_yc |= (alive && R.yc[c] != 0.0) ? bit : 0;
+    if (WANT_M) {
+        R.m_mx |= (alive && R.mx[c] != 0.0) ? bit : 0;
+        R.m_my |= (alive && R.my[c] != 0.0) ? bit : 0;
     }
-    R.m_xs = mxs; R.m_xc = mxc; R.m_ys = mys; R.m_yc = myc; R.m_mx = mmx; R.m_my = mmy;
-    R.m_kp = ((a0 && R.kpx[0] != 0.0) ? 1 : 0) | ((a1 && R.kpx[1] != 0.0) ? 2 : 0) |
-             ((a0 && R.kpy[0] != 0.0) ? 4 : 0) | ((a1 && R.kpy[1] != 0.0) ? 8 : 0);
+}
+
+// Lanes (comp x, comp y) of the lower element: candidates 0..2, RHS, first Kup entry.
+template <bool WANT_M>
+FCFV_HD void rows_put0(FaceRows& R, bool alive, const LaneRow& Lx, const LaneRow& Ly) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        R.xs[j] = Lx.vs[j]; R.xc[j] = Lx.vc[j]; R.ys[j] = Ly.vs[j]; R.yc[j] = Ly.vc[j];
+        R.mx[j] = WANT_M ? Lx.ms[j] : 0.0; R.my[j] = WANT_M ? Ly.ms[j] : 0.0;
+        if (j > 0) rows_mark<WANT_M>(R, j, alive);
+    }
+    R.fux = Lx.fu; R.fuy = Ly.fu;
+    R.kpx[0] = Lx.kp; R.kpy[0] = Ly.kp; R.kpe[0] = Lx.e;
+    R.m_kp |= ((alive && Lx.kp != 0.0) ? 1 : 0) | ((alive && Ly.kp != 0.0) ? 4 : 0);
+}
+
+// Lanes of the higher element: its row-face column is summed into candidate 0 (lower element
+// first, like sparse()), its other two faces become candidates 3..4.  With on == false (the face
+// has no second element; the lanes then hold a discarded re-read of the first) nothing is added.
+template <bool WANT_M>
+FCFV_HD void rows_put1(FaceRows& R, bool on, bool alive, const LaneRow& Lx, const LaneRow& Ly) {
+    R.xs[0] = on ? R.xs[0] + Lx.vs[0] : R.xs[0]; R.xc[0] = on ? R.xc[0] + Lx.vc[0] : R.xc[0];
+    R.ys[0] = on ? R.ys[0] + Ly.vs[0] : R.ys[0]; R.yc[0] = on ? R.yc[0] + Ly.vc[0] : R.yc[0];
+    if (WANT_M) { R.mx[0] = on ? R.mx[0] + Lx.ms[0] : R.mx[0]; R.my[0] = on ? R.my[0] + Ly.ms[0] : R.my[0]; }
+#pragma unroll
+    for (int j = 1; j < 3; j++) {
+        R.xs[2 + j] = Lx.vs[j]; R.xc[2 + j] = Lx.vc[j]; R.ys[2 + j] = Ly.vs[j]; R.yc[2 + j] = Ly.vc[j];
+        R.mx[2 + j] = WANT_M ? Lx.ms[j] : 0.0; R.my[2 + j] = WANT_M ? Ly.ms[j] : 0.0;
+        rows_mark<WANT_M>(R, 2 + j, on && alive);
+    }
+    R.fux = on ? R.fux + Lx.fu : R.fux; R.fuy = on ? R.fuy + Ly.fu : R.fuy;
+    R.kpx[1] = Lx.kp; R.kpy[1] = Ly.kp; R.kpe[1] = Lx.e;
+    R.m_kp |= ((on && alive && Lx.kp != 0.0) ? 2 : 0) | ((on && alive && Ly.kp != 0.0) ? 8 : 0);
+}
+
+// merged row-face column and RHS; alive: the face's rows are produced (owned face with an element)
+template <bool WANT_M>
+FCFV_HD void rows_finish(FaceRows& R, bool alive) {
+    if (R.fux == 0.0) R.fux = 0.0;   // Array(dropzeros(sparse)): -0.0 -> +0.0
+    if (R.fuy == 0.0) R.fuy = 0.0;
+    rows_mark<WANT_M>(R, 0, alive);
 }
 
 FCFV_HD int popc6(int x) {

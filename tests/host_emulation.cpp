@@ -70,7 +70,7 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
     for (int f = 0; f < nf; f++) {   // count pass
         FaceRows R; int fpe[2]; double fpv[2];
         unpack_conn(f, M.fconn[f], M.fbc[f], C);
-        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], C.bc[0], true, false, load, R, fpe, fpv);
+        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], C, true, false, load, R, fpe, fpv);
         cnt[0][f] = rows_nuu_x(R); cnt[1][f] = rows_nuu_y(R);
         cnt[2][f] = rows_nup_x(R); cnt[3][f] = rows_nup_y(R);
         cnt[4][f] = rows_nmu_x(R); cnt[5][f] = rows_nmu_y(R);
@@ -86,7 +86,7 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
     for (int f = 0; f < nf; f++) {   // fill pass (same placement arithmetic as k_asm_fill)
         FaceRows R; int fpe[2]; double fpv[2];
         unpack_conn(f, M.fconn[f], M.fbc[f], C);
-        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], C.bc[0], true, true, load, R, fpe, fpv);
+        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], C, true, true, load, R, fpe, fpv);
         for (int s = 0; s < 2; s++) if (fpe[s] >= 0) fp[fpe[s]] = fpv[s];
         fu[f] = R.fux; fu[nf + f] = R.fuy;
         rows_emit_uu(R, nf, [&](int comp, int pos, int col, double v) {

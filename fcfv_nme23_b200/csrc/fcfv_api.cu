@@ -615,6 +615,7 @@ int launch_assemble(fcfv_t* h, double A) {
     int* local = P<int>(h->bases);
     long long* chunk_tot = P<long long>(h->chunks);
     long long* chunk_base = chunk_tot + (size_t)kNumSums * nchunks;
+    TLAUNCH(h, T_OTHER, k_asm_fp, nblocks(h->nf, 256), 256, M, D, P<double>(h->fp));   // fp was zeroed by the caller
     TLAUNCH(h, T_COEF, k_elem_coef<VARIANT>, nblocks(h->nel, 256), 256, M.nel, L.alpha, M.ke, M.dl, M.Om, (double*)Cf.ia, (double*)Cf.c11,
             (double*)Cf.c12, (double*)Cf.c21, (double*)Cf.c22);
     TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, WANT_M, ANISO>), nblk, kAsmBlock, M, L, Cf, D, A, sums, nblk);
@@ -626,12 +627,12 @@ int launch_assemble(fcfv_t* h, double A) {
         TLAUNCH(h, T_SCAN, k_scan_chunks<long long>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals),
                 (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)omu.rowptr, M.nf, (int)WANT_M);
         TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, ANISO, long long>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk,
-                nchunks, ouu, oup, omu, P<double>(h->fu), P<double>(h->fp));
+                nchunks, ouu, oup, omu, P<double>(h->fu));
     } else {
         TLAUNCH(h, T_SCAN, k_scan_chunks<int>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals), (int*)ouu.rowptr,
                 (int*)oup.rowptr, (int*)omu.rowptr, M.nf, (int)WANT_M);
         TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, ANISO, int>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk, nchunks,
-                ouu, oup, omu, P<double>(h->fu), P<double>(h->fp));
+                ouu, oup, omu, P<double>(h->fu));
     }
     return FCFV_OK;
 }

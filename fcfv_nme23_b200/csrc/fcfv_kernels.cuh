@@ -150,44 +150,38 @@ FCFV_HD void slot_lanes(const FaceElem& F, int e, double A, double vx, double vy
     lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 1, A, vy, syx, syy, Ly);
 }
 
-// fp[e] (Discretisation:194) from the record built for row face i: the sum runs over the faces in
-// their local order j = 0,1,2 (record position face_pos(i, j)), Dirichlet faces only.
-FCFV_HD double slot_fp(const FaceElem& F, int i, const FaceDataView& D) {
+// fp[e] (Discretisation:194) is non-zero only for elements with a Dirichlet face; everything else
+// keeps the +0.0 the array is initialised with.  It is produced by the thread of the element's
+// FIRST Dirichlet face in local order (one writer per element) in a pass over the faces that
+// skips every non-Dirichlet face at once (k_asm_fp).  Returns false when face f (local index i of
+// element e) is not that face.
+FCFV_HD bool face_fp(const MeshView& M, const FaceDataView& D, int e, int i, double& fp) {
+    const int nel = M.nel;
     bool dir[3]; double G[3], nx[3], ny[3], dvx[3], dvy[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const int k = face_pos(i, j);
-        const int g = pick3(k, F.g);
-        dir[j] = pick3(k, F.bc) == 1;
-        G[j] = pick3(k, F.G); nx[j] = pick3(k, F.nx); ny[j] = pick3(k, F.ny);
+        const int g = M.e2f[j * nel + e];
+        dir[j] = M.bc[g] == 1;
+        G[j] = M.G[j * nel + e]; nx[j] = M.nx[j * nel + e]; ny[j] = M.ny[j * nel + e];
         dvx[j] = dir[j] ? D.VxDir[g] : 0.0;
         dvy[j] = dir[j] ? D.VyDir[g] : 0.0;
     }
-    return element_fp(G, nx, ny, dir, dvx, dvy);
-}
-
-// fp[e] is non-zero only for elements with a Dirichlet face; it is produced by the thread of the
-// element's FIRST Dirichlet face in local order (one writer per element), everything else keeps
-// the +0.0 the array is initialised with.
-FCFV_HD bool is_first_dirichlet(const FaceElem& F, int i) {
-    bool first = F.bc[0] == 1;
-    if (i >= 1) first = first && (i == 1 ? F.bc[1] : F.bc[2]) != 1;   // local face 0 sits at position i
-    if (i == 2) first = first && F.bc[1] != 1;                          // local face 1 stays at position 1
-    return first;
+    const bool first = pick3(i, dir) && !(i >= 1 && dir[0]) && !(i == 2 && dir[1]);
+    if (!first) return false;
+    fp = element_fp(G, nx, ny, dir, dvx, dvy);
+    return true;
 }
 
 // Both rows of face f -- what one assembly thread computes; shared by the count pass, the fill
-// pass and the host emulation.  pr = f2e[f], C = connectivity record of f; load(second, e, i, F) provides the record
-// of element e with row face i in front (second: take face ids / tags of the higher element).  With do_fp a Dirichlet face also returns fp of the adjacent owned
-// elements it is the first Dirichlet face of, so that fp needs no pass of its own.
-template <int VARIANT, int FORM, bool WANT_M, typename Loader>
-FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f, int2 pr, const FaceConn& C, bool owned, bool do_fp,
-                      Loader&& load, FaceRows& R, int fp_elem[2], double fp_val[2]) {
-    fp_elem[0] = fp_elem[1] = -1; fp_val[0] = fp_val[1] = 0.0;
+// pass and the host emulation.  pr = f2e[f], C = connectivity record of f; load(second, e, i, F)
+// provides the record of element e with row face i in front (second: take face ids / tags of the
+// higher element); the values leave through `sink` (see RowVals).
+template <int VARIANT, int FORM, bool WANT_M, typename Loader, typename Sink>
+FCFV_HD void asm_face(const FaceDataView& D, double A, int f, int2 pr, const FaceConn& C, bool owned, Loader&& load,
+                      const Sink& sink, FaceRows& R) {
     const int bcf = C.bc[0];
     const bool has0 = pr.x >= 0, has1 = has0 && pr.y != pr.x;
-    const bool want_fp = do_fp && bcf == 1;
-    if (has0 && (owned || want_fp)) {
+    if (has0 && owned) {
         rows_begin(R, C.k);
         double vx = 0.0, vy = 0.0, sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
         if (bcf == 1) { vx = D.VxDir[f]; vy = D.VyDir[f]; }
@@ -198,11 +192,7 @@ FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f,
             FaceElem F;
             load(false, e, i, F);
             slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
-            rows_put0<WANT_M>(R, owned, Lx, Ly);
-            if (want_fp && (M.elem_owned == nullptr || M.elem_owned[e]) && is_first_dirichlet(F, i)) {
-                fp_val[0] = slot_fp(F, i, D);
-                fp_elem[0] = e;
-            }
+            rows_put0<WANT_M>(R, true, Lx, Ly, sink);
         }
         {
             // No branch around the second element: a missing one re-reads the first and is discarded,
@@ -212,16 +202,11 @@ FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f,
             FaceElem F;
             load(has1, e, i, F);
             slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
-            rows_put1<WANT_M>(R, has1, owned, Lx, Ly);
-            if (has1 && want_fp && (M.elem_owned == nullptr || M.elem_owned[e]) && is_first_dirichlet(F, i)) {
-                fp_val[1] = slot_fp(F, i, D);
-                fp_elem[1] = e;
-            }
+            rows_put1<WANT_M>(R, has1, true, Lx, Ly, sink);
         }
-        rows_finish<WANT_M>(R, owned);
-        if (!owned) { R.fux = 0.0; R.fuy = 0.0; }   // rows of faces owned by another rank stay empty (only fp was wanted)
+        rows_finish<WANT_M>(R, true, sink);
     } else {
-        rows_clear(R);
+        rows_clear(R);   // faces without elements, faces owned by another rank
     }
 }
 
@@ -230,7 +215,10 @@ FCFV_HD void asm_face(const MeshView& M, const FaceDataView& D, double A, int f,
 // kernels
 // =============================================================================================
 constexpr int kBlock = 128;          // threads per block for element / face kernels
-constexpr int kAsmBlock = 128;       // assembly: one thread per face (both rows)
+#ifndef FCFV_ASM_BLOCK
+#define FCFV_ASM_BLOCK 128
+#endif
+constexpr int kAsmBlock = FCFV_ASM_BLOCK;   // assembly: one thread per face (both rows); <= 128 (packed block counts)
 constexpr int kAsmFaces = kAsmBlock;
 constexpr int kMaxRow = 10;          // max entries of a Kuu row (5 faces x 2 components)
 constexpr int kNumSums = 6;          // Kuu-x, Kuu-y, Kup-x, Kup-y, Muu-x, Muu-y
@@ -475,28 +463,36 @@ __device__ __forceinline__ void prefetch_elem(const MeshView& M, const LocalView
 }
 
 // rows of the block's face of this thread
-template <int VARIANT, int FORM, bool WANT_M, bool ANISO>
+template <int VARIANT, int FORM, bool WANT_M, bool ANISO, typename Sink>
 __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceDataView& D, double A,
-                                               bool do_fp, int& f, bool& inrange, FaceRows& R, int fpe[2], double fpv[2]) {
+                                               const Sink& sink, int& f, bool& inrange, FaceRows& R) {
     f = blockIdx.x * kAsmFaces + threadIdx.x;
     inrange = f < M.nf;
     const int2 pr = inrange ? M.f2e[f] : make_int2(-1, -1);
     FaceConn C;
     unpack_conn(f, inrange ? M.fconn[f] : make_int4(-1, -1, -1, -1), inrange ? M.fbc[f] : 0x11111, C);
     const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
-#if FCFV_PREFETCH_TILES > 0
-    const long long fa = (long long)f + (long long)FCFV_PREFETCH_TILES * kAsmFaces;
-    int2 pa = make_int2(-1, -1);
-    if (fa < M.nf) pa = M.f2e[fa];                      // consumed at the end of the kernel
-#endif
     auto load = [&](bool second, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO>(M, L, Cf, C, second, e, i, F); };
-    asm_face<VARIANT, FORM, WANT_M>(M, D, A, f, pr, C, owned, do_fp && inrange, load, R, fpe, fpv);
-#if FCFV_PREFETCH_TILES > 0
-    if (pa.x >= 0) {
-        prefetch_elem(M, L, Cf, pa.x >> 2);
-        if (pa.y != pa.x) prefetch_elem(M, L, Cf, pa.y >> 2);
+    asm_face<VARIANT, FORM, WANT_M>(D, A, f, pr, C, owned, load, sink, R);
+}
+
+// fp: one thread per face, only Dirichlet faces do anything
+__global__ void __launch_bounds__(256)
+k_asm_fp(MeshView M, FaceDataView D, double* __restrict__ fp) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= M.nf) return;
+    if (((M.fbc[f] & 15) - 1) != 1) return;
+    const int2 pr = M.f2e[f];
+    if (pr.x < 0) return;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; s2++) {
+        if (s2 == 1 && pr.y == pr.x) break;
+        const int code = s2 == 0 ? pr.x : pr.y;
+        const int e = code >> 2, i = code & 3;
+        if (M.elem_owned != nullptr && !M.elem_owned[e]) continue;
+        double v;
+        if (face_fp(M, D, e, i, v)) fp[e] = v;
     }
-#endif
 }
 
 // row lengths of a face packed in one 64-bit word: Kuu x, Kuu y (11 bits: <= 1280 per block),
@@ -545,8 +541,8 @@ __global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_COUNT_MINBLOCKS)
 k_asm_count(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, int* __restrict__ sums, int nblk) {
     __shared__ unsigned long long sw64[kAsmBlock / 32];
     FaceRows R;
-    int f, fpe[2]; bool inrange; double fpv[2];
-    tile_face_rows<VARIANT, FORM, WANT_M, ANISO>(M, L, Cf, D, A, false, f, inrange, R, fpe, fpv);
+    int f; bool inrange;
+    tile_face_rows<VARIANT, FORM, WANT_M, ANISO>(M, L, Cf, D, A, NullSink(), f, inrange, R);
     unsigned long long tot;
     block_excl_scan64<kAsmBlock>(rows_counts<WANT_M>(R), tot, sw64);
     if (threadIdx.x == 0) {
@@ -662,28 +658,29 @@ constexpr int kStageBytesP = 2 * kHalfP * (8 + 4);
 template <int VARIANT, int FORM, bool WANT_M, bool ANISO, typename RP>
 __global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_FILL_MINBLOCKS)
 k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const int* __restrict__ local, const long long* __restrict__ chunk_base,
-           int nblk, int nchunks, CsrOut Kuu, CsrOut Kup, CsrOut Muu, double* __restrict__ fu, double* __restrict__ fp) {
+           int nblk, int nchunks, CsrOut Kuu, CsrOut Kup, CsrOut Muu, double* __restrict__ fu) {
     __shared__ __align__(16) unsigned char raw[kStageBytes];      // Kuu (then Muu) staging
     __shared__ __align__(16) unsigned char rawp[kStageBytesP];    // Kup staging
     __shared__ unsigned long long sw64[kAsmBlock / 32];
+    __shared__ long long sbase[kNumSums];
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int nf = M.nf;
+    // global offsets of this tile's segments: fetched by a few threads while the rows are computed,
+    // published by the barriers of the block scan
+    if (tid < (WANT_M ? 6 : 4)) sbase[tid] = chunk_base[(size_t)tid * nchunks + b / kScanChunk] + local[(size_t)tid * nblk + b];
     FaceRows R;
-    int f, fpe[2]; bool inrange; double fpv[2];
-    tile_face_rows<VARIANT, FORM, WANT_M, ANISO>(M, L, Cf, D, A, true, f, inrange, R, fpe, fpv);
-    if (fpe[0] >= 0) fp[fpe[0]] = fpv[0];
-    if (fpe[1] >= 0) fp[fpe[1]] = fpv[1];
+    RowVals V;
+    int f; bool inrange;
+    tile_face_rows<VARIANT, FORM, WANT_M, ANISO>(M, L, Cf, D, A, RowValsSink{&V}, f, inrange, R);
     if (inrange) {
         fu[f] = R.fux;
         fu[(size_t)nf + f] = R.fuy;
     }
     unsigned long long tot;
     const unsigned long long off = block_excl_scan64<kAsmBlock>(rows_counts<WANT_M>(R), tot, sw64);
-    const int ch = b / kScanChunk;
-    auto gbase = [&](int q) -> long long { return chunk_base[(size_t)q * nchunks + ch] + local[(size_t)q * nblk + b]; };
-    const long long bux = gbase(0), buy = gbase(1), bpx = gbase(2), bpy = gbase(3);
-    const long long bmx = WANT_M ? gbase(4) : 0, bmy = WANT_M ? gbase(5) : 0;
+    const long long bux = sbase[0], buy = sbase[1], bpx = sbase[2], bpy = sbase[3];
+    const long long bmx = WANT_M ? sbase[4] : 0, bmy = WANT_M ? sbase[5] : 0;
     if (inrange) {
         ((RP*)Kuu.rowptr)[f] = (RP)(bux + cfield(off, 0));
         ((RP*)Kuu.rowptr)[(size_t)nf + f] = (RP)(buy + cfield(off, 1));
@@ -704,7 +701,7 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
         double* vy = sval + kHalf + cfield(off, 1) + (int)(buy & 1);
         int* cx = scol + cfield(off, 0) + (int)(bux & 3);
         int* cy = scol + kHalf + cfield(off, 1) + (int)(buy & 3);
-        rows_emit_uu(R, nf, [&](int comp, int pos, int col, double v) {
+        rows_emit_uu(R, V, nf, [&](int comp, int pos, int col, double v) {
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });
@@ -714,7 +711,7 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
         double* vy = pval + kHalfP + cfield(off, 3) + (int)(bpy & 1);
         int* cx = pcol + cfield(off, 2) + (int)(bpx & 3);
         int* cy = pcol + kHalfP + cfield(off, 3) + (int)(bpy & 3);
-        rows_emit_up(R, [&](int comp, int pos, int col, double v) {   // columns = element ids, ascending
+        rows_emit_up(R, V.kpx, V.kpy, [&](int comp, int pos, int col, double v) {   // columns = element ids, ascending
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });
@@ -743,7 +740,7 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
         double* vy = sval + kHalf + cfield(off, 5) + (int)(bmy & 1);
         int* cx = scol + cfield(off, 4) + (int)(bmx & 3);
         int* cy = scol + kHalf + cfield(off, 5) + (int)(bmy & 3);
-        rows_emit_mu(R, nf, [&](int comp, int pos, int col, double v) {
+        rows_emit_mu(R, V, nf, [&](int comp, int pos, int col, double v) {
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });

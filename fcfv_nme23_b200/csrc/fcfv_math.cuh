@@ -295,34 +295,52 @@ FCFV_HD void lane_row_inactive(LaneRow& R) {
 // set when candidate c is stored (alive and != +-0.0, dropzeros), and the position of c inside the
 // part is popc(mask & lt[c]) with lt[c] = (1 << rank(c)) - 1.
 // ---------------------------------------------------------------------------------------------
-struct FaceRows {
+struct FaceRows {          // what stays in registers of the rows of one face
     int key[5];
     int lt[5];
-    double xs[5], xc[5];   // row (f,x): x-column block ("same"), y-column block ("cross")
-    double ys[5], yc[5];   // row (f,y): y-column block ("same"), x-column block ("cross")
-    double mx[5], my[5];   // Muu rows (same-component block only)
+    double x0s, x0c, y0s, y0c, m0x, m0y;   // candidate 0 (the row face's own column) while the two elements are summed
     double fux, fuy;
-    double kpx[2], kpy[2]; // Kup entries, lower / higher element
-    int kpe[2];
+    int kpe[2];                                // Kup columns: lower / higher element
     int m_xs, m_xc, m_ys, m_yc, m_mx, m_my;   // rank-space masks of stored entries
     int m_kp;                                  // bit 0 kpx[0], 1 kpx[1], 2 kpy[0], 3 kpy[1]
 };
 
+// The values of the rows, indexed by candidate: xs/xc = row (f,x) in the x-column block ("same") /
+// y-column block ("cross"), ys/yc = row (f,y) in the y-column / x-column block, mx/my = Muu rows,
+// kpx/kpy = Kup entries of the lower / higher element.  They leave asm_face through a sink as soon
+// as they are final: the count pass drops them, the fill pass parks them in shared memory (so that
+// they do not occupy registers while the second element is processed), the host emulation keeps
+// them in a RowVals.
+struct RowVals {
+    double xs[5], xc[5], ys[5], yc[5], mx[5], my[5];
+    double kpx[2], kpy[2];
+};
+
+struct NullSink {
+    FCFV_HD void cand(int, double, double, double, double, double, double) const {}
+    FCFV_HD void kup(int, double, double) const {}
+};
+
+struct RowValsSink {
+    RowVals* V;
+    FCFV_HD void cand(int c, double xs, double xc, double ys, double yc, double mx, double my) const {
+        V->xs[c] = xs; V->xc[c] = xc; V->ys[c] = ys; V->yc[c] = yc; V->mx[c] = mx; V->my[c] = my;
+    }
+    FCFV_HD void kup(int s, double kx, double ky) const { V->kpx[s] = kx; V->kpy[s] = ky; }
+};
+
 FCFV_HD void rows_clear(FaceRows& R) {
 #pragma unroll
-    for (int c = 0; c < 5; c++) {
-        R.key[c] = kDeadKey; R.lt[c] = 0;
-        R.xs[c] = R.xc[c] = R.ys[c] = R.yc[c] = R.mx[c] = R.my[c] = 0.0;
-    }
+    for (int c = 0; c < 5; c++) { R.key[c] = kDeadKey; R.lt[c] = 0; }
+    R.x0s = R.x0c = R.y0s = R.y0c = R.m0x = R.m0y = 0.0;
     R.fux = R.fuy = 0.0;
-    R.kpx[0] = R.kpx[1] = R.kpy[0] = R.kpy[1] = 0.0;
     R.kpe[0] = R.kpe[1] = -1;
     R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_mx = R.m_my = R.m_kp = 0;
 }
 
 // Column faces and their ranks are known before any element data arrives (face connectivity
 // record): keys k[0..4], absent faces (< 0) rank last.  Masks start empty and are filled while the
-// values are produced, so that a pass that only counts keeps no values alive.
+// values are produced.
 FCFV_HD void rows_begin(FaceRows& R, const int k[5]) {
 #pragma unroll
     for (int c = 0; c < 5; c++) R.key[c] = k[c] < 0 ? kDeadKey : k[c];
@@ -338,61 +356,68 @@ FCFV_HD void rows_begin(FaceRows& R, const int k[5]) {
         }
 #pragma unroll
     for (int c = 0; c < 5; c++) R.lt[c] = (1 << rks[c]) - 1;
+    R.kpe[0] = R.kpe[1] = -1;
     R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_mx = R.m_my = R.m_kp = 0;
 }
 
+// marks the stored (alive and != +-0.0: dropzeros) entries of candidate c
 template <bool WANT_M>
-FCFV_HD void rows_mark(FaceRows& R, int c, bool alive) {
+FCFV_HD void rows_mark(FaceRows& R, int c, bool alive, double xs, double xc, double ys, double yc, double mx, double my) {
     const int bit = R.lt[c] + 1;
-    R.m_xs |= (alive && R.xs[c] != 0.0) ? bit : 0;
-    R.m_xc |= (alive && R.xc[c] != 0.0) ? bit : 0;
-    R.m_ys |= (alive && R.ys[c] != 0.0) ? bit : 0;
-    R.m_yc |= (alive && R.yc[c] != 0.0) ? bit : 0;
+    R.m_xs |= (alive && xs != 0.0) ? bit : 0;
+    R.m_xc |= (alive && xc != 0.0) ? bit : 0;
+    R.m_ys |= (alive && ys != 0.0) ? bit : 0;
+    R.m_yc |= (alive && yc != 0.0) ? bit : 0;
     if (WANT_M) {
-        R.m_mx |= (alive && R.mx[c] != 0.0) ? bit : 0;
-        R.m_my |= (alive && R.my[c] != 0.0) ? bit : 0;
+        R.m_mx |= (alive && mx != 0.0) ? bit : 0;
+        R.m_my |= (alive && my != 0.0) ? bit : 0;
     }
 }
 
 // Lanes (comp x, comp y) of the lower element: candidates 0..2, RHS, first Kup entry.
-template <bool WANT_M>
-FCFV_HD void rows_put0(FaceRows& R, bool alive, const LaneRow& Lx, const LaneRow& Ly) {
+template <bool WANT_M, typename Sink>
+FCFV_HD void rows_put0(FaceRows& R, bool alive, const LaneRow& Lx, const LaneRow& Ly, const Sink& sink) {
+    R.x0s = Lx.vs[0]; R.x0c = Lx.vc[0]; R.y0s = Ly.vs[0]; R.y0c = Ly.vc[0];
+    R.m0x = WANT_M ? Lx.ms[0] : 0.0; R.m0y = WANT_M ? Ly.ms[0] : 0.0;
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        R.xs[j] = Lx.vs[j]; R.xc[j] = Lx.vc[j]; R.ys[j] = Ly.vs[j]; R.yc[j] = Ly.vc[j];
-        R.mx[j] = WANT_M ? Lx.ms[j] : 0.0; R.my[j] = WANT_M ? Ly.ms[j] : 0.0;
-        if (j > 0) rows_mark<WANT_M>(R, j, alive);
+    for (int j = 1; j < 3; j++) {
+        const double mx = WANT_M ? Lx.ms[j] : 0.0, my = WANT_M ? Ly.ms[j] : 0.0;
+        rows_mark<WANT_M>(R, j, alive, Lx.vs[j], Lx.vc[j], Ly.vs[j], Ly.vc[j], mx, my);
+        sink.cand(j, Lx.vs[j], Lx.vc[j], Ly.vs[j], Ly.vc[j], mx, my);
     }
     R.fux = Lx.fu; R.fuy = Ly.fu;
-    R.kpx[0] = Lx.kp; R.kpy[0] = Ly.kp; R.kpe[0] = Lx.e;
+    R.kpe[0] = Lx.e;
     R.m_kp |= ((alive && Lx.kp != 0.0) ? 1 : 0) | ((alive && Ly.kp != 0.0) ? 4 : 0);
+    sink.kup(0, Lx.kp, Ly.kp);
 }
 
 // Lanes of the higher element: its row-face column is summed into candidate 0 (lower element
 // first, like sparse()), its other two faces become candidates 3..4.  With on == false (the face
 // has no second element; the lanes then hold a discarded re-read of the first) nothing is added.
-template <bool WANT_M>
-FCFV_HD void rows_put1(FaceRows& R, bool on, bool alive, const LaneRow& Lx, const LaneRow& Ly) {
-    R.xs[0] = on ? R.xs[0] + Lx.vs[0] : R.xs[0]; R.xc[0] = on ? R.xc[0] + Lx.vc[0] : R.xc[0];
-    R.ys[0] = on ? R.ys[0] + Ly.vs[0] : R.ys[0]; R.yc[0] = on ? R.yc[0] + Ly.vc[0] : R.yc[0];
-    if (WANT_M) { R.mx[0] = on ? R.mx[0] + Lx.ms[0] : R.mx[0]; R.my[0] = on ? R.my[0] + Ly.ms[0] : R.my[0]; }
+template <bool WANT_M, typename Sink>
+FCFV_HD void rows_put1(FaceRows& R, bool on, bool alive, const LaneRow& Lx, const LaneRow& Ly, const Sink& sink) {
+    R.x0s = on ? R.x0s + Lx.vs[0] : R.x0s; R.x0c = on ? R.x0c + Lx.vc[0] : R.x0c;
+    R.y0s = on ? R.y0s + Ly.vs[0] : R.y0s; R.y0c = on ? R.y0c + Ly.vc[0] : R.y0c;
+    if (WANT_M) { R.m0x = on ? R.m0x + Lx.ms[0] : R.m0x; R.m0y = on ? R.m0y + Ly.ms[0] : R.m0y; }
 #pragma unroll
     for (int j = 1; j < 3; j++) {
-        R.xs[2 + j] = Lx.vs[j]; R.xc[2 + j] = Lx.vc[j]; R.ys[2 + j] = Ly.vs[j]; R.yc[2 + j] = Ly.vc[j];
-        R.mx[2 + j] = WANT_M ? Lx.ms[j] : 0.0; R.my[2 + j] = WANT_M ? Ly.ms[j] : 0.0;
-        rows_mark<WANT_M>(R, 2 + j, on && alive);
+        const double mx = WANT_M ? Lx.ms[j] : 0.0, my = WANT_M ? Ly.ms[j] : 0.0;
+        rows_mark<WANT_M>(R, 2 + j, on && alive, Lx.vs[j], Lx.vc[j], Ly.vs[j], Ly.vc[j], mx, my);
+        sink.cand(2 + j, Lx.vs[j], Lx.vc[j], Ly.vs[j], Ly.vc[j], mx, my);
     }
     R.fux = on ? R.fux + Lx.fu : R.fux; R.fuy = on ? R.fuy + Ly.fu : R.fuy;
-    R.kpx[1] = Lx.kp; R.kpy[1] = Ly.kp; R.kpe[1] = Lx.e;
+    R.kpe[1] = Lx.e;
     R.m_kp |= ((on && alive && Lx.kp != 0.0) ? 2 : 0) | ((on && alive && Ly.kp != 0.0) ? 8 : 0);
+    sink.kup(1, Lx.kp, Ly.kp);
 }
 
 // merged row-face column and RHS; alive: the face's rows are produced (owned face with an element)
-template <bool WANT_M>
-FCFV_HD void rows_finish(FaceRows& R, bool alive) {
+template <bool WANT_M, typename Sink>
+FCFV_HD void rows_finish(FaceRows& R, bool alive, const Sink& sink) {
     if (R.fux == 0.0) R.fux = 0.0;   // Array(dropzeros(sparse)): -0.0 -> +0.0
     if (R.fuy == 0.0) R.fuy = 0.0;
-    rows_mark<WANT_M>(R, 0, alive);
+    rows_mark<WANT_M>(R, 0, alive, R.x0s, R.x0c, R.y0s, R.y0c, R.m0x, R.m0y);
+    sink.cand(0, R.x0s, R.x0c, R.y0s, R.y0c, R.m0x, R.m0y);
 }
 
 FCFV_HD int popc6(int x) {
@@ -411,41 +436,56 @@ FCFV_HD int rows_nup_y(const FaceRows& R) { return ((R.m_kp >> 2) & 1) + ((R.m_k
 FCFV_HD int rows_nmu_x(const FaceRows& R) { return popc6(R.m_mx); }
 FCFV_HD int rows_nmu_y(const FaceRows& R) { return popc6(R.m_my); }
 
-// emit(comp, position inside the row, column, value); rows are laid out [x columns | y columns].
+// emit(position inside the row, column, value); rows are laid out [x columns | y columns].
 // Positions are formed unconditionally so that the conditional part is just the store.
 template <typename Emit>
-FCFV_HD void rows_emit_uu(const FaceRows& R, int nf, Emit&& emit) {
-    const int n_xs = popc6(R.m_xs), n_yc = popc6(R.m_yc);
+FCFV_HD void rows_emit_uu_x(const FaceRows& R, const double xs[5], const double xc[5], int nf, Emit&& emit) {
+    const int n_xs = popc6(R.m_xs);
 #pragma unroll
     for (int c = 0; c < 5; c++) {
         const int lt = R.lt[c], bit = lt + 1;
         const int p_xs = popc6(R.m_xs & lt), p_xc = n_xs + popc6(R.m_xc & lt);
-        const int p_yc = popc6(R.m_yc & lt), p_ys = n_yc + popc6(R.m_ys & lt);
-        if (R.m_xs & bit) emit(0, p_xs, R.key[c], R.xs[c]);
-        if (R.m_xc & bit) emit(0, p_xc, R.key[c] + nf, R.xc[c]);
-        if (R.m_yc & bit) emit(1, p_yc, R.key[c], R.yc[c]);
-        if (R.m_ys & bit) emit(1, p_ys, R.key[c] + nf, R.ys[c]);
+        if (R.m_xs & bit) emit(p_xs, R.key[c], xs[c]);
+        if (R.m_xc & bit) emit(p_xc, R.key[c] + nf, xc[c]);
     }
 }
 
 template <typename Emit>
-FCFV_HD void rows_emit_mu(const FaceRows& R, int nf, Emit&& emit) {
+FCFV_HD void rows_emit_uu_y(const FaceRows& R, const double ys[5], const double yc[5], int nf, Emit&& emit) {
+    const int n_yc = popc6(R.m_yc);
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        const int lt = R.lt[c], bit = lt + 1;
+        const int p_yc = popc6(R.m_yc & lt), p_ys = n_yc + popc6(R.m_ys & lt);
+        if (R.m_yc & bit) emit(p_yc, R.key[c], yc[c]);
+        if (R.m_ys & bit) emit(p_ys, R.key[c] + nf, ys[c]);
+    }
+}
+
+template <typename Emit>
+FCFV_HD void rows_emit_uu(const FaceRows& R, const RowVals& V, int nf, Emit&& emit) {
+    rows_emit_uu_x(R, V.xs, V.xc, nf, [&](int pos, int col, double v) { emit(0, pos, col, v); });
+    rows_emit_uu_y(R, V.ys, V.yc, nf, [&](int pos, int col, double v) { emit(1, pos, col, v); });
+}
+
+template <typename Emit>
+FCFV_HD void rows_emit_mu(const FaceRows& R, const RowVals& V, int nf, Emit&& emit) {
 #pragma unroll
     for (int c = 0; c < 5; c++) {
         const int lt = R.lt[c], bit = lt + 1;
         const int p_x = popc6(R.m_mx & lt), p_y = popc6(R.m_my & lt);
-        if (R.m_mx & bit) emit(0, p_x, R.key[c], R.mx[c]);
-        if (R.m_my & bit) emit(1, p_y, R.key[c] + nf, R.my[c]);
+        if (R.m_mx & bit) emit(0, p_x, R.key[c], V.mx[c]);
+        if (R.m_my & bit) emit(1, p_y, R.key[c] + nf, V.my[c]);
     }
 }
 
 // columns = element ids, lower element first
 template <typename Emit>
-FCFV_HD void rows_emit_up(const FaceRows& R, Emit&& emit) {
-    if (R.m_kp & 1) emit(0, 0, R.kpe[0], R.kpx[0]);
-    if (R.m_kp & 2) emit(0, R.m_kp & 1, R.kpe[1], R.kpx[1]);
-    if (R.m_kp & 4) emit(1, 0, R.kpe[0], R.kpy[0]);
-    if (R.m_kp & 8) emit(1, (R.m_kp >> 2) & 1, R.kpe[1], R.kpy[1]);
+FCFV_HD void rows_emit_up(const FaceRows& R, const double kpx[2], const double kpy[2], Emit&& emit) {
+    if (R.m_kp & 1) emit(0, 0, R.kpe[0], kpx[0]);
+    if (R.m_kp & 2) emit(0, R.m_kp & 1, R.kpe[1], kpx[1]);
+    if (R.m_kp & 4) emit(1, 0, R.kpe[0], kpy[0]);
+    if (R.m_kp & 8) emit(1, (R.m_kp >> 2) & 1, R.kpe[1], kpy[1]);
 }
 
 // fp[e] :194 -- sequential over the three faces, Dirichlet faces only contribute.

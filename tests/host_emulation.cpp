@@ -68,9 +68,9 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
     std::vector<int> cnt[6];
     for (auto& c : cnt) c.assign(nf, 0);
     for (int f = 0; f < nf; f++) {   // count pass
-        FaceRows R; int fpe[2]; double fpv[2];
+        FaceRows R;
         unpack_conn(f, M.fconn[f], M.fbc[f], C);
-        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], C, true, false, load, R, fpe, fpv);
+        asm_face<VARIANT, FORM, true>(D, A, f, M.f2e[f], C, true, load, NullSink(), R);
         cnt[0][f] = rows_nuu_x(R); cnt[1][f] = rows_nuu_y(R);
         cnt[2][f] = rows_nup_x(R); cnt[3][f] = rows_nup_y(R);
         cnt[4][f] = rows_nmu_x(R); cnt[5][f] = rows_nmu_y(R);
@@ -83,17 +83,27 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
         rps[m][2 * nf] = run;
     }
     for (int e = 0; e < M.nel; e++) fp[e] = 0.0;
+    for (int f = 0; f < nf; f++) {   // k_asm_fp
+        if (((M.fbc[f] & 15) - 1) != 1 || M.f2e[f].x < 0) continue;
+        const int2 pr = M.f2e[f];
+        for (int s2 = 0; s2 < 2; s2++) {
+            if (s2 == 1 && pr.y == pr.x) break;
+            const int code = s2 == 0 ? pr.x : pr.y;
+            double v;
+            if (face_fp(M, D, code >> 2, code & 3, v)) fp[code >> 2] = v;
+        }
+    }
     for (int f = 0; f < nf; f++) {   // fill pass (same placement arithmetic as k_asm_fill)
-        FaceRows R; int fpe[2]; double fpv[2];
+        FaceRows R;
         unpack_conn(f, M.fconn[f], M.fbc[f], C);
-        asm_face<VARIANT, FORM, true>(M, D, A, f, M.f2e[f], C, true, true, load, R, fpe, fpv);
-        for (int s = 0; s < 2; s++) if (fpe[s] >= 0) fp[fpe[s]] = fpv[s];
+        RowVals V;
+        asm_face<VARIANT, FORM, true>(D, A, f, M.f2e[f], C, true, load, RowValsSink{&V}, R);
         fu[f] = R.fux; fu[nf + f] = R.fuy;
-        rows_emit_uu(R, nf, [&](int comp, int pos, int col, double v) {
+        rows_emit_uu(R, V, nf, [&](int comp, int pos, int col, double v) {
             const long long p = rp_uu[(long long)comp * nf + f] + pos; v_uu[p] = v; c_uu[p] = col; });
-        rows_emit_up(R, [&](int comp, int pos, int col, double v) {
+        rows_emit_up(R, V.kpx, V.kpy, [&](int comp, int pos, int col, double v) {
             const long long p = rp_up[(long long)comp * nf + f] + pos; v_up[p] = v; c_up[p] = col; });
-        rows_emit_mu(R, nf, [&](int comp, int pos, int col, double v) {
+        rows_emit_mu(R, V, nf, [&](int comp, int pos, int col, double v) {
             const long long p = rp_mu[(long long)comp * nf + f] + pos; v_mu[p] = v; c_mu[p] = col; });
     }
 }

@@ -114,6 +114,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel, nel):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu capture taken at this mesh size
+    (profiles/*traffic*.json, written by tools/ncu_traffic.py); None when there is none."""
+    import glob
+    best = None
+    for pth in sorted(glob.glob(os.path.join(ROOT, "profiles", "*traffic*.json"))):
+        try:
+            t = json.load(open(pth))
+            if int(t["nel"]) == int(nel) and kernel in t["kernels"]:
+                best = (float(t["kernels"][kernel]["dram_bytes"]), os.path.basename(pth))
+        except Exception:
+            pass
+    return best
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -286,8 +301,10 @@ def run_ours(args, rank, world, local_rank):
     phase_of = {"k_asm_fill": "assembly", "k_asm_count": "assembly", "k_res_elem": "residual", "k_local": "local"}
     dom_bytes = ab[phase_of.get(dom, "assembly")]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = measured_traffic(dom, h.nel)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_ms": dom_ms,
                 "pipeline": {"algorithmic_bytes_per_step": ab["total"], "achieved": ab["total"] * args.steps / (ms * 1e-3) / 1e9,
                              "frac": ab["total"] * args.steps / (ms * 1e-3) / 1e9 / peak,

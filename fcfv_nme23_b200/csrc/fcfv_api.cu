@@ -615,7 +615,7 @@ int launch_assemble(fcfv_t* h, double A) {
     int* local = P<int>(h->bases);
     long long* chunk_tot = P<long long>(h->chunks);
     long long* chunk_base = chunk_tot + (size_t)kNumSums * nchunks;
-    TLAUNCH(h, T_OTHER, k_asm_fp, nblocks(h->nf, 256), 256, M, D, P<double>(h->fp));   // fp was zeroed by the caller
+    TLAUNCH(h, T_OTHER, k_asm_fp, nblocks((h->nf + 3) / 4, 256), 256, M, D, P<double>(h->fp));   // fp was zeroed by the caller
     TLAUNCH(h, T_COEF, k_elem_coef<VARIANT>, nblocks(h->nel, 256), 256, M.nel, L.alpha, M.ke, M.dl, M.Om, (double*)Cf.ia, (double*)Cf.c11,
             (double*)Cf.c12, (double*)Cf.c21, (double*)Cf.c22);
     TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, WANT_M, ANISO>), nblk, kAsmBlock, M, L, Cf, D, A, sums, nblk);

@@ -476,22 +476,31 @@ __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalVie
     asm_face<VARIANT, FORM, WANT_M>(D, A, f, pr, C, owned, load, sink, R);
 }
 
-// fp: one thread per face, only Dirichlet faces do anything
+// fp: one thread per 4 faces (one 16-byte load of the packed tags), only Dirichlet faces do anything
 __global__ void __launch_bounds__(256)
 k_asm_fp(MeshView M, FaceDataView D, double* __restrict__ fp) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= M.nf) return;
-    if (((M.fbc[f] & 15) - 1) != 1) return;
-    const int2 pr = M.f2e[f];
-    if (pr.x < 0) return;
+    const int f0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (f0 >= M.nf) return;
+    int tags[4] = {0x11111, 0x11111, 0x11111, 0x11111};
+    if (f0 + 3 < M.nf) {
+        const int4 t = *reinterpret_cast<const int4*>(M.fbc + f0);
+        tags[0] = t.x; tags[1] = t.y; tags[2] = t.z; tags[3] = t.w;
+    } else {
+        for (int q = 0; q < 4 && f0 + q < M.nf; q++) tags[q] = M.fbc[f0 + q];
+    }
 #pragma unroll
-    for (int s2 = 0; s2 < 2; s2++) {
-        if (s2 == 1 && pr.y == pr.x) break;
-        const int code = s2 == 0 ? pr.x : pr.y;
-        const int e = code >> 2, i = code & 3;
-        if (M.elem_owned != nullptr && !M.elem_owned[e]) continue;
-        double v;
-        if (face_fp(M, D, e, i, v)) fp[e] = v;
+    for (int q = 0; q < 4; q++) {
+        if (((tags[q] & 15) - 1) != 1) continue;
+        const int2 pr = M.f2e[f0 + q];
+        if (pr.x < 0) continue;
+        for (int s2 = 0; s2 < 2; s2++) {
+            if (s2 == 1 && pr.y == pr.x) break;
+            const int code = s2 == 0 ? pr.x : pr.y;
+            const int e = code >> 2, i = code & 3;
+            if (M.elem_owned != nullptr && !M.elem_owned[e]) continue;
+            double v;
+            if (face_fp(M, D, e, i, v)) fp[e] = v;
+        }
     }
 }
 

@@ -23,3 +23,9 @@ if [ "$WHAT" = all ] || [ "$WHAT" = prof ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_asm_fill|k_asm_count|k_res_elem|k_local' -s 4 -c 4 \
       -o $OUT/${TAG}_full -f python bench.py --mesh-n 1581 --steps 2 --warmup 1 --no-e2e --no-cpu > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
+if [ "$WHAT" = all ] || [ "$WHAT" = traffic ]; then
+  # DRAM bytes of the hot kernels at the bench's own size (50M elements), one step
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+      -k regex:'k_asm_fill|k_asm_count|k_res_elem|k_local|k_elem_coef|k_res_face|k_face_tau' -s 7 -c 7 \
+      -o $OUT/${TAG}_traffic50M -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/${TAG}_ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
+fi

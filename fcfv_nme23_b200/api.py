@@ -413,6 +413,19 @@ def ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey, VxD
     return norms
 
 
+def ComputeElementValues(mesh, Vxh, Vyh, Pe, α, β, Ζ, VxDir, VyDir, Formulation):
+    """src/DiscretisationFCFV_Stokes.jl:52-94 -> (Vxe, Vye, τxxe, τyye, τxye).  ``Pe``, ``VxDir``, ``VyDir`` and
+    ``Formulation`` are accepted for signature parity; the reference does not read them."""
+    h = handle_for(mesh)
+    _refresh(mesh, h)
+    nel, nf = h.nel, h.nf
+    a = _Arg()
+    out = [np.empty(nel) for _ in range(5)]
+    h.check(h.lib.fcfv_element_values(h._h, a.d(Vxh, nf), a.d(Vyh, nf), a.d(α, nel), a.d(β, 2 * nel), a.d(Ζ, 4 * nel),
+                                      *[_out(o) for o in out]))
+    return tuple(out)
+
+
 # ---------------------------------------------------------------------------------------------
 # Powell-Hestenes lines of StokesSolvers! that consume the device CSR (SolversFCFV_Stokes.jl:40-49)
 # ---------------------------------------------------------------------------------------------

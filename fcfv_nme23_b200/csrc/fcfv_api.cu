@@ -940,6 +940,39 @@ int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, 
 }
 
 // -------------------------------------------------------------------------------------------------
+int fcfv_element_values(fcfv_t* h, const double* Vxh, const double* Vyh, const double* alpha, const double* beta,
+                        const double* Z, double* Vxe, double* Vye, double* Txxe, double* Tyye, double* Txye) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_element_values: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    const long long nel = h->nel, nf = h->nf;
+    if ((Vxh == nullptr) != (Vyh == nullptr)) return fail(h, FCFV_ERR_INVALID, "fcfv_element_values: pass both Vxh and Vyh or neither");
+    if (Vxh) {
+        TRY(upload(h, h->Vxh, Vxh, sizeof(double) * nf));
+        TRY(upload(h, h->Vyh, Vyh, sizeof(double) * nf));
+        if (!h->have_solution) { TRY(ensure(h, h->Pe, sizeof(double) * nel)); CU(cudaMemsetAsync(h->Pe.p, 0, sizeof(double) * nel, h->stream)); }
+        h->have_solution = true;
+    }
+    if (alpha || beta || Z) {
+        const bool was_async = h->async;
+        h->async = true;
+        const int rc = fcfv_set_local(h, alpha, beta, Z);
+        h->async = was_async;
+        TRY(rc);
+    }
+    TRY(need(h, h->have_solution, "fcfv_element_values: no face velocities (fcfv_set_solution)"));
+    TRY(need(h, h->have_local, "fcfv_element_values: local coefficients missing"));
+    TRY(ensure(h, h->tmp2, sizeof(double) * 5 * nel));
+    double* out = P<double>(h->tmp2);
+    LAUNCH(h, k_elem_values, nblocks(nel), kBlock, mesh_view(h), local_view(h), sol_view(h), out);
+    CU(cudaGetLastError());
+    double* dst[5] = {Vxe, Vye, Txxe, Tyye, Txye};
+    for (int k = 0; k < 5; k++)
+        if (dst[k]) TRY(copy(h, dst[k], out + (size_t)k * nel, sizeof(double) * nel));
+    return sync(h);
+}
+
+// -------------------------------------------------------------------------------------------------
 namespace {
 int ph_inputs(fcfv_t* h, const double* u, const double* p, double** du, double** dp) {
     // u (2nf) and p (nel) staged in tmp: [u | p]

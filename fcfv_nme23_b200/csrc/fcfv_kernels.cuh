@@ -874,6 +874,29 @@ k_reduce_partials(const double* __restrict__ partial, int n, int stride, double*
     }
 }
 
+// ---- ComputeElementValues (Discretisation:52-94) -------------------------------------------------
+// out: Vxe, Vye, Txxe, Tyye, Txye as five consecutive arrays of nel doubles
+__global__ void __launch_bounds__(kBlock)
+k_elem_values(MeshView M, LocalView L, SolutionView S, double* __restrict__ out) {
+    const int e = blockIdx.x * kBlock + threadIdx.x;
+    const int nel = M.nel;
+    if (e >= nel) return;
+    double G[3], nx[3], ny[3], tau[3], uhx[3], uhy[3];
+    int bc[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int f = M.e2f[i * nel + e];
+        G[i] = M.G[i * nel + e]; nx[i] = M.nx[i * nel + e]; ny[i] = M.ny[i * nel + e];
+        bc[i] = M.bc[f]; tau[i] = M.tau[f];
+        uhx[i] = S.Vxh[f]; uhy[i] = S.Vyh[f];
+    }
+    ElemValues o;
+    element_values(M.Om[e], M.ke[e], M.dl[e], L.alpha[e], L.beta[e], L.beta[nel + e], L.Z[e], L.Z[nel + e], L.Z[2 * nel + e],
+                   L.Z[3 * nel + e], G, nx, ny, bc, tau, uhx, uhy, o);
+    out[e] = o.Vx; out[(size_t)nel + e] = o.Vy; out[2 * (size_t)nel + e] = o.Txx; out[3 * (size_t)nel + e] = o.Tyy;
+    out[4 * (size_t)nel + e] = o.Txy;
+}
+
 // ---- a9 Powell-Hestenes -------------------------------------------------------------------------
 // ru = (fu - Kuu*u) - Kup*p, one thread per row, products accumulated in ascending column order
 // (the order Julia's CSC mat-vec produces for each row), per-block sum of ru^2.

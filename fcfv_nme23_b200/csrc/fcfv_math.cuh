@@ -582,4 +582,31 @@ FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, do
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// ComputeElementValues for one element (src/DiscretisationFCFV_Stokes.jl:52-94): element velocity
+// and deviatoric stress from the face velocities.  tau[i] = mesh.τ of the element's faces.
+// ---------------------------------------------------------------------------------------------
+struct ElemValues { double Vx, Vy, Txx, Tyy, Txy; };
+
+FCFV_HD void element_values(double Om, double eta, double dl, double alpha, double b1, double b2, double Z11, double Z21,
+                            double Z12, double Z22, const double G[3], const double nx[3], const double ny[3], const int bc[3],
+                            const double tau[3], const double uhx[3], const double uhy[3], ElemValues& o) {
+    const double D11 = eta, D12 = eta / dl, D22 = eta;
+    o.Vx = b1 / alpha;
+    o.Vy = b2 / alpha;
+    o.Txx = (eta / Om) * Z11;
+    o.Tyy = (eta / Om) * Z22;
+    o.Txy = ((eta / Om) * 0.5) * (Z12 + Z21);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const bool nd = bc[i] != 1;
+        o.Vx += ((bmul(nd, G[i]) * tau[i]) * uhx[i]) / alpha;
+        o.Vy += ((bmul(nd, G[i]) * tau[i]) * uhy[i]) / alpha;
+        o.Txx += (((bmul(nd, D11) / Om) * G[i]) * nx[i]) * uhx[i];
+        o.Tyy += (((bmul(nd, D22) / Om) * G[i]) * ny[i]) * uhy[i];
+        o.Txy += (bmul(nd, D12) * 0.5) * (((1.0 / Om) * G[i]) * (nx[i] * uhy[i] + ny[i] * uhx[i]));
+    }
+    o.Txx *= 2.0; o.Tyy *= 2.0; o.Txy *= 2.0;
+}
+
 }  // namespace fcfv

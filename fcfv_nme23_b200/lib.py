@@ -74,6 +74,7 @@ def load():
         "fcfv_ph_residual": [vp] + [vp] * 5,
         "fcfv_ph_update_p": [vp, dbl, vp, vp],
         "fcfv_ph_fusc": [vp, dbl, vp, vp],
+        "fcfv_element_values": [vp] + [vp] * 10,
         "fcfv_set_sources": [vp, vp, vp],
         "fcfv_set_face_data": [vp] + [vp] * 6,
         "fcfv_set_solution": [vp, vp, vp, vp],

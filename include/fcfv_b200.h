@@ -119,6 +119,14 @@ int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, 
                    const double* SyxNeu, double* norms, double* F_nodes_x, double* F_nodes_y,
                    double* F_glob2);
 
+/* ---- ComputeElementValues (src/DiscretisationFCFV_Stokes.jl:52-94) --------------------------
+ * Element velocities and deviatoric stresses from the face velocities.  Vxh/Vyh NULL = resident
+ * solution (fcfv_set_solution), alpha/beta/Z NULL = resident local coefficients; uses mesh.τ as
+ * resident.  Outputs nel doubles each (NULL skips).  The reference's Pe, VxDir, VyDir and
+ * Formulation arguments are unused there (:52) and have no counterpart here. */
+int fcfv_element_values(fcfv_t* h, const double* Vxh, const double* Vyh, const double* alpha, const double* beta,
+                        const double* Z, double* Vxe, double* Vye, double* Txxe, double* Tyye, double* Txye);
+
 /* ---- a9: Powell-Hestenes residual / updates on the resident CSR --------------------------
  * src/SolversFCFV_Stokes.jl:40-42: ru = fu - Kuu*u - Kup*p, rp = fp - Kpu*u (Kpu = -Kup'),
  * nrm = {norm(ru), norm(rp)};  :23,49: p += (gamma*ke/Ω) .* (fp - Kpu*u);

@@ -10,7 +10,7 @@ module FCFV_B200
 
 using SparseArrays, Printf
 
-export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1,
+export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
        MeshGeometry!, PHResidual, PHUpdateP!, PHFusc
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
@@ -180,6 +180,21 @@ function ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey
     @printf("Residual of global equation 19a: %2.2e\n", norms[5])
     @printf("Residual of global equation 19b: %2.2e\n", norms[6])
     return
+end
+
+"""src/DiscretisationFCFV_Stokes.jl:52-94 -- same positional arguments; Pe, VxDir, VyDir, Formulation are unused there."""
+function ComputeElementValues(mesh, Vxh, Vyh, Pe, α, β, Ζ, VxDir, VyDir, Formulation)
+    h = handle_for(mesh); refresh!(h, mesh)
+    nel = mesh.nel
+    vxh, vyh, a, b, z = f64(Vxh), f64(Vyh), f64(α), f64(β), f64(Ζ)
+    Vxe, Vye, τxxe, τyye, τxye = zeros(nel), zeros(nel), zeros(nel), zeros(nel), zeros(nel)
+    GC.@preserve vxh vyh a b z Vxe Vye τxxe τyye τxye begin
+        check(h, ccall((:fcfv_element_values, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h.ptr, vxh, vyh, a, b, z, Vxe, Vye, τxxe, τyye, τxye))
+    end
+    return Vxe, Vye, τxxe, τyye, τxye
 end
 
 # --- the Powell-Hestenes lines of StokesSolvers! that consume the device CSR (SolversFCFV_Stokes.jl:40-49)

@@ -220,6 +220,28 @@ int emu_residuals(int formulation, int tau_mode, long long nel, long long nf, co
     return 0;
 }
 
+int emu_element_values(long long nel, long long nf, const long long* e2f, const long long* bc, const double* Om, const double* nx,
+                       const double* ny, const double* G, const double* ke, const double* dl, const double* tau,
+                       const double* alpha, const double* beta, const double* Z, const double* Vxh, const double* Vyh,
+                       double* out /* 5*nel */) {
+    HostMesh H;
+    build_mesh(H, nel, nf, e2f, bc, Om, nx, ny, G, ke, dl, ke, tau);
+    const MeshView& M = H.view;
+    for (int e = 0; e < (int)nel; e++) {   // k_elem_values
+        double g[3], n1[3], n2[3], t[3], uhx[3], uhy[3]; int b[3];
+        for (int i = 0; i < 3; i++) {
+            int f = M.e2f[i * nel + e];
+            g[i] = G[i * nel + e]; n1[i] = nx[i * nel + e]; n2[i] = ny[i * nel + e]; b[i] = M.bc[f]; t[i] = tau[f];
+            uhx[i] = Vxh[f]; uhy[i] = Vyh[f];
+        }
+        ElemValues o;
+        element_values(Om[e], ke[e], dl[e], alpha[e], beta[e], beta[nel + e], Z[e], Z[nel + e], Z[2 * nel + e], Z[3 * nel + e],
+                       g, n1, n2, b, t, uhx, uhy, o);
+        out[e] = o.Vx; out[nel + e] = o.Vy; out[2 * nel + e] = o.Txx; out[3 * nel + e] = o.Tyy; out[4 * nel + e] = o.Txy;
+    }
+    return 0;
+}
+
 // strip layout + local face ids of the device generator (integer logic only)
 int emu_strip_connectivity(long long n, long long row0, long long row1, long long* sizes /* nel, nf, rlo, rhi */,
                            int* e2f /* 3*nel or NULL */) {

@@ -217,3 +217,24 @@ def residual_arrays(mesh, Vxh, Vyh, Pe, ae, be, ze, sex, sey, VxDir, VyDir, Sxx,
 def residual_norms(arrs):
     r = lambda x: np.linalg.norm(np.ravel(x)) / np.sqrt(np.size(x))
     return np.array([r(arrs[k]) for k in ("F_eq1", "F_eq2", "F_eq3", "F_nodes_x", "F_nodes_y", "F_glob2")])
+
+
+def element_values(mesh, Vxh, Vyh, alpha, beta, Z):
+    """Independent NumPy restatement of ComputeElementValues (DiscretisationFCFV_Stokes.jl:52-94), vectorised over
+    elements, faces visited in order i = 1,2,3 like the reference."""
+    e2f = np.asarray(mesh.e2f, dtype=np.int64) - 1
+    nd = (np.asarray(mesh.bc)[e2f] != 1).astype(float)            # (bc != 1), nel x 3
+    tau = np.asarray(mesh.τ)[e2f]
+    ux, uy = np.asarray(Vxh)[e2f], np.asarray(Vyh)[e2f]
+    eta, Om, dl = np.asarray(mesh.ke), np.asarray(mesh.Ω), np.asarray(mesh.δ)
+    G, nx, ny = np.asarray(mesh.Γ), np.asarray(mesh.n_x), np.asarray(mesh.n_y)
+    Vx, Vy = beta[:, 0] / alpha, beta[:, 1] / alpha
+    Txx, Tyy = eta / Om * Z[:, 0, 0], eta / Om * Z[:, 1, 1]
+    Txy = eta / Om * 0.5 * (Z[:, 0, 1] + Z[:, 1, 0])
+    for i in range(3):
+        Vx = Vx + nd[:, i] * G[:, i] * tau[:, i] * ux[:, i] / alpha
+        Vy = Vy + nd[:, i] * G[:, i] * tau[:, i] * uy[:, i] / alpha
+        Txx = Txx + nd[:, i] * eta / Om * G[:, i] * nx[:, i] * ux[:, i]
+        Tyy = Tyy + nd[:, i] * eta / Om * G[:, i] * ny[:, i] * uy[:, i]
+        Txy = Txy + nd[:, i] * (eta / dl) * 0.5 * (1.0 / Om * G[:, i] * (nx[:, i] * uy[:, i] + ny[:, i] * ux[:, i]))
+    return Vx, Vy, 2.0 * Txx, 2.0 * Tyy, 2.0 * Txy

@@ -99,6 +99,11 @@ def test_local_assembly_residual(case, api, oracle, golden):
                 assert gn[k] < 1e-9
         for k in ("F_nodes_x", "F_nodes_y", "F_glob2"):
             assert rel_inf(garr[k], arr[k]) <= TOL, (tau_mode, k)
+    # ---- ComputeElementValues (bitwise: same operation order, no BLAS on either side)
+    ev = oracle.ComputeElementValues(m, d["Vxh"], d["Vyh"], d["Pe"], a, b, Z, d["VxDir"], d["VyDir"], case.form)
+    gev = api.ComputeElementValues(g, d["Vxh"], d["Vyh"], d["Pe"], ga, gb, gZ, d["VxDir"], d["VyDir"], case.form)
+    for k in range(5):
+        assert np.array_equal(gev[k], ev[k]), ("element values", k)
     # ---- Powell-Hestenes lines on the resident CSR
     u = np.concatenate([d["Vxh"], d["Vyh"]])
     ru, rp, nrm = oracle.ph_residual(m, Kuu, Kup, fu, fp, u, d["Pe"])

@@ -99,3 +99,18 @@ def test_residuals(case, tau_mode, oracle, emu):
             assert got[k] < 1e-9, (k, got[k], norms[k])
     assert rel_inf(Fx, arr["F_nodes_x"]) <= 1e-12 and rel_inf(Fy, arr["F_nodes_y"]) <= 1e-12
     assert rel_inf(Fg2, arr["F_glob2"]) <= 1e-12
+
+
+@pytest.mark.parametrize("case", [c for c in cases.all_cases(small_only=True) if c.variant == 0], ids=lambda c: c.name)
+def test_element_values_bitwise(case, oracle, emu):
+    """ComputeElementValues (Discretisation:52-94): kernel arithmetic == oracle, bit for bit."""
+    m, d = cases.build(case)
+    nel, nf = m.nel, m.nf
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, case.form)
+    ref = oracle.ComputeElementValues(m, d["Vxh"], d["Vyh"], d["Pe"], a, b, Z, d["VxDir"], d["VyDir"], case.form)
+    out = np.zeros(5 * nel)
+    args = [_i(m.e2f), _i(m.bc), _d(m.Ω), _d(m.n_x), _d(m.n_y), _d(m.Γ), _d(m.ke), _d(m.δ), _d(m.τ), _d(a), _d(b), _d(Z),
+            _d(d["Vxh"]), _d(d["Vyh"])]
+    assert emu.emu_element_values(C.c_longlong(nel), C.c_longlong(nf), *map(_p, args), _p(out)) == 0
+    for k in range(5):
+        assert np.array_equal(out[k * nel:(k + 1) * nel], ref[k]), k

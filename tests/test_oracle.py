@@ -12,6 +12,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 import cases
+from helpers import rel_inf
 import np_restatement as R
 
 
@@ -194,3 +195,31 @@ def test_known_answer_exact_flows(mesh, field, form, oracle):
     Kuu, Muu, Kup, fu, fp, _, _ = oracle.ElementAssemblyLoop(m, a, b, Z, VxDir, VyDir, z, z, z, z, form)
     ru, rp, nrm = oracle.ph_residual(m, Kuu, Kup, fu, fp, np.concatenate([VxDir, VyDir]), P)
     assert nrm[0] < 1e-11 and nrm[1] < 1e-11
+
+
+@pytest.mark.parametrize("case", [c for c in cases.all_cases(small_only=True) if c.variant == 0], ids=lambda c: c.name)
+def test_element_values_against_numpy(case, oracle):
+    """ComputeElementValues: C oracle vs the independent NumPy restatement (1e-13: products are grouped
+    alike, NumPy may differ in the last bit only through (bc!=1) handled as a float factor)."""
+    import np_restatement as NP
+    m, d = cases.build(case)
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, case.form)
+    ref = oracle.ComputeElementValues(m, d["Vxh"], d["Vyh"], d["Pe"], a, b, Z, d["VxDir"], d["VyDir"], case.form)
+    got = NP.element_values(m, d["Vxh"], d["Vyh"], a, b, Z)
+    for r, g in zip(ref, got):
+        assert rel_inf(g, r) <= 1e-13
+
+
+def test_element_values_known_answer(oracle):
+    """Uniform face velocity and zero sources/Dirichlet data on an all-interior-tagged mesh: every element
+    velocity equals the face velocity and the deviatoric stress vanishes (sum_i Gamma_i n_i = 0)."""
+    m, d = cases.build(cases.Case("S6", "solkz", 0, "SymmetricGradient", tau_r=3.0))
+    m.bc = np.zeros_like(m.bc)
+    m.τe = np.full(m.nel, 3.0)                      # uniform stabilisation: face tau == element tau
+    zf, ze = np.zeros(m.nf), np.zeros(m.nel)
+    a, b, Z = oracle.ComputeFCFV(m, ze, ze, zf, zf, zf, zf, zf, zf, 3.0, "SymmetricGradient")
+    Vx, Vy, Txx, Tyy, Txy = oracle.ComputeElementValues(m, np.full(m.nf, 2.0), np.full(m.nf, -3.0), ze, a, b, Z, zf, zf,
+                                                        "SymmetricGradient")
+    assert np.allclose(Vx, 2.0, rtol=1e-13) and np.allclose(Vy, -3.0, rtol=1e-13)
+    scale = (m.ke / m.Ω * m.Γ.max(axis=1)).max() * 3.0
+    assert max(np.abs(Txx).max(), np.abs(Tyy).max(), np.abs(Txy).max()) <= 1e-13 * scale

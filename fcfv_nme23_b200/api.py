@@ -413,6 +413,18 @@ def ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey, VxD
     return norms
 
 
+def SchurComplement(mesh, penalty):
+    """Kuusc = Kuu .- Kup*(Kppi*Kpu), Kppi = spdiagm(penalty.*ke./Ω), Kpu = -Kup' (src/SolversFCFV_Stokes.jl:6,23-25),
+    produced by the assembly kernels themselves (one extra term per adjacent element) instead of a host sparse
+    product.  Call after ElementAssemblyLoop[NEW] on the same mesh; returns a scipy CSC matrix with the fields of the
+    SparseMatrixCSC Julia would build."""
+    h = handle_for(mesh)
+    _refresh(mesh, h)
+    nnz = C.c_int64(0)
+    h.check(h.lib.fcfv_schur(h._h, float(penalty), C.byref(nnz)))
+    return h.export_scipy_csc(_L.KUUSC)
+
+
 def ComputeElementValues(mesh, Vxh, Vyh, Pe, α, β, Ζ, VxDir, VyDir, Formulation):
     """src/DiscretisationFCFV_Stokes.jl:52-94 -> (Vxe, Vye, τxxe, τyye, τxye).  ``Pe``, ``VxDir``, ``VyDir`` and
     ``Formulation`` are accepted for signature parity; the reference does not read them."""

@@ -72,10 +72,12 @@ struct fcfv_handle {
     // local coefficients
     DBuf alpha, beta, Z;
     // per-element assembly coefficients (k_elem_coef): ia, c11 and, when some delta != 1, c12 c21 c22
-    DBuf coef, coefx;
+    DBuf coef, coefx, coefs;
     bool delta_dirty = true, aniso = false;
     // assembly
-    Csr Kuu, Kup, Muu;
+    Csr Kuu, Kup, Muu, Kuusc;
+    int last_variant = -1, last_form = -1;   // parameters of the last assembly (fcfv_schur reuses them)
+    double last_A = 1.0;
     DBuf fu, fp, sums, bases, chunks, totals;
     long long totals_host[9] = {0};
     bool totals_valid = false;
@@ -312,8 +314,8 @@ int fcfv_destroy(fcfv_t* h) {
                    &h->elem_owned, &h->face_owned, &h->tau_ref, &h->sex, &h->sey, &h->VxDir, &h->VyDir, &h->sxx,
                    &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
                    &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,
-                   &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->chunks, &h->totals,
-                   &h->Fg, &h->partial, &h->sumsq, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx};
+                   &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->Kuusc.rowptr, &h->Kuusc.col, &h->Kuusc.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->chunks, &h->totals,
+                   &h->Fg, &h->partial, &h->sumsq, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx, &h->coefs};
     for (DBuf* b : all) release(h, *b);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     cudaEventDestroy(h->ev0);
@@ -376,7 +378,7 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
     h->have_mesh = false; h->have_local = false;
     h->delta_dirty = true;
-    h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = -1;
+    h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = h->Kuusc.nnz = -1;
     h->nel = nel; h->nf = nf; h->nel_global = nel; h->nf_global = nf;
     h->have_elem_owned = h->have_face_owned = h->have_tau_ref = false;
     // connectivity: int64 1-based -> int32 0-based on the device
@@ -596,19 +598,20 @@ int fcfv_compute_local(fcfv_t* h, int formulation, double A, const double* sex, 
 // -------------------------------------------------------------------------------------------------
 namespace {
 
-CoefView coef_view(fcfv_t* h) {
+CoefView coef_view(fcfv_t* h, bool schur) {
     double* c = P<double>(h->coef);
     double* x = P<double>(h->coefx);
     const size_t nel = (size_t)h->nel;
-    return CoefView{c, c + nel, h->aniso ? x : nullptr, h->aniso ? x + nel : nullptr, h->aniso ? x + 2 * nel : nullptr};
+    return CoefView{c, c + nel, h->aniso ? x : nullptr, h->aniso ? x + nel : nullptr, h->aniso ? x + 2 * nel : nullptr,
+                    schur ? P<double>(h->coefs) : nullptr};
 }
 
-template <int VARIANT, int FORM, bool WANT_M, bool ANISO>
-int launch_assemble(fcfv_t* h, double A) {
+template <int VARIANT, int FORM, int EXTRA, bool ANISO>
+int launch_assemble(fcfv_t* h, double A, double gamma) {
     const MeshView M = mesh_view(h);
     const LocalView L = local_view(h);
     const FaceDataView D = face_view(h);
-    const CoefView Cf = coef_view(h);
+    const CoefView Cf = coef_view(h, EXTRA == kExtraSchur);
     const int nblk = nblocks(h->nf, kAsmFaces);
     const int nchunks = nblocks(nblk, kScanChunk);
     int* sums = P<int>(h->sums);
@@ -616,32 +619,39 @@ int launch_assemble(fcfv_t* h, double A) {
     long long* chunk_tot = P<long long>(h->chunks);
     long long* chunk_base = chunk_tot + (size_t)kNumSums * nchunks;
     TLAUNCH(h, T_OTHER, k_asm_fp, nblocks((h->nf + 3) / 4, 256), 256, M, D, P<double>(h->fp));   // fp was zeroed by the caller
-    TLAUNCH(h, T_COEF, k_elem_coef<VARIANT>, nblocks(h->nel, 256), 256, M.nel, L.alpha, M.ke, M.dl, M.Om, (double*)Cf.ia, (double*)Cf.c11,
-            (double*)Cf.c12, (double*)Cf.c21, (double*)Cf.c22);
-    TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, WANT_M, ANISO>), nblk, kAsmBlock, M, L, Cf, D, A, sums, nblk);
+    TLAUNCH(h, T_COEF, k_elem_coef<VARIANT>, nblocks(h->nel, 256), 256, M.nel, L.alpha, M.ke, M.dl, M.Om, gamma, (double*)Cf.ia,
+            (double*)Cf.c11, (double*)Cf.c12, (double*)Cf.c21, (double*)Cf.c22, (double*)Cf.cs);
+    TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, EXTRA, ANISO>), nblk, kAsmBlock, M, L, Cf, D, A, sums, nblk);
     TLAUNCH(h, T_SCAN, k_scan_local, dim3(nchunks, kNumSums), 1024, sums, local, nblk, nchunks, chunk_tot);
+    Csr& X = EXTRA == kExtraSchur ? h->Kuusc : h->Muu;   // third block
     CsrOut ouu{h->Kuu.rowptr.p, P<int>(h->Kuu.col), P<double>(h->Kuu.val)};
     CsrOut oup{h->Kup.rowptr.p, P<int>(h->Kup.col), P<double>(h->Kup.val)};
-    CsrOut omu{h->Muu.rowptr.p, P<int>(h->Muu.col), P<double>(h->Muu.val)};
+    CsrOut oex{X.rowptr.p, P<int>(X.col), P<double>(X.val)};
     if (h->rp64) {
         TLAUNCH(h, T_SCAN, k_scan_chunks<long long>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals),
-                (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)omu.rowptr, M.nf, (int)WANT_M);
-        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, ANISO, long long>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk,
-                nchunks, ouu, oup, omu, P<double>(h->fu));
+                (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)oex.rowptr, M.nf, (int)(EXTRA != kExtraNone));
+        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, EXTRA, ANISO, long long>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk,
+                nchunks, ouu, oup, oex, P<double>(h->fu));
     } else {
         TLAUNCH(h, T_SCAN, k_scan_chunks<int>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals), (int*)ouu.rowptr,
-                (int*)oup.rowptr, (int*)omu.rowptr, M.nf, (int)WANT_M);
-        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, WANT_M, ANISO, int>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk, nchunks,
-                ouu, oup, omu, P<double>(h->fu));
+                (int*)oup.rowptr, (int*)oex.rowptr, M.nf, (int)(EXTRA != kExtraNone));
+        TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, EXTRA, ANISO, int>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk, nchunks,
+                ouu, oup, oex, P<double>(h->fu));
     }
     return FCFV_OK;
 }
 
 template <int VARIANT, int FORM>
-int launch_assemble_m(fcfv_t* h, double A, int want_muu) {
-    if (VARIANT == kLoopNew && h->aniso)
-        return want_muu ? launch_assemble<VARIANT, FORM, true, true>(h, A) : launch_assemble<VARIANT, FORM, false, true>(h, A);
-    return want_muu ? launch_assemble<VARIANT, FORM, true, false>(h, A) : launch_assemble<VARIANT, FORM, false, false>(h, A);
+int launch_assemble_x(fcfv_t* h, double A, int extra, double gamma) {
+    const bool an = VARIANT == kLoopNew && h->aniso;
+    switch (extra) {
+        case kExtraMuu:
+            return an ? launch_assemble<VARIANT, FORM, kExtraMuu, true>(h, A, gamma) : launch_assemble<VARIANT, FORM, kExtraMuu, false>(h, A, gamma);
+        case kExtraSchur:
+            return an ? launch_assemble<VARIANT, FORM, kExtraSchur, true>(h, A, gamma) : launch_assemble<VARIANT, FORM, kExtraSchur, false>(h, A, gamma);
+        default:
+            return an ? launch_assemble<VARIANT, FORM, kExtraNone, true>(h, A, gamma) : launch_assemble<VARIANT, FORM, kExtraNone, false>(h, A, gamma);
+    }
 }
 
 int fetch_totals(fcfv_t* h) {
@@ -650,15 +660,14 @@ int fetch_totals(fcfv_t* h) {
     TRY(sync(h));
     h->Kuu.nnz = h->totals_host[6];
     h->Kup.nnz = h->totals_host[7];
-    if (h->Muu.nnz != -1) h->Muu.nnz = h->totals_host[8];
+    if (h->Muu.nnz == -2) h->Muu.nnz = h->totals_host[8];
+    if (h->Kuusc.nnz == -2) h->Kuusc.nnz = h->totals_host[8];
     h->totals_valid = true;
     return FCFV_OK;
 }
 
-}  // namespace
-
-int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int want_muu) {
-    if (!h) return FCFV_ERR_INVALID;
+// extra: kExtraNone / kExtraMuu / kExtraSchur (gamma = Powell-Hestenes penalty, only read for the latter)
+int run_assemble_impl(fcfv_t* h, int variant, int formulation, double A, int extra, double gamma) {
     TRY(check_form(h, formulation));
     if (variant != FCFV_LOOP_OLD && variant != FCFV_LOOP_NEW)
         return fail(h, FCFV_ERR_INVALID, "variant must be FCFV_LOOP_OLD or FCFV_LOOP_NEW (got %d)", variant);
@@ -677,10 +686,16 @@ int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int wan
     TRY(ensure(h, h->Kup.rowptr, rpw * (2 * nf + 1)));
     TRY(ensure(h, h->Kup.col, sizeof(int) * 4 * nf));
     TRY(ensure(h, h->Kup.val, sizeof(double) * 4 * nf));
-    if (want_muu) {
+    if (extra == kExtraMuu) {
         TRY(ensure(h, h->Muu.rowptr, rpw * (2 * nf + 1)));
         TRY(ensure(h, h->Muu.col, sizeof(int) * 10 * nf));
         TRY(ensure(h, h->Muu.val, sizeof(double) * 10 * nf));
+    }
+    if (extra == kExtraSchur) {
+        TRY(ensure(h, h->Kuusc.rowptr, rpw * (2 * nf + 1)));
+        TRY(ensure(h, h->Kuusc.col, sizeof(int) * 20 * nf));
+        TRY(ensure(h, h->Kuusc.val, sizeof(double) * 20 * nf));
+        TRY(ensure(h, h->coefs, sizeof(double) * nel));
     }
     TRY(ensure(h, h->fu, sizeof(double) * 2 * nf));
     TRY(ensure(h, h->fp, sizeof(double) * nel));
@@ -701,23 +716,51 @@ int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int wan
     h->Kuu.nrows = 2 * nf; h->Kuu.ncols = 2 * nf;
     h->Kup.nrows = 2 * nf; h->Kup.ncols = nel;
     h->Muu.nrows = 2 * nf; h->Muu.ncols = 2 * nf;
+    h->Kuusc.nrows = 2 * nf; h->Kuusc.ncols = 2 * nf;
     h->Kuu.nnz = h->Kup.nnz = -2;            // assembled, count not fetched yet
-    h->Muu.nnz = want_muu ? -2 : -1;
+    if (extra != kExtraSchur) h->Muu.nnz = extra == kExtraMuu ? -2 : -1;   // fcfv_schur leaves an assembled Muu in place
+    h->Kuusc.nnz = extra == kExtraSchur ? -2 : -1;
     h->totals_valid = false;
-    // elements that are not owned / have no local face 0 thread keep fp = 0
+    h->last_variant = variant; h->last_form = formulation; h->last_A = A;
+    // only elements with a Dirichlet face get a value from k_asm_fp, everything else keeps +0.0
     CU(cudaMemsetAsync(h->fp.p, 0, sizeof(double) * nel, h->stream));
     CU(cudaEventRecord(h->ev0, h->stream));
     int rc;
     if (variant == FCFV_LOOP_OLD)
-        rc = formulation == FCFV_GRADIENT ? launch_assemble_m<kLoopOld, kGradient>(h, A, want_muu)
-                                          : launch_assemble_m<kLoopOld, kSymmetricGradient>(h, A, want_muu);
+        rc = formulation == FCFV_GRADIENT ? launch_assemble_x<kLoopOld, kGradient>(h, A, extra, gamma)
+                                          : launch_assemble_x<kLoopOld, kSymmetricGradient>(h, A, extra, gamma);
     else
-        rc = formulation == FCFV_GRADIENT ? launch_assemble_m<kLoopNew, kGradient>(h, A, want_muu)
-                                          : launch_assemble_m<kLoopNew, kSymmetricGradient>(h, A, want_muu);
+        rc = formulation == FCFV_GRADIENT ? launch_assemble_x<kLoopNew, kGradient>(h, A, extra, gamma)
+                                          : launch_assemble_x<kLoopNew, kSymmetricGradient>(h, A, extra, gamma);
     TRY(rc);
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaGetLastError());
     return finish(h);
+}
+
+}  // namespace
+
+int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int want_muu) {
+    if (!h) return FCFV_ERR_INVALID;
+    return run_assemble_impl(h, variant, formulation, A, want_muu ? kExtraMuu : kExtraNone, 0.0);
+}
+
+int fcfv_run_assemble_schur(fcfv_t* h, int variant, int formulation, double A, double gamma) {
+    if (!h) return FCFV_ERR_INVALID;
+    return run_assemble_impl(h, variant, formulation, A, kExtraSchur, gamma);
+}
+
+int fcfv_schur(fcfv_t* h, double gamma, int64_t* nnz_sc) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->last_variant >= 0 && h->Kuu.nnz != -1, "fcfv_schur: call fcfv_assemble first"));
+    const bool was_async = h->async;
+    h->async = true;
+    const int rc = run_assemble_impl(h, h->last_variant, h->last_form, h->last_A, kExtraSchur, gamma);
+    h->async = was_async;
+    TRY(rc);
+    TRY(fetch_totals(h));
+    if (nnz_sc) *nnz_sc = h->Kuusc.nnz;
+    return FCFV_OK;
 }
 
 int fcfv_get_nnz(fcfv_t* h, int64_t* nnz_uu, int64_t* nnz_up, int64_t* nnz_muu) {
@@ -761,6 +804,7 @@ Csr* block_of(fcfv_t* h, int block) {
         case FCFV_KUU: return &h->Kuu;
         case FCFV_KUP: return &h->Kup;
         case FCFV_MUU: return &h->Muu;
+        case FCFV_KUUSC: return &h->Kuusc;
         default: return nullptr;
     }
 }
@@ -1145,7 +1189,7 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     if (S.nel >= (1LL << 29) || S.nf >= (1LL << 30)) return fail(h, FCFV_ERR_INVALID, "fcfv_generate_structured: strip too large");
     h->have_mesh = false; h->have_local = false;
     h->delta_dirty = true;
-    h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = -1;
+    h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = h->Kuusc.nnz = -1;
     const long long nel = S.nel, nf = S.nf;
     h->nel = nel; h->nf = nf;
     h->nel_global = 4 * n * n; h->nf_global = 6 * n * n + 2 * n;

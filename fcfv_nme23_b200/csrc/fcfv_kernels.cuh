@@ -40,7 +40,8 @@ struct MeshView {
 struct LocalView { const double *alpha, *beta, *Z; };
 // per-element assembly coefficients (k_elem_coef): 1/alpha, c11 (old: eta/Omega, NEW: D11) and, only
 // when some delta != 1 (c12 != nullptr), the other three entries of D
-struct CoefView { const double *ia, *c11, *c12, *c21, *c22; };
+// cs = (gamma*ke)/Omega of the Schur complement (nullptr unless that block is assembled)
+struct CoefView { const double *ia, *c11, *c12, *c21, *c22, *cs; };
 struct FaceDataView { const double *VxDir, *VyDir, *sxx, *syy, *sxy, *syx; };
 struct SolutionView { const double *Vxh, *Vyh, *Pe; };
 
@@ -48,7 +49,7 @@ struct SolutionView { const double *Vxh, *Vyh, *Pe; };
 struct FaceElem {
     int g[3], bc[3];
     double tau[3], G[3], nx[3], ny[3];
-    double ia, c11, c12, c21, c22;
+    double ia, c11, c12, c21, c22, cs;
     double b1, b2, Z11, Z21, Z12, Z22;
 };
 
@@ -98,7 +99,7 @@ FCFV_HD void face_conn_of(const int* e2f, const int8_t* bc, int nel, int f, int2
 // index is then a compile-time constant (no local memory).  The values do not depend on the order
 // in which the pairs (i, j) are visited.  Face ids and bc tags come from the face's connectivity
 // record (slot 0: candidates 0,1,2; slot 1: 0,3,4), so that nothing here waits for e2f.
-template <int VARIANT, bool ANISO>
+template <int VARIANT, bool ANISO, int EXTRA>
 FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceConn& C, bool second, int e, int i,
                             FaceElem& E) {
     const int nel = M.nel;
@@ -115,6 +116,7 @@ FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, const CoefVie
     }
     E.ia = Cf.ia[e];
     E.c11 = Cf.c11[e];
+    E.cs = EXTRA == kExtraSchur ? Cf.cs[e] : 0.0;
     if (VARIANT == kLoopNew && ANISO) { E.c12 = Cf.c12[e]; E.c21 = Cf.c21[e]; E.c22 = Cf.c22[e]; }
     else { E.c12 = E.c11; E.c21 = E.c11; E.c22 = E.c11; }   // delta == 1 everywhere: D12 = D21 = D22 = D11 (old loop: unused)
     E.b1 = L.beta[e]; E.b2 = L.beta[nel + e];
@@ -129,7 +131,7 @@ FCFV_HD void lane_view(const FaceElem& F, int comp, LaneElem& E) {
         E.nr[j] = comp == 0 ? F.nx[j] : F.ny[j];
         E.no[j] = comp == 0 ? F.ny[j] : F.nx[j];
     }
-    E.ia = F.ia; E.c = F.c11;
+    E.ia = F.ia; E.c = F.c11; E.cs = F.cs;
     E.Drr = comp == 0 ? F.c11 : F.c22;
     E.Dro = comp == 0 ? F.c12 : F.c21;
     E.br = comp == 0 ? F.b1 : F.b2;
@@ -140,14 +142,14 @@ FCFV_HD void lane_view(const FaceElem& F, int comp, LaneElem& E) {
 }
 
 // Contributions of one adjacent element (already loaded, row face first, F) to rows (f,x), (f,y).
-template <int VARIANT, int FORM, bool WANT_M>
+template <int VARIANT, int FORM, int EXTRA>
 FCFV_HD void slot_lanes(const FaceElem& F, int e, double A, double vx, double vy, double sxx, double sxy,
                         double syx, double syy, LaneRow& Lx, LaneRow& Ly) {
     LaneElem E;
     lane_view(F, 0, E);
-    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 0, A, vx, sxx, sxy, Lx);   // row face at index 0
+    lane_row<VARIANT, FORM, EXTRA>(E, e, 0, 0, A, vx, sxx, sxy, Lx);   // row face at index 0
     lane_view(F, 1, E);
-    lane_row<VARIANT, FORM, WANT_M>(E, e, 0, 1, A, vy, syx, syy, Ly);
+    lane_row<VARIANT, FORM, EXTRA>(E, e, 0, 1, A, vy, syx, syy, Ly);
 }
 
 // fp[e] (Discretisation:194) is non-zero only for elements with a Dirichlet face; everything else
@@ -176,7 +178,7 @@ FCFV_HD bool face_fp(const MeshView& M, const FaceDataView& D, int e, int i, dou
 // pass and the host emulation.  pr = f2e[f], C = connectivity record of f; load(second, e, i, F)
 // provides the record of element e with row face i in front (second: take face ids / tags of the
 // higher element); the values leave through `sink` (see RowVals).
-template <int VARIANT, int FORM, bool WANT_M, typename Loader, typename Sink>
+template <int VARIANT, int FORM, int EXTRA, typename Loader, typename Sink>
 FCFV_HD void asm_face(const FaceDataView& D, double A, int f, int2 pr, const FaceConn& C, bool owned, Loader&& load,
                       const Sink& sink, FaceRows& R) {
     const int bcf = C.bc[0];
@@ -191,8 +193,8 @@ FCFV_HD void asm_face(const FaceDataView& D, double A, int f, int2 pr, const Fac
             const int e = pr.x >> 2, i = pr.x & 3;
             FaceElem F;
             load(false, e, i, F);
-            slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
-            rows_put0<WANT_M>(R, true, Lx, Ly, sink);
+            slot_lanes<VARIANT, FORM, EXTRA>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
+            rows_put0<EXTRA>(R, true, Lx, Ly, sink);
         }
         {
             // No branch around the second element: a missing one re-reads the first and is discarded,
@@ -201,10 +203,10 @@ FCFV_HD void asm_face(const FaceDataView& D, double A, int f, int2 pr, const Fac
             const int e = code >> 2, i = code & 3;
             FaceElem F;
             load(has1, e, i, F);
-            slot_lanes<VARIANT, FORM, WANT_M>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
-            rows_put1<WANT_M>(R, has1, true, Lx, Ly, sink);
+            slot_lanes<VARIANT, FORM, EXTRA>(F, e, A, vx, vy, sxx, sxy, syx, syy, Lx, Ly);
+            rows_put1<EXTRA>(R, has1, true, Lx, Ly, sink);
         }
-        rows_finish<WANT_M>(R, true, sink);
+        rows_finish<EXTRA>(R, true, sink);
     } else {
         rows_clear(R);   // faces without elements, faces owned by another rank
     }
@@ -422,14 +424,15 @@ __global__ void k_delta_flag(const double* __restrict__ dl, int nel, int* __rest
 template <int VARIANT>
 __global__ void __launch_bounds__(256)
 k_elem_coef(int nel, const double* __restrict__ alpha, const double* __restrict__ ke, const double* __restrict__ dl,
-            const double* __restrict__ Om, double* __restrict__ ia, double* __restrict__ c11, double* __restrict__ c12,
-            double* __restrict__ c21, double* __restrict__ c22) {
+            const double* __restrict__ Om, double gamma, double* __restrict__ ia, double* __restrict__ c11, double* __restrict__ c12,
+            double* __restrict__ c21, double* __restrict__ c22, double* __restrict__ cs) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nel) return;
     double a, d11, d12, d21, d22;
     element_coef<VARIANT>(alpha[e], ke[e], (VARIANT == kLoopNew && c12 != nullptr) ? dl[e] : 1.0, Om[e], a, d11, d12, d21, d22);
     ia[e] = a; c11[e] = d11;
     if (VARIANT == kLoopNew && c12 != nullptr) { c12[e] = d12; c21[e] = d21; c22[e] = d22; }
+    if (cs != nullptr) cs[e] = (gamma * ke[e]) / Om[e];   // penalty.*mesh.ke./mesh.Ω (SolversFCFV_Stokes.jl:23)
 }
 
 // ---- a5/a6/a7 assembly --------------------------------------------------------------------------
@@ -463,7 +466,7 @@ __device__ __forceinline__ void prefetch_elem(const MeshView& M, const LocalView
 }
 
 // rows of the block's face of this thread
-template <int VARIANT, int FORM, bool WANT_M, bool ANISO, typename Sink>
+template <int VARIANT, int FORM, int EXTRA, bool ANISO, typename Sink>
 __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceDataView& D, double A,
                                                const Sink& sink, int& f, bool& inrange, FaceRows& R) {
     f = blockIdx.x * kAsmFaces + threadIdx.x;
@@ -472,8 +475,8 @@ __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalVie
     FaceConn C;
     unpack_conn(f, inrange ? M.fconn[f] : make_int4(-1, -1, -1, -1), inrange ? M.fbc[f] : 0x11111, C);
     const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
-    auto load = [&](bool second, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO>(M, L, Cf, C, second, e, i, F); };
-    asm_face<VARIANT, FORM, WANT_M>(D, A, f, pr, C, owned, load, sink, R);
+    auto load = [&](bool second, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO, EXTRA>(M, L, Cf, C, second, e, i, F); };
+    asm_face<VARIANT, FORM, EXTRA>(D, A, f, pr, C, owned, load, sink, R);
 }
 
 // fp: one thread per 4 faces (one 16-byte load of the packed tags), only Dirichlet faces do anything
@@ -505,17 +508,17 @@ k_asm_fp(MeshView M, FaceDataView D, double* __restrict__ fp) {
 }
 
 // row lengths of a face packed in one 64-bit word: Kuu x, Kuu y (11 bits: <= 1280 per block),
-// Kup x, Kup y (9 bits: <= 256), Muu x, Muu y (10 bits: <= 640)
-__device__ __forceinline__ int cshift(int q) { return q == 0 ? 0 : q == 1 ? 11 : q == 2 ? 22 : q == 3 ? 31 : q == 4 ? 40 : 50; }
+// Kup x, Kup y (9 bits: <= 256), third block x, y (11 bits)
+__device__ __forceinline__ int cshift(int q) { return q == 0 ? 0 : q == 1 ? 11 : q == 2 ? 22 : q == 3 ? 31 : q == 4 ? 40 : 51; }
 __device__ __forceinline__ int cfield(unsigned long long c, int q) {
-    const unsigned wd = q < 2 ? 11u : q < 4 ? 9u : 10u;
+    const unsigned wd = (q == 2 || q == 3) ? 9u : 11u;
     return (int)((c >> cshift(q)) & ((1u << wd) - 1u));
 }
-template <bool WANT_M>
+template <int EXTRA>
 __device__ __forceinline__ unsigned long long rows_counts(const FaceRows& R) {
     unsigned long long c = (unsigned long long)rows_nuu_x(R) | ((unsigned long long)rows_nuu_y(R) << cshift(1)) |
                            ((unsigned long long)rows_nup_x(R) << cshift(2)) | ((unsigned long long)rows_nup_y(R) << cshift(3));
-    if (WANT_M) c |= ((unsigned long long)rows_nmu_x(R) << cshift(4)) | ((unsigned long long)rows_nmu_y(R) << cshift(5));
+    if (EXTRA != kExtraNone) c |= ((unsigned long long)rows_nex_x<EXTRA>(R) << cshift(4)) | ((unsigned long long)rows_nex_y<EXTRA>(R) << cshift(5));
     return c;
 }
 
@@ -545,15 +548,15 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
 }
 
 // count pass: sums[q*nblk + b] = number of stored entries block b will write for quantity q
-template <int VARIANT, int FORM, bool WANT_M, bool ANISO>
+template <int VARIANT, int FORM, int EXTRA, bool ANISO>
 __global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_COUNT_MINBLOCKS)
 k_asm_count(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, int* __restrict__ sums, int nblk) {
     __shared__ unsigned long long sw64[kAsmBlock / 32];
     FaceRows R;
     int f; bool inrange;
-    tile_face_rows<VARIANT, FORM, WANT_M, ANISO>(M, L, Cf, D, A, NullSink(), f, inrange, R);
+    tile_face_rows<VARIANT, FORM, EXTRA, ANISO>(M, L, Cf, D, A, NullSink(), f, inrange, R);
     unsigned long long tot;
-    block_excl_scan64<kAsmBlock>(rows_counts<WANT_M>(R), tot, sw64);
+    block_excl_scan64<kAsmBlock>(rows_counts<EXTRA>(R), tot, sw64);
     if (threadIdx.x == 0) {
         const int b = blockIdx.x;
 #pragma unroll
@@ -664,7 +667,7 @@ __device__ __forceinline__ void flush_segment_edges(const double* sval, const in
 constexpr int kHalfP = 2 * kAsmFaces + 8;              // Kup staging capacity per component
 constexpr int kStageBytesP = 2 * kHalfP * (8 + 4);
 
-template <int VARIANT, int FORM, bool WANT_M, bool ANISO, typename RP>
+template <int VARIANT, int FORM, int EXTRA, bool ANISO, typename RP>
 __global__ void __launch_bounds__(kAsmBlock, FCFV_ASM_FILL_MINBLOCKS)
 k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const int* __restrict__ local, const long long* __restrict__ chunk_base,
            int nblk, int nchunks, CsrOut Kuu, CsrOut Kup, CsrOut Muu, double* __restrict__ fu) {
@@ -677,17 +680,18 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
     const int nf = M.nf;
     // global offsets of this tile's segments: fetched by a few threads while the rows are computed,
     // published by the barriers of the block scan
-    if (tid < (WANT_M ? 6 : 4)) sbase[tid] = chunk_base[(size_t)tid * nchunks + b / kScanChunk] + local[(size_t)tid * nblk + b];
+    if (tid < ((EXTRA != kExtraNone) ? 6 : 4)) sbase[tid] = chunk_base[(size_t)tid * nchunks + b / kScanChunk] + local[(size_t)tid * nblk + b];
     FaceRows R;
     RowVals V;
     int f; bool inrange;
-    tile_face_rows<VARIANT, FORM, WANT_M, ANISO>(M, L, Cf, D, A, RowValsSink{&V}, f, inrange, R);
+    constexpr bool WANT_M = EXTRA != kExtraNone;   // a third block (Muu or the Schur complement) is assembled
+    tile_face_rows<VARIANT, FORM, EXTRA, ANISO>(M, L, Cf, D, A, RowValsSink{&V}, f, inrange, R);
     if (inrange) {
         fu[f] = R.fux;
         fu[(size_t)nf + f] = R.fuy;
     }
     unsigned long long tot;
-    const unsigned long long off = block_excl_scan64<kAsmBlock>(rows_counts<WANT_M>(R), tot, sw64);
+    const unsigned long long off = block_excl_scan64<kAsmBlock>(rows_counts<EXTRA>(R), tot, sw64);
     const long long bux = sbase[0], buy = sbase[1], bpx = sbase[2], bpy = sbase[3];
     const long long bmx = WANT_M ? sbase[4] : 0, bmy = WANT_M ? sbase[5] : 0;
     if (inrange) {
@@ -742,14 +746,14 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
         else flush_segment_edges(pval + kHalfP, pcol + kHalfP, cfield(tot, 3), bpy, Kup, t);
     }
     if (WANT_M) {
-        // ---- Muu (block diagonal: row (f,comp) only holds columns (g,comp)) reuses the Kuu buffer
+        // ---- third block (Muu or the Schur complement) reuses the Kuu buffer
         if (tid == 0) tma_store_wait_read();
         __syncthreads();
         double* vx = sval + cfield(off, 4) + (int)(bmx & 1);
         double* vy = sval + kHalf + cfield(off, 5) + (int)(bmy & 1);
         int* cx = scol + cfield(off, 4) + (int)(bmx & 3);
         int* cy = scol + kHalf + cfield(off, 5) + (int)(bmy & 3);
-        rows_emit_mu(R, V, nf, [&](int comp, int pos, int col, double v) {
+        rows_emit_ex<EXTRA>(R, V, nf, [&](int comp, int pos, int col, double v) {
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });

@@ -26,6 +26,10 @@ constexpr int kSymmetricGradient = 1;
 constexpr int kLoopOld = 0;
 constexpr int kLoopNew = 1;
 constexpr int kDeadKey = 0x7fffffff;
+// optional third block of an assembly: none, Muu, or the Schur complement Kuu - Kup*(Kppi*Kpu)
+constexpr int kExtraNone = 0;
+constexpr int kExtraMuu = 1;
+constexpr int kExtraSchur = 2;
 
 // Julia: *(b::Bool, x::Float64) = ifelse(b, x, copysign(0.0, x))
 FCFV_HD double bmul(bool b, double x) { return b ? x : copysign(0.0, x); }
@@ -187,6 +191,7 @@ struct LaneElem {
     int g[3], bc[3];
     double tau[3], G[3], nr[3], no[3];
     double ia;             // 1/alpha
+    double cs;             // (gamma*ke)/Omega of the Powell-Hestenes Schur complement (kExtraSchur only)
     double c;              // old loop: eta * (1/Omega)
     double Drr, Dro;       // D[r,r], D[r,o] (NEW loop)
     double br;             // beta[e, comp]
@@ -198,6 +203,7 @@ struct LaneRow {
     int key[3];            // column face ids, kDeadKey when dropped / merged into the partner
     double vs[3], vc[3];   // same / cross component values
     double ms[3];          // Muu values (same component block only)
+    double ts[3], tc[3];   // terms of Kup*(Kppi*Kpu) in the same / cross component block (kExtraSchur)
     double fu, kp;         // RHS share, Kup value
     int e, i;              // element, local index of the row face in it
     bool active;
@@ -236,10 +242,13 @@ FCFV_HD void pair_values(const LaneElem& E, int p, int q, int comp, double A, do
 // Row (f, comp) contributions of one element.  i = local index of f in the element.
 // vDir = Dirichlet value of component comp on f; Sr1, Sr2 = Neumann stress row of component comp
 // (comp x: sxx, sxy; comp y: syx, syy) -- only read by the caller when the face is Neumann.
-template <int VARIANT, int FORM, bool WANT_M>
+template <int VARIANT, int FORM, int EXTRA>
 FCFV_HD void lane_row(const LaneElem& E, int e, int i, int comp, double A, double vDir, double Sr1, double Sr2,
                       LaneRow& R) {
+    constexpr bool WANT_M = EXTRA == kExtraMuu;
     R.e = e; R.i = i; R.active = true;
+    // Kup[(f,comp), e] (:180-185)
+    const double kp_row = 0.0 - bmul(pick3(i, E.bc) != 1, pick3(i, E.G)) * pick3(i, E.nr);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         double same, cross, msame, t0, t1;
@@ -254,6 +263,16 @@ FCFV_HD void lane_row(const LaneElem& E, int e, int i, int comp, double A, doubl
         }
         R.key[j] = E.g[j];
         R.vs[j] = same; R.vc[j] = cross; R.ms[j] = WANT_M ? msame : 0.0;
+        if (EXTRA == kExtraSchur) {
+            // (Kup*(Kppi*Kpu))[(f,comp),(g_j,b)] = Kup[(f,comp),e] * (coef_e * Kpu[e,(g_j,b)]), Kpu = -Kup'
+            // (SolversFCFV_Stokes.jl:6,23-25); one term per element
+            const double Gj = bmul(E.bc[j] != 1, E.G[j]);
+            const double kps = 0.0 - Gj * E.nr[j], kpc = 0.0 - Gj * E.no[j];
+            R.ts[j] = kp_row * (E.cs * (-kps));
+            R.tc[j] = kp_row * (E.cs * (-kpc));
+        } else {
+            R.ts[j] = R.tc[j] = 0.0;
+        }
     }
     // RHS :167-178 / :310-323
     const int bci = pick3(i, E.bc);
@@ -276,13 +295,13 @@ FCFV_HD void lane_row(const LaneElem& E, int e, int i, int comp, double A, doubl
         fe = mGi * (((((-E.ia) * ti) * E.br) + ((E.Drr * nix) * E.Z1r + (E.Drr * niy) * E.Z2r)) - tir * Xi);
     }
     R.fu = 0.0 + (bmul(bci != 1, fe) + bmul(bci == 1, vDir) * 1.0);   // :191-192
-    R.kp = 0.0 - bmul(bci != 1, Gi) * nir;                             // :180-185
+    R.kp = kp_row;
 }
 
 FCFV_HD void lane_row_inactive(LaneRow& R) {
     R.e = -1; R.i = 0; R.active = false;
 #pragma unroll
-    for (int j = 0; j < 3; j++) { R.key[j] = kDeadKey; R.vs[j] = R.vc[j] = R.ms[j] = 0.0; }
+    for (int j = 0; j < 3; j++) { R.key[j] = kDeadKey; R.vs[j] = R.vc[j] = R.ms[j] = R.ts[j] = R.tc[j] = 0.0; }
     R.fu = 0.0; R.kp = 0.0;
 }
 
@@ -299,32 +318,37 @@ struct FaceRows {          // what stays in registers of the rows of one face
     int key[5];
     int lt[5];
     double x0s, x0c, y0s, y0c, m0x, m0y;   // candidate 0 (the row face's own column) while the two elements are summed
+    double t0xs, t0xc, t0ys, t0yc;           // same for the terms of Kup*(Kppi*Kpu) (kExtraSchur)
     double fux, fuy;
     int kpe[2];                                // Kup columns: lower / higher element
-    int m_xs, m_xc, m_ys, m_yc, m_mx, m_my;   // rank-space masks of stored entries
+    int m_xs, m_xc, m_ys, m_yc;               // rank-space masks of stored Kuu entries
+    int m_ex[4];                              // third block: Muu {x, y, -, -} or Schur {xs, xc, ys, yc}
     int m_kp;                                  // bit 0 kpx[0], 1 kpx[1], 2 kpy[0], 3 kpy[1]
 };
 
-// The values of the rows, indexed by candidate: xs/xc = row (f,x) in the x-column block ("same") /
-// y-column block ("cross"), ys/yc = row (f,y) in the y-column / x-column block, mx/my = Muu rows,
-// kpx/kpy = Kup entries of the lower / higher element.  They leave asm_face through a sink as soon
-// as they are final: the count pass drops them, the fill pass parks them in shared memory (so that
-// they do not occupy registers while the second element is processed), the host emulation keeps
-// them in a RowVals.
+// The values of one candidate column: xs/xc = row (f,x) in the x-column block ("same") / y-column
+// block ("cross"), ys/yc = row (f,y) in the y-column / x-column block; ex = third block (Muu: x, y
+// rows; Schur complement: xs, xc, ys, yc).
+struct CandVals { double xs, xc, ys, yc, ex[4]; };
+
+// They leave asm_face through a sink as soon as they are final: the count pass drops them, the fill
+// pass and the host emulation keep them in a RowVals.
 struct RowVals {
-    double xs[5], xc[5], ys[5], yc[5], mx[5], my[5];
+    double xs[5], xc[5], ys[5], yc[5], ex[4][5];
     double kpx[2], kpy[2];
 };
 
 struct NullSink {
-    FCFV_HD void cand(int, double, double, double, double, double, double) const {}
+    FCFV_HD void cand(int, const CandVals&) const {}
     FCFV_HD void kup(int, double, double) const {}
 };
 
 struct RowValsSink {
     RowVals* V;
-    FCFV_HD void cand(int c, double xs, double xc, double ys, double yc, double mx, double my) const {
-        V->xs[c] = xs; V->xc[c] = xc; V->ys[c] = ys; V->yc[c] = yc; V->mx[c] = mx; V->my[c] = my;
+    FCFV_HD void cand(int c, const CandVals& v) const {
+        V->xs[c] = v.xs; V->xc[c] = v.xc; V->ys[c] = v.ys; V->yc[c] = v.yc;
+#pragma unroll
+        for (int q = 0; q < 4; q++) V->ex[q][c] = v.ex[q];
     }
     FCFV_HD void kup(int s, double kx, double ky) const { V->kpx[s] = kx; V->kpy[s] = ky; }
 };
@@ -333,9 +357,11 @@ FCFV_HD void rows_clear(FaceRows& R) {
 #pragma unroll
     for (int c = 0; c < 5; c++) { R.key[c] = kDeadKey; R.lt[c] = 0; }
     R.x0s = R.x0c = R.y0s = R.y0c = R.m0x = R.m0y = 0.0;
+    R.t0xs = R.t0xc = R.t0ys = R.t0yc = 0.0;
     R.fux = R.fuy = 0.0;
     R.kpe[0] = R.kpe[1] = -1;
-    R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_mx = R.m_my = R.m_kp = 0;
+    R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_kp = 0;
+    R.m_ex[0] = R.m_ex[1] = R.m_ex[2] = R.m_ex[3] = 0;
 }
 
 // Column faces and their ranks are known before any element data arrives (face connectivity
@@ -357,33 +383,49 @@ FCFV_HD void rows_begin(FaceRows& R, const int k[5]) {
 #pragma unroll
     for (int c = 0; c < 5; c++) R.lt[c] = (1 << rks[c]) - 1;
     R.kpe[0] = R.kpe[1] = -1;
-    R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_mx = R.m_my = R.m_kp = 0;
+    R.m_xs = R.m_xc = R.m_ys = R.m_yc = R.m_kp = 0;
+    R.m_ex[0] = R.m_ex[1] = R.m_ex[2] = R.m_ex[3] = 0;
 }
 
 // marks the stored (alive and != +-0.0: dropzeros) entries of candidate c
-template <bool WANT_M>
-FCFV_HD void rows_mark(FaceRows& R, int c, bool alive, double xs, double xc, double ys, double yc, double mx, double my) {
+template <int EXTRA>
+FCFV_HD void rows_mark(FaceRows& R, int c, bool alive, const CandVals& v) {
     const int bit = R.lt[c] + 1;
-    R.m_xs |= (alive && xs != 0.0) ? bit : 0;
-    R.m_xc |= (alive && xc != 0.0) ? bit : 0;
-    R.m_ys |= (alive && ys != 0.0) ? bit : 0;
-    R.m_yc |= (alive && yc != 0.0) ? bit : 0;
-    if (WANT_M) {
-        R.m_mx |= (alive && mx != 0.0) ? bit : 0;
-        R.m_my |= (alive && my != 0.0) ? bit : 0;
+    R.m_xs |= (alive && v.xs != 0.0) ? bit : 0;
+    R.m_xc |= (alive && v.xc != 0.0) ? bit : 0;
+    R.m_ys |= (alive && v.ys != 0.0) ? bit : 0;
+    R.m_yc |= (alive && v.yc != 0.0) ? bit : 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (EXTRA == kExtraSchur || (EXTRA == kExtraMuu && q < 2)) R.m_ex[q] |= (alive && v.ex[q] != 0.0) ? bit : 0;
+}
+
+// candidate values of faces j = 1, 2 of an element (single contribution).  Schur complement:
+// Kuu .- C keeps Kuu[i,j] - C[i,j] wherever either is stored and drops zeros (sparse broadcast);
+// a missing operand is +0.0, which a - c reproduces.
+template <int EXTRA>
+FCFV_HD void cand_of(const LaneRow& Lx, const LaneRow& Ly, int j, CandVals& v) {
+    v.xs = Lx.vs[j]; v.xc = Lx.vc[j]; v.ys = Ly.vs[j]; v.yc = Ly.vc[j];
+    v.ex[0] = v.ex[1] = v.ex[2] = v.ex[3] = 0.0;
+    if (EXTRA == kExtraMuu) { v.ex[0] = Lx.ms[j]; v.ex[1] = Ly.ms[j]; }
+    if (EXTRA == kExtraSchur) {
+        v.ex[0] = Lx.vs[j] - Lx.ts[j]; v.ex[1] = Lx.vc[j] - Lx.tc[j];
+        v.ex[2] = Ly.vs[j] - Ly.ts[j]; v.ex[3] = Ly.vc[j] - Ly.tc[j];
     }
 }
 
 // Lanes (comp x, comp y) of the lower element: candidates 0..2, RHS, first Kup entry.
-template <bool WANT_M, typename Sink>
+template <int EXTRA, typename Sink>
 FCFV_HD void rows_put0(FaceRows& R, bool alive, const LaneRow& Lx, const LaneRow& Ly, const Sink& sink) {
     R.x0s = Lx.vs[0]; R.x0c = Lx.vc[0]; R.y0s = Ly.vs[0]; R.y0c = Ly.vc[0];
-    R.m0x = WANT_M ? Lx.ms[0] : 0.0; R.m0y = WANT_M ? Ly.ms[0] : 0.0;
+    R.m0x = EXTRA == kExtraMuu ? Lx.ms[0] : 0.0; R.m0y = EXTRA == kExtraMuu ? Ly.ms[0] : 0.0;
+    R.t0xs = Lx.ts[0]; R.t0xc = Lx.tc[0]; R.t0ys = Ly.ts[0]; R.t0yc = Ly.tc[0];
 #pragma unroll
     for (int j = 1; j < 3; j++) {
-        const double mx = WANT_M ? Lx.ms[j] : 0.0, my = WANT_M ? Ly.ms[j] : 0.0;
-        rows_mark<WANT_M>(R, j, alive, Lx.vs[j], Lx.vc[j], Ly.vs[j], Ly.vc[j], mx, my);
-        sink.cand(j, Lx.vs[j], Lx.vc[j], Ly.vs[j], Ly.vc[j], mx, my);
+        CandVals v;
+        cand_of<EXTRA>(Lx, Ly, j, v);
+        rows_mark<EXTRA>(R, j, alive, v);
+        sink.cand(j, v);
     }
     R.fux = Lx.fu; R.fuy = Ly.fu;
     R.kpe[0] = Lx.e;
@@ -392,18 +434,24 @@ FCFV_HD void rows_put0(FaceRows& R, bool alive, const LaneRow& Lx, const LaneRow
 }
 
 // Lanes of the higher element: its row-face column is summed into candidate 0 (lower element
-// first, like sparse()), its other two faces become candidates 3..4.  With on == false (the face
-// has no second element; the lanes then hold a discarded re-read of the first) nothing is added.
-template <bool WANT_M, typename Sink>
+// first, like sparse() and the sparse product do), its other two faces become candidates 3..4.
+// With on == false (the face has no second element; the lanes then hold a discarded re-read of
+// the first) nothing is added.
+template <int EXTRA, typename Sink>
 FCFV_HD void rows_put1(FaceRows& R, bool on, bool alive, const LaneRow& Lx, const LaneRow& Ly, const Sink& sink) {
     R.x0s = on ? R.x0s + Lx.vs[0] : R.x0s; R.x0c = on ? R.x0c + Lx.vc[0] : R.x0c;
     R.y0s = on ? R.y0s + Ly.vs[0] : R.y0s; R.y0c = on ? R.y0c + Ly.vc[0] : R.y0c;
-    if (WANT_M) { R.m0x = on ? R.m0x + Lx.ms[0] : R.m0x; R.m0y = on ? R.m0y + Ly.ms[0] : R.m0y; }
+    if (EXTRA == kExtraMuu) { R.m0x = on ? R.m0x + Lx.ms[0] : R.m0x; R.m0y = on ? R.m0y + Ly.ms[0] : R.m0y; }
+    if (EXTRA == kExtraSchur) {
+        R.t0xs = on ? R.t0xs + Lx.ts[0] : R.t0xs; R.t0xc = on ? R.t0xc + Lx.tc[0] : R.t0xc;
+        R.t0ys = on ? R.t0ys + Ly.ts[0] : R.t0ys; R.t0yc = on ? R.t0yc + Ly.tc[0] : R.t0yc;
+    }
 #pragma unroll
     for (int j = 1; j < 3; j++) {
-        const double mx = WANT_M ? Lx.ms[j] : 0.0, my = WANT_M ? Ly.ms[j] : 0.0;
-        rows_mark<WANT_M>(R, 2 + j, on && alive, Lx.vs[j], Lx.vc[j], Ly.vs[j], Ly.vc[j], mx, my);
-        sink.cand(2 + j, Lx.vs[j], Lx.vc[j], Ly.vs[j], Ly.vc[j], mx, my);
+        CandVals v;
+        cand_of<EXTRA>(Lx, Ly, j, v);
+        rows_mark<EXTRA>(R, 2 + j, on && alive, v);
+        sink.cand(2 + j, v);
     }
     R.fux = on ? R.fux + Lx.fu : R.fux; R.fuy = on ? R.fuy + Ly.fu : R.fuy;
     R.kpe[1] = Lx.e;
@@ -412,12 +460,17 @@ FCFV_HD void rows_put1(FaceRows& R, bool on, bool alive, const LaneRow& Lx, cons
 }
 
 // merged row-face column and RHS; alive: the face's rows are produced (owned face with an element)
-template <bool WANT_M, typename Sink>
+template <int EXTRA, typename Sink>
 FCFV_HD void rows_finish(FaceRows& R, bool alive, const Sink& sink) {
     if (R.fux == 0.0) R.fux = 0.0;   // Array(dropzeros(sparse)): -0.0 -> +0.0
     if (R.fuy == 0.0) R.fuy = 0.0;
-    rows_mark<WANT_M>(R, 0, alive, R.x0s, R.x0c, R.y0s, R.y0c, R.m0x, R.m0y);
-    sink.cand(0, R.x0s, R.x0c, R.y0s, R.y0c, R.m0x, R.m0y);
+    CandVals v;
+    v.xs = R.x0s; v.xc = R.x0c; v.ys = R.y0s; v.yc = R.y0c;
+    v.ex[0] = v.ex[1] = v.ex[2] = v.ex[3] = 0.0;
+    if (EXTRA == kExtraMuu) { v.ex[0] = R.m0x; v.ex[1] = R.m0y; }
+    if (EXTRA == kExtraSchur) { v.ex[0] = R.x0s - R.t0xs; v.ex[1] = R.x0c - R.t0xc; v.ex[2] = R.y0s - R.t0ys; v.ex[3] = R.y0c - R.t0yc; }
+    rows_mark<EXTRA>(R, 0, alive, v);
+    sink.cand(0, v);
 }
 
 FCFV_HD int popc6(int x) {
@@ -433,8 +486,11 @@ FCFV_HD int rows_nuu_x(const FaceRows& R) { return popc6(R.m_xs | (R.m_xc << 5))
 FCFV_HD int rows_nuu_y(const FaceRows& R) { return popc6(R.m_ys | (R.m_yc << 5)); }
 FCFV_HD int rows_nup_x(const FaceRows& R) { return (R.m_kp & 1) + ((R.m_kp >> 1) & 1); }
 FCFV_HD int rows_nup_y(const FaceRows& R) { return ((R.m_kp >> 2) & 1) + ((R.m_kp >> 3) & 1); }
-FCFV_HD int rows_nmu_x(const FaceRows& R) { return popc6(R.m_mx); }
-FCFV_HD int rows_nmu_y(const FaceRows& R) { return popc6(R.m_my); }
+// third block: Muu rows hold one part, Schur rows two
+template <int EXTRA>
+FCFV_HD int rows_nex_x(const FaceRows& R) { return EXTRA == kExtraSchur ? popc6(R.m_ex[0] | (R.m_ex[1] << 5)) : popc6(R.m_ex[0]); }
+template <int EXTRA>
+FCFV_HD int rows_nex_y(const FaceRows& R) { return EXTRA == kExtraSchur ? popc6(R.m_ex[2] | (R.m_ex[3] << 5)) : popc6(R.m_ex[1]); }
 
 // emit(position inside the row, column, value); rows are laid out [x columns | y columns].
 // Positions are formed unconditionally so that the conditional part is just the store.
@@ -468,14 +524,29 @@ FCFV_HD void rows_emit_uu(const FaceRows& R, const RowVals& V, int nf, Emit&& em
     rows_emit_uu_y(R, V.ys, V.yc, nf, [&](int pos, int col, double v) { emit(1, pos, col, v); });
 }
 
-template <typename Emit>
-FCFV_HD void rows_emit_mu(const FaceRows& R, const RowVals& V, int nf, Emit&& emit) {
+// third block.  Muu: row (f,comp) only holds columns (g,comp).  Schur complement: laid out like Kuu.
+template <int EXTRA, typename Emit>
+FCFV_HD void rows_emit_ex(const FaceRows& R, const RowVals& V, int nf, Emit&& emit) {
+    if (EXTRA == kExtraMuu) {
 #pragma unroll
-    for (int c = 0; c < 5; c++) {
-        const int lt = R.lt[c], bit = lt + 1;
-        const int p_x = popc6(R.m_mx & lt), p_y = popc6(R.m_my & lt);
-        if (R.m_mx & bit) emit(0, p_x, R.key[c], V.mx[c]);
-        if (R.m_my & bit) emit(1, p_y, R.key[c] + nf, V.my[c]);
+        for (int c = 0; c < 5; c++) {
+            const int lt = R.lt[c], bit = lt + 1;
+            const int p_x = popc6(R.m_ex[0] & lt), p_y = popc6(R.m_ex[1] & lt);
+            if (R.m_ex[0] & bit) emit(0, p_x, R.key[c], V.ex[0][c]);
+            if (R.m_ex[1] & bit) emit(1, p_y, R.key[c] + nf, V.ex[1][c]);
+        }
+    } else {
+        const int n_xs = popc6(R.m_ex[0]), n_yc = popc6(R.m_ex[3]);
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            const int lt = R.lt[c], bit = lt + 1;
+            const int p_xs = popc6(R.m_ex[0] & lt), p_xc = n_xs + popc6(R.m_ex[1] & lt);
+            const int p_yc = popc6(R.m_ex[3] & lt), p_ys = n_yc + popc6(R.m_ex[2] & lt);
+            if (R.m_ex[0] & bit) emit(0, p_xs, R.key[c], V.ex[0][c]);
+            if (R.m_ex[1] & bit) emit(0, p_xc, R.key[c] + nf, V.ex[1][c]);
+            if (R.m_ex[3] & bit) emit(1, p_yc, R.key[c], V.ex[3][c]);
+            if (R.m_ex[2] & bit) emit(1, p_ys, R.key[c] + nf, V.ex[2][c]);
+        }
     }
 }
 

@@ -19,7 +19,7 @@ FCFV_OK = 0
 GRADIENT, SYMMETRIC_GRADIENT = 0, 1
 LOOP_OLD, LOOP_NEW = 0, 1
 TAU_REFERENCE, TAU_FACE = 0, 1
-KUU, KUP, MUU = 0, 1, 2
+KUU, KUP, MUU, KUUSC = 0, 1, 2, 3
 CSR0, CSC1_INT64 = 0, 1
 
 _lib = None
@@ -75,6 +75,8 @@ def load():
         "fcfv_ph_update_p": [vp, dbl, vp, vp],
         "fcfv_ph_fusc": [vp, dbl, vp, vp],
         "fcfv_element_values": [vp] + [vp] * 10,
+        "fcfv_schur": [vp, dbl, P(i64)],
+        "fcfv_run_assemble_schur": [vp, ci, ci, dbl, dbl],
         "fcfv_set_sources": [vp, vp, vp],
         "fcfv_set_face_data": [vp] + [vp] * 6,
         "fcfv_set_solution": [vp, vp, vp, vp],

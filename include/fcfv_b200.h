@@ -39,7 +39,7 @@ enum { FCFV_OK = 0, FCFV_ERR_INVALID = 1, FCFV_ERR_CUDA = 2, FCFV_ERR_STATE = 3,
 enum { FCFV_GRADIENT = 0, FCFV_SYMMETRIC_GRADIENT = 1 };  /* Formulation == :Gradient / :SymmetricGradient */
 enum { FCFV_LOOP_OLD = 0, FCFV_LOOP_NEW = 1 };             /* ElementAssemblyLoop / ElementAssemblyLoopNEW  */
 enum { FCFV_TAU_REFERENCE = 0, FCFV_TAU_FACE = 1 };        /* residual: mesh.τ[e] (as written) / mesh.τ[e2f[e,i]] */
-enum { FCFV_KUU = 0, FCFV_KUP = 1, FCFV_MUU = 2 };
+enum { FCFV_KUU = 0, FCFV_KUP = 1, FCFV_MUU = 2, FCFV_KUUSC = 3 };   /* KUUSC: Schur complement, see fcfv_schur */
 enum { FCFV_CSR0 = 0, FCFV_CSC1_INT64 = 1 };               /* export layouts */
 
 /* ---- life cycle ---------------------------------------------------------------------- */
@@ -94,6 +94,15 @@ int fcfv_assemble(fcfv_t* h, int variant, int formulation, double A, const doubl
                   const double* sxxNeu, const double* syyNeu, const double* sxyNeu,
                   const double* syxNeu, int want_muu, int64_t* nnz_uu, int64_t* nnz_up,
                   int64_t* nnz_muu, double* seconds);
+
+/* ---- Powell-Hestenes Schur complement, fused into the assembly (src/SolversFCFV_Stokes.jl:23-25)
+ * Kuusc = Kuu .- Kup*(Kppi*Kpu) with Kppi = spdiagm(gamma .* ke ./ Ω), Kpu = -Kup': the same face-to-face
+ * rows as Kuu with one extra term per adjacent element, so the fill pass writes it next to Kuu / Kup
+ * instead of a host-side sparse product.  Entries whose value is exactly +-0.0 are dropped (what
+ * Julia's sparse broadcast `.-` does).  Block id FCFV_KUUSC for fcfv_export / fcfv_device_csr.
+ * fcfv_schur re-runs the last fcfv_assemble (same loop, formulation, A) on the resident data. */
+int fcfv_schur(fcfv_t* h, double gamma, int64_t* nnz_sc);
+int fcfv_run_assemble_schur(fcfv_t* h, int variant, int formulation, double A, double gamma);
 
 /* Bytes per row-pointer entry of the device CSR (4 or 8). */
 int fcfv_index_width(fcfv_t* h);

@@ -11,14 +11,14 @@ module FCFV_B200
 using SparseArrays, Printf
 
 export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
-       MeshGeometry!, PHResidual, PHUpdateP!, PHFusc
+       SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
 
 const GRADIENT, SYMMETRIC_GRADIENT = Cint(0), Cint(1)
 const LOOP_OLD, LOOP_NEW = Cint(0), Cint(1)
 const TAU_REFERENCE, TAU_FACE = Cint(0), Cint(1)
-const KUU, KUP, MUU = Cint(0), Cint(1), Cint(2)
+const KUU, KUP, MUU, KUUSC = Cint(0), Cint(1), Cint(2), Cint(3)
 const CSC1_INT64 = Cint(1)
 const A = 1.0                      # src/DiscretisationFCFV_Stokes.jl:1-2
 
@@ -198,6 +198,15 @@ function ComputeElementValues(mesh, Vxh, Vyh, Pe, α, β, Ζ, VxDir, VyDir, Form
 end
 
 # --- the Powell-Hestenes lines of StokesSolvers! that consume the device CSR (SolversFCFV_Stokes.jl:40-49)
+"""Kuusc = Kuu .- Kup*(Kppi*Kpu) of StokesSolvers! (src/SolversFCFV_Stokes.jl:23-25), assembled on the GPU next to
+Kuu / Kup.  Call after ElementAssemblyLoop[NEW] on the same mesh; `lu(Kuusc)` / `cholesky(Hermitian(Kuusc))` follow."""
+function SchurComplement(mesh, penalty)
+    h = handle_for(mesh); refresh!(h, mesh)
+    n = Ref{Int64}(0)
+    check(h, ccall((:fcfv_schur, LIB), Cint, (Ptr{Cvoid}, Float64, Ref{Int64}), h.ptr, penalty, n))
+    return export_csc(h, KUUSC)
+end
+
 """ru = fu - Kuu*u - Kup*p, rp = fp - Kpu*u, (norm(ru), norm(rp))"""
 function PHResidual(mesh, u, p)
     h = handle_for(mesh)

@@ -693,3 +693,82 @@ int oracle_element_values(i64 nel, const i64 *e2f, const i64 *bcarr,
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------ */
+/* Schur complement of the Powell-Hestenes solver, literally as Julia's      */
+/* SparseArrays evaluates  src/SolversFCFV_Stokes.jl:6,23-25 :               */
+/*   Kpu   = -Kup'                      (adjoint, then unary minus)          */
+/*   coef  = penalty.*mesh.ke./mesh.Ω   ((penalty*ke)/Ω)                     */
+/*   Kppi  = spdiagm(coef)                                                   */
+/*   Kuusc = Kuu .- Kup*(Kppi*Kpu)                                           */
+/* SparseArrays semantics restated (Julia stdlib, version unpinned by the    */
+/* reference's Project.toml):  A*B is Gustavson's column-by-column product   */
+/* (for column j of B: for each stored B[k,j] in ascending k, for each stored*/
+/* A[i,k]: the first product of a row is assigned, later ones are added),    */
+/* numerical zeros stay stored, rows come out sorted;  A .- B is the         */
+/* zero-preserving sparse broadcast: result entries over the union of the    */
+/* stored patterns, f(a, 0.0) / f(0.0, b) where one side is missing, and a   */
+/* result is only stored if it is not zero.                                  */
+/* All matrices are Julia CSC triples (1-based colptr / rowval).             */
+/* Kuu: n x n (n = 2 nf), Kup: n x nel.  Output capacity: nnz(Kuu)+36*nel.   */
+/* ------------------------------------------------------------------------ */
+int oracle_schur(i64 n, i64 nel, const i64 *uu_cp, const i64 *uu_rv, const double *uu_v,
+                 const i64 *up_cp, const i64 *up_rv, const double *up_v,
+                 const double *ke, const double *Omega, double penalty,
+                 i64 *sc_cp, i64 *sc_rv, double *sc_v, i64 *sc_nnz) {
+    const i64 nnzp = up_cp[nel] - 1;
+    /* Kpu = -Kup' : nel x n, CSC.  Transpose by counting rows of Kup. */
+    i64 *pu_cp = calloc((size_t)n + 2, sizeof(i64));
+    i64 *pu_rv = malloc(sizeof(i64) * (size_t)(nnzp > 0 ? nnzp : 1));
+    double *pu_v = malloc(sizeof(double) * (size_t)(nnzp > 0 ? nnzp : 1));
+    i64 *next = malloc(sizeof(i64) * (size_t)(n + 1));
+    double *coef = malloc(sizeof(double) * (size_t)(nel > 0 ? nel : 1));
+    double *x = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    i64 *xb = calloc((size_t)(n > 0 ? n : 1), sizeof(i64));
+    i64 *rows = malloc(sizeof(i64) * (size_t)(n > 0 ? n : 1));
+    if (!pu_cp || !pu_rv || !pu_v || !next || !coef || !x || !xb || !rows) return 1;
+    for (i64 k = 0; k < nnzp; k++) pu_cp[up_rv[k]]++;          /* count per row i (1-based) -> column i of Kpu */
+    { i64 run = 1; for (i64 j = 1; j <= n; j++) { i64 c = pu_cp[j]; pu_cp[j] = run; run += c; } pu_cp[n + 1] = run; }
+    for (i64 j = 1; j <= n; j++) next[j] = pu_cp[j];
+    for (i64 e = 1; e <= nel; e++)                             /* ascending e keeps rows of Kpu sorted */
+        for (i64 k = up_cp[e - 1]; k < up_cp[e]; k++) {
+            const i64 i = up_rv[k - 1];
+            const i64 p = next[i]++;
+            pu_rv[p - 1] = e;
+            pu_v[p - 1] = -up_v[k - 1];
+        }
+    for (i64 e = 0; e < nel; e++) coef[e] = (penalty * ke[e]) / Omega[e];
+    /* B = Kppi*Kpu scales row e of Kpu: B[e,j] = coef[e]*Kpu[e,j]   (one product per entry) */
+    /* C = Kup*B and Kuusc = Kuu .- C, column by column */
+    i64 out = 0;
+    sc_cp[0] = 1;
+    for (i64 j = 1; j <= n; j++) {
+        i64 nr = 0;
+        for (i64 kb = pu_cp[j]; kb < pu_cp[j + 1]; kb++) {     /* stored B[e,j], ascending e */
+            const i64 e = pu_rv[kb - 1];
+            const double b = coef[e - 1] * pu_v[kb - 1];
+            for (i64 ka = up_cp[e - 1]; ka < up_cp[e]; ka++) { /* stored Kup[i,e], ascending i */
+                const i64 i = up_rv[ka - 1];
+                const double prod = up_v[ka - 1] * b;
+                if (xb[i - 1] != j) { xb[i - 1] = j; x[i - 1] = prod; rows[nr++] = i; }
+                else x[i - 1] += prod;
+            }
+        }
+        /* sort the rows of column j of C (insertion sort: <= 10 entries per column) */
+        for (i64 a = 1; a < nr; a++) { i64 r = rows[a], b2 = a; while (b2 > 0 && rows[b2 - 1] > r) { rows[b2] = rows[b2 - 1]; b2--; } rows[b2] = r; }
+        /* merge with column j of Kuu: zero-preserving broadcast of (a, c) -> a - c */
+        i64 ka = uu_cp[j - 1], ea = uu_cp[j], kc = 0;
+        while (ka < ea || kc < nr) {
+            i64 ra = ka < ea ? uu_rv[ka - 1] : (n + 1), rc = kc < nr ? rows[kc] : (n + 1);
+            i64 r; double v;
+            if (ra == rc) { r = ra; v = uu_v[ka - 1] - x[rc - 1]; ka++; kc++; }
+            else if (ra < rc) { r = ra; v = uu_v[ka - 1] - 0.0; ka++; }
+            else { r = rc; v = 0.0 - x[rc - 1]; kc++; }
+            if (v != 0.0) { sc_rv[out] = r; sc_v[out] = v; out++; }
+        }
+        sc_cp[j] = out + 1;
+    }
+    *sc_nnz = out;
+    free(pu_cp); free(pu_rv); free(pu_v); free(next); free(coef); free(x); free(xb); free(rows);
+    return 0;
+}

@@ -184,6 +184,20 @@ def ComputeElementValues(mesh, Vxh, Vyh, Pe, α, β, Ζ, VxDir, VyDir, Formulati
     return tuple(o)
 
 
+def schur_complement(mesh, Kuu, Kup, penalty):
+    """Kuusc = Kuu .- Kup*(Kppi*Kpu), Kppi = spdiagm(penalty.*ke./Ω), Kpu = -Kup' (SolversFCFV_Stokes.jl:6,23-25).
+    Kuu, Kup: Julia CSC triples; returns the CSC triple of Kuusc."""
+    nel, n = mesh.nel, 2 * mesh.nf
+    cap = len(Kuu[2]) + 36 * nel
+    cp, rv, v = np.zeros(n + 1, np.int64), np.zeros(cap, np.int64), np.zeros(cap)
+    nnz = C.c_int64(0)
+    rc = lib().oracle_schur(C.c_int64(n), C.c_int64(nel), _p(_i(Kuu[0])), _p(_i(Kuu[1])), _p(_d(Kuu[2])), _p(_i(Kup[0])),
+                            _p(_i(Kup[1])), _p(_d(Kup[2])), _p(_d(mesh.ke)), _p(_d(mesh.Ω)), C.c_double(penalty),
+                            _p(cp), _p(rv), _p(v), C.byref(nnz))
+    assert rc == 0
+    return cp, rv[:nnz.value].copy(), v[:nnz.value].copy()
+
+
 def csc_to_scipy(csc, shape):
     """Julia-style CSC triple -> scipy.sparse.csc_matrix (test helper)."""
     import scipy.sparse as sp

@@ -47,8 +47,9 @@ void build_mesh(HostMesh& H, long long nel, long long nf, const long long* e2f, 
 // Serial stand-in for k_asm_count / k_asm_fill: thread = face becomes a loop iteration, the block
 // scan becomes a running sum, the tile cache becomes a direct load; asm_face, the rank-space
 // placement (rows_emit_*) and the counts are the kernels' own code.
-template <int VARIANT, int FORM>
-void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, double A, long long* rp_uu, int* c_uu,
+// EXTRA = kExtraMuu: third block Muu; kExtraSchur: third block Kuu - Kup*(Kppi*Kpu) with penalty gamma
+template <int VARIANT, int FORM, int EXTRA>
+void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, double A, double gamma, long long* rp_uu, int* c_uu,
               double* v_uu, long long* rp_up, int* c_up, double* v_up, long long* rp_mu, int* c_mu, double* v_mu,
               double* fu, double* fp) {
     const int nf = M.nf;
@@ -56,24 +57,27 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
     const int nel = M.nel;
     bool aniso = false;
     for (int e = 0; e < nel; e++) aniso = aniso || M.dl[e] != 1.0;
-    std::vector<double> ia(nel), c11(nel), c12(nel), c21(nel), c22(nel);
-    for (int e = 0; e < nel; e++)
+    std::vector<double> ia(nel), c11(nel), c12(nel), c21(nel), c22(nel), cs(nel);
+    for (int e = 0; e < nel; e++) {
         element_coef<VARIANT>(L.alpha[e], M.ke[e], (VARIANT == kLoopNew && aniso) ? M.dl[e] : 1.0, M.Om[e], ia[e], c11[e], c12[e], c21[e], c22[e]);
-    const CoefView Cf{ia.data(), c11.data(), aniso ? c12.data() : nullptr, aniso ? c21.data() : nullptr, aniso ? c22.data() : nullptr};
+        cs[e] = (gamma * M.ke[e]) / M.Om[e];
+    }
+    const CoefView Cf{ia.data(), c11.data(), aniso ? c12.data() : nullptr, aniso ? c21.data() : nullptr, aniso ? c22.data() : nullptr,
+                      cs.data()};
     FaceConn C;
     auto load = [&](bool second, int e, int i, FaceElem& F) {
-        if (aniso) load_face_elem<VARIANT, true>(M, L, Cf, C, second, e, i, F);
-        else load_face_elem<VARIANT, false>(M, L, Cf, C, second, e, i, F);
+        if (aniso) load_face_elem<VARIANT, true, EXTRA>(M, L, Cf, C, second, e, i, F);
+        else load_face_elem<VARIANT, false, EXTRA>(M, L, Cf, C, second, e, i, F);
     };
     std::vector<int> cnt[6];
     for (auto& c : cnt) c.assign(nf, 0);
     for (int f = 0; f < nf; f++) {   // count pass
         FaceRows R;
         unpack_conn(f, M.fconn[f], M.fbc[f], C);
-        asm_face<VARIANT, FORM, true>(D, A, f, M.f2e[f], C, true, load, NullSink(), R);
+        asm_face<VARIANT, FORM, EXTRA>(D, A, f, M.f2e[f], C, true, load, NullSink(), R);
         cnt[0][f] = rows_nuu_x(R); cnt[1][f] = rows_nuu_y(R);
         cnt[2][f] = rows_nup_x(R); cnt[3][f] = rows_nup_y(R);
-        cnt[4][f] = rows_nmu_x(R); cnt[5][f] = rows_nmu_y(R);
+        cnt[4][f] = rows_nex_x<EXTRA>(R); cnt[5][f] = rows_nex_y<EXTRA>(R);
     }
     long long* rps[3] = {rp_uu, rp_up, rp_mu};
     for (int m = 0; m < 3; m++) {
@@ -97,13 +101,13 @@ void assemble(const MeshView& M, const LocalView& L, const FaceDataView& D, doub
         FaceRows R;
         unpack_conn(f, M.fconn[f], M.fbc[f], C);
         RowVals V;
-        asm_face<VARIANT, FORM, true>(D, A, f, M.f2e[f], C, true, load, RowValsSink{&V}, R);
+        asm_face<VARIANT, FORM, EXTRA>(D, A, f, M.f2e[f], C, true, load, RowValsSink{&V}, R);
         fu[f] = R.fux; fu[nf + f] = R.fuy;
         rows_emit_uu(R, V, nf, [&](int comp, int pos, int col, double v) {
             const long long p = rp_uu[(long long)comp * nf + f] + pos; v_uu[p] = v; c_uu[p] = col; });
         rows_emit_up(R, V.kpx, V.kpy, [&](int comp, int pos, int col, double v) {
             const long long p = rp_up[(long long)comp * nf + f] + pos; v_up[p] = v; c_up[p] = col; });
-        rows_emit_mu(R, V, nf, [&](int comp, int pos, int col, double v) {
+        rows_emit_ex<EXTRA>(R, V, nf, [&](int comp, int pos, int col, double v) {
             const long long p = rp_mu[(long long)comp * nf + f] + pos; v_mu[p] = v; c_mu[p] = col; });
     }
 }
@@ -162,11 +166,31 @@ int emu_assemble(int variant, int formulation, double A, long long nel, long lon
     build_mesh(H, nel, nf, e2f, bc, Om, nx, ny, G, ke, dl, ke, tau);
     LocalView L{alpha, beta, Z};
     FaceDataView D{VxDir, VyDir, sxx, syy, sxy, syx};
-#define ARGS H.view, L, D, A, rp_uu, c_uu, v_uu, rp_up, c_up, v_up, rp_mu, c_mu, v_mu, fu, fp
-    if (variant == 0 && formulation == 0) assemble<kLoopOld, kGradient>(ARGS);
-    else if (variant == 0) assemble<kLoopOld, kSymmetricGradient>(ARGS);
-    else if (formulation == 0) assemble<kLoopNew, kGradient>(ARGS);
-    else assemble<kLoopNew, kSymmetricGradient>(ARGS);
+#define ARGS H.view, L, D, A, 0.0, rp_uu, c_uu, v_uu, rp_up, c_up, v_up, rp_mu, c_mu, v_mu, fu, fp
+    if (variant == 0 && formulation == 0) assemble<kLoopOld, kGradient, kExtraMuu>(ARGS);
+    else if (variant == 0) assemble<kLoopOld, kSymmetricGradient, kExtraMuu>(ARGS);
+    else if (formulation == 0) assemble<kLoopNew, kGradient, kExtraMuu>(ARGS);
+    else assemble<kLoopNew, kSymmetricGradient, kExtraMuu>(ARGS);
+#undef ARGS
+    return 0;
+}
+
+// same with the Schur complement (penalty gamma) as third block
+int emu_assemble_schur(int variant, int formulation, double A, double gamma, long long nel, long long nf, const long long* e2f,
+                       const long long* bc, const double* Om, const double* nx, const double* ny, const double* G,
+                       const double* ke, const double* dl, const double* tau, const double* alpha, const double* beta,
+                       const double* Z, const double* VxDir, const double* VyDir, const double* sxx, const double* syy,
+                       const double* sxy, const double* syx, long long* rp_uu, int* c_uu, double* v_uu, long long* rp_up,
+                       int* c_up, double* v_up, long long* rp_mu, int* c_mu, double* v_mu, double* fu, double* fp) {
+    HostMesh H;
+    build_mesh(H, nel, nf, e2f, bc, Om, nx, ny, G, ke, dl, ke, tau);
+    LocalView L{alpha, beta, Z};
+    FaceDataView D{VxDir, VyDir, sxx, syy, sxy, syx};
+#define ARGS H.view, L, D, A, gamma, rp_uu, c_uu, v_uu, rp_up, c_up, v_up, rp_mu, c_mu, v_mu, fu, fp
+    if (variant == 0 && formulation == 0) assemble<kLoopOld, kGradient, kExtraSchur>(ARGS);
+    else if (variant == 0) assemble<kLoopOld, kSymmetricGradient, kExtraSchur>(ARGS);
+    else if (formulation == 0) assemble<kLoopNew, kGradient, kExtraSchur>(ARGS);
+    else assemble<kLoopNew, kSymmetricGradient, kExtraSchur>(ARGS);
 #undef ARGS
     return 0;
 }

@@ -99,11 +99,20 @@ def test_local_assembly_residual(case, api, oracle, golden):
                 assert gn[k] < 1e-9
         for k in ("F_nodes_x", "F_nodes_y", "F_glob2"):
             assert rel_inf(garr[k], arr[k]) <= TOL, (tau_mode, k)
+    # ---- Schur complement fused into the assembly: fields of Julia's SparseMatrixCSC, bit for bit
+    ref_sc = oracle.schur_complement(m, Kuu, Kup, 1.0e4)
+    gsc = api.SchurComplement(g, 1.0e4)
+    cp, rv, v = h.export_csc(L.KUUSC)
+    assert np.array_equal(cp, ref_sc[0]) and np.array_equal(rv, ref_sc[1]) and np.array_equal(v, ref_sc[2]), "Kuusc CSC"
+    assert gsc.nnz == len(ref_sc[2]) == gold["nnz_sc"] and gold["Kuusc"] == digest(cp, rv, v)
+    assert_csr_equal(h.export_csr(L.KUU), csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu after schur")
+    assert_csr_equal(h.export_csr(L.KUP), csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup after schur")
     # ---- ComputeElementValues (bitwise: same operation order, no BLAS on either side)
     ev = oracle.ComputeElementValues(m, d["Vxh"], d["Vyh"], d["Pe"], a, b, Z, d["VxDir"], d["VyDir"], case.form)
     gev = api.ComputeElementValues(g, d["Vxh"], d["Vyh"], d["Pe"], ga, gb, gZ, d["VxDir"], d["VyDir"], case.form)
     for k in range(5):
         assert np.array_equal(gev[k], ev[k]), ("element values", k)
+    assert gold["elem_values"] == digest(*gev)
     # ---- Powell-Hestenes lines on the resident CSR
     u = np.concatenate([d["Vxh"], d["Vyh"]])
     ru, rp, nrm = oracle.ph_residual(m, Kuu, Kup, fu, fp, u, d["Pe"])

@@ -35,16 +35,21 @@ def emu_local(emu, m, d, form, A=1.0):
     return al, be.reshape((nel, 2), order="F"), Z.reshape((nel, 2, 2), order="F"), tau
 
 
-def emu_assemble(emu, m, al, be, Z, d, variant, form, A=1.0):
+def emu_assemble(emu, m, al, be, Z, d, variant, form, A=1.0, schur=None):
+    """schur=None: third block is Muu; schur=gamma: third block is Kuu - Kup*(Kppi*Kpu)."""
     nel, nf = m.nel, m.nf
     uu = (np.zeros(2 * nf + 1, np.int64), np.zeros(20 * nf, np.int32), np.zeros(20 * nf))
     up = (np.zeros(2 * nf + 1, np.int64), np.zeros(4 * nf, np.int32), np.zeros(4 * nf))
-    mu = (np.zeros(2 * nf + 1, np.int64), np.zeros(10 * nf, np.int32), np.zeros(10 * nf))
+    mu = (np.zeros(2 * nf + 1, np.int64), np.zeros(20 * nf, np.int32), np.zeros(20 * nf))
     fu, fp = np.zeros(2 * nf), np.zeros(nel)
     a = [_i(m.e2f), _i(m.bc), _d(m.Ω), _d(m.n_x), _d(m.n_y), _d(m.Γ), _d(m.ke), _d(m.δ), _d(m.τ), _d(al), _d(be), _d(Z),
          _d(d["VxDir"]), _d(d["VyDir"])] + [_d(x) for x in d["neu"]]
-    rc = emu.emu_assemble(C.c_int(variant), C.c_int(FORM[form]), C.c_double(A), C.c_longlong(nel), C.c_longlong(nf),
-                          *map(_p, a), *map(_p, uu), *map(_p, up), *map(_p, mu), _p(fu), _p(fp))
+    if schur is None:
+        rc = emu.emu_assemble(C.c_int(variant), C.c_int(FORM[form]), C.c_double(A), C.c_longlong(nel), C.c_longlong(nf),
+                              *map(_p, a), *map(_p, uu), *map(_p, up), *map(_p, mu), _p(fu), _p(fp))
+    else:
+        rc = emu.emu_assemble_schur(C.c_int(variant), C.c_int(FORM[form]), C.c_double(A), C.c_double(schur), C.c_longlong(nel),
+                                    C.c_longlong(nf), *map(_p, a), *map(_p, uu), *map(_p, up), *map(_p, mu), _p(fu), _p(fp))
     assert rc == 0
     trim = lambda t: (t[0], t[1][:t[0][-1]], t[2][:t[0][-1]])
     return trim(uu), trim(up), trim(mu), fu, fp
@@ -114,3 +119,20 @@ def test_element_values_bitwise(case, oracle, emu):
     assert emu.emu_element_values(C.c_longlong(nel), C.c_longlong(nf), *map(_p, args), _p(out)) == 0
     for k in range(5):
         assert np.array_equal(out[k * nel:(k + 1) * nel], ref[k]), k
+
+
+@pytest.mark.parametrize("case", cases.all_cases(), ids=lambda c: c.name)
+def test_schur_complement_bitwise(case, oracle, emu):
+    """Kuusc = Kuu .- Kup*(Kppi*Kpu) (Solvers:23-25) produced by the assembly itself: pattern and values
+    identical to the oracle's restatement of Julia's sparse product / broadcast."""
+    m, d = cases.build(case)
+    nel, nf = m.nel, m.nf
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, case.form)
+    fn = oracle.ElementAssemblyLoop if case.variant == 0 else oracle.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, _, _ = fn(m, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], case.form)
+    gamma = 1.0e4
+    ref = oracle.schur_complement(m, Kuu, Kup, gamma)
+    euu, eup, esc, efu, efp = emu_assemble(emu, m, a, b, Z, d, case.variant, case.form, schur=gamma)
+    assert_csr_equal(euu, csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu")
+    assert_csr_equal(eup, csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup")
+    assert_csr_equal(esc, csc_triple_to_csr(ref, (2 * nf, 2 * nf)), "Kuusc")

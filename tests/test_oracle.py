@@ -40,6 +40,10 @@ def test_golden_digests(case, oracle):
     assert gold["local"] == digest(a, b.ravel(order="F"), Z.ravel(order="F"), m.τ)
     assert gold["Kuu"] == digest(*Kuu) and gold["Muu"] == digest(*Muu) and gold["Kup"] == digest(*Kup)
     assert gold["rhs"] == digest(fu, fp)
+    Ksc = oracle.schur_complement(m, Kuu, Kup, 1.0e4)
+    assert gold["nnz_sc"] == len(Ksc[2]) and gold["Kuusc"] == digest(*Ksc)
+    ev = oracle.ComputeElementValues(m, d["Vxh"], d["Vyh"], d["Pe"], a, b, Z, d["VxDir"], d["VyDir"], case.form)
+    assert gold["elem_values"] == digest(*ev)
     for mode, key in (("REFERENCE", "norms_reference"), ("FACE", "norms_face")):
         n = oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"],
                                                   d["VyDir"], *d["neu"], case.form, tau_mode=mode)
@@ -223,3 +227,22 @@ def test_element_values_known_answer(oracle):
     assert np.allclose(Vx, 2.0, rtol=1e-13) and np.allclose(Vy, -3.0, rtol=1e-13)
     scale = (m.ke / m.Ω * m.Γ.max(axis=1)).max() * 3.0
     assert max(np.abs(Txx).max(), np.abs(Tyy).max(), np.abs(Txy).max()) <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("case", cases.all_cases(small_only=True), ids=lambda c: c.name)
+def test_schur_against_scipy(case, oracle):
+    """The oracle's Schur complement (Julia's A*B / .- semantics restated) against SciPy's sparse algebra:
+    same pattern after dropping zeros, values to round-off (each entry is a sum of <= 2 products)."""
+    m, d = cases.build(case)
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, case.form)
+    fn = oracle.ElementAssemblyLoop if case.variant == 0 else oracle.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, _, _ = fn(m, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], case.form)
+    n = 2 * m.nf
+    S = oracle.csc_to_scipy(oracle.schur_complement(m, Kuu, Kup, 1.0e4), (n, n))
+    A, P = oracle.csc_to_scipy(Kuu, (n, n)), oracle.csc_to_scipy(Kup, (n, m.nel))
+    R = (A - P @ (sp.diags(1.0e4 * m.ke / m.Ω) @ (-P.T))).tocsc()
+    R.eliminate_zeros(); R.sort_indices()
+    assert np.array_equal(S.indptr, R.indptr) and np.array_equal(S.indices, R.indices)
+    assert rel_inf(S.data, R.data) <= 1e-14
+    if case.form == "SymmetricGradient":   # the symmetric formulation gives a symmetric Schur complement (Cholesky branch)
+        assert abs(S - S.T).max() <= 1e-12 * abs(S).max()

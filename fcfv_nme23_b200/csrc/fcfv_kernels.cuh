@@ -99,20 +99,37 @@ FCFV_HD void face_conn_of(const int* e2f, const int8_t* bc, int nel, int f, int2
 // index is then a compile-time constant (no local memory).  The values do not depend on the order
 // in which the pairs (i, j) are visited.  Face ids and bc tags come from the face's connectivity
 // record (slot 0: candidates 0,1,2; slot 1: 0,3,4), so that nothing here waits for e2f.
-template <int VARIANT, bool ANISO, int EXTRA>
+#ifndef FCFV_NATURAL_COUNT
+#define FCFV_NATURAL_COUNT 1   // 1: the count pass loads Γ, n in natural face order (one SoA plane per request) and swaps in registers
+#endif
+
+template <int VARIANT, bool ANISO, int EXTRA, bool NATURAL = false>
 FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceConn& C, bool second, int e, int i,
                             FaceElem& E) {
     const int nel = M.nel;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const int j = k == 0 ? i : (k == i ? 0 : k);
         const int g = k == 0 ? C.k[0] : (second ? C.k[2 + k] : C.k[k]);
         E.g[k] = g;
         E.bc[k] = k == 0 ? C.bc[0] : (second ? C.bc[2 + k] : C.bc[k]);
         E.tau[k] = M.tau[g];
-        E.G[k] = M.G[j * nel + e];
-        E.nx[k] = M.nx[j * nel + e];
-        E.ny[k] = M.ny[j * nel + e];
+    }
+    if (NATURAL) {
+        double G[3], nx[3], ny[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) { G[j] = M.G[j * nel + e]; nx[j] = M.nx[j * nel + e]; ny[j] = M.ny[j * nel + e]; }
+        // record position 0 <- local face i, position i <- local face 0, the third stays
+        E.G[0] = pick3(i, G); E.nx[0] = pick3(i, nx); E.ny[0] = pick3(i, ny);
+        E.G[1] = i == 1 ? G[0] : G[1]; E.nx[1] = i == 1 ? nx[0] : nx[1]; E.ny[1] = i == 1 ? ny[0] : ny[1];
+        E.G[2] = i == 2 ? G[0] : G[2]; E.nx[2] = i == 2 ? nx[0] : nx[2]; E.ny[2] = i == 2 ? ny[0] : ny[2];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int j = k == 0 ? i : (k == i ? 0 : k);
+            E.G[k] = M.G[j * nel + e];
+            E.nx[k] = M.nx[j * nel + e];
+            E.ny[k] = M.ny[j * nel + e];
+        }
     }
     E.ia = Cf.ia[e];
     E.c11 = Cf.c11[e];
@@ -466,7 +483,7 @@ __device__ __forceinline__ void prefetch_elem(const MeshView& M, const LocalView
 }
 
 // rows of the block's face of this thread
-template <int VARIANT, int FORM, int EXTRA, bool ANISO, typename Sink>
+template <int VARIANT, int FORM, int EXTRA, bool ANISO, bool NATURAL, typename Sink>
 __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceDataView& D, double A,
                                                const Sink& sink, int& f, bool& inrange, FaceRows& R) {
     f = blockIdx.x * kAsmFaces + threadIdx.x;
@@ -475,7 +492,7 @@ __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalVie
     FaceConn C;
     unpack_conn(f, inrange ? M.fconn[f] : make_int4(-1, -1, -1, -1), inrange ? M.fbc[f] : 0x11111, C);
     const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
-    auto load = [&](bool second, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO, EXTRA>(M, L, Cf, C, second, e, i, F); };
+    auto load = [&](bool second, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO, EXTRA, NATURAL>(M, L, Cf, C, second, e, i, F); };
     asm_face<VARIANT, FORM, EXTRA>(D, A, f, pr, C, owned, load, sink, R);
 }
 
@@ -554,7 +571,7 @@ k_asm_count(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, int*
     __shared__ unsigned long long sw64[kAsmBlock / 32];
     FaceRows R;
     int f; bool inrange;
-    tile_face_rows<VARIANT, FORM, EXTRA, ANISO>(M, L, Cf, D, A, NullSink(), f, inrange, R);
+    tile_face_rows<VARIANT, FORM, EXTRA, ANISO, FCFV_NATURAL_COUNT != 0>(M, L, Cf, D, A, NullSink(), f, inrange, R);
     unsigned long long tot;
     block_excl_scan64<kAsmBlock>(rows_counts<EXTRA>(R), tot, sw64);
     if (threadIdx.x == 0) {
@@ -685,7 +702,7 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
     RowVals V;
     int f; bool inrange;
     constexpr bool WANT_M = EXTRA != kExtraNone;   // a third block (Muu or the Schur complement) is assembled
-    tile_face_rows<VARIANT, FORM, EXTRA, ANISO>(M, L, Cf, D, A, RowValsSink{&V}, f, inrange, R);
+    tile_face_rows<VARIANT, FORM, EXTRA, ANISO, false>(M, L, Cf, D, A, RowValsSink{&V}, f, inrange, R);
     if (inrange) {
         fu[f] = R.fux;
         fu[(size_t)nf + f] = R.fuy;

@@ -375,3 +375,42 @@ def test_partitioned_mesh_on_gpu(mesh_name, setting, variant, form, nparts, api,
         big = norms[tm] > 1e-9
         assert np.all(np.abs(got[big] - norms[tm][big]) <= TOL * norms[tm][big]), (tm, got, norms[tm])
         assert np.all(got[~big] < 1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["Gradient", "SymmetricGradient"])
+def test_anisotropic_delta_gpu(form, api, oracle):
+    """delta != 1: ElementAssemblyLoopNEW through the ANISO kernels (full 2x2 D per element), residuals, element
+    values and the Schur complement against the oracle (sparsity exact, values <= 1e-12: LAPACK inv in the reference)."""
+    from fcfv_nme23_b200 import lib as L
+    case = cases.Case("H1", "solkz", 1, form, tau_r=10.0)
+    m, d = cases.build(case)
+    g, _ = cases.build(case)
+    for x in (m, g):
+        x.δ = np.where(x.xc > 0.5, 1.0 + 0.75 * np.abs(np.sin(7.0 * x.yc)) + 0.25, 1.0)
+    nel, nf = m.nel, m.nf
+    neu = d["neu"]
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, form)
+    ga, gb, gZ = api.ComputeFCFV(g, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, form)
+    assert np.array_equal(ga, a) and np.array_equal(gb, b) and np.array_equal(gZ, Z)
+    Kuu, Muu, Kup, fu, fp, _, _ = oracle.ElementAssemblyLoopNEW(m, a, b, Z, d["VxDir"], d["VyDir"], *neu, form)
+    gKuu, gMuu, gKup, gfu, gfp, _ = api.ElementAssemblyLoopNEW(g, ga, gb, gZ, d["VxDir"], d["VyDir"], *neu, form)
+    h = api.handle_for(g)
+    assert_csr_equal(h.export_csr(L.KUU), csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu", bitwise=False, rtol=TOL)
+    assert_csr_equal(h.export_csr(L.KUP), csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup")
+    assert_csr_equal(h.export_csr(L.MUU), csc_triple_to_csr(Muu, (2 * nf, 2 * nf)), "Muu", bitwise=False, rtol=TOL)
+    assert rel_inf(gfu, fu) <= TOL and np.array_equal(gfp, fp)
+    ref_sc = oracle.schur_complement(m, Kuu, Kup, 1.0e4)
+    api.SchurComplement(g, 1.0e4)
+    assert_csr_equal(h.export_csr(L.KUUSC), csc_triple_to_csr(ref_sc, (2 * nf, 2 * nf)), "Kuusc", bitwise=False, rtol=TOL)
+    norms = oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"],
+                                                  d["VyDir"], *neu, form, tau_mode="FACE")
+    gn = api.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], g, ga, gb, gZ, d["sex"], d["sey"], d["VxDir"],
+                                            d["VyDir"], *neu, form, tau_mode="FACE", verbose=False)
+    big = norms > 1e-9
+    assert np.all(np.abs(gn[big] - norms[big]) <= TOL * norms[big])
+    ev = oracle.ComputeElementValues(m, d["Vxh"], d["Vyh"], d["Pe"], a, b, Z, d["VxDir"], d["VyDir"], form)
+    gev = api.ComputeElementValues(g, d["Vxh"], d["Vyh"], d["Pe"], ga, gb, gZ, d["VxDir"], d["VyDir"], form)
+    for k in range(5):
+        assert np.array_equal(gev[k], ev[k])
+    h.close()

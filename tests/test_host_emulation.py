@@ -136,3 +136,34 @@ def test_schur_complement_bitwise(case, oracle, emu):
     assert_csr_equal(euu, csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu")
     assert_csr_equal(eup, csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup")
     assert_csr_equal(esc, csc_triple_to_csr(ref, (2 * nf, 2 * nf)), "Kuusc")
+
+
+def _with_delta(m):
+    """Anisotropy factor delta != 1 in part of the domain (examples/AnisoViscousInclusionFCFV_v0.jl:154-159 style)."""
+    m.δ = np.where(m.xc > 0.5, 1.0 + 0.75 * np.abs(np.sin(7.0 * m.yc)) + 0.25, 1.0)
+    return m
+
+
+@pytest.mark.parametrize("form", ["Gradient", "SymmetricGradient"])
+@pytest.mark.parametrize("mesh", ["S6", "H1"])
+def test_anisotropic_delta(mesh, form, oracle, emu):
+    """ElementAssemblyLoopNEW with delta != 1 (:234-235, two 2x2 inverses; LAPACK in the reference): sparsity exact,
+    values <= 1e-12 relative; also the Schur complement and the element values (delta enters D12)."""
+    case = cases.Case(mesh, "solkz", 1, form, tau_r=10.0)
+    m, d = cases.build(case)
+    _with_delta(m)
+    nel, nf = m.nel, m.nf
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, form)
+    Kuu, Muu, Kup, fu, fp, _, _ = oracle.ElementAssemblyLoopNEW(m, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], form)
+    euu, eup, emu_, efu, efp = emu_assemble(emu, m, a, b, Z, d, 1, form)
+    assert_csr_equal(euu, csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu", bitwise=False, rtol=1e-12)
+    assert_csr_equal(eup, csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup")
+    assert_csr_equal(emu_, csc_triple_to_csr(Muu, (2 * nf, 2 * nf)), "Muu", bitwise=False, rtol=1e-12)
+    assert rel_inf(efu, fu.ravel()) <= 1e-12 and np.array_equal(efp, fp)
+    ref = oracle.schur_complement(m, Kuu, Kup, 1.0e4)
+    _, _, esc, _, _ = emu_assemble(emu, m, a, b, Z, d, 1, form, schur=1.0e4)
+    assert_csr_equal(esc, csc_triple_to_csr(ref, (2 * nf, 2 * nf)), "Kuusc", bitwise=False, rtol=1e-12)
+    # a different delta must change the matrix (the anisotropic branch is really taken)
+    m1, _ = cases.build(case)
+    K1 = oracle.ElementAssemblyLoopNEW(m1, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], form)[0]
+    assert len(K1[2]) != len(Kuu[2]) or not np.array_equal(K1[2], Kuu[2])

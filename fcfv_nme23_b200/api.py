@@ -466,3 +466,12 @@ def ph_fusc(mesh, penalty, p):
     out = np.empty(2 * h.nf)
     h.check(h.lib.fcfv_ph_fusc(h._h, float(penalty), a.d(p, h.nel), _out(out)))
     return out
+
+
+def center_pressure(mesh, Pe):
+    """Pe .- mean(Pe) (src/SolversFCFV_Stokes.jl:20); returns (Pe_centered, mean)."""
+    h = handle_for(mesh)
+    out = np.array(Pe, dtype=np.float64).ravel().copy()
+    mean = C.c_double(0.0)
+    h.check(h.lib.fcfv_center_pressure(h._h, _out(out), C.byref(mean)))
+    return out, float(mean.value)

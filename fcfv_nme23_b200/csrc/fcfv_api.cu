@@ -1079,6 +1079,32 @@ int fcfv_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p) {
     return sync(h);
 }
 
+int fcfv_center_pressure(fcfv_t* h, double* Pe, double* mean) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_center_pressure: no mesh set"));
+    if (!Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_center_pressure: null Pe");
+    CU(cudaSetDevice(h->device));
+    const long long nel = h->nel;
+    const int nbe = nblocks(nel);
+    TRY(ensure(h, h->tmp, sizeof(double) * nel));
+    TRY(ensure(h, h->partial, sizeof(double) * 6 * std::max<long long>(nbe, nblocks(h->nf))));
+    double* dp = P<double>(h->tmp);
+    double* ss = P<double>(h->sumsq);
+    TRY(copy(h, dp, Pe, sizeof(double) * nel));
+    LAUNCH(h, k_sum_owned, nbe, kBlock, (int)nel, dp, h->have_elem_owned ? P<uint8_t>(h->elem_owned) : nullptr, P<double>(h->partial));
+    LAUNCH(h, k_reduce_partials, 1, 1024, P<double>(h->partial), nbe, nbe, ss + 7);
+    CU(cudaGetLastError());
+    if (h->comm) TRY(fcfv_comm_allreduce_sum(h, ss + 7, 1));
+    LAUNCH(h, k_sub_mean, nblocks(nel, 256), 256, (int)nel, dp, ss + 7, (double)h->nel_global);
+    CU(cudaGetLastError());
+    double hs = 0.0;
+    CU(cudaMemcpyAsync(&hs, ss + 7, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+    TRY(copy(h, Pe, dp, sizeof(double) * nel));
+    TRY(sync(h));
+    if (mean) *mean = hs / (double)h->nel_global;
+    return FCFV_OK;
+}
+
 int fcfv_ph_fusc(fcfv_t* h, double gamma, const double* p, double* fusc) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_fusc: nothing assembled"));

@@ -974,13 +974,28 @@ k_ph_rp(MeshView M, const double* __restrict__ fp, const double* __restrict__ u,
     double sq = 0.0;
     if (e < M.nel) {
         const double v = fp[e] - kpu_dot_u(M, e, u);
-        if (mode == 0) { if (rp) rp[e] = v; sq = v * v; }
+        if (mode == 0) { if (rp) rp[e] = v; sq = (M.elem_owned == nullptr || M.elem_owned[e]) ? v * v : 0.0; }   // ghosts are counted by their owner
         else { const double coef = (gamma * M.ke[e]) / M.Om[e]; p[e] = p[e] + coef * v; }
     }
     if (mode == 0) {
         const double t = block_sum(sq, sd);
         if (threadIdx.x == 0) partial[blockIdx.x] = t;
     }
+}
+
+// Pe .-= mean(Pe) (SolversFCFV_Stokes.jl:20): per-block sums over owned elements, then p[e] -= sum / n
+__global__ void __launch_bounds__(kBlock)
+k_sum_owned(int nel, const double* __restrict__ p, const uint8_t* __restrict__ owned, double* __restrict__ partial) {
+    __shared__ double sd[kBlock / 32];
+    const int e = blockIdx.x * kBlock + threadIdx.x;
+    const double v = (e < nel && (owned == nullptr || owned[e])) ? p[e] : 0.0;
+    const double t = block_sum(v, sd);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+
+__global__ void k_sub_mean(int nel, double* __restrict__ p, const double* __restrict__ sum, double n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nel) p[e] = p[e] - sum[0] / n;
 }
 
 __global__ void k_ph_w(int nel, const double* __restrict__ ke, const double* __restrict__ Om,

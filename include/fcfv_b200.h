@@ -143,6 +143,9 @@ int fcfv_element_values(fcfv_t* h, const double* Vxh, const double* Vyh, const d
 int fcfv_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, double* rp, double* nrm);
 int fcfv_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p);
 int fcfv_ph_fusc(fcfv_t* h, double gamma, const double* p, double* fusc);
+/* src/SolversFCFV_Stokes.jl:20 (:CoupledBackslash): Pe .= Pe .- mean(Pe); the sum runs over owned elements
+ * and is all-reduced over the communicator if one is attached (mean of the global pressure). */
+int fcfv_center_pressure(fcfv_t* h, double* Pe, double* mean);
 
 /* ---- device-resident pipeline (what bench.py times as `value`) ---------------------------
  * Upload once, then run the kernels on resident data without host traffic.  The host-buffer

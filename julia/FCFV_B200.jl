@@ -11,7 +11,7 @@ module FCFV_B200
 using SparseArrays, Printf
 
 export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
-       SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc
+       SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
 
@@ -231,6 +231,14 @@ function PHFusc(mesh, penalty, p)
     pp, out = f64(vec(p)), zeros(2h.nf)
     GC.@preserve pp out check(h, ccall((:fcfv_ph_fusc, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}), h.ptr, penalty, pp, out))
     return out
+end
+
+"""Pe .= Pe .- mean(Pe) (src/SolversFCFV_Stokes.jl:20)"""
+function CenterPressure!(mesh, Pe)
+    h = handle_for(mesh)
+    m = Ref{Float64}(0.0)
+    GC.@preserve Pe check(h, ccall((:fcfv_center_pressure, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), h.ptr, Pe, m))
+    return Pe
 end
 
 end # module

@@ -120,6 +120,8 @@ def test_local_assembly_residual(case, api, oracle, golden):
     assert rel_inf(gru, ru) <= TOL and rel_inf(grp, rp) <= TOL and rel_inf(gnrm, nrm) <= TOL
     assert rel_inf(api.ph_update_p(g, 1e4, u, d["Pe"]), oracle.ph_update_p(m, Kup, fp, 1e4, u, d["Pe"])) <= TOL
     assert rel_inf(api.ph_fusc(g, 1e4, d["Pe"]), oracle.ph_fusc(m, Kup, fu, fp, 1e4, d["Pe"])) <= TOL
+    pc, mean = api.center_pressure(g, d["Pe"])          # Solvers:20, Pe .- mean(Pe)
+    assert abs(mean - d["Pe"].mean()) <= TOL * max(1.0, abs(d["Pe"]).max()) and rel_inf(pc, d["Pe"] - d["Pe"].mean()) <= TOL
     h.close()
 
 

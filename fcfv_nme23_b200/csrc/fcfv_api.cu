@@ -66,7 +66,7 @@ struct fcfv_handle {
     bool have_elem_owned = false, have_face_owned = false, have_tau_ref = false;
 
     // mesh
-    DBuf e2f, bc, f2e, fconn, fbc, Om, G, nx, ny, ke, dl, taue, tau, elem_owned, face_owned, tau_ref;
+    DBuf e2f, bc, f2e, fconn, fbc, ebc, Om, G, nx, ny, ke, dl, taue, tau, elem_owned, face_owned, tau_ref;
     // data
     DBuf sex, sey, VxDir, VyDir, sxx, syy, sxy, syx, Vxh, Vyh, Pe;
     // local coefficients
@@ -209,7 +209,7 @@ MeshView mesh_view(fcfv_t* h) {
     MeshView M;
     M.nel = (int)h->nel; M.nf = (int)h->nf;
     M.e2f = P<int>(h->e2f); M.bc = P<int8_t>(h->bc); M.f2e = P<int2>(h->f2e);
-    M.fconn = P<int4>(h->fconn); M.fbc = P<int>(h->fbc);
+    M.fconn = P<int4>(h->fconn); M.fbc = P<int>(h->fbc); M.ebc = P<int>(h->ebc);
     M.Om = P<double>(h->Om); M.G = P<double>(h->G); M.nx = P<double>(h->nx); M.ny = P<double>(h->ny);
     M.ke = P<double>(h->ke); M.dl = P<double>(h->dl); M.taue = P<double>(h->taue); M.tau = P<double>(h->tau);
     M.elem_owned = h->have_elem_owned ? P<uint8_t>(h->elem_owned) : nullptr;
@@ -254,6 +254,8 @@ int build_fconn(fcfv_t* h) {
     TRY(ensure(h, h->fbc, sizeof(int) * nf));
     LAUNCH(h, k_fconn, nblocks(nf, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), P<int2>(h->f2e), (int)nel, (int)nf, P<int4>(h->fconn),
            P<int>(h->fbc));
+    TRY(ensure(h, h->ebc, sizeof(int) * nel));
+    LAUNCH(h, k_ebc, nblocks(nel, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), (int)nel, P<int>(h->ebc));
     return FCFV_OK;
 }
 
@@ -310,7 +312,7 @@ int fcfv_destroy(fcfv_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
-    DBuf* all[] = {&h->e2f, &h->bc, &h->f2e, &h->fconn, &h->fbc, &h->Om, &h->G, &h->nx, &h->ny, &h->ke, &h->dl, &h->taue, &h->tau,
+    DBuf* all[] = {&h->e2f, &h->bc, &h->f2e, &h->fconn, &h->fbc, &h->ebc, &h->Om, &h->G, &h->nx, &h->ny, &h->ke, &h->dl, &h->taue, &h->tau,
                    &h->elem_owned, &h->face_owned, &h->tau_ref, &h->sex, &h->sey, &h->VxDir, &h->VyDir, &h->sxx,
                    &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
                    &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,

@@ -30,6 +30,7 @@ struct MeshView {
     const int2* f2e;
     const int4* fconn;           // per face: the other two faces of the lower (x, y) and higher (z, w) element, -1 when absent
     const int* fbc;              // per face: bc tags of (f, x, y, z, w) packed 4 bits each (tag + 1)
+    const int* ebc;              // per element: bc tags of its three faces packed 4 bits each (tag + 1)
     const double *Om, *G, *nx, *ny, *ke, *dl, *taue;
     const double* tau;
     const uint8_t* elem_owned;   // nullable
@@ -366,6 +367,17 @@ __global__ void k_fconn(const int* __restrict__ e2f, const int8_t* __restrict__ 
     fbc[f] = p;
 }
 
+// per-element copy of the bc tags of its faces (static per mesh): the element kernels know the tags
+// together with e2f instead of one dependent gather later
+__global__ void k_ebc(const int* __restrict__ e2f, const int8_t* __restrict__ bc, int nel, int* __restrict__ ebc) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nel) return;
+    int p = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) p |= (((int)bc[e2f[j * nel + e]] + 1) & 15) << (4 * j);
+    ebc[e] = p;
+}
+
 // ---- a3: tau[f] = taue[highest-numbered adjacent element] (Discretisation:40, last writer) ----
 __global__ void k_face_tau(const int2* __restrict__ f2e, const double* __restrict__ taue, double* __restrict__ tau,
                            int nf) {
@@ -416,11 +428,12 @@ k_local(MeshView M, const double* __restrict__ sex, const double* __restrict__ s
     if (e >= nel) return;
     double G[3], nx[3], ny[3], vx[3], vy[3];
     bool dir[3];
+    const int tags = M.ebc[e];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int f = M.e2f[i * nel + e];
         G[i] = M.G[i * nel + e]; nx[i] = M.nx[i * nel + e]; ny[i] = M.ny[i * nel + e];
-        dir[i] = M.bc[f] == 1;
+        dir[i] = (((tags >> (4 * i)) & 15) - 1) == 1;
         vx[i] = dir[i] ? VxDir[f] : 0.0;
         vy[i] = dir[i] ? VyDir[f] : 0.0;
     }
@@ -803,18 +816,19 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
     const int nel = M.nel;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
     if (e < nel) {
-        double G[3], nx[3], ny[3], tau[3], uhx[3], uhy[3], udx[3], udy[3], tix[3], tiy[3];
+        double G[3], nx[3], ny[3], tau[3], ux[3], uy[3], tix[3], tiy[3];
         int bc[3];
         const double tau_e = (tau_mode == 0) ? (M.tau_ref ? M.tau_ref[e] : M.tau[e < M.nf ? e : 0]) : 0.0;
+        const int tags = M.ebc[e];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int f = M.e2f[i * nel + e];
             G[i] = M.G[i * nel + e]; nx[i] = M.nx[i * nel + e]; ny[i] = M.ny[i * nel + e];
-            bc[i] = M.bc[f];
+            bc[i] = ((tags >> (4 * i)) & 15) - 1;
             tau[i] = (tau_mode == 0) ? tau_e : M.tau[f];
-            uhx[i] = S.Vxh[f]; uhy[i] = S.Vyh[f];
-            udx[i] = udy[i] = 0.0; tix[i] = tiy[i] = 0.0;
-            if (bc[i] == 1) { udx[i] = D.VxDir[f]; udy[i] = D.VyDir[f]; }
+            ux[i] = bc[i] == 1 ? D.VxDir[f] : S.Vxh[f];   // Dirichlet faces take VDir (:62-66)
+            uy[i] = bc[i] == 1 ? D.VyDir[f] : S.Vyh[f];
+            tix[i] = tiy[i] = 0.0;
             if (bc[i] == 2) {   // tractions only enter through t*Xi (:59-61,69)
                 tix[i] = nx[i] * D.sxx[f] + ny[i] * D.sxy[f];
                 tiy[i] = nx[i] * D.syx[f] + ny[i] * D.syy[f];
@@ -823,7 +837,7 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
         ElemRes r;
         element_residual<FORM>(M.Om[e], M.ke[e], M.dl[e], L.alpha[e], L.beta[e], L.beta[nel + e], L.Z[e],
                                L.Z[nel + e], L.Z[2 * nel + e], L.Z[3 * nel + e], sex[e], sey[e], S.Pe[e], G, nx, ny,
-                               bc, tau, uhx, uhy, udx, udy, tix, tiy, r);
+                               bc, tau, ux, uy, tix, tiy, r);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             Fg[(size_t)(2 * i) * nel + e] = r.Fg1[i][0];
@@ -904,11 +918,12 @@ k_elem_values(MeshView M, LocalView L, SolutionView S, double* __restrict__ out)
     if (e >= nel) return;
     double G[3], nx[3], ny[3], tau[3], uhx[3], uhy[3];
     int bc[3];
+    const int tags = M.ebc[e];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int f = M.e2f[i * nel + e];
         G[i] = M.G[i * nel + e]; nx[i] = M.nx[i * nel + e]; ny[i] = M.ny[i * nel + e];
-        bc[i] = M.bc[f]; tau[i] = M.tau[f];
+        bc[i] = ((tags >> (4 * i)) & 15) - 1; tau[i] = M.tau[f];
         uhx[i] = S.Vxh[f]; uhy[i] = S.Vyh[f];
     }
     ElemValues o;

@@ -585,8 +585,10 @@ template <int FORM>
 FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, double b1, double b2, double Z11,
                               double Z21, double Z12, double Z22, double sex, double sey, double Pe,
                               const double G[3], const double nx[3], const double ny[3], const int bc[3],
-                              const double tau[3], const double uhx[3], const double uhy[3], const double udx[3],
-                              const double udy[3], const double tix[3], const double tiy[3], ElemRes& r) {
+                              const double tau[3], const double ux[3], const double uy[3], const double tix[3],
+                              const double tiy[3], ElemRes& r) {
+    // ux, uy: the face velocity the reference uses on face i -- VDir on Dirichlet faces (:62-66), the hybrid
+    // unknown elsewhere (pass A only visits non-Dirichlet faces, :17)
     // pass A :12-32
     double ue[2] = {b1 / alpha, b2 / alpha};
     const double mi = -1.0 / Om;
@@ -594,7 +596,7 @@ FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, do
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         if (bc[i] != 1) {
-            const double n[2] = {nx[i], ny[i]}, u[2] = {uhx[i], uhy[i]};
+            const double n[2] = {nx[i], ny[i]}, u[2] = {ux[i], uy[i]};
             ue[0] = ue[0] + ((G[i] * tau[i]) * u[0]) / alpha;
             ue[1] = ue[1] + ((G[i] * tau[i]) * u[1]) / alpha;
             const double s = (1.0 / Om) * G[i];
@@ -624,7 +626,7 @@ FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, do
         const double Xi = 0.0 + bmul(bc[i] == 2, 1.0);
         const double Ji = 0.0 + bmul(bc[i] == -1, 1.0);
         const double t[2] = {tix[i], tiy[i]};
-        const double u[2] = {bc[i] == 1 ? udx[i] : uhx[i], bc[i] == 1 ? udy[i] : uhy[i]};
+        const double u[2] = {ux[i], uy[i]};
 #pragma unroll
         for (int b = 0; b < 2; b++) {
             const double nDL = n[0] * (D[0][b] * L[0][b]) + n[1] * (D[1][b] * L[1][b]);

@@ -16,7 +16,7 @@ using namespace fcfv;
 namespace {
 struct HostMesh {
     std::vector<int> e2f; std::vector<int8_t> bc; std::vector<int2> f2e;
-    std::vector<int4> fconn; std::vector<int> fbc;
+    std::vector<int4> fconn; std::vector<int> fbc, ebc;
     MeshView view;
 };
 
@@ -35,11 +35,17 @@ void build_mesh(HostMesh& H, long long nel, long long nf, const long long* e2f, 
             cnt[f]++;
         }
     for (long long f = 0; f < nf; f++) if (!cnt[f]) H.f2e[f] = int2{-1, -1};
+    H.ebc.resize(nel);
+    for (long long e = 0; e < nel; e++) {   // k_ebc
+        int p = 0;
+        for (int j = 0; j < 3; j++) p |= (((int)H.bc[H.e2f[j * nel + e]] + 1) & 15) << (4 * j);
+        H.ebc[e] = p;
+    }
     H.fconn.resize(nf); H.fbc.resize(nf);
     for (long long f = 0; f < nf; f++)   // k_fconn
         face_conn_of(H.e2f.data(), H.bc.data(), (int)nel, (int)f, H.f2e[f], H.fconn[f], H.fbc[f]);
     MeshView& M = H.view;
-    M.nel = (int)nel; M.nf = (int)nf; M.e2f = H.e2f.data(); M.bc = H.bc.data(); M.f2e = H.f2e.data(); M.fconn = H.fconn.data(); M.fbc = H.fbc.data();
+    M.nel = (int)nel; M.nf = (int)nf; M.e2f = H.e2f.data(); M.bc = H.bc.data(); M.f2e = H.f2e.data(); M.fconn = H.fconn.data(); M.fbc = H.fbc.data(); M.ebc = H.ebc.data();
     M.Om = Om; M.G = G; M.nx = nx; M.ny = ny; M.ke = ke; M.dl = dl; M.taue = taue; M.tau = tau;
     M.elem_owned = nullptr; M.face_owned = nullptr; M.tau_ref = nullptr;
 }
@@ -207,23 +213,22 @@ int emu_residuals(int formulation, int tau_mode, long long nel, long long nf, co
     std::vector<double> Fg(6 * nel);
     for (int q = 0; q < 6; q++) sumsq[q] = 0.0;
     for (int e = 0; e < (int)nel; e++) {   // k_res_elem
-        double g[3], n1[3], n2[3], t[3], uhx[3], uhy[3], udx[3], udy[3], tix[3], tiy[3]; int b[3];
+        double g[3], n1[3], n2[3], t[3], ux[3], uy[3], tix[3], tiy[3]; int b[3];
         for (int i = 0; i < 3; i++) {
             int f = M.e2f[i * nel + e];
             g[i] = G[i * nel + e]; n1[i] = nx[i * nel + e]; n2[i] = ny[i * nel + e]; b[i] = M.bc[f];
             t[i] = tau_mode == 0 ? tau[e] : tau[f];
-            uhx[i] = Vxh[f]; uhy[i] = Vyh[f]; udx[i] = udy[i] = tix[i] = tiy[i] = 0.0;
-            if (b[i] == 1) { udx[i] = VxDir[f]; udy[i] = VyDir[f]; }
+            ux[i] = b[i] == 1 ? VxDir[f] : Vxh[f]; uy[i] = b[i] == 1 ? VyDir[f] : Vyh[f]; tix[i] = tiy[i] = 0.0;
             if (b[i] == 2) { tix[i] = n1[i] * sxx[f] + n2[i] * sxy[f]; tiy[i] = n1[i] * syx[f] + n2[i] * syy[f]; }
         }
         ElemRes r;
         if (formulation == 0)
             element_residual<kGradient>(Om[e], ke[e], dl[e], alpha[e], beta[e], beta[nel + e], Z[e], Z[nel + e], Z[2 * nel + e],
-                                        Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, uhx, uhy, udx, udy, tix, tiy, r);
+                                        Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, ux, uy, tix, tiy, r);
         else
             element_residual<kSymmetricGradient>(Om[e], ke[e], dl[e], alpha[e], beta[e], beta[nel + e], Z[e], Z[nel + e],
-                                                 Z[2 * nel + e], Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, uhx, uhy,
-                                                 udx, udy, tix, tiy, r);
+                                                 Z[2 * nel + e], Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, ux, uy,
+                                                 tix, tiy, r);
         for (int i = 0; i < 3; i++) { Fg[(2 * i) * nel + e] = r.Fg1[i][0]; Fg[(2 * i + 1) * nel + e] = r.Fg1[i][1]; }
         Fg2[e] = r.Fg2;
         sumsq[0] += r.F1[0][0] * r.F1[0][0] + r.F1[1][0] * r.F1[1][0] + r.F1[0][1] * r.F1[0][1] + r.F1[1][1] * r.F1[1][1];

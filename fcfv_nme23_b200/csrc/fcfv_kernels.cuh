@@ -816,28 +816,30 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
     const int nel = M.nel;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
     if (e < nel) {
-        double G[3], nx[3], ny[3], tau[3], ux[3], uy[3], tix[3], tiy[3];
-        int bc[3];
+        double G[3], nx[3], ny[3], tau[3], ux[3], uy[3];
+        int bc[3], fid[3];
         const double tau_e = (tau_mode == 0) ? (M.tau_ref ? M.tau_ref[e] : M.tau[e < M.nf ? e : 0]) : 0.0;
         const int tags = M.ebc[e];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int f = M.e2f[i * nel + e];
+            fid[i] = f;
             G[i] = M.G[i * nel + e]; nx[i] = M.nx[i * nel + e]; ny[i] = M.ny[i * nel + e];
             bc[i] = ((tags >> (4 * i)) & 15) - 1;
             tau[i] = (tau_mode == 0) ? tau_e : M.tau[f];
             ux[i] = bc[i] == 1 ? D.VxDir[f] : S.Vxh[f];   // Dirichlet faces take VDir (:62-66)
             uy[i] = bc[i] == 1 ? D.VyDir[f] : S.Vyh[f];
-            tix[i] = tiy[i] = 0.0;
-            if (bc[i] == 2) {   // tractions only enter through t*Xi (:59-61,69)
-                tix[i] = nx[i] * D.sxx[f] + ny[i] * D.sxy[f];
-                tiy[i] = nx[i] * D.syx[f] + ny[i] * D.syy[f];
-            }
         }
+        auto traction = [&](int i, double& tx, double& ty) {   // Neumann faces only
+            const int f = pick3(i, fid);
+            const double n1 = pick3(i, nx), n2 = pick3(i, ny);
+            tx = n1 * D.sxx[f] + n2 * D.sxy[f];
+            ty = n1 * D.syx[f] + n2 * D.syy[f];
+        };
         ElemRes r;
         element_residual<FORM>(M.Om[e], M.ke[e], M.dl[e], L.alpha[e], L.beta[e], L.beta[nel + e], L.Z[e],
                                L.Z[nel + e], L.Z[2 * nel + e], L.Z[3 * nel + e], sex[e], sey[e], S.Pe[e], G, nx, ny,
-                               bc, tau, ux, uy, tix, tiy, r);
+                               bc, tau, ux, uy, traction, r);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             Fg[(size_t)(2 * i) * nel + e] = r.Fg1[i][0];

@@ -581,12 +581,14 @@ struct ElemRes {
     double F3;          // F_eq3[e]
 };
 
-template <int FORM>
+// traction(i, tx, ty): t = n * sigma_Neu of face i (:59-61), only called for Neumann faces (it enters through
+// t*Xi, :69) -- evaluated where it is used so that it occupies no registers on the other faces
+template <int FORM, typename Traction>
 FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, double b1, double b2, double Z11,
                               double Z21, double Z12, double Z22, double sex, double sey, double Pe,
                               const double G[3], const double nx[3], const double ny[3], const int bc[3],
-                              const double tau[3], const double ux[3], const double uy[3], const double tix[3],
-                              const double tiy[3], ElemRes& r) {
+                              const double tau[3], const double ux[3], const double uy[3], Traction&& traction,
+                              ElemRes& r) {
     // ux, uy: the face velocity the reference uses on face i -- VDir on Dirichlet faces (:62-66), the hybrid
     // unknown elsewhere (pass A only visits non-Dirichlet faces, :17)
     // pass A :12-32
@@ -625,7 +627,8 @@ FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, do
         const double n[2] = {nx[i], ny[i]};
         const double Xi = 0.0 + bmul(bc[i] == 2, 1.0);
         const double Ji = 0.0 + bmul(bc[i] == -1, 1.0);
-        const double t[2] = {tix[i], tiy[i]};
+        double t[2] = {0.0, 0.0};
+        if (bc[i] == 2) traction(i, t[0], t[1]);
         const double u[2] = {ux[i], uy[i]};
 #pragma unroll
         for (int b = 0; b < 2; b++) {

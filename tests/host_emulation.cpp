@@ -213,22 +213,25 @@ int emu_residuals(int formulation, int tau_mode, long long nel, long long nf, co
     std::vector<double> Fg(6 * nel);
     for (int q = 0; q < 6; q++) sumsq[q] = 0.0;
     for (int e = 0; e < (int)nel; e++) {   // k_res_elem
-        double g[3], n1[3], n2[3], t[3], ux[3], uy[3], tix[3], tiy[3]; int b[3];
+        double g[3], n1[3], n2[3], t[3], ux[3], uy[3]; int b[3], fid[3];
         for (int i = 0; i < 3; i++) {
             int f = M.e2f[i * nel + e];
             g[i] = G[i * nel + e]; n1[i] = nx[i * nel + e]; n2[i] = ny[i * nel + e]; b[i] = M.bc[f];
             t[i] = tau_mode == 0 ? tau[e] : tau[f];
-            ux[i] = b[i] == 1 ? VxDir[f] : Vxh[f]; uy[i] = b[i] == 1 ? VyDir[f] : Vyh[f]; tix[i] = tiy[i] = 0.0;
-            if (b[i] == 2) { tix[i] = n1[i] * sxx[f] + n2[i] * sxy[f]; tiy[i] = n1[i] * syx[f] + n2[i] * syy[f]; }
+            ux[i] = b[i] == 1 ? VxDir[f] : Vxh[f]; uy[i] = b[i] == 1 ? VyDir[f] : Vyh[f]; fid[i] = f;
         }
+        auto traction = [&](int i, double& tx, double& ty) {
+            const int f = fid[i];
+            tx = n1[i] * sxx[f] + n2[i] * sxy[f]; ty = n1[i] * syx[f] + n2[i] * syy[f];
+        };
         ElemRes r;
         if (formulation == 0)
             element_residual<kGradient>(Om[e], ke[e], dl[e], alpha[e], beta[e], beta[nel + e], Z[e], Z[nel + e], Z[2 * nel + e],
-                                        Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, ux, uy, tix, tiy, r);
+                                        Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, ux, uy, traction, r);
         else
             element_residual<kSymmetricGradient>(Om[e], ke[e], dl[e], alpha[e], beta[e], beta[nel + e], Z[e], Z[nel + e],
                                                  Z[2 * nel + e], Z[3 * nel + e], sex[e], sey[e], Pe[e], g, n1, n2, b, t, ux, uy,
-                                                 tix, tiy, r);
+                                                 traction, r);
         for (int i = 0; i < 3; i++) { Fg[(2 * i) * nel + e] = r.Fg1[i][0]; Fg[(2 * i + 1) * nel + e] = r.Fg1[i][1]; }
         Fg2[e] = r.Fg2;
         sumsq[0] += r.F1[0][0] * r.F1[0][0] + r.F1[1][0] * r.F1[1][0] + r.F1[0][1] * r.F1[0][1] + r.F1[1][1] * r.F1[1][1];

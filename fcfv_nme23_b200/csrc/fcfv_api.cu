@@ -82,7 +82,7 @@ struct fcfv_handle {
     long long totals_host[9] = {0};
     bool totals_valid = false;
     // residual
-    DBuf Fg, partial, sumsq;
+    DBuf Fg, partial, sumsq, red_scratch, red_tickets;
     // scratch
     DBuf tmp, tmp2, err_flag, phw;
     // per-kernel device timers (fcfv_set_timing): event pairs resolved lazily
@@ -298,11 +298,13 @@ int fcfv_create(fcfv_t** out, int device) {
         return FCFV_ERR_CUDA;
     }
     if (ensure(h, h->err_flag, sizeof(int)) || ensure(h, h->totals, sizeof(long long) * 16) ||
-        ensure(h, h->sumsq, sizeof(double) * 8)) {
+        ensure(h, h->sumsq, sizeof(double) * 8) || ensure(h, h->red_scratch, sizeof(double) * 6 * kRedSlices) ||
+        ensure(h, h->red_tickets, sizeof(unsigned int) * 8)) {
         delete h;
         return FCFV_ERR_ALLOC;
     }
     cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream);
+    cudaMemsetAsync(h->red_tickets.p, 0, sizeof(unsigned int) * 8, h->stream);
     *out = h;
     return FCFV_OK;
 }
@@ -317,7 +319,7 @@ int fcfv_destroy(fcfv_t* h) {
                    &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
                    &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,
                    &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->Kuusc.rowptr, &h->Kuusc.col, &h->Kuusc.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->chunks, &h->totals,
-                   &h->Fg, &h->partial, &h->sumsq, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx, &h->coefs};
+                   &h->Fg, &h->partial, &h->sumsq, &h->red_scratch, &h->red_tickets, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx, &h->coefs};
     for (DBuf* b : all) release(h, *b);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     cudaEventDestroy(h->ev0);
@@ -925,9 +927,8 @@ int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, 
     TLAUNCH(h, T_RES_FACE, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, (double*)nullptr, (double*)nullptr);
     // sumsq order = print order: F_eq1, F_eq2, F_eq3, F_nodes_x, F_nodes_y, F_glob2
     double* ss = P<double>(h->sumsq);
-    TLAUNCH(h, T_REDUCE, k_reduce_partials, 3, 1024, part, nbe, stride, ss);                                // eq1, eq2, eq3
-    TLAUNCH(h, T_REDUCE, k_reduce_partials, 2, 1024, part + 4 * (size_t)stride, nbf, stride, ss + 3);       // nodes x, y
-    TLAUNCH(h, T_REDUCE, k_reduce_partials, 1, 1024, part + 3 * (size_t)stride, nbe, stride, ss + 5);       // glob2
+    TLAUNCH(h, T_REDUCE, k_reduce_residuals, dim3(kRedSlices, 6), 256, part, nbe, nbf, stride, P<double>(h->red_scratch),
+            P<unsigned int>(h->red_tickets), ss);
     CU(cudaGetLastError());
     if (h->comm) TRY(fcfv_comm_allreduce_sum(h, ss, 6));
     if (sumsq || norms) {

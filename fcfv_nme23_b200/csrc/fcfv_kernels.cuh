@@ -911,6 +911,46 @@ k_reduce_partials(const double* __restrict__ partial, int n, int stride, double*
     }
 }
 
+// The six residual sums in ONE launch: grid (kRedSlices, 6).  Block (r, q) sums slice r of quantity q in a
+// fixed order into scratch; the last block of a quantity to finish (ticket counter) adds the kRedSlices slice
+// sums in index order -- the result does not depend on which block that is.
+// q: 0 F_eq1, 1 F_eq2, 2 F_eq3 (element partial rows 0..2), 3 F_nodes_x, 4 F_nodes_y (face partial rows 4, 5),
+// 5 F_glob2 (element partial row 3) = print order of the reference (:101-106).
+constexpr int kRedSlices = 64;
+__global__ void __launch_bounds__(256)
+k_reduce_residuals(const double* __restrict__ partial, int nbe, int nbf, int stride, double* __restrict__ scratch,
+                   unsigned int* __restrict__ tickets, double* __restrict__ out) {
+    __shared__ double sd[8];
+    __shared__ bool last;
+    const int q = blockIdx.y, r = blockIdx.x;
+    const int row = q < 3 ? q : (q < 5 ? q + 1 : 3);
+    const int n = (q == 3 || q == 4) ? nbf : nbe;
+    const double* p = partial + (size_t)row * stride;
+    const int chunk = (n + kRedSlices - 1) / kRedSlices;
+    const int lo = r * chunk, hi = min(n, lo + chunk);
+    double s = 0.0;
+    for (int k = lo + threadIdx.x; k < hi; k += 256) s += p[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) sd[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; k++) t += sd[k];
+        scratch[q * kRedSlices + r] = t;
+        __threadfence();
+        last = atomicAdd(&tickets[q], 1u) == kRedSlices - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (int k = 0; k < kRedSlices; k++) t += ((volatile double*)scratch)[q * kRedSlices + k];
+        out[q] = t;
+        tickets[q] = 0;
+    }
+}
+
 // ---- ComputeElementValues (Discretisation:52-94) -------------------------------------------------
 // out: Vxe, Vye, Txxe, Tyye, Txye as five consecutive arrays of nel doubles
 __global__ void __launch_bounds__(kBlock)

@@ -21,8 +21,8 @@ using namespace fcfv;
 
 struct Id128 { char b[128]; };   // ncclUniqueId
 
-enum { T_TAU = 0, T_LOCAL, T_COEF, T_COUNT, T_SCAN, T_FILL, T_RES_ELEM, T_RES_FACE, T_REDUCE, T_PH, T_OTHER, kNumTimers };
-static const char* const kTimerNames[kNumTimers] = {"k_face_tau", "k_local", "k_elem_coef", "k_asm_count", "k_scan", "k_asm_fill",
+enum { T_LOCAL = 0, T_COEF, T_COUNT, T_SCAN, T_FILL, T_RES_ELEM, T_RES_FACE, T_REDUCE, T_PH, T_OTHER, kNumTimers };
+static const char* const kTimerNames[kNumTimers] = {"k_local", "k_elem_coef", "k_asm_count", "k_scan", "k_asm_fill",
                                                     "k_res_elem", "k_res_face", "k_reduce_partials", "k_ph", "other"};
 struct TimerRec { int id; cudaEvent_t a, b; };
 
@@ -255,7 +255,7 @@ int build_fconn(fcfv_t* h) {
     LAUNCH(h, k_fconn, nblocks(nf, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), P<int2>(h->f2e), (int)nel, (int)nf, P<int4>(h->fconn),
            P<int>(h->fbc));
     TRY(ensure(h, h->ebc, sizeof(int) * nel));
-    LAUNCH(h, k_ebc, nblocks(nel, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), (int)nel, P<int>(h->ebc));
+    LAUNCH(h, k_ebc, nblocks(nel, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), P<int2>(h->f2e), (int)nel, P<int>(h->ebc));
     return FCFV_OK;
 }
 
@@ -560,13 +560,13 @@ int fcfv_run_local(fcfv_t* h, int formulation, double A) {
     TRY(need(h, h->have_sources && h->have_face_data, "fcfv_run_local: sources / face data not set"));
     CU(cudaSetDevice(h->device));
     const MeshView M = mesh_view(h);
-    TLAUNCH(h, T_TAU, k_face_tau, nblocks(h->nf, 256), 256, M.f2e, M.taue, P<double>(h->tau), M.nf);
+    // mesh.τ is set by the element kernel (one writer per face: its highest adjacent element)
     if (formulation == FCFV_GRADIENT)
         TLAUNCH(h, T_LOCAL, k_local<kGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey), P<double>(h->VxDir),
-               P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z));
+               P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z), P<double>(h->tau));
     else
         TLAUNCH(h, T_LOCAL, k_local<kSymmetricGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey),
-               P<double>(h->VxDir), P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z));
+               P<double>(h->VxDir), P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z), P<double>(h->tau));
     CU(cudaGetLastError());
     h->have_local = true;
     return finish(h);

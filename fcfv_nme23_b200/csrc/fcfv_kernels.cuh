@@ -368,23 +368,21 @@ __global__ void k_fconn(const int* __restrict__ e2f, const int8_t* __restrict__ 
 }
 
 // per-element copy of the bc tags of its faces (static per mesh): the element kernels know the tags
-// together with e2f instead of one dependent gather later
-__global__ void k_ebc(const int* __restrict__ e2f, const int8_t* __restrict__ bc, int nel, int* __restrict__ ebc) {
+// together with e2f instead of one dependent gather later.  Bits 12..14: the element is the
+// highest-numbered one adjacent to its local face j, i.e. the last writer of mesh.τ[face]
+// (Discretisation:40), so that ComputeFCFV can set τ from the element side.
+__global__ void k_ebc(const int* __restrict__ e2f, const int8_t* __restrict__ bc, const int2* __restrict__ f2e, int nel,
+                      int* __restrict__ ebc) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nel) return;
     int p = 0;
 #pragma unroll
-    for (int j = 0; j < 3; j++) p |= (((int)bc[e2f[j * nel + e]] + 1) & 15) << (4 * j);
+    for (int j = 0; j < 3; j++) {
+        const int f = e2f[j * nel + e];
+        p |= (((int)bc[f] + 1) & 15) << (4 * j);
+        p |= ((f2e[f].y >> 2) == e ? 1 : 0) << (12 + j);
+    }
     ebc[e] = p;
-}
-
-// ---- a3: tau[f] = taue[highest-numbered adjacent element] (Discretisation:40, last writer) ----
-__global__ void k_face_tau(const int2* __restrict__ f2e, const double* __restrict__ taue, double* __restrict__ tau,
-                           int nf) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nf) return;
-    const int hi = f2e[f].y;
-    if (hi >= 0) tau[f] = taue[hi >> 2];
 }
 
 // ---- a2 geometry -------------------------------------------------------------------------------
@@ -422,12 +420,13 @@ template <int FORM>
 __global__ void __launch_bounds__(kBlock)
 k_local(MeshView M, const double* __restrict__ sex, const double* __restrict__ sey,
         const double* __restrict__ VxDir, const double* __restrict__ VyDir, double A, double* __restrict__ alpha,
-        double* __restrict__ beta, double* __restrict__ Z) {
+        double* __restrict__ beta, double* __restrict__ Z, double* __restrict__ tau) {
     const int e = blockIdx.x * kBlock + threadIdx.x;
     const int nel = M.nel;
     if (e >= nel) return;
     double G[3], nx[3], ny[3], vx[3], vy[3];
     bool dir[3];
+    int fid[3];
     const int tags = M.ebc[e];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -436,9 +435,15 @@ k_local(MeshView M, const double* __restrict__ sex, const double* __restrict__ s
         dir[i] = (((tags >> (4 * i)) & 15) - 1) == 1;
         vx[i] = dir[i] ? VxDir[f] : 0.0;
         vy[i] = dir[i] ? VyDir[f] : 0.0;
+        fid[i] = f;
     }
+    const double te = M.taue[e];
+    // mesh.τ[face] = τe of the last writer (:40) = the highest adjacent element: one writer per face, no race
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        if ((tags >> (12 + i)) & 1) tau[fid[i]] = te;
     ElemLocal o;
-    element_local<FORM>(M.Om[e], M.taue[e], sex[e], sey[e], G, nx, ny, dir, vx, vy, A, o);
+    element_local<FORM>(M.Om[e], te, sex[e], sey[e], G, nx, ny, dir, vx, vy, A, o);
     alpha[e] = o.alpha;
     beta[e] = o.b1; beta[nel + e] = o.b2;
     Z[e] = o.Z11; Z[nel + e] = o.Z21; Z[2 * nel + e] = o.Z12; Z[3 * nel + e] = o.Z22;

@@ -265,7 +265,9 @@ int alloc_mesh_dependent(fcfv_t* h) {
     TRY(ensure(h, h->alpha, sizeof(double) * nel));
     TRY(ensure(h, h->beta, sizeof(double) * 2 * nel));
     TRY(ensure(h, h->Z, sizeof(double) * 4 * nel));
-    h->rp64 = 20 * nf >= (1LL << 31);
+    // 64-bit row pointers once the CSR capacity can exceed 2^31 entries (FCFV_FORCE_RP64=1 forces them: test hook)
+    const char* force64 = getenv("FCFV_FORCE_RP64");
+    h->rp64 = 20 * nf >= (1LL << 31) || (force64 && force64[0] == '1');
     return FCFV_OK;
 }
 

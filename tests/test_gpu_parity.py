@@ -416,3 +416,36 @@ def test_anisotropic_delta_gpu(form, api, oracle):
     for k in range(5):
         assert np.array_equal(gev[k], ev[k])
     h.close()
+
+
+@pytest.mark.gpu
+def test_int64_row_pointers(api, oracle, monkeypatch):
+    """Meshes whose CSR capacity exceeds 2^31 entries switch to 64-bit row pointers (fcfv_index_width == 8).  The
+    code path is forced on a small mesh and must give the same CSR / CSC as the oracle, Schur complement included."""
+    from fcfv_nme23_b200 import lib as L
+    monkeypatch.setenv("FCFV_FORCE_RP64", "1")
+    case = cases.Case("H1", "solkz", 1, "SymmetricGradient", tau_r=10.0)
+    m, d = cases.build(case)
+    g, _ = cases.build(case)
+    nel, nf = m.nel, m.nf
+    neu = d["neu"]
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form)
+    Kuu, Muu, Kup, fu, fp, _, _ = oracle.ElementAssemblyLoopNEW(m, a, b, Z, d["VxDir"], d["VyDir"], *neu, case.form)
+    ga, gb, gZ = api.ComputeFCFV(g, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form)
+    api.ElementAssemblyLoopNEW(g, ga, gb, gZ, d["VxDir"], d["VyDir"], *neu, case.form)
+    h = api.handle_for(g)
+    assert h.lib.fcfv_index_width(h._h) == 8
+    rp, ci, v = h.export_csr(L.KUU)
+    assert rp.dtype == np.int64
+    assert_csr_equal((rp, ci, v), csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu")
+    assert_csr_equal(h.export_csr(L.KUP), csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup")
+    assert_csr_equal(h.export_csr(L.MUU), csc_triple_to_csr(Muu, (2 * nf, 2 * nf)), "Muu")
+    ref_sc = oracle.schur_complement(m, Kuu, Kup, 1.0e4)
+    api.SchurComplement(g, 1.0e4)
+    cp, rv, vv = h.export_csc(L.KUUSC)
+    assert np.array_equal(cp, ref_sc[0]) and np.array_equal(rv, ref_sc[1]) and np.array_equal(vv, ref_sc[2])
+    u = np.concatenate([d["Vxh"], d["Vyh"]])
+    ru, rp_, nrm = oracle.ph_residual(m, Kuu, Kup, fu, fp, u, d["Pe"])
+    gru, grp, gnrm = api.ph_residual(g, u, d["Pe"])
+    assert rel_inf(gru, ru) <= TOL and rel_inf(grp, rp_) <= TOL
+    h.close()

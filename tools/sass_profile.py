@@ -51,7 +51,7 @@ def main():
     kname = rows[0][1]
     hdr = rows[1]
     ci = {h: i for i, h in enumerate(hdr)}
-    mangled = {"k_asm_fill": "k_asm_fillILi1ELi1ELb0ELb0EiE", "k_asm_count": "k_asm_countILi1ELi1ELb0ELb0E",
+    mangled = {"k_asm_fill": "k_asm_fillILi1ELi1ELi0ELb0EiE", "k_asm_count": "k_asm_countILi1ELi1ELi0ELb0E",
                "k_res_elem": "k_res_elemILi1E", "k_local": "k_localILi1E"}.get(kre, kre)
     table = sass_lines(lib, mangled)
     base = None

@@ -44,6 +44,13 @@ N_DEFAULT = 3536       # S(3536): 50,013,184 elements (BASELINE config 4)
 CPU_SAMPLE_N = 500     # S(500): 1,000,000 elements (BASELINE config 3) -- bounded CPU sample
 
 
+def workload_name(n1, world, scaling):
+    """Name of the workload both arms are quoted on (n1 = quads per side of the single-GPU mesh)."""
+    n = int(round(n1 * world ** 0.5)) if scaling == "weak" else n1
+    return (f"SolKz S({n}) criss-cross triangulation, {4 * n * n} elements, ElementAssemblyLoopNEW :SymmetricGradient, "
+            "tau_e=10*max(ke,1)")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -212,7 +219,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"SolKz S({N_DEFAULT if args.n is None else args.n}) NEW :SymmetricGradient; CPU sample S({n})"},
+            "config": {"workload": workload_name(N_DEFAULT if args.n is None else args.n, args.gpus, args.scaling),
+                       "sample": f"each step = one bounded sample S({n}) of that workload on 1 host thread (the reference has no threading)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -328,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"SolKz S({n}) criss-cross triangulation, {total_el} elements, ElementAssemblyLoopNEW :SymmetricGradient, tau_e=10*max(ke,1)",
+                "config": {"workload": workload_name(n1, world, args.scaling),
                            "elements_per_rank": owned_el, "partition": f"{world} strips of quad rows + ghost rows" if world > 1 else "none",
                            "l2": "inputs (>40 GB per rank at the default size) exceed the 126 MB L2; no flush needed",
                            "nnz_uu_rank0": nnz_uu, "nnz_up_rank0": nnz_up, "rowptr_bytes": rpw,

@@ -449,3 +449,44 @@ def test_int64_row_pointers(api, oracle, monkeypatch):
     gru, grp, gnrm = api.ph_residual(g, u, d["Pe"])
     assert rel_inf(gru, ru) <= TOL and rel_inf(grp, rp_) <= TOL
     h.close()
+
+
+@pytest.mark.gpu
+def test_config4_50M_properties(api):
+    """BASELINE config 4 size (S(3536), 50 013 184 elements) on one GPU: size-independent properties of the device
+    result -- closed-form sizes, CSR row pointers, SURVEY §4 identity 1 through norms, run-to-run determinism."""
+    import ctypes as C
+    from fcfv_nme23_b200 import lib as L
+    n = 3536
+    h = api.Handle(0)
+    h.generate_structured(n, setting="solkz", tau_r=10.0)
+    assert h.nel == 4 * n * n == 50013184 and h.nf == 6 * n * n + 2 * n
+    form = "SymmetricGradient"
+    h.run_local(form); h.run_assemble(L.LOOP_NEW, form)
+    ss, norms = h.run_residuals(form, "FACE")
+    nnz_uu, nnz_up, _ = h.get_nnz()
+    assert 24.99 < nnz_uu / h.nel < 25.0 and 4.999 < nnz_up / h.nel < 5.0
+    w = h.lib.fcfv_index_width(h._h)
+    rp = np.empty(2 * h.nf + 1, dtype=np.int64 if w == 8 else np.int32)
+    h.check(h.lib.fcfv_export(h._h, L.KUU, L.CSR0, C.c_void_p(rp.ctypes.data), None, None))
+    d = np.diff(rp.astype(np.int64))
+    assert rp[0] == 0 and int(rp[-1]) == nnz_uu and d.min() >= 1 and d.max() <= 10
+    # Dirichlet rows hold exactly the unit diagonal: 8n boundary faces x 2 components
+    assert int((d == 1).sum()) == 2 * 4 * n
+    del rp, d
+    # identity 1: ||fu - Kuu u - Kup p||^2 = F_nodes sums + Dirichlet rows (VDir - u)^2 ;  ||fp - Kpu u||^2 = F_glob2 sum
+    dd, dm = h.get_data(), h.get_mesh()
+    u = np.concatenate([dd["Vxh"], dd["Vyh"]])
+    nrm = np.zeros(2)
+    h.check(h.lib.fcfv_ph_residual(h._h, C.c_void_p(u.ctypes.data), C.c_void_p(dd["Pe"].ctypes.data), None, None,
+                                   C.c_void_p(nrm.ctypes.data)))
+    bd = dm["bc"] == 1
+    dir2 = ((dd["VxDir"][bd] - dd["Vxh"][bd]) ** 2).sum() + ((dd["VyDir"][bd] - dd["Vyh"][bd]) ** 2).sum()
+    assert abs(nrm[0] ** 2 - (ss[3] + ss[4] + dir2)) <= 1e-9 * nrm[0] ** 2
+    assert abs(nrm[1] ** 2 - ss[5]) <= 1e-9 * ss[5]
+    del dd, dm, u
+    # determinism
+    h.run_assemble(L.LOOP_NEW, form)
+    ss2, _ = h.run_residuals(form, "FACE")
+    assert h.get_nnz()[:2] == (nnz_uu, nnz_up) and np.array_equal(ss, ss2)
+    h.close()

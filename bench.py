@@ -381,11 +381,14 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
     nnz = [C.c_int64(0) for _ in range(3)]
     sec = C.c_double(0.0)
 
-    def step():
-        h.check(lib.fcfv_set_mesh(h._h, nel, nf, ptr(P["e2f"]), ptr(P["bc"]), ptr(P["Ω"]), ptr(P["n_x"]), ptr(P["n_y"]),
-                                  ptr(P["Γ"]), ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel))
-        if world > 1:
-            h.check(lib.fcfv_set_ownership(h._h, ptr(P["eo"]), ptr(P["fo"]), nel_g, nf_g, None))
+    def step(with_mesh=True):
+        if with_mesh:
+            h.check(lib.fcfv_set_mesh(h._h, nel, nf, ptr(P["e2f"]), ptr(P["bc"]), ptr(P["Ω"]), ptr(P["n_x"]), ptr(P["n_y"]),
+                                      ptr(P["Γ"]), ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel))
+            if world > 1:
+                h.check(lib.fcfv_set_ownership(h._h, ptr(P["eo"]), ptr(P["fo"]), nel_g, nf_g, None))
+        else:   # what the shim does on a mesh it has already uploaded: refresh the mutable fields only
+            h.check(lib.fcfv_update_fields(h._h, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, None))
         h.check(lib.fcfv_compute_local(h._h, form, 1.0, ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]),
                                        ptr(out["alpha"]), ptr(out["beta"]), ptr(out["Z"]), ptr(out["tau"])))
         h.check(lib.fcfv_assemble(h._h, VARIANT, form, 1.0, None, None, None, ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), ptr(Dd["sxx"]),
@@ -411,8 +414,22 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    # same pass on a mesh that is already resident (second and later calls on one FCFV_Mesh object)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(with_mesh=False)
+    h.sync()
+    dt2 = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt2], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt2 = float(t.item())
     return {"value": total_el * steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "mesh_resident": {"value": total_el * steps / dt2 / 1e6, "ms_per_step": 1e3 * dt2 / steps,
+                              "h2d_bytes_per_step": int(h2d - (128 * nel + 8 * nf) + 24 * nel - ((nel + nf) if world > 1 else 0)),
+                              "note": "fcfv_update_fields instead of fcfv_set_mesh (mesh uploaded once per FCFV_Mesh object)"},
             "api": "fcfv_set_mesh + fcfv_compute_local + fcfv_assemble + fcfv_residuals, pinned host buffers, CSR left device-resident"}
 
 

@@ -54,10 +54,9 @@ struct FaceElem {
     double b1, b2, Z11, Z21, Z12, Z22;
 };
 
-// Local face j of an element sits at position perm(i, j) of the record built for row face i: the
-// row face is SWAPPED to position 0 (j == i -> 0, j == 0 -> i, the third face stays).  Nothing
-// downstream depends on the order of the two other faces (columns are ranked by face id).
-FCFV_HD int face_pos(int i, int j) { return j == i ? 0 : (j == 0 ? i : j); }
+// The record of an element built for row face i holds the row face at position 0: local face j sits
+// at position (j == i ? 0 : j == 0 ? i : j) -- a swap, not a rotation.  Nothing downstream depends on
+// the order of the two other faces (columns are ranked by face id).
 
 // Column faces of the rows of face f and their bc tags: k[0] = f, k[1..2] = the other faces of the
 // lower element, k[3..4] = those of the higher element (static per mesh: fconn / fbc arrays).

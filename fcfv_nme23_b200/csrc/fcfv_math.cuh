@@ -206,7 +206,6 @@ struct LaneRow {
     double ts[3], tc[3];   // terms of Kup*(Kppi*Kpu) in the same / cross component block (kExtraSchur)
     double fu, kp;         // RHS share, Kup value
     int e, i;              // element, local index of the row face in it
-    bool active;
 };
 
 // value of loop pair (p = i_loop, q = j_loop) of the reference: "same" = u1u1/u2u2 entry of component
@@ -246,7 +245,7 @@ template <int VARIANT, int FORM, int EXTRA>
 FCFV_HD void lane_row(const LaneElem& E, int e, int i, int comp, double A, double vDir, double Sr1, double Sr2,
                       LaneRow& R) {
     constexpr bool WANT_M = EXTRA == kExtraMuu;
-    R.e = e; R.i = i; R.active = true;
+    R.e = e; R.i = i;
     // Kup[(f,comp), e] (:180-185)
     const double kp_row = 0.0 - bmul(pick3(i, E.bc) != 1, pick3(i, E.G)) * pick3(i, E.nr);
 #pragma unroll
@@ -296,13 +295,6 @@ FCFV_HD void lane_row(const LaneElem& E, int e, int i, int comp, double A, doubl
     }
     R.fu = 0.0 + (bmul(bci != 1, fe) + bmul(bci == 1, vDir) * 1.0);   // :191-192
     R.kp = kp_row;
-}
-
-FCFV_HD void lane_row_inactive(LaneRow& R) {
-    R.e = -1; R.i = 0; R.active = false;
-#pragma unroll
-    for (int j = 0; j < 3; j++) { R.key[j] = kDeadKey; R.vs[j] = R.vc[j] = R.ms[j] = R.ts[j] = R.tc[j] = 0.0; }
-    R.fu = 0.0; R.kp = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -846,31 +846,41 @@ int fcfv_export(fcfv_t* h, int block, int layout, void* ptr, void* idx, double* 
     }
     if (layout != FCFV_CSC1_INT64) return fail(h, FCFV_ERR_INVALID, "unknown layout %d", layout);
     if (!ptr || !idx || !val) return fail(h, FCFV_ERR_INVALID, "fcfv_export: CSC export needs ptr, idx and val");
-    // CSR -> Julia CSC: stable counting sort by column on the host (API boundary, not the hot path);
-    // rows are visited in ascending order, so rows are ascending inside every column.
-    std::vector<char> rp(rpw * (nrows + 1));
-    std::vector<int> col((size_t)nnz);
-    std::vector<double> v((size_t)nnz);
-    CU(cudaMemcpyAsync(rp.data(), c->rowptr.p, rp.size(), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(col.data(), c->col.p, sizeof(int) * nnz, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(v.data(), c->val.p, sizeof(double) * nnz, cudaMemcpyDeviceToHost, h->stream));
-    TRY(sync(h));
-    int64_t* colptr = (int64_t*)ptr;
-    int64_t* rowval = (int64_t*)idx;
-    std::vector<int64_t> next((size_t)ncols + 1, 0);
-    for (long long k = 0; k < nnz; k++) next[col[k] + 1]++;
-    for (long long j = 0; j < ncols; j++) next[j + 1] += next[j];
-    for (long long j = 0; j <= ncols; j++) colptr[j] = next[j] + 1;
-    auto rowptr_at = [&](long long r) -> long long {
-        return h->rp64 ? ((const long long*)rp.data())[r] : (long long)((const int*)rp.data())[r];
+    // CSR -> Julia CSC on the device (k_csc_*): count, scan, scatter, per-column sort by row
+    if (nrows >= (1LL << 31) || ncols >= (1LL << 31)) return fail(h, FCFV_ERR_INVALID, "fcfv_export: block too large");
+    DBuf d_cp, d_rv, d_nz, d_cur, d_chunks;
+    auto body = [&]() -> int {
+        const int nchunks = (int)((ncols + 4095) / 4096);
+        TRY(ensure(h, d_cp, sizeof(long long) * (ncols + 1)));
+        TRY(ensure(h, d_rv, sizeof(long long) * std::max<long long>(nnz, 1)));
+        TRY(ensure(h, d_nz, sizeof(double) * std::max<long long>(nnz, 1)));
+        TRY(ensure(h, d_cur, sizeof(unsigned int) * std::max<long long>(ncols, 1)));
+        TRY(ensure(h, d_chunks, sizeof(unsigned long long) * (nchunks + 1)));
+        CU(cudaMemsetAsync(d_cp.p, 0, sizeof(long long) * (ncols + 1), h->stream));
+        CU(cudaMemsetAsync(d_cur.p, 0, sizeof(unsigned int) * std::max<long long>(ncols, 1), h->stream));
+        unsigned long long* cnt = P<unsigned long long>(d_cp);
+        if (h->rp64) LAUNCH(h, k_csc_count<long long>, nblocks(nrows, 256), 256, (int)nrows, P<long long>(c->rowptr), P<int>(c->col), cnt);
+        else LAUNCH(h, k_csc_count<int>, nblocks(nrows, 256), 256, (int)nrows, P<int>(c->rowptr), P<int>(c->col), cnt);
+        LAUNCH(h, k_scan64_local, nchunks, 1024, cnt, ncols, P<unsigned long long>(d_chunks));
+        LAUNCH(h, k_scan64_chunks, 1, 1, P<unsigned long long>(d_chunks), nchunks);
+        LAUNCH(h, k_scan64_finish, nblocks(ncols + 1, 256), 256, cnt, ncols, P<unsigned long long>(d_chunks), nchunks);
+        if (h->rp64)
+            LAUNCH(h, k_csc_scatter<long long>, nblocks(nrows, 256), 256, (int)nrows, P<long long>(c->rowptr), P<int>(c->col), P<double>(c->val),
+                   P<long long>(d_cp), P<unsigned int>(d_cur), P<long long>(d_rv), P<double>(d_nz));
+        else
+            LAUNCH(h, k_csc_scatter<int>, nblocks(nrows, 256), 256, (int)nrows, P<int>(c->rowptr), P<int>(c->col), P<double>(c->val),
+                   P<long long>(d_cp), P<unsigned int>(d_cur), P<long long>(d_rv), P<double>(d_nz));
+        LAUNCH(h, k_csc_sort, nblocks(ncols, 256), 256, (int)ncols, P<long long>(d_cp), P<long long>(d_rv), P<double>(d_nz));
+        CU(cudaGetLastError());
+        TRY(copy(h, ptr, d_cp.p, sizeof(long long) * (ncols + 1)));
+        TRY(copy(h, idx, d_rv.p, sizeof(long long) * nnz));
+        TRY(copy(h, val, d_nz.p, sizeof(double) * nnz));
+        return sync(h);
     };
-    for (long long r = 0; r < nrows; r++)
-        for (long long k = rowptr_at(r); k < rowptr_at(r + 1); k++) {
-            const int64_t p = next[col[k]]++;
-            rowval[p] = r + 1;
-            val[p] = v[k];
-        }
-    return FCFV_OK;
+    const int rc = body();
+    cudaStreamSynchronize(h->stream);
+    for (DBuf* bf : {&d_cp, &d_rv, &d_nz, &d_cur, &d_chunks}) release(h, *bf);
+    return rc;
 }
 
 int fcfv_export_rhs(fcfv_t* h, double* fu, double* fp) {

@@ -979,6 +979,73 @@ k_elem_values(MeshView M, LocalView L, SolutionView S, double* __restrict__ out)
     out[4 * (size_t)nel + e] = o.Txy;
 }
 
+// ---- CSR -> Julia CSC (SparseMatrixCSC{Float64,Int64}: 1-based colptr / rowval, rows ascending in a column) ----
+// The reference's consumers (sparse product, lu, cholesky) take CSC, so the export transposes on the
+// device: count per column (integer atomics), exclusive scan, scatter with an atomic cursor, then an
+// insertion sort of every column by row (<= 10 entries for Kuu, <= 6 for Kup).  Rows are unique inside a
+// column, so the sorted result does not depend on the order in which the scatter ran.
+template <typename RP>
+__global__ void k_csc_count(int nrows, const RP* __restrict__ rowptr, const int* __restrict__ col, unsigned long long* __restrict__ cnt) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    for (RP k = rowptr[r]; k < rowptr[r + 1]; k++) atomicAdd(&cnt[col[k]], 1ULL);
+}
+
+// colptr1[j] = 1 + exclusive prefix (written in place over cnt by the caller's scan); cursor starts at 0
+template <typename RP>
+__global__ void k_csc_scatter(int nrows, const RP* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                              const long long* __restrict__ colptr1, unsigned int* __restrict__ cursor,
+                              long long* __restrict__ rowval, double* __restrict__ nzval) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    for (RP k = rowptr[r]; k < rowptr[r + 1]; k++) {
+        const int c = col[k];
+        const long long p = (colptr1[c] - 1) + atomicAdd(&cursor[c], 1u);
+        rowval[p] = (long long)r + 1;
+        nzval[p] = val[k];
+    }
+}
+
+__global__ void k_csc_sort(int ncols, const long long* __restrict__ colptr1, long long* __restrict__ rowval, double* __restrict__ nzval) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    const long long lo = colptr1[c] - 1, hi = colptr1[c + 1] - 1;
+    for (long long a = lo + 1; a < hi; a++) {
+        const long long r = rowval[a];
+        const double v = nzval[a];
+        long long b = a;
+        while (b > lo && rowval[b - 1] > r) { rowval[b] = rowval[b - 1]; nzval[b] = nzval[b - 1]; b--; }
+        rowval[b] = r; nzval[b] = v;
+    }
+}
+
+// in-place exclusive scan of n counts -> 1-based column pointers (+ the total at [n]); chunks of 1024*4
+__global__ void __launch_bounds__(1024)
+k_scan64_local(unsigned long long* __restrict__ a, long long n, unsigned long long* __restrict__ chunk_tot) {
+    __shared__ unsigned long long sw[32];
+    const long long i0 = (long long)blockIdx.x * 4096 + (long long)threadIdx.x * 4;
+    unsigned long long v[4], t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = (i0 + k < n) ? a[i0 + k] : 0ULL; t += v[k]; }
+    unsigned long long total;
+    unsigned long long run = block_excl_scan64<1024>(t, total, sw);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (i0 + k < n) a[i0 + k] = run; run += v[k]; }
+    if (threadIdx.x == 0) chunk_tot[blockIdx.x] = total;
+}
+
+__global__ void k_scan64_chunks(unsigned long long* __restrict__ chunk_tot, int nchunks) {   // one thread: few thousand chunks
+    unsigned long long run = 0;
+    for (int c = 0; c < nchunks; c++) { const unsigned long long t = chunk_tot[c]; chunk_tot[c] = run; run += t; }
+    chunk_tot[nchunks] = run;
+}
+
+__global__ void k_scan64_finish(unsigned long long* __restrict__ a, long long n, const unsigned long long* __restrict__ chunk_base, int nchunks) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = a[i] + chunk_base[i / 4096] + 1ULL;
+    if (i == n) a[n] = chunk_base[nchunks] + 1ULL;
+}
+
 // ---- a9 Powell-Hestenes -------------------------------------------------------------------------
 // ru = (fu - Kuu*u) - Kup*p, one thread per row, products accumulated in ascending column order
 // (the order Julia's CSC mat-vec produces for each row), per-block sum of ru^2.

@@ -110,7 +110,8 @@ int fcfv_index_width(fcfv_t* h);
 int fcfv_block_size(fcfv_t* h, int block, int64_t* nrows, int64_t* ncols, int64_t* nnz);
 /* Copy a block out.  FCFV_CSR0: ptr has nrows+1 entries of fcfv_index_width bytes, idx int32,
  * 0-based.  FCFV_CSC1_INT64: ptr ncols+1, idx nnz, both int64 and 1-based, rows ascending in a
- * column -- the fields of Julia's SparseMatrixCSC{Float64,Int64}. */
+ * column -- the fields of Julia's SparseMatrixCSC{Float64,Int64}.  The transposition runs on the device
+ * (count / scan / scatter / per-column sort by row: deterministic), the host only receives the result. */
 int fcfv_export(fcfv_t* h, int block, int layout, void* ptr, void* idx, double* val);
 int fcfv_export_rhs(fcfv_t* h, double* fu, double* fp);
 /* Device pointers of the resident CSR for GPU consumers (valid until the next assemble). */

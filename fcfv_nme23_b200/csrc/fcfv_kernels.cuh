@@ -1,18 +1,22 @@
 // fcfv_kernels.cuh -- CUDA kernels (sm_100a, FP64, no tensor cores: nothing here is a dense
-// contraction; every kernel is bound by HBM traffic) for the FCFV hot path.
+// contraction; the path is bound by HBM traffic and gather latency) for the FCFV hot path.
 //
 // Data layout in HBM (structure of arrays, exactly the reference's column-major matrices):
 //   e2f  int32 [3][nel] 0-based      G, nx, ny  double [3][nel]     Om, ke, dl, taue  double [nel]
 //   bc   int8  [nf]                  tau, VxDir, VyDir, s??Neu, Vxh, Vyh  double [nf]
 //   f2e  int2  [nf]: (lo, hi) codes 4*e+i of the <=2 (element, local face) pairs of a face
-//   alpha [nel], beta [2][nel], Z [4][nel] (Z11, Z21, Z12, Z22)
+//   fconn int4 [nf], fbc int32 [nf]: the other faces of both adjacent elements and the bc tags of all
+//        five column faces of a face row; ebc int32 [nel]: bc tags of an element's faces + "I am the
+//        highest adjacent element" bits (all three static per mesh)
+//   alpha [nel], beta [2][nel], Z [4][nel] (Z11, Z21, Z12, Z22); ia, c11 [nel] per-assembly coefficients
 //   CSR:  rowptr int32|int64 [nrows+1], col int32 [cap], val double [cap]
 //
 // Thread mappings: element kernels = one thread per element (consecutive threads read
 // consecutive entries of every SoA array: fully coalesced 8-byte loads); face kernels = one
 // thread per face (coalesced face arrays, gathers of the <=2 adjacent elements hit L1/L2 because
 // face ids follow element order).  Assembly is a gather by face row: no atomics on floating
-// point, every (row, col) value is produced by one thread with a fixed operation order.
+// point, every (row, col) value is produced by one thread with a fixed operation order; the
+// compacted rows leave the SM through shared-memory staging and TMA bulk stores.
 #pragma once
 #include "fcfv_math.cuh"
 

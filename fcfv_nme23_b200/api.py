@@ -195,6 +195,10 @@ class Handle:
     def run_assemble(self, variant, formulation, A=A_DEFAULT, want_muu=False):
         self.check(self.lib.fcfv_run_assemble(self._h, int(variant), formulation_id(formulation), float(A), int(bool(want_muu))))
 
+    def run_pipeline(self, variant, formulation, tau_mode="FACE", A=A_DEFAULT):
+        """run_local + run_assemble + run_residuals as one replayed CUDA graph (launch-bound small meshes)."""
+        self.check(self.lib.fcfv_run_pipeline(self._h, int(variant), formulation_id(formulation), float(A), _TAU_MODES[tau_mode]))
+
     def run_residuals(self, formulation, tau_mode="REFERENCE", fetch=True):
         if not fetch:
             self.check(self.lib.fcfv_run_residuals(self._h, formulation_id(formulation), _TAU_MODES[tau_mode], None, None))

@@ -92,6 +92,10 @@ struct fcfv_handle {
     size_t events_used = 0;
     double timer_ms[kNumTimers] = {0};
     long long timer_calls[kNumTimers] = {0};
+    // CUDA graph of one pass (fcfv_run_pipeline): replayed while nothing it captured has changed
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_key[6] = {-1, -1, -1, -1, -1, -1};   // variant, formulation, tau_mode, alloc epoch, nel, bits of A
+    long long alloc_epoch = 0;                           // bumped whenever a device buffer is (re)allocated
     // nccl
     NcclApi nccl;
     void* comm = nullptr;
@@ -167,6 +171,7 @@ int ensure(fcfv_t* h, DBuf& b, size_t bytes) {
     if (bytes == 0) bytes = 8;
     if (b.cap >= bytes) return FCFV_OK;
     if (b.p) { CU(cudaFree(b.p)); h->bytes -= b.cap; b.p = nullptr; b.cap = 0; }
+    h->alloc_epoch++;
     cudaError_t e = cudaMalloc(&b.p, bytes);
     if (e != cudaSuccess) {
         b.p = nullptr;
@@ -324,6 +329,7 @@ int fcfv_destroy(fcfv_t* h) {
                    &h->Fg, &h->partial, &h->sumsq, &h->red_scratch, &h->red_tickets, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx, &h->coefs};
     for (DBuf* b : all) release(h, *b);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -956,6 +962,61 @@ int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, 
         return FCFV_OK;
     }
     return finish(h);
+}
+
+// One pass of the resident pipeline (local coefficients -> assembly -> residual sums) as a CUDA graph: for small
+// meshes the pass is bound by launch latency (ten kernels of a few microseconds), a replayed graph removes it.
+// The graph is rebuilt when its key changes: loop / formulation / tau mode / A, the mesh size, or any device
+// buffer was reallocated (alloc_epoch); ownership / ghost flags and the anisotropy switch are re-checked through
+// the direct pass that precedes every capture.  With a communicator or per-kernel timing the pass runs directly.
+int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau_mode) {
+    if (!h) return FCFV_ERR_INVALID;
+    auto direct = [&]() -> int {
+        const bool was_async = h->async;
+        h->async = true;
+        int rc = fcfv_run_local(h, formulation, A);
+        if (!rc) rc = fcfv_run_assemble(h, variant, formulation, A, 0);
+        if (!rc) rc = fcfv_run_residuals(h, formulation, tau_mode, nullptr, nullptr);
+        h->async = was_async;
+        return rc;
+    };
+    if (h->comm || h->timing) { TRY(direct()); return finish(h); }
+    long long abits;
+    memcpy(&abits, &A, sizeof abits);
+    const long long flags = (h->have_elem_owned ? 1 : 0) | (h->have_face_owned ? 2 : 0) | (h->have_tau_ref ? 4 : 0) | (h->aniso ? 8 : 0);
+    const long long key[6] = {variant, formulation, tau_mode + 16 * flags, h->alloc_epoch, h->nel, abits};
+    if (h->graph_exec && !h->delta_dirty && memcmp(key, h->graph_key, sizeof key) == 0) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaGraphLaunch(h->graph_exec, h->stream));
+        h->launches += 10;
+        h->have_local = true;
+        h->Kuu.nnz = h->Kup.nnz = -2; h->Muu.nnz = -1; h->Kuusc.nnz = -1;
+        h->totals_valid = false;
+        return finish(h);
+    }
+    // direct pass first: validates the arguments, sizes every buffer and settles the lazy state
+    TRY(direct());
+    TRY(sync(h));
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    const long long flags2 = (h->have_elem_owned ? 1 : 0) | (h->have_face_owned ? 2 : 0) | (h->have_tau_ref ? 4 : 0) | (h->aniso ? 8 : 0);
+    const long long key2[6] = {variant, formulation, tau_mode + 16 * flags2, h->alloc_epoch, h->nel, abits};
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const long long launches0 = h->launches;
+    const int rc = direct();
+    h->launches = launches0;                       // captured, not launched
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc) return rc;
+        return fail(h, FCFV_ERR_CUDA, "fcfv_run_pipeline: stream capture failed: %s", cudaGetErrorString(ce));
+    }
+    ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { h->graph_exec = nullptr; return fail(h, FCFV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+    memcpy(h->graph_key, key2, sizeof key2);
+    return finish(h);   // the direct pass above already produced this call's result
 }
 
 int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, const double* Vyh, const double* Pe,

@@ -76,6 +76,7 @@ def load():
         "fcfv_ph_fusc": [vp, dbl, vp, vp],
         "fcfv_element_values": [vp] + [vp] * 10,
         "fcfv_schur": [vp, dbl, P(i64)],
+        "fcfv_run_pipeline": [vp, ci, ci, dbl, ci],
         "fcfv_center_pressure": [vp, vp, P(dbl)],
         "fcfv_run_assemble_schur": [vp, ci, ci, dbl, dbl],
         "fcfv_set_sources": [vp, vp, vp],

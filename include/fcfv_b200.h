@@ -161,6 +161,10 @@ int fcfv_run_assemble(fcfv_t* h, int variant, int formulation, double A, int wan
 /* sumsq[6]: sums of squares over owned elements/faces (device-reduced, then all-reduced over
  * the communicator if one is attached); norms[6] as fcfv_residuals.  Either may be NULL. */
 int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, double* norms);
+/* fcfv_run_local + fcfv_run_assemble (no Muu) + fcfv_run_residuals as one CUDA graph, captured on first use and
+ * replayed while loop / formulation / A / tau mode / mesh / buffers are unchanged: removes the launch latency that
+ * bounds a pass on small meshes (BASELINE configs 1-2).  Results are read with the fcfv_get_* / fcfv_export calls. */
+int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau_mode);
 int fcfv_get_local(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau);
 int fcfv_get_nnz(fcfv_t* h, int64_t* nnz_uu, int64_t* nnz_up, int64_t* nnz_muu);
 /* run_* calls enqueue on the handle's stream and return without synchronising when async != 0. */

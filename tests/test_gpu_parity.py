@@ -490,3 +490,34 @@ def test_config4_50M_properties(api):
     ss2, _ = h.run_residuals(form, "FACE")
     assert h.get_nnz()[:2] == (nnz_uu, nnz_up) and np.array_equal(ss, ss2)
     h.close()
+
+
+@pytest.mark.gpu
+def test_graph_pipeline_matches_direct_calls(api):
+    """fcfv_run_pipeline (one replayed CUDA graph per pass) against the three direct calls: identical CSR bytes, nnz and
+    residual sums; replays see updated fields (same device buffers), a new mesh size rebuilds the graph."""
+    from fcfv_nme23_b200 import lib as L
+    form, variant = "SymmetricGradient", 1
+    for n in (9, 14):                                   # second size: buffers grow / mesh changes -> new graph
+        h = api.Handle(0)
+        h.generate_structured(n, setting="solkz", tau_r=10.0)
+        h.run_local(form); h.run_assemble(variant, form)
+        ss_ref, _ = h.run_residuals(form, "FACE")
+        ref = h.export_csr(L.KUU); refp = h.export_csr(L.KUP); rhs = h.export_rhs(); nnz = h.get_nnz()
+        for rep in range(3):                            # capture, then replays
+            h.run_pipeline(variant, form, "FACE")
+            h.sync()
+            assert h.get_nnz() == nnz
+            for a, b in zip(h.export_csr(L.KUU) + h.export_csr(L.KUP) + h.export_rhs(), ref + refp + rhs):
+                assert np.array_equal(a, b)
+            ss, _ = h.run_residuals(form, "FACE")
+            assert np.array_equal(ss, ss_ref)
+        # change a field in place: the replay must see it
+        m = h.get_mesh()
+        h.update_fields(ke=m["ke"] * 2.0)
+        h.run_pipeline(variant, form, "FACE"); h.sync()
+        got = h.export_csr(L.KUU)
+        h.run_local(form); h.run_assemble(variant, form)
+        exp = h.export_csr(L.KUU)
+        assert all(np.array_equal(a, b) for a, b in zip(got, exp)) and not np.array_equal(got[2], ref[2])
+        h.close()

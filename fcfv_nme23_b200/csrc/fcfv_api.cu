@@ -94,7 +94,7 @@ struct fcfv_handle {
     long long timer_calls[kNumTimers] = {0};
     // CUDA graph of one pass (fcfv_run_pipeline): replayed while nothing it captured has changed
     cudaGraphExec_t graph_exec = nullptr;
-    long long graph_key[6] = {-1, -1, -1, -1, -1, -1};   // variant, formulation, tau_mode, alloc epoch, nel, bits of A
+    long long graph_key[7] = {-1, -1, -1, -1, -1, -1, -1};   // variant, formulation, tau_mode + flags, alloc epoch, nel, nf, bits of A
     long long alloc_epoch = 0;                           // bumped whenever a device buffer is (re)allocated
     // nccl
     NcclApi nccl;
@@ -984,7 +984,7 @@ int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau
     long long abits;
     memcpy(&abits, &A, sizeof abits);
     const long long flags = (h->have_elem_owned ? 1 : 0) | (h->have_face_owned ? 2 : 0) | (h->have_tau_ref ? 4 : 0) | (h->aniso ? 8 : 0);
-    const long long key[6] = {variant, formulation, tau_mode + 16 * flags, h->alloc_epoch, h->nel, abits};
+    const long long key[7] = {variant, formulation, tau_mode + 16 * flags, h->alloc_epoch, h->nel, h->nf, abits};
     if (h->graph_exec && !h->delta_dirty && memcmp(key, h->graph_key, sizeof key) == 0) {
         CU(cudaSetDevice(h->device));
         CU(cudaGraphLaunch(h->graph_exec, h->stream));
@@ -999,7 +999,7 @@ int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau
     TRY(sync(h));
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     const long long flags2 = (h->have_elem_owned ? 1 : 0) | (h->have_face_owned ? 2 : 0) | (h->have_tau_ref ? 4 : 0) | (h->aniso ? 8 : 0);
-    const long long key2[6] = {variant, formulation, tau_mode + 16 * flags2, h->alloc_epoch, h->nel, abits};
+    const long long key2[7] = {variant, formulation, tau_mode + 16 * flags2, h->alloc_epoch, h->nel, h->nf, abits};
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     const long long launches0 = h->launches;

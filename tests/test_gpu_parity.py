@@ -521,3 +521,30 @@ def test_graph_pipeline_matches_direct_calls(api):
         exp = h.export_csr(L.KUU)
         assert all(np.array_equal(a, b) for a, b in zip(got, exp)) and not np.array_equal(got[2], ref[2])
         h.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_module_constant_A_not_one_gpu(variant, api, oracle):
+    """A = 0.9: the kernels' general path for the symmetric formulation (A == 1.0 runs a specialised instantiation)."""
+    from fcfv_nme23_b200 import lib as L
+    case = cases.Case("H1", "solkz", variant, "SymmetricGradient", tau_r=10.0)
+    m, d = cases.build(case)
+    g, _ = cases.build(case)
+    nel, nf = m.nel, m.nf
+    neu = d["neu"]
+    A = 0.9
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form, A=A)
+    ga, gb, gZ = api.ComputeFCFV(g, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form, A=A)
+    assert np.array_equal(ga, a) and np.array_equal(gb, b) and np.array_equal(gZ, Z)
+    ofn = oracle.ElementAssemblyLoop if variant == 0 else oracle.ElementAssemblyLoopNEW
+    gfn = api.ElementAssemblyLoop if variant == 0 else api.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, _, _ = ofn(m, a, b, Z, d["VxDir"], d["VyDir"], *neu, case.form, A=A)
+    gfn(g, ga, gb, gZ, d["VxDir"], d["VyDir"], *neu, case.form, A=A)
+    h = api.handle_for(g)
+    assert_csr_equal(h.export_csr(L.KUU), csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu")
+    assert_csr_equal(h.export_csr(L.KUP), csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup")
+    assert_csr_equal(h.export_csr(L.MUU), csc_triple_to_csr(Muu, (2 * nf, 2 * nf)), "Muu")
+    gfu, gfp = h.export_rhs()
+    assert np.array_equal(gfu, fu.ravel()) and np.array_equal(gfp, fp)
+    h.close()

@@ -167,3 +167,27 @@ def test_anisotropic_delta(mesh, form, oracle, emu):
     m1, _ = cases.build(case)
     K1 = oracle.ElementAssemblyLoopNEW(m1, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], form)[0]
     assert len(K1[2]) != len(Kuu[2]) or not np.array_equal(K1[2], Kuu[2])
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_module_constant_A_not_one(variant, oracle, emu):
+    """A = 0.9 (the alternative commented out in DiscretisationFCFV_Stokes.jl:1-2): the general code path of the
+    symmetric formulation (A == 1.0 takes a specialised one), bit for bit."""
+    case = cases.Case("H1", "solkz", variant, "SymmetricGradient", tau_r=10.0)
+    m, d = cases.build(case)
+    m2, _ = cases.build(case)
+    nel, nf = m.nel, m.nf
+    A = 0.9
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, case.form, A=A)
+    ea, eb, eZ, etau = emu_local(emu, m2, d, case.form, A=A)
+    assert np.array_equal(ea, a) and np.array_equal(eb, b) and np.array_equal(eZ, Z)
+    fn = oracle.ElementAssemblyLoop if variant == 0 else oracle.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, _, _ = fn(m, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], case.form, A=A)
+    m2.τ = etau
+    euu, eup, emu_, efu, efp = emu_assemble(emu, m2, ea, eb, eZ, d, variant, case.form, A=A)
+    assert_csr_equal(euu, csc_triple_to_csr(Kuu, (2 * nf, 2 * nf)), "Kuu")
+    assert_csr_equal(eup, csc_triple_to_csr(Kup, (2 * nf, nel)), "Kup")
+    assert_csr_equal(emu_, csc_triple_to_csr(Muu, (2 * nf, 2 * nf)), "Muu")
+    assert np.array_equal(efu, fu.ravel()) and np.array_equal(efp, fp)
+    K1 = fn(m, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], case.form, A=1.0)[0]
+    assert not np.array_equal(K1[2], Kuu[2])        # A really enters

@@ -48,6 +48,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and not os.environ.get("FCFV_LIB"):
+        try:                                   # same image on the GPU boxes: nvcc is there, build in-tree once
+            build()
+        except Exception as exc:               # noqa: BLE001 -- reported below
+            raise FCFVError(f"{LIB_PATH} is missing and could not be built ({exc}); there is no CPU fallback") from exc
     if not os.path.exists(LIB_PATH):
         raise FCFVError(f"{LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU fallback)")

@@ -61,3 +61,29 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text and "fcfv_oracle" not in text, fn
+
+
+def test_plain_c_client_links_and_runs():
+    """A C99 translation unit including the header links against the library with gcc (C linkage, no C++ / torch types
+    in the signatures); with a GPU it also runs the one-triangle case through the host-buffer entry points."""
+    src = os.path.join(ROOT, "tests", "c_abi_client.c")
+    exe = os.path.join(ROOT, "tests", "c_abi_client")
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", exe, src, "-L" + libdir, "-lfcfv_b200",
+                           "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode in (0, 77), r.stdout + r.stderr
+    try:
+        import torch
+        if torch.cuda.is_available():
+            assert r.returncode == 0 and "C client OK" in r.stdout, r.stdout
+    except ImportError:
+        pass
+
+
+@pytest.mark.gpu
+def test_plain_c_client_on_gpu():
+    """The C client's compute sequence (set_mesh -> compute_local -> assemble -> CSC export) on the device."""
+    test_plain_c_client_links_and_runs()
+    r = subprocess.run([os.path.join(ROOT, "tests", "c_abi_client")], capture_output=True, text=True)
+    assert r.returncode == 0 and "C client OK" in r.stdout, r.stdout + r.stderr

@@ -479,3 +479,19 @@ def center_pressure(mesh, Pe):
     mean = C.c_double(0.0)
     h.check(h.lib.fcfv_center_pressure(h._h, _out(out), C.byref(mean)))
     return out, float(mean.value)
+
+
+def first_seen_faces(e2f, nf, device=0):
+    """``fcfv_first_seen_faces``: (new_of_old, e2f_new) of the reference's first-seen face numbering, computed on the
+    GPU from ``e2f`` (nel x 3, 1-based).  See ``mesh.renumber_faces`` for applying it to a mesh."""
+    e2f = np.asarray(e2f, dtype=np.int64)
+    nel = e2f.shape[0]
+    h = Handle(device)
+    a = _Arg()
+    perm = np.empty(nf, dtype=np.int64)
+    out = np.empty((nel, 3), dtype=np.int64, order="F")
+    try:
+        h.check(h.lib.fcfv_first_seen_faces(h._h, nel, int(nf), a.i(e2f, 3 * nel), _out(perm), _out(out)))
+    finally:
+        h.close()
+    return perm, out

@@ -507,6 +507,67 @@ int fcfv_geometry(fcfv_t* h, int64_t nel, int64_t nf, int64_t nv, const int64_t*
 }
 
 // -------------------------------------------------------------------------------------------------
+namespace {
+// in-place: counts -> 1-based exclusive ranks (+ total + 1 at [n])
+int scan64_ranks(fcfv_t* h, unsigned long long* a, long long n, DBuf& chunks) {
+    const int nchunks = (int)((n + 4095) / 4096);
+    TRY(ensure(h, chunks, sizeof(unsigned long long) * (nchunks + 1)));
+    LAUNCH(h, k_scan64_local, nchunks, 1024, a, n, P<unsigned long long>(chunks));
+    LAUNCH(h, k_scan64_chunks, 1, 1, P<unsigned long long>(chunks), nchunks);
+    LAUNCH(h, k_scan64_finish, nblocks(n + 1, 256), 256, a, n, P<unsigned long long>(chunks), nchunks);
+    return FCFV_OK;
+}
+}  // namespace
+
+int fcfv_first_seen_faces(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, int64_t* new_of_old, int64_t* e2f_new) {
+    if (!h) return FCFV_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    if (nel < 0 || nf < 0 || nel >= (1LL << 29) || nf >= (1LL << 30)) return fail(h, FCFV_ERR_INVALID, "fcfv_first_seen_faces: size out of range");
+    if (!e2f) return fail(h, FCFV_ERR_INVALID, "fcfv_first_seen_faces: null e2f");
+    DBuf d_e2f, d_f2e, d_cnt, d_flag, d_orph, d_perm, d_out, d_chunks;
+    auto body = [&]() -> int {
+        CU(cudaMemsetAsync(h->err_flag.p, 0, sizeof(int), h->stream));
+        TRY(upload(h, h->tmp, e2f, sizeof(int64_t) * 3 * nel));
+        TRY(ensure(h, d_e2f, sizeof(int) * 3 * nel));
+        LAUNCH(h, k_convert_e2f, nblocks(3 * nel, 256), 256, P<long long>(h->tmp), P<int>(d_e2f), (long long)(3 * nel), (int)nf, P<int>(h->err_flag));
+        TRY(ensure(h, d_f2e, sizeof(int2) * nf));
+        TRY(ensure(h, d_cnt, sizeof(int) * nf));
+        LAUNCH(h, k_f2e_init, nblocks(nf, 256), 256, P<int2>(d_f2e), P<int>(d_cnt), (int)nf);
+        LAUNCH(h, k_f2e_build, nblocks(nel, 256), 256, P<int>(d_e2f), P<int2>(d_f2e), P<int>(d_cnt), (int)nel);
+        LAUNCH(h, k_f2e_orphans, nblocks(nf, 256), 256, P<int2>(d_f2e), P<int>(d_cnt), (int)nf);
+        int flag = 0;
+        TRY(read_err_flag(h, &flag));
+        if (flag) return fail(h, FCFV_ERR_INVALID, "fcfv_first_seen_faces: e2f contains a face id outside 1..nf");
+        const long long ncode = 4 * nel;
+        TRY(ensure(h, d_flag, sizeof(unsigned long long) * (ncode + 1)));
+        TRY(ensure(h, d_orph, sizeof(unsigned long long) * (nf + 1)));
+        CU(cudaMemsetAsync(d_flag.p, 0, sizeof(unsigned long long) * (ncode + 1), h->stream));
+        LAUNCH(h, k_fs_mark, nblocks(nf, 256), 256, P<int2>(d_f2e), (int)nf, P<unsigned long long>(d_flag));
+        LAUNCH(h, k_fs_orphan, nblocks(nf, 256), 256, P<int2>(d_f2e), (int)nf, P<unsigned long long>(d_orph));
+        TRY(scan64_ranks(h, P<unsigned long long>(d_flag), ncode, d_chunks));
+        TRY(scan64_ranks(h, P<unsigned long long>(d_orph), nf, d_chunks));
+        unsigned long long total1 = 0;
+        CU(cudaMemcpyAsync(&total1, P<unsigned long long>(d_flag) + ncode, sizeof total1, cudaMemcpyDeviceToHost, h->stream));
+        TRY(sync(h));
+        TRY(ensure(h, d_perm, sizeof(long long) * std::max<long long>(nf, 1)));
+        LAUNCH(h, k_fs_perm, nblocks(nf, 256), 256, P<int2>(d_f2e), (int)nf, P<unsigned long long>(d_flag), (long long)(total1 - 1),
+               P<unsigned long long>(d_orph), P<long long>(d_perm));
+        if (new_of_old) TRY(copy(h, new_of_old, d_perm.p, sizeof(long long) * nf));
+        if (e2f_new) {
+            TRY(ensure(h, d_out, sizeof(long long) * std::max<long long>(3 * nel, 1)));
+            LAUNCH(h, k_fs_apply, nblocks(3 * nel, 256), 256, P<int>(d_e2f), (long long)(3 * nel), P<long long>(d_perm), P<long long>(d_out));
+            TRY(copy(h, e2f_new, d_out.p, sizeof(long long) * 3 * nel));
+        }
+        CU(cudaGetLastError());
+        return sync(h);
+    };
+    const int rc = body();
+    cudaStreamSynchronize(h->stream);
+    for (DBuf* b : {&d_e2f, &d_f2e, &d_cnt, &d_flag, &d_orph, &d_perm, &d_out, &d_chunks}) release(h, *b);
+    return rc;
+}
+
+// -------------------------------------------------------------------------------------------------
 int fcfv_set_sources(fcfv_t* h, const double* sex, const double* sey) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_set_sources: no mesh set"));

@@ -359,6 +359,12 @@ __global__ void k_f2e_check(int2* __restrict__ f2e, const int* __restrict__ cnt,
     }
 }
 
+// faces without elements: (-1, -1) (renumbering utility; k_f2e_check does it together with the validation)
+__global__ void k_f2e_orphans(int2* __restrict__ f2e, const int* __restrict__ cnt, int nf) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < nf && cnt[f] == 0) f2e[f] = make_int2(-1, -1);
+}
+
 // per-face connectivity record of the assembly (static per mesh; rebuilt when bc or e2f change)
 __global__ void k_fconn(const int* __restrict__ e2f, const int8_t* __restrict__ bc, const int2* __restrict__ f2e, int nel, int nf,
                         int4* __restrict__ fconn, int* __restrict__ fbc) {
@@ -1048,6 +1054,35 @@ __global__ void k_scan64_finish(unsigned long long* __restrict__ a, long long n,
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = a[i] + chunk_base[i / 4096] + 1ULL;
     if (i == n) a[n] = chunk_base[nchunks] + 1ULL;
+}
+
+// ---- first-seen face renumbering (mesh preparation) ---------------------------------------------------------
+// The kernels gather the records of the elements next to consecutive faces: they are fast when face ids follow
+// the element order, as in the reference's own meshes (meshes/ReadMeshesDat.jl:36-88 numbers a face when the
+// element loop first meets it).  For a mesh numbered otherwise this computes that numbering from e2f alone:
+// key(f) = 4*e + i of the first (element, local face) that references f; new id = rank of the key.
+__global__ void k_fs_mark(const int2* __restrict__ f2e, int nf, unsigned long long* __restrict__ flag) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < nf && f2e[f].x >= 0) flag[f2e[f].x] = 1ULL;        // keys are unique: one writer per entry
+}
+
+// rank1[code] = 1-based rank after the scan; faces without elements keep the ids after all the others
+__global__ void k_fs_perm(const int2* __restrict__ f2e, int nf, const unsigned long long* __restrict__ rank1, long long nused,
+                          const unsigned long long* __restrict__ orphan_rank1, long long* __restrict__ new_of_old) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int code = f2e[f].x;
+    new_of_old[f] = code >= 0 ? (long long)rank1[code] : nused + (long long)orphan_rank1[f];
+}
+
+__global__ void k_fs_orphan(const int2* __restrict__ f2e, int nf, unsigned long long* __restrict__ flag) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < nf) flag[f] = f2e[f].x < 0 ? 1ULL : 0ULL;
+}
+
+__global__ void k_fs_apply(const int* __restrict__ e2f, long long n3, const long long* __restrict__ new_of_old, long long* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n3) out[k] = new_of_old[e2f[k]];
 }
 
 // ---- a9 Powell-Hestenes -------------------------------------------------------------------------

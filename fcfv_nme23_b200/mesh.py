@@ -309,3 +309,34 @@ def MakeStructuredMesh(n, τr=1.0, *, geometry=True) -> FCFV_Mesh:
         from .api import mesh_geometry
         mesh_geometry(m, τr)
     return m
+
+
+def first_seen_face_permutation(e2f, nf):
+    """Host statement of what ``fcfv_first_seen_faces`` computes on the device: the face numbering of
+    meshes/ReadMeshesDat.jl:36-88 (a face gets the next id when the element loop first meets it), from ``e2f`` alone.
+    Returns ``new_of_old`` (nf, 1-based): faces no element references keep the ids after all the others."""
+    e2f = np.asarray(e2f, dtype=np.int64)
+    nel = e2f.shape[0]
+    code = (4 * np.arange(nel, dtype=np.int64)[:, None] + np.arange(3, dtype=np.int64)[None, :]).ravel()   # 4*e + i
+    first = np.full(nf, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(first, e2f.ravel() - 1, code)
+    used = first != np.iinfo(np.int64).max
+    new_of_old = np.empty(nf, dtype=np.int64)
+    order = np.argsort(first[used], kind="stable")
+    ids = np.flatnonzero(used)
+    new_of_old[ids[order]] = np.arange(1, ids.size + 1)
+    new_of_old[~used] = ids.size + np.arange(1, (~used).sum() + 1)
+    return new_of_old
+
+
+def renumber_faces(mesh: FCFV_Mesh, new_of_old):
+    """Applies a face renumbering to a mesh in place: ``e2f`` and every face array it carries (``bc, xf, yf, τ``)."""
+    p = np.asarray(new_of_old, dtype=np.int64) - 1
+    mesh.e2f = _f(p[np.asarray(mesh.e2f, dtype=np.int64) - 1] + 1, np.int64)
+    for name in ("bc", "xf", "yf", "τ"):
+        a = getattr(mesh, name, None)
+        if a is not None and np.ndim(a) == 1 and len(a) == mesh.nf:
+            out = np.empty_like(np.asarray(a))
+            out[p] = np.asarray(a)
+            setattr(mesh, name, out)
+    return mesh

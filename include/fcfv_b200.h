@@ -77,6 +77,15 @@ int fcfv_geometry(fcfv_t* h, int64_t nel, int64_t nf, int64_t nv, const int64_t*
                   const double* yf, int numbering, double tau_r, double* Omega, double* xc,
                   double* yc, double* nx, double* ny, double* Gamma, double* tau);
 
+/* ---- mesh preparation: first-seen face numbering (meshes/ReadMeshesDat.jl:36-88) -----------------
+ * The face kernels gather the records of the elements next to consecutive faces; they are fast when face ids
+ * follow the element order, which is how the reference numbers the faces of its own meshes (a face gets the next
+ * id when the element loop first meets it).  For a mesh numbered otherwise this returns that numbering, computed
+ * from e2f alone: new_of_old[f] (nf, 1-based) and e2f_new (nel x 3); faces no element references keep the ids after
+ * all the others, in their old order.  The caller permutes its face arrays once (x_new[new_of_old[f]] = x_old[f]);
+ * stand-alone, does not need fcfv_set_mesh.  Either output may be NULL. */
+int fcfv_first_seen_faces(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, int64_t* new_of_old, int64_t* e2f_new);
+
 /* ---- a4: ComputeFCFV (src/DiscretisationFCFV_Stokes.jl:8-44) ---------------------------
  * Outputs alpha nel, beta nel x 2, Z nel x 2 x 2, tau nf (mesh.τ after the call: face f gets
  * τe of its highest-numbered adjacent element, faces without elements keep their value). */

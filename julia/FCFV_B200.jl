@@ -11,7 +11,7 @@ module FCFV_B200
 using SparseArrays, Printf
 
 export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
-       SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!
+       SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!, RenumberFacesFirstSeen!
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
 
@@ -239,6 +239,28 @@ function CenterPressure!(mesh, Pe)
     m = Ref{Float64}(0.0)
     GC.@preserve Pe check(h, ccall((:fcfv_center_pressure, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), h.ptr, Pe, m))
     return Pe
+end
+
+"""Mesh preparation: renumber the faces of `mesh` in the order the element loop first meets them (the numbering of the
+reference's own `.dat` meshes, meshes/ReadMeshesDat.jl:36-88) -- the GPU kernels gather element data by face and are
+several times faster when face ids follow the element order.  Permutes `e2f` and the face arrays `bc, xf, yf, τ` in
+place; call it right after the mesh is created, before any face data is built from `xf, yf`.  Returns `new_of_old`."""
+function RenumberFacesFirstSeen!(mesh)
+    h = Handle()
+    e2f = i64(mesh.e2f)
+    perm = Vector{Int64}(undef, mesh.nf)
+    e2f_new = Matrix{Int64}(undef, mesh.nel, 3)
+    GC.@preserve e2f perm e2f_new check(h, ccall((:fcfv_first_seen_faces, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), h.ptr, mesh.nel, mesh.nf, e2f, perm, e2f_new))
+    mesh.e2f = e2f_new
+    for name in (:bc, :xf, :yf, :τ)
+        a = getfield(mesh, name)
+        if !ismissing(a) && length(a) == mesh.nf
+            b = similar(a); b[perm] = a; setfield!(mesh, name, b)
+        end
+    end
+    delete!(HANDLES, mesh)            # connectivity changed: upload again on next use
+    return perm
 end
 
 end # module

@@ -548,3 +548,22 @@ def test_module_constant_A_not_one_gpu(variant, api, oracle):
     gfu, gfp = h.export_rhs()
     assert np.array_equal(gfu, fu.ravel()) and np.array_equal(gfp, fp)
     h.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["S17", "LowRes", "H2"])
+def test_first_seen_faces_device_matches_host(name, api):
+    """fcfv_first_seen_faces (device) == mesh.first_seen_face_permutation (host) on shuffled meshes, and a mesh
+    renumbered with it assembles the same matrix up to that permutation of rows and columns."""
+    from fcfv_nme23_b200 import mesh as M
+    m = cases.load_mesh(name)
+    rng = np.random.default_rng(5)
+    sh = rng.permutation(m.nf) + 1
+    e2f_sh = np.asfortranarray(sh[np.asarray(m.e2f) - 1])
+    perm, e2f_new = api.first_seen_faces(e2f_sh, m.nf)
+    assert np.array_equal(perm, M.first_seen_face_permutation(e2f_sh, m.nf))
+    assert np.array_equal(e2f_new, perm[e2f_sh - 1])
+    # with unreferenced faces
+    e2f = np.asfortranarray(np.array([[1, 4, 6], [4, 2, 7]], dtype=np.int64))
+    p, _ = api.first_seen_faces(e2f, 8)
+    assert p.tolist() == [1, 4, 6, 2, 7, 3, 5, 8]

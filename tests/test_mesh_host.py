@@ -83,3 +83,29 @@ def test_partition_invariants(mesh_name, nparts):
         owned_rows.append(fo)
     allrows = np.concatenate(owned_rows)
     assert np.array_equal(np.sort(allrows), np.nonzero(hi >= 0)[0])   # every face owned exactly once
+
+
+def test_first_seen_face_permutation():
+    """Host statement of fcfv_first_seen_faces: identity on meshes that are numbered first-seen (S(n), the .dat
+    meshes), recovers that numbering from any shuffle, is a permutation on the advancing-front meshes."""
+    import cases
+    from fcfv_nme23_b200 import mesh as M
+    for name in ("S6", "H1"):
+        m = cases.load_mesh(name)
+        assert np.array_equal(M.first_seen_face_permutation(m.e2f, m.nf), np.arange(1, m.nf + 1)), name
+        sh = np.random.default_rng(3).permutation(m.nf) + 1
+        e2f_sh = sh[np.asarray(m.e2f) - 1]
+        p = M.first_seen_face_permutation(e2f_sh, m.nf)
+        assert np.array_equal(p[e2f_sh - 1], np.asarray(m.e2f)), name
+    m = cases.load_mesh("LowRes")
+    p = M.first_seen_face_permutation(m.e2f, m.nf)
+    assert np.array_equal(np.sort(p), np.arange(1, m.nf + 1)) and (p != np.arange(1, m.nf + 1)).any()
+    # renumbering a mesh keeps it the same mesh: face data follows the faces
+    bc0, xf0 = m.bc.copy(), m.xf.copy()
+    e2f0 = np.asarray(m.e2f).copy()
+    M.renumber_faces(m, p)
+    assert np.array_equal(m.bc[np.asarray(m.e2f) - 1], bc0[e2f0 - 1]) and np.array_equal(m.xf[np.asarray(m.e2f) - 1], xf0[e2f0 - 1])
+    assert np.array_equal(M.first_seen_face_permutation(m.e2f, m.nf), np.arange(1, m.nf + 1))
+    # faces nobody references go last, in their old order
+    e2f = np.array([[1, 4, 6], [4, 2, 7]], dtype=np.int64)
+    assert M.first_seen_face_permutation(e2f, 8).tolist() == [1, 4, 6, 2, 7, 3, 5, 8]

@@ -48,3 +48,8 @@ run("as generated", ident_e, ident_f)
 run("elements shuffled", rng.permutation(nel), ident_f)
 run("faces shuffled", ident_e, rng.permutation(nf))
 run("both shuffled", rng.permutation(nel), rng.permutation(nf))
+# the remedy for arbitrary FACE numbering: fcfv_first_seen_faces (mesh preparation)
+pf = rng.permutation(nf)
+e2f_sh = np.asfortranarray(pf[M["e2f"] - 1] + 1)
+new_of_old, _ = api.first_seen_faces(e2f_sh, nf)
+run("faces shuffled + first-seen", ident_e, (new_of_old - 1)[pf])

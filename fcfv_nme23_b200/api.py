@@ -495,3 +495,18 @@ def first_seen_faces(e2f, nf, device=0):
     finally:
         h.close()
     return perm, out
+
+
+def hilbert_elements(xc, yc, device=0):
+    """``fcfv_hilbert_elements``: ``old_of_new`` (nel, 1-based) of the elements sorted along a Hilbert curve through
+    their centroids, computed on the GPU.  ``mesh.renumber_elements`` applies it to a mesh."""
+    xc, yc = np.ascontiguousarray(xc, dtype=np.float64).ravel(), np.ascontiguousarray(yc, dtype=np.float64).ravel()
+    nel = xc.size
+    h = Handle(device)
+    a = _Arg()
+    out = np.empty(nel, dtype=np.int64)
+    try:
+        h.check(h.lib.fcfv_hilbert_elements(h._h, nel, a.d(xc, nel), a.d(yc, nel), _out(out)))
+    finally:
+        h.close()
+    return out

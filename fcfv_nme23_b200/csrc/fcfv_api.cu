@@ -6,6 +6,7 @@
 #include "../../include/fcfv_b200.h"
 #include "fcfv_kernels.cuh"
 #include "fcfv_generate.cuh"
+#include "fcfv_prep.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -564,6 +565,29 @@ int fcfv_first_seen_faces(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f
     const int rc = body();
     cudaStreamSynchronize(h->stream);
     for (DBuf* b : {&d_e2f, &d_f2e, &d_cnt, &d_flag, &d_orph, &d_perm, &d_out, &d_chunks}) release(h, *b);
+    return rc;
+}
+
+int fcfv_hilbert_elements(fcfv_t* h, int64_t nel, const double* xc, const double* yc, int64_t* old_of_new) {
+    if (!h) return FCFV_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    if (nel < 0 || nel >= (1LL << 31)) return fail(h, FCFV_ERR_INVALID, "fcfv_hilbert_elements: size out of range");
+    if (!xc || !yc || !old_of_new) return fail(h, FCFV_ERR_INVALID, "fcfv_hilbert_elements: null array");
+    DBuf d_x, d_y, d_out, d_tmp;
+    auto body = [&]() -> int {
+        TRY(upload(h, d_x, xc, sizeof(double) * nel));
+        TRY(upload(h, d_y, yc, sizeof(double) * nel));
+        TRY(ensure(h, d_out, sizeof(long long) * std::max<long long>(nel, 1)));
+        size_t bytes = 0;
+        CU(hilbert_element_order(h->stream, (int)nel, P<double>(d_x), P<double>(d_y), P<long long>(d_out), nullptr, 0, &bytes));
+        TRY(ensure(h, d_tmp, bytes));
+        CU(hilbert_element_order(h->stream, (int)nel, P<double>(d_x), P<double>(d_y), P<long long>(d_out), d_tmp.p, d_tmp.cap, nullptr));
+        TRY(copy(h, old_of_new, d_out.p, sizeof(long long) * nel));
+        return sync(h);
+    };
+    const int rc = body();
+    cudaStreamSynchronize(h->stream);
+    for (DBuf* b : {&d_x, &d_y, &d_out, &d_tmp}) release(h, *b);
     return rc;
 }
 

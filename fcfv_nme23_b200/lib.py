@@ -82,6 +82,7 @@ def load():
         "fcfv_element_values": [vp] + [vp] * 10,
         "fcfv_schur": [vp, dbl, P(i64)],
         "fcfv_first_seen_faces": [vp, i64, i64, vp, vp, vp],
+        "fcfv_hilbert_elements": [vp, i64, vp, vp, vp],
         "fcfv_run_pipeline": [vp, ci, ci, dbl, ci],
         "fcfv_center_pressure": [vp, vp, P(dbl)],
         "fcfv_run_assemble_schur": [vp, ci, ci, dbl, dbl],

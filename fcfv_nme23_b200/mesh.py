@@ -340,3 +340,73 @@ def renumber_faces(mesh: FCFV_Mesh, new_of_old):
             out[p] = np.asarray(a)
             setattr(mesh, name, out)
     return mesh
+
+
+HILBERT_BITS = 20
+
+
+def hilbert_index(x, y, bits=HILBERT_BITS):
+    """Index of the integer cells (x, y) along the Hilbert curve of a 2^bits x 2^bits grid (vectorised)."""
+    x, y = np.asarray(x, dtype=np.int64).copy(), np.asarray(y, dtype=np.int64).copy()
+    d = np.zeros_like(x)
+    s = 1 << (bits - 1)
+    while s > 0:
+        rx, ry = ((x & s) != 0).astype(np.int64), ((y & s) != 0).astype(np.int64)
+        d += s * s * ((3 * rx) ^ ry)
+        x &= s - 1
+        y &= s - 1
+        flip = (ry == 0) & (rx == 1)
+        x, y = np.where(flip, s - 1 - x, x), np.where(flip, s - 1 - y, y)
+        swap = ry == 0
+        x, y = np.where(swap, y, x), np.where(swap, x, y)
+        s >>= 1
+    return d
+
+
+def hilbert_element_order(xc, yc):
+    """Host statement of what ``fcfv_hilbert_elements`` computes on the device: ``old_of_new`` (nel, 1-based), the
+    elements sorted along a Hilbert curve through their centroids (2^20 cells per direction over the bounding box,
+    elements of one cell keep their order)."""
+    xc, yc = np.asarray(xc, dtype=np.float64).ravel(), np.asarray(yc, dtype=np.float64).ravel()
+    if xc.size == 0:
+        return np.empty(0, dtype=np.int64)
+    cells, top = float(1 << HILBERT_BITS), (1 << HILBERT_BITS) - 1
+
+    def quantise(v):
+        w = v.max() - v.min()
+        s = cells / w if w > 0.0 else 0.0
+        return np.clip(((v - v.min()) * s).astype(np.int64), 0, top)
+    key = hilbert_index(quantise(xc), quantise(yc))
+    return np.argsort(key, kind="stable").astype(np.int64) + 1
+
+
+def renumber_elements(mesh: FCFV_Mesh, old_of_new):
+    """Applies an element order to a mesh in place: every element array it carries (rows of ``e2v, e2f, n_x, n_y, Γ, e2e``,
+    ``xc, yc, Ω, τe, ke, λ, phase, δ, N_x, N_y``) and the element ids stored in ``f2e`` / ``e2e``.  Face ids do not
+    change; follow with ``renumber_faces(mesh, first_seen_face_permutation(mesh.e2f, mesh.nf))``."""
+    o = np.asarray(old_of_new, dtype=np.int64) - 1
+    nel = mesh.nel
+    assert o.shape == (nel,)
+    new_of_old = np.empty(nel + 1, dtype=np.int64)          # 1-based lookup; ids <= 0 (no neighbour) stay
+    new_of_old[0] = 0
+    new_of_old[o + 1] = np.arange(1, nel + 1)
+    for name in ("e2v", "e2f", "n_x", "n_y", "Γ", "e2e", "xc", "yc", "Ω", "τe", "ke", "λ", "phase", "δ", "N_x", "N_y",
+                 "elem_owned", "elem_global"):
+        a = getattr(mesh, name, None)
+        if a is None:
+            continue
+        a = np.asarray(a)
+        if a.shape[0] == nel:
+            b = a[o]
+        elif a.ndim == 1 and a.shape[0] > nel:               # τe sized nf in some drivers: the first nel entries are the elements'
+            b = a.copy()
+            b[:nel] = a[o]
+        else:
+            continue
+        setattr(mesh, name, np.asfortranarray(b) if b.ndim == 2 else b)
+    for name in ("f2e", "e2e"):
+        a = getattr(mesh, name, None)
+        if a is not None:
+            a = np.asarray(a, dtype=np.int64)
+            setattr(mesh, name, np.asfortranarray(np.where(a > 0, new_of_old[np.maximum(a, 0)], a)))
+    return mesh

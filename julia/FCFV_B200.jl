@@ -11,7 +11,8 @@ module FCFV_B200
 using SparseArrays, Printf
 
 export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
-       SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!, RenumberFacesFirstSeen!
+       SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!, RenumberFacesFirstSeen!,
+       RenumberElementsHilbert!, PrepareNumbering!
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
 
@@ -261,6 +262,48 @@ function RenumberFacesFirstSeen!(mesh)
     end
     delete!(HANDLES, mesh)            # connectivity changed: upload again on next use
     return perm
+end
+
+"""    RenumberElementsHilbert!(mesh) -> old_of_new
+
+For a mesh whose ELEMENTS come in an order without spatial coherence: sorts them along a Hilbert curve through their
+centroids (`mesh.xc, mesh.yc`) and permutes every element array of the mesh (`src/CreateMeshFCFV.jl:10-44`) and the
+element ids stored in `f2e` / `e2e`.  Element-sized arrays built by the driver (`sex`, `sey`, `Pe`, ...) must be built
+after the call, or permuted with the returned `old_of_new` (`x = x[old_of_new]`).  Follow with
+`RenumberFacesFirstSeen!(mesh)` (or call `PrepareNumbering!`).  Triangle output does not need it."""
+function RenumberElementsHilbert!(mesh)
+    h = Handle()
+    nel = mesh.nel
+    xc, yc = f64(mesh.xc), f64(mesh.yc)
+    order = Vector{Int64}(undef, nel)
+    GC.@preserve xc yc order check(h, ccall((:fcfv_hilbert_elements, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}), h.ptr, nel, xc, yc, order))
+    new_of_old = invperm(order)
+    for name in (:e2v, :e2f, :n_x, :n_y, :Γ, :e2e, :xc, :yc, :Ω, :τe, :ke, :λ, :phase, :δ, :N_x, :N_y)
+        a = getfield(mesh, name)
+        ismissing(a) && continue
+        if size(a, 1) == nel
+            setfield!(mesh, name, ndims(a) == 2 ? a[order, :] : a[order])
+        elseif ndims(a) == 1 && length(a) > nel        # τe sized nf (ViscousInclusionFCFV_v2.jl:127)
+            b = copy(a); b[1:nel] = a[order]; setfield!(mesh, name, b)
+        end
+    end
+    for name in (:f2e, :e2e)
+        a = getfield(mesh, name)
+        ismissing(a) && continue
+        setfield!(mesh, name, map(e -> e > 0 ? new_of_old[e] : e, a))
+    end
+    delete!(HANDLES, mesh)
+    return order
+end
+
+"""    PrepareNumbering!(mesh) -> (old_of_new_elements, new_of_old_faces)
+
+Both preparation steps: Hilbert element order, then first-seen face numbering."""
+function PrepareNumbering!(mesh)
+    oe = RenumberElementsHilbert!(mesh)
+    pf = RenumberFacesFirstSeen!(mesh)
+    return oe, pf
 end
 
 end # module

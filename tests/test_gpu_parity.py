@@ -567,3 +567,57 @@ def test_first_seen_faces_device_matches_host(name, api):
     e2f = np.asfortranarray(np.array([[1, 4, 6], [4, 2, 7]], dtype=np.int64))
     p, _ = api.first_seen_faces(e2f, 8)
     assert p.tolist() == [1, 4, 6, 2, 7, 3, 5, 8]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["H1", "LowRes"])
+def test_numbering_preparation_on_device(name, api):
+    """fcfv_hilbert_elements + fcfv_first_seen_faces on a mesh whose elements and faces come in random order: the
+    device results equal the host statements, and the prepared mesh assembles the same system bit for bit up to the
+    permutation of rows and columns (uniform τe, so that the highest-element τ rule does not see the numbering)."""
+    from fcfv_nme23_b200 import mesh as M
+    form = "SymmetricGradient"
+    case = cases.Case(name, "inclusion", 1, form, tau_r=2.0)
+    m0, d = cases.build(case)
+    nel, nf = m0.nel, m0.nf
+    neu = d["neu"]
+    a0, b0, Z0 = api.ComputeFCFV(m0, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, form)
+    Kuu0, _, Kup0, fu0, fp0, _ = api.ElementAssemblyLoopNEW(m0, a0, b0, Z0, d["VxDir"], d["VyDir"], *neu, form)
+    api.handle_for(m0).close()
+
+    rng = np.random.default_rng(21)
+    ms, _ = cases.build(case)
+    old_e = rng.permutation(nel) + 1                       # element k of ms = element old_e[k] of m0
+    pf = rng.permutation(nf) + 1                           # face f of m0 -> face pf[f] of ms
+    M.renumber_elements(ms, old_e)
+    M.renumber_faces(ms, pf)
+    # preparation, device against host
+    order = api.hilbert_elements(ms.xc, ms.yc)
+    assert np.array_equal(order, M.hilbert_element_order(ms.xc, ms.yc))
+    M.renumber_elements(ms, order)
+    old_e = old_e[order - 1]
+    perm, e2f_new = api.first_seen_faces(np.asfortranarray(ms.e2f), nf)
+    assert np.array_equal(perm, M.first_seen_face_permutation(ms.e2f, nf))
+    M.renumber_faces(ms, perm)
+    assert np.array_equal(np.asarray(ms.e2f), e2f_new)
+    pf = perm[pf - 1]
+    jump = np.hypot(np.diff(ms.xc), np.diff(ms.yc))
+    assert np.median(jump) < 4.0 * np.sqrt(np.median(ms.Ω))
+
+    def faces(x):
+        out = np.empty_like(x); out[pf - 1] = x; return out
+    sex, sey = d["sex"][old_e - 1], d["sey"][old_e - 1]
+    fd = [faces(x) for x in (d["VxDir"], d["VyDir"], *neu)]
+    a, b, Z = api.ComputeFCFV(ms, sex, sey, *fd, case.tau_r, form)
+    assert np.array_equal(a, a0[old_e - 1]) and np.array_equal(b, b0[old_e - 1]) and np.array_equal(Z, Z0[old_e - 1])
+    Kuu, _, Kup, fu, fp, _ = api.ElementAssemblyLoopNEW(ms, a, b, Z, *fd, form)
+    api.handle_for(ms).close()
+    dof = np.concatenate([pf - 1, nf + pf - 1])            # dof of m0 -> dof of ms
+    back_uu = Kuu.tocsr()[dof][:, dof].tocsc()
+    back_up = Kup.tocsr()[dof][:, np.argsort(old_e)].tocsc()
+    for got, ref, tag in ((back_uu, Kuu0, "Kuu"), (back_up, Kup0, "Kup")):
+        got.sort_indices(); ref = ref.copy(); ref.sort_indices()
+        assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices), tag
+        assert np.array_equal(got.data, ref.data), tag
+    assert np.array_equal(np.asarray(fu).ravel()[dof], np.asarray(fu0).ravel())
+    assert np.array_equal(np.asarray(fp).ravel(), np.asarray(fp0).ravel()[old_e - 1])

@@ -109,3 +109,46 @@ def test_first_seen_face_permutation():
     # faces nobody references go last, in their old order
     e2f = np.array([[1, 4, 6], [4, 2, 7]], dtype=np.int64)
     assert M.first_seen_face_permutation(e2f, 8).tolist() == [1, 4, 6, 2, 7, 3, 5, 8]
+
+
+def test_hilbert_element_order():
+    """Host statement of fcfv_hilbert_elements: the curve visits every cell once and moves to an edge-neighbour
+    each step; the element order is a permutation that keeps consecutive elements close; renumbering a mesh with it
+    keeps it the same mesh and the oracle assembles the same matrix up to the row / column permutation."""
+    import cases
+    from fcfv_nme23_b200 import mesh as M
+    from oracle import oracle as O
+    n = 16
+    X, Y = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    d = M.hilbert_index(X.ravel(), Y.ravel(), bits=4)
+    assert np.array_equal(np.sort(d), np.arange(n * n))
+    o = np.argsort(d)
+    step = np.abs(np.diff(X.ravel()[o])) + np.abs(np.diff(Y.ravel()[o]))
+    assert (step == 1).all()
+    # the 20-bit index restricted to a coarse grid visits the coarse cells in the 4-bit curve's order
+    big = M.hilbert_index(X.ravel() << 16, Y.ravel() << 16)
+    assert np.array_equal(np.argsort(big), o)
+
+    m = cases.load_mesh("S17")
+    rng = np.random.default_rng(11)
+    sh = rng.permutation(m.nel) + 1                  # an element order without any coherence
+    ms = M.renumber_elements(cases.load_mesh("S17"), sh)
+    order = M.hilbert_element_order(ms.xc, ms.yc)
+    assert np.array_equal(np.sort(order), np.arange(1, m.nel + 1))
+    mh = M.renumber_elements(ms, order)
+    jump = np.hypot(np.diff(mh.xc), np.diff(mh.yc))
+    assert np.median(jump) < 1.5 / 17 and jump.max() < 6.0 / 17       # neighbours in memory are neighbours in the plane
+    M.renumber_faces(mh, M.first_seen_face_permutation(mh.e2f, mh.nf))
+    # same mesh: element k of mh is element sh[order[k]-1] of m, with the same geometry on the same faces
+    old = sh[order - 1] - 1
+    assert np.array_equal(mh.Ω, m.Ω[old]) and np.array_equal(mh.n_x, m.n_x[old]) and np.array_equal(mh.Γ, m.Γ[old])
+    assert np.array_equal(mh.xf[np.asarray(mh.e2f) - 1], m.xf[np.asarray(m.e2f)[old] - 1])
+    if mh.f2e is not None:
+        f2e = np.asarray(mh.f2e)
+        for e in range(0, mh.nel, 37):
+            for i in range(3):
+                assert e + 1 in f2e[mh.e2f[e, i] - 1]
+    # degenerate boxes and the empty mesh
+    assert M.hilbert_element_order(np.zeros(5), np.arange(5.0)).tolist() == [1, 2, 3, 4, 5]
+    assert M.hilbert_element_order(np.zeros(3), np.zeros(3)).tolist() == [1, 2, 3]
+    assert M.hilbert_element_order([], []).size == 0

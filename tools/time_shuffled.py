@@ -53,3 +53,18 @@ pf = rng.permutation(nf)
 e2f_sh = np.asfortranarray(pf[M["e2f"] - 1] + 1)
 new_of_old, _ = api.first_seen_faces(e2f_sh, nf)
 run("faces shuffled + first-seen", ident_e, (new_of_old - 1)[pf])
+
+# the remedy for an arbitrary ELEMENT order: fcfv_hilbert_elements, then first-seen faces.  Centroids of S(n):
+# cell (i, j) of element e = e // 4, triangle k = e % 4 of the criss-cross cell.
+from fcfv_nme23_b200 import mesh as MM
+cell, k = np.arange(nel) // 4, np.arange(nel) % 4
+dx = np.array([0.5, 5.0 / 6.0, 0.5, 1.0 / 6.0])[k]; dy = np.array([1.0 / 6.0, 0.5, 5.0 / 6.0, 0.5])[k]
+xc, yc = (cell % n + dx) / n, (cell // n + dy) / n
+order = api.hilbert_elements(xc, yc) - 1
+new_of_old, _ = api.first_seen_faces(np.asfortranarray(M["e2f"][order]), nf)
+run("hilbert elements + first-seen", order, new_of_old - 1)
+pe = rng.permutation(nel)
+order = pe[api.hilbert_elements(xc[pe], yc[pe]) - 1]
+pf = rng.permutation(nf)
+new_of_old, _ = api.first_seen_faces(np.asfortranarray(pf[M["e2f"][order] - 1] + 1), nf)
+run("both shuffled + hilbert + f-s", order, (new_of_old - 1)[pf])

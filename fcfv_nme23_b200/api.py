@@ -135,6 +135,17 @@ class Handle:
     def sync(self):
         self.check(self.lib.fcfv_sync(self._h))
 
+    def host_register(self, *arrays):
+        """Page-locks NumPy arrays that are passed to the host-buffer entries repeatedly (``fcfv_host_register``)."""
+        for a in arrays:
+            if a is not None and a.nbytes:
+                self.check(self.lib.fcfv_host_register(self._h, C.c_void_p(a.ctypes.data), a.nbytes))
+
+    def host_unregister(self, *arrays):
+        for a in arrays:
+            if a is not None and a.nbytes:
+                self.check(self.lib.fcfv_host_unregister(self._h, C.c_void_p(a.ctypes.data)))
+
     # -- mesh ---------------------------------------------------------------------------------
     def set_mesh(self, mesh):
         a = _Arg()

@@ -351,6 +351,30 @@ int fcfv_sync(fcfv_t* h) {
     return sync(h);
 }
 
+int fcfv_host_register(fcfv_t* h, void* ptr, int64_t bytes) {
+    if (!h) return FCFV_ERR_INVALID;
+    if (!ptr || bytes <= 0) return fail(h, FCFV_ERR_INVALID, "fcfv_host_register: empty range");
+    CU(cudaSetDevice(h->device));
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();      // not sticky: do not let a later launch check pick it up
+        return fail(h, FCFV_ERR_CUDA, "fcfv_host_register: %s", cudaGetErrorString(e));
+    }
+    return FCFV_OK;
+}
+
+int fcfv_host_unregister(fcfv_t* h, void* ptr) {
+    if (!h) return FCFV_ERR_INVALID;
+    if (!ptr) return fail(h, FCFV_ERR_INVALID, "fcfv_host_unregister: null pointer");
+    CU(cudaSetDevice(h->device));
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, FCFV_ERR_CUDA, "fcfv_host_unregister: %s", cudaGetErrorString(e));
+    }
+    return FCFV_OK;
+}
+
 int fcfv_set_timing(fcfv_t* h, int on) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(sync(h));

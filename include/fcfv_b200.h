@@ -189,6 +189,11 @@ int fcfv_get_nnz(fcfv_t* h, int64_t* nnz_uu, int64_t* nnz_up, int64_t* nnz_muu);
 int fcfv_set_async(fcfv_t* h, int async);
 int fcfv_sync(fcfv_t* h);
 void* fcfv_stream(fcfv_t* h);               /* cudaStream_t */
+/* Optional: page-locks host arrays the caller passes again and again (mesh fields, boundary data, outputs), so
+ * that the copies of the host-buffer entries run at PCIe speed instead of through the driver's staging buffer
+ * (Julia / NumPy arrays are pageable).  The range must stay allocated until fcfv_host_unregister. */
+int fcfv_host_register(fcfv_t* h, void* ptr, int64_t bytes);
+int fcfv_host_unregister(fcfv_t* h, void* ptr);
 /* Per-kernel device timing: when on, every hot-path kernel launch is bracketed by CUDA events on the
  * handle's stream; fcfv_get_timers returns the accumulated milliseconds and launch counts per
  * kernel (arrays of fcfv_num_timers() entries, names via fcfv_timer_name).  set_timing resets. */

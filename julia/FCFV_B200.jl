@@ -12,7 +12,7 @@ using SparseArrays, Printf
 
 export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
        SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!, RenumberFacesFirstSeen!,
-       RenumberElementsHilbert!, PrepareNumbering!
+       RenumberElementsHilbert!, PrepareNumbering!, PinArrays
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
 
@@ -305,5 +305,33 @@ function PrepareNumbering!(mesh)
     pf = RenumberFacesFirstSeen!(mesh)
     return oe, pf
 end
+
+"""    PinArrays(mesh_or_handle, arrays...) -> token
+
+Optional.  Page-locks Julia arrays that are passed to the entries above again and again (`mesh.e2f`, `mesh.n_x`, ...,
+`VxDir`, `sex`, outputs), so that their copies run at PCIe speed (≈ 53 GB/s) instead of through the driver's staging
+buffer (≈ 12 GB/s for pageable memory): 4× on the host-buffer path.  Costs ≈ 0.12 s per GB once.  The token keeps
+the arrays alive and un-pins them when it is finalised; do not `resize!` a pinned array."""
+mutable struct PinToken
+    h::Handle
+    arrays::Vector{Any}
+end
+
+function PinArrays(h::Handle, arrays...)
+    kept = Any[]
+    for a in arrays
+        (a isa Array && sizeof(a) > 0) || continue
+        check(h, ccall((:fcfv_host_register, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), h.ptr, pointer(a), sizeof(a)))
+        push!(kept, a)
+    end
+    t = PinToken(h, kept)
+    finalizer(t) do tok
+        for a in tok.arrays
+            ccall((:fcfv_host_unregister, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), tok.h.ptr, pointer(a))
+        end
+    end
+    return t
+end
+PinArrays(mesh, arrays...) = PinArrays(handle_for(mesh), arrays...)
 
 end # module

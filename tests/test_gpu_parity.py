@@ -621,3 +621,26 @@ def test_numbering_preparation_on_device(name, api):
         assert np.array_equal(got.data, ref.data), tag
     assert np.array_equal(np.asarray(fu).ravel()[dof], np.asarray(fu0).ravel())
     assert np.array_equal(np.asarray(fp).ravel(), np.asarray(fp0).ravel()[old_e - 1])
+
+
+@pytest.mark.gpu
+def test_host_register_roundtrip(api):
+    """fcfv_host_register / fcfv_host_unregister: page-locking the caller's arrays changes nothing but the copy speed;
+    registering twice or unregistering an unknown range is reported, not fatal."""
+    case = cases.Case("H1", "solkz", 1, "SymmetricGradient", tau_r=10.0)
+    m, d = cases.build(case)
+    neu = d["neu"]
+    a0, b0, Z0 = api.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form)
+    h = api.handle_for(m)
+    arrs = [np.ascontiguousarray(d[k], dtype=np.float64) for k in ("sex", "sey", "VxDir", "VyDir")]
+    h.host_register(*arrs)
+    a1, b1, Z1 = api.ComputeFCFV(m, *arrs, *neu, case.tau_r, case.form)
+    assert np.array_equal(a0, a1) and np.array_equal(b0, b1) and np.array_equal(Z0, Z1)
+    with pytest.raises(RuntimeError):
+        h.host_register(arrs[0])                   # already registered
+    h.host_unregister(*arrs)
+    with pytest.raises(RuntimeError):
+        h.host_unregister(arrs[0])                 # not registered any more
+    a2, _, _ = api.ComputeFCFV(m, *arrs, *neu, case.tau_r, case.form)   # the handle is still usable
+    assert np.array_equal(a0, a2)
+    h.close()

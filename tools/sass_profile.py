@@ -20,8 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def sass_lines(lib, mangled_re):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
-    cubin = glob.glob(os.path.join(tmp, "*.cubin"))[0]
-    out = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    out = "".join(subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+                  for cubin in sorted(glob.glob(os.path.join(tmp, "*.cubin"))))
     table, cur, active = {}, None, False
     for ln in out.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)

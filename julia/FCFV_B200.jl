@@ -22,6 +22,9 @@ const TAU_REFERENCE, TAU_FACE = Cint(0), Cint(1)
 const KUU, KUP, MUU, KUUSC = Cint(0), Cint(1), Cint(2), Cint(3)
 const CSC1_INT64 = Cint(1)
 const A = 1.0                      # src/DiscretisationFCFV_Stokes.jl:1-2
+# Muu is returned by the assembly loops and passed to StokesSolvers!, which never reads it (SolversFCFV_Stokes.jl:6).
+# WANT_MUU[] = false returns an empty 2nf x 2nf matrix in its place and skips its assembly and export.
+const WANT_MUU = Ref(true)
 
 mutable struct Handle
     ptr::Ptr{Cvoid}
@@ -141,9 +144,10 @@ function assemble(variant::Cint, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNe
         check(h, ccall((:fcfv_assemble, LIB), Cint,
             (Ptr{Cvoid}, Cint, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
              Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
-            h.ptr, variant, form_id(Formulation), A, a, b, z, vx, vy, sxx, syy, sxy, syx, 1, n1, n2, n3, sec))
+            h.ptr, variant, form_id(Formulation), A, a, b, z, vx, vy, sxx, syy, sxy, syx, WANT_MUU[] ? 1 : 0, n1, n2, n3, sec))
     end
-    Kuu, Muu, Kup = export_csc(h, KUU), export_csc(h, MUU), export_csc(h, KUP)
+    Kuu, Kup = export_csc(h, KUU), export_csc(h, KUP)
+    Muu = WANT_MUU[] ? export_csc(h, MUU) : spzeros(2nf, 2nf)
     fu, fp = zeros(2nf, 1), zeros(nel)                  # fu is a 2nf x 1 Matrix in the reference
     GC.@preserve fu fp check(h, ccall((:fcfv_export_rhs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h.ptr, fu, fp))
     return Kuu, Muu, Kup, fu, fp, sec[]                 # sec plays `tsparse`

@@ -489,26 +489,6 @@ k_elem_coef(int nel, const double* __restrict__ alpha, const double* __restrict_
 // The gathers go through L1/L2 (face ids follow element order, so neighbouring threads share lines).
 constexpr int kHalf = kMaxRow * kAsmFaces + 8;        // staging capacity per component (+ alignment shift)
 constexpr int kStageBytes = 2 * kHalf * (8 + 4);
-#ifndef FCFV_PREFETCH_TILES
-#define FCFV_PREFETCH_TILES 0        // > 0: prefetch the records of the tile this many blocks ahead into L2
-#endif
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// L2 prefetch of the SoA lines of element e (all lanes of a warp hit the same few lines)
-__device__ __forceinline__ void prefetch_elem(const MeshView& M, const LocalView& L, const CoefView& Cf, int e) {
-    const int nel = M.nel;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const size_t o = (size_t)j * nel + e;
-        prefetch_l2(M.e2f + o); prefetch_l2(M.G + o); prefetch_l2(M.nx + o); prefetch_l2(M.ny + o);
-    }
-    prefetch_l2(Cf.ia + e); prefetch_l2(Cf.c11 + e);
-    prefetch_l2(L.beta + e); prefetch_l2(L.beta + nel + e);
-#pragma unroll
-    for (int q = 0; q < 4; q++) prefetch_l2(L.Z + (size_t)q * nel + e);
-}
-
 // rows of the block's face of this thread
 template <int VARIANT, int FORM, int EXTRA, bool ANISO, bool NATURAL, typename Sink>
 __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceDataView& D, double A,

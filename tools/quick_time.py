@@ -33,6 +33,11 @@ def main():
     nnz = h.get_nnz()
     bytes_alg = h.nel * (214 + 302 + 156 + 24 + 8) + h.nf * (60 + 16) + 12 * (nnz[0] + nnz[1]) + 8 * (2 * h.nf + 1)
     print(f"step      {ms:8.3f} ms  {h.nel / ms / 1e3:9.1f} Mel/s  nnz {nnz}  alg GB/s {bytes_alg / ms / 1e6:.0f}  dev GB {h.device_bytes / 1e9:.2f}")
+    # per-kernel device times (CUDA events around every hot-path launch)
+    h.sync(); h.set_timing(True)
+    for _ in range(5): step()
+    h.sync()
+    print("  ".join(f"{k}={ms / max(c, 1) * (c / 5):.3f}" for k, (ms, c) in h.get_timers().items() if c))
     h.close()
 
 main()

@@ -303,6 +303,29 @@ __device__ __forceinline__ double block_sum(double v, double* sd) {
     return r;
 }
 
+// N sums at once with a single barrier (same operations per quantity as block_sum: identical results).  `sd`
+// holds N * kBlock/32 doubles and must not be reused by the caller afterwards without a barrier.
+template <int N>
+__device__ __forceinline__ void block_sums(double (&v)[N], double* sd) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < N; q++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], d);
+        if (lane == 0) sd[q * (kBlock / 32) + w] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < kBlock / 32; k++) r += sd[q * (kBlock / 32) + k];
+            v[q] = r;
+        }
+    }
+}
+
 // ---- mesh set-up ---------------------------------------------------------------------------
 __global__ void k_convert_e2f(const long long* __restrict__ in, int* __restrict__ out, long long n3, int nf,
                               int* __restrict__ err) {
@@ -805,7 +828,7 @@ __global__ void __launch_bounds__(kBlock, FCFV_RES_MINBLOCKS)
 k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double* __restrict__ sex,
            const double* __restrict__ sey, int tau_mode, double* __restrict__ Fg, double* __restrict__ partial,
            int nblk, double* __restrict__ F_glob2_out) {
-    __shared__ double sd[kBlock / 32];
+    __shared__ double sd[4 * (kBlock / 32)];
     const int e = blockIdx.x * kBlock + threadIdx.x;
     const int nel = M.nel;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
@@ -847,11 +870,12 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
             s4 = r.Fg2 * r.Fg2;
         }
     }
-    const double t1 = block_sum(s1, sd), t2 = block_sum(s2, sd), t3 = block_sum(s3, sd), t4 = block_sum(s4, sd);
+    double t[4] = {s1, s2, s3, s4};
+    block_sums<4>(t, sd);
     if (threadIdx.x == 0) {
         const int b = blockIdx.x;
-        partial[0 * (size_t)nblk + b] = t1; partial[1 * (size_t)nblk + b] = t2;
-        partial[2 * (size_t)nblk + b] = t3; partial[3 * (size_t)nblk + b] = t4;
+        partial[0 * (size_t)nblk + b] = t[0]; partial[1 * (size_t)nblk + b] = t[1];
+        partial[2 * (size_t)nblk + b] = t[2]; partial[3 * (size_t)nblk + b] = t[3];
     }
 }
 
@@ -859,7 +883,7 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
 __global__ void __launch_bounds__(kBlock)
 k_res_face(MeshView M, const double* __restrict__ Fg, double* __restrict__ partial, int nblk,
            double* __restrict__ Fx_out, double* __restrict__ Fy_out) {
-    __shared__ double sd[kBlock / 32];
+    __shared__ double sd[2 * (kBlock / 32)];
     const int f = blockIdx.x * kBlock + threadIdx.x;
     const int nel = M.nel;
     double sx = 0.0, sy = 0.0;
@@ -880,10 +904,11 @@ k_res_face(MeshView M, const double* __restrict__ Fg, double* __restrict__ parti
         if (Fy_out) Fy_out[f] = Fy;
         if (M.face_owned == nullptr || M.face_owned[f]) { sx = Fx * Fx; sy = Fy * Fy; }
     }
-    const double tx = block_sum(sx, sd), ty = block_sum(sy, sd);
+    double t[2] = {sx, sy};
+    block_sums<2>(t, sd);
     if (threadIdx.x == 0) {
-        partial[0 * (size_t)nblk + blockIdx.x] = tx;
-        partial[1 * (size_t)nblk + blockIdx.x] = ty;
+        partial[0 * (size_t)nblk + blockIdx.x] = t[0];
+        partial[1 * (size_t)nblk + blockIdx.x] = t[1];
     }
 }
 

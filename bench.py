@@ -318,6 +318,14 @@ def run_ours(args, rank, world, local_rank):
                              "frac": ab["total"] * args.steps / (ms * 1e-3) / 1e9 / peak,
                              "bytes_per_element": ab["total"] / h.nel},
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items() if v[1] > 0}}
+    # the same algorithmic bytes against every kernel of the assembly phase (coefficients, count pass, scans, fill),
+    # and the fill kernel's own measured DRAM traffic against its duration
+    asm_ms = sum(timers[k][0] for k in ("k_elem_coef", "k_asm_count", "k_scan", "k_asm_fill") if k in timers) / args.steps
+    if asm_ms > 0:
+        roofline["assembly_phase"] = {"ms_per_step": asm_ms, "achieved": ab["assembly"] / (asm_ms * 1e-3) / 1e9,
+                                      "frac": ab["assembly"] / (asm_ms * 1e-3) / 1e9 / peak}
+    if traffic:
+        roofline["traffic_rate"] = {"achieved": traffic[0] / (dom_ms * 1e-3) / 1e9, "frac": traffic[0] / (dom_ms * 1e-3) / 1e9 / peak}
 
     # ---- e2e through the host-buffer C ABI ---------------------------------------------------
     e2e = None

@@ -86,6 +86,9 @@ class Partition:
 
 
 def partition_mesh(mesh: FCFV_Mesh, nparts: int, rank: int) -> Partition:
+    """Rank ``rank``'s share of ``mesh``: a contiguous range of elements, the lower neighbours of the faces it owns
+    and the τ donors of every face it touches (module docstring).  A face belongs to the rank of its highest-numbered
+    adjacent element; faces no element references belong to no rank (their rows are empty in the global system too)."""
     nel, nf = int(mesh.nel), int(mesh.nf)
     e2f = np.asarray(mesh.e2f, dtype=np.int64) - 1
     lo, hi = face_adjacency(mesh.e2f, nf)

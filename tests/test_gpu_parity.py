@@ -322,6 +322,8 @@ def test_large_mesh_properties(api):
 @pytest.mark.parametrize("mesh_name,setting,variant,form,nparts", [
     ("LowRes", "inclusion", 0, "Gradient", 3),
     ("H1", "solkz", 1, "SymmetricGradient", 2),
+    ("random:5", "random", 1, "SymmetricGradient", 3),      # tests/test_random_meshes.py: no numbering coherence at all
+    ("random:2", "random", 0, "Gradient", 4),
 ])
 def test_partitioned_mesh_on_gpu(mesh_name, setting, variant, form, nparts, api, oracle):
     """General (unstructured) element partition through the C ABI, ranks run one after the other on
@@ -330,7 +332,11 @@ def test_partitioned_mesh_on_gpu(mesh_name, setting, variant, form, nparts, api,
     from fcfv_nme23_b200 import lib as L
     from fcfv_nme23_b200.partition import partition_mesh
     case = cases.Case(mesh_name, setting, variant, form, tau_r=2.0 if setting == "inclusion" else 10.0)
-    gm, d = cases.build(case)
+    if setting == "random":
+        from test_random_meshes import random_case
+        gm, d = random_case(int(mesh_name.split(":")[1]))
+    else:
+        gm, d = cases.build(case)
     a, b, Z = oracle.ComputeFCFV(gm, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, form)
     ofn = oracle.ElementAssemblyLoop if variant == 0 else oracle.ElementAssemblyLoopNEW
     Kuu, Muu, Kup, fu, fp, _, _ = ofn(gm, a, b, Z, d["VxDir"], d["VyDir"], *d["neu"], form)

@@ -37,7 +37,11 @@ def _worker(rank, world, port, mesh_name, setting, variant, form, q):
         from oracle import oracle as O
         from fcfv_nme23_b200.partition import partition_mesh
         case = cases.Case(mesh_name, setting, variant, form, tau_r=2.0 if setting == "inclusion" else 10.0)
-        gm, d = cases.build(case)
+        if setting == "random":
+            from test_random_meshes import random_case
+            gm, d = random_case(int(mesh_name.split(":")[1]))
+        else:
+            gm, d = cases.build(case)
         P = partition_mesh(gm, world, rank)
         m = P.mesh
         sf, se = P.scatter_face, P.scatter_elem
@@ -78,7 +82,11 @@ def _worker(rank, world, port, mesh_name, setting, variant, form, q):
                     assert k not in seen, "row produced twice"
                     seen[k] = val
                 fpall.update(fpp)
-            ok = len(seen) == 2 * gm.nf and len(fpall) == gm.nel
+            # faces no element references belong to no rank: their rows are empty in the global system as well
+            unseen = np.setdiff1d(np.arange(2 * gm.nf), np.fromiter(seen.keys(), dtype=np.int64))
+            ok = bool(np.all(np.diff(grp)[unseen] == 0) and np.all(np.diff(grpp)[unseen] == 0) and np.all(gfu[unseen, 0] == 0.0))
+            used = np.zeros(gm.nf, bool); used[np.asarray(gm.e2f).ravel() - 1] = True
+            ok &= len(seen) == 2 * int(used.sum()) and len(fpall) == gm.nel
             for gr, (cols, vals, pc, pv, f) in seen.items():
                 ok &= cols == gci[grp[gr]:grp[gr + 1]].tolist() and vals == gv[grp[gr]:grp[gr + 1]].tolist()
                 ok &= pc == gcip[grpp[gr]:grpp[gr + 1]].tolist() and pv == gvp[grpp[gr]:grpp[gr + 1]].tolist()
@@ -99,6 +107,7 @@ def _worker(rank, world, port, mesh_name, setting, variant, form, q):
     ("LowRes", "inclusion", 0, "Gradient"),
     ("H1", "solkz", 1, "SymmetricGradient"),
     ("S6", "inclusion", 1, "Gradient"),
+    ("random:5", "random", 1, "SymmetricGradient"),       # random Delaunay mesh, random numbering, faces without elements
 ])
 def test_two_ranks_reproduce_global_rows(mesh_name, setting, variant, form):
     ctx = mp.get_context("spawn")

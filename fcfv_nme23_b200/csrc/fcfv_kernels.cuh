@@ -205,7 +205,7 @@ FCFV_HD void asm_face(const FaceDataView& D, double A, int f, int2 pr, const Fac
     const int bcf = C.bc[0];
     const bool has0 = pr.x >= 0, has1 = has0 && pr.y != pr.x;
     if (has0 && owned) {
-        rows_begin(R, C.k);
+        rows_begin<Sink::kRanked>(R, C.k);
         double vx = 0.0, vy = 0.0, sxx = 0.0, sxy = 0.0, syx = 0.0, syy = 0.0;
         if (bcf == 1) { vx = D.VxDir[f]; vy = D.VyDir[f]; }
         if (bcf == 2) { sxx = D.sxx[f]; sxy = D.sxy[f]; syx = D.syx[f]; syy = D.syy[f]; }   // tractions only enter through t*Xi

@@ -331,11 +331,13 @@ struct RowVals {
 };
 
 struct NullSink {
+    static constexpr bool kRanked = false;     // nothing is placed: the column ranks are not needed
     FCFV_HD void cand(int, const CandVals&) const {}
     FCFV_HD void kup(int, double, double) const {}
 };
 
 struct RowValsSink {
+    static constexpr bool kRanked = true;
     RowVals* V;
     FCFV_HD void cand(int c, const CandVals& v) const {
         V->xs[c] = v.xs; V->xc[c] = v.xc; V->ys[c] = v.ys; V->yc[c] = v.yc;
@@ -359,19 +361,25 @@ FCFV_HD void rows_clear(FaceRows& R) {
 // Column faces and their ranks are known before any element data arrives (face connectivity
 // record): keys k[0..4], absent faces (< 0) rank last.  Masks start empty and are filled while the
 // values are produced.
+// RANKED = false (count pass): only the number of stored entries matters, any five distinct bits do.
+template <bool RANKED>
 FCFV_HD void rows_begin(FaceRows& R, const int k[5]) {
 #pragma unroll
     for (int c = 0; c < 5; c++) R.key[c] = k[c] < 0 ? kDeadKey : k[c];
     // ranks from the 10 pairwise comparisons (ties only between dead keys: broken by index)
-    int rks[5] = {0, 0, 0, 0, 0};
+    int rks[5] = {0, 1, 2, 3, 4};
+    if (RANKED) {
 #pragma unroll
-    for (int c = 0; c < 5; c++)
+        for (int c = 0; c < 5; c++) rks[c] = 0;
 #pragma unroll
-        for (int d = c + 1; d < 5; d++) {
-            const int t = (R.key[d] < R.key[c]) ? 1 : 0;
-            rks[c] += t;
-            rks[d] += 1 - t;
-        }
+        for (int c = 0; c < 5; c++)
+#pragma unroll
+            for (int d = c + 1; d < 5; d++) {
+                const int t = (R.key[d] < R.key[c]) ? 1 : 0;
+                rks[c] += t;
+                rks[d] += 1 - t;
+            }
+    }
 #pragma unroll
     for (int c = 0; c < 5; c++) R.lt[c] = (1 << rks[c]) - 1;
     R.kpe[0] = R.kpe[1] = -1;

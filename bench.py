@@ -187,6 +187,20 @@ def sample_inputs(n):
 
 
 # --------------------------------------------------------------------------------------------
+def host_cpu():
+    """(model name, logical cores) of the box the CPU arm runs on."""
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return model, os.cpu_count()
+
+
 def run_reference(args, rank, world):
     """CPU arm: the reference's algorithm (oracle port; Julia itself is not installable here) on the
     host cores, each step one bounded sample S(cpu_n) of the workload."""
@@ -221,7 +235,8 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(N_DEFAULT if args.n is None else args.n, args.gpus, args.scaling),
                        "sample": f"each step = one bounded sample S({n}) of that workload on 1 host thread (the reference has no threading)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                             "host_cpu": host_cpu()[0], "host_cores": host_cpu()[1]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -336,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu:
         mesh_arrays, data = sample_inputs(args.cpu_n)
         val, parts = cpu_port_throughput(mesh_arrays, data, reps=2)
-        cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+        cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "host_cpu": host_cpu()[0], "host_cores": host_cpu()[1],
                "sample": f"S({args.cpu_n}) = {int(mesh_arrays['Ω'].size)} elements (BASELINE config 3 size), best of 2; "
                          f"local {parts[1]:.2f}s + assembly {parts[2]:.2f}s + residual {parts[3]:.2f}s; "
                          "restated reference (C, -O2, no FMA), not Julia"}

@@ -600,6 +600,10 @@ def test_numbering_preparation_on_device(name, api):
     # preparation, device against host
     order = api.hilbert_elements(ms.xc, ms.yc)
     assert np.array_equal(order, M.hilbert_element_order(ms.xc, ms.yc))
+    if name == "H1":                                     # degenerate boxes, ties, the empty mesh
+        for x, y in ((np.zeros(5), np.arange(5.0)), (np.zeros(3), np.zeros(3)), (np.array([0.3, 0.3, 0.1, 0.3]), np.array([0.2, 0.2, 0.9, 0.2]))):
+            assert np.array_equal(api.hilbert_elements(x, y), M.hilbert_element_order(x, y))
+        assert api.hilbert_elements(np.zeros(0), np.zeros(0)).size == 0
     M.renumber_elements(ms, order)
     old_e = old_e[order - 1]
     perm, e2f_new = api.first_seen_faces(np.asfortranarray(ms.e2f), nf)

@@ -238,7 +238,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                              "host_cpu": host_cpu()[0], "host_cores": host_cpu()[1]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -369,7 +369,7 @@ def run_ours(args, rank, world, local_rank):
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     h.close()
     if world > 1:
         dist.destroy_process_group()
@@ -456,11 +456,28 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
             "api": "fcfv_set_mesh + fcfv_compute_local + fcfv_assemble + fcfv_residuals, pinned host buffers, CSR left device-resident"}
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries print to stdout on their own (NCCL's version banner): keep fd 1 for the result line only
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

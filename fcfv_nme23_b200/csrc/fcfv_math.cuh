@@ -593,7 +593,8 @@ FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, do
     // unknown elsewhere (pass A only visits non-Dirichlet faces, :17)
     // pass A :12-32
     double ue[2] = {b1 / alpha, b2 / alpha};
-    const double mi = -1.0 / Om;
+    const double iOm = 1.0 / Om;          // -1.0/Ω == -(1.0/Ω) bit for bit: one division serves :14 and :22
+    const double mi = -iOm;
     double L[2][2] = {{mi * Z11, mi * Z12}, {mi * Z21, mi * Z22}};
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -601,7 +602,7 @@ FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, do
             const double n[2] = {nx[i], ny[i]}, u[2] = {ux[i], uy[i]};
             ue[0] = ue[0] + ((G[i] * tau[i]) * u[0]) / alpha;
             ue[1] = ue[1] + ((G[i] * tau[i]) * u[1]) / alpha;
-            const double s = (1.0 / Om) * G[i];
+            const double s = iOm * G[i];
 #pragma unroll
             for (int a = 0; a < 2; a++)
 #pragma unroll

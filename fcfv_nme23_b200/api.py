@@ -112,6 +112,11 @@ class Handle:
         return int(self.lib.fcfv_kernel_launches(self._h))
 
     @property
+    def staged_copies(self):
+        """Transfers from / to pageable host memory that went through the multi-threaded staging path."""
+        return int(self.lib.fcfv_staged_copies(self._h))
+
+    @property
     def device_bytes(self):
         return int(self.lib.fcfv_device_bytes(self._h))
 

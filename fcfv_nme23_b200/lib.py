@@ -123,6 +123,8 @@ def load():
     lib.fcfv_stream.restype = vp
     lib.fcfv_kernel_launches.argtypes = [vp]
     lib.fcfv_kernel_launches.restype = i64
+    lib.fcfv_staged_copies.argtypes = [vp]
+    lib.fcfv_staged_copies.restype = i64
     lib.fcfv_device_bytes.argtypes = [vp]
     lib.fcfv_device_bytes.restype = i64
     _lib = lib

@@ -318,8 +318,8 @@ end
 """    PinArrays(mesh_or_handle, arrays...) -> token
 
 Optional.  Page-locks Julia arrays that are passed to the entries above again and again (`mesh.e2f`, `mesh.n_x`, ...,
-`VxDir`, `sex`, outputs), so that their copies run at PCIe speed (≈ 53 GB/s) instead of through the driver's staging
-buffer (≈ 12 GB/s for pageable memory): 4× on the host-buffer path.  Costs ≈ 0.12 s per GB once.  The token keeps
+`VxDir`, `sex`, outputs), so that their copies run at PCIe speed (≈ 53 GB/s) instead of through the library's staging
+threads (≈ 35 GB/s for pageable memory).  Costs ≈ 0.12 s per GB once.  The token keeps
 the arrays alive and un-pins them when it is finalised; do not `resize!` a pinned array."""
 function PinArrays(h::Handle, arrays...)
     kept = Any[]

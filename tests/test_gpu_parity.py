@@ -675,3 +675,45 @@ def test_example_driver_solves_the_inclusion_problem(form, new_loop):
     left, right = m.xc < 0.5, m.xc > 0.5
     assert abs(r["Vxe"][left].mean() + r["Vxe"][right].mean()) < 1e-8
     assert np.isfinite(r["Txxe"]).all() and np.abs(r["Txxe"]).max() > 0.1
+
+
+def test_staged_pageable_copies_give_identical_results(monkeypatch, api, oracle):
+    """Pageable host arrays above FCFV_STAGED_MIN_BYTES travel through the multi-threaded staging path (worker
+    threads, page-locked chunks): with the threshold forced down to 1 KiB every array of a small mesh takes it --
+    odd sizes, slices shorter than a chunk, empty slices -- and every result equals the direct path's, bit for bit.
+    A second mesh is large enough for chunked slices (several chunks per worker)."""
+    from fcfv_nme23_b200 import lib as L
+    case = cases.Case("LowRes", "inclusion", 0, "Gradient")
+    ref = {}
+    for tag, env in (("direct", "0"), ("staged", "1024")):
+        monkeypatch.setenv("FCFV_STAGED_MIN_BYTES", env)
+        m, d = cases.build(case)
+        neu = d["neu"]
+        a, b, Z = api.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, 2.0, case.form)
+        K, Mu, P, fu, fp, _ = api.ElementAssemblyLoop(m, a, b, Z, d["VxDir"], d["VyDir"], *neu, case.form)
+        n = api.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"], d["VyDir"],
+                                               *neu, case.form, verbose=False)
+        h = api.handle_for(m)
+        assert (h.staged_copies > 20) == (tag == "staged"), (tag, h.staged_copies)
+        ref[tag] = (a, b, Z, m.τ.copy(), K.indptr, K.indices, K.data, P.indptr, P.indices, P.data, Mu.data, np.asarray(fu), fp, n)
+        h.close()
+    for x, y in zip(ref["direct"], ref["staged"]):
+        assert np.array_equal(x, y)
+    # several chunks per worker: S(520), 1.08 M elements, arrays of 8.7 - 26 MB against the default 8 MiB threshold
+    monkeypatch.delenv("FCFV_STAGED_MIN_BYTES")
+    h = api.Handle(0)
+    h.generate_structured(520, setting="solkz", tau_r=10.0)
+    M0, D0 = h.get_mesh(), h.get_data()               # D2H of large arrays into fresh pageable memory: staged
+    assert h.staged_copies > 0
+    h.run_local("SymmetricGradient")
+    al0 = h.get_local()[0]
+    h.close()
+    from fcfv_nme23_b200.mesh import FCFV_Mesh
+    m = FCFV_Mesh(nel=M0["Ω"].size, nf=M0["bc"].size, nf_el=3)
+    for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe"):
+        setattr(m, k, M0[k])
+    z = np.zeros(m.nf)
+    a, b, Z = api.ComputeFCFV(m, D0["sex"], D0["sey"], D0["VxDir"], D0["VyDir"], z, z, z, z, 10.0, "SymmetricGradient")
+    h2 = api.handle_for(m)
+    assert h2.staged_copies > 10 and np.array_equal(a, al0)
+    h2.close()

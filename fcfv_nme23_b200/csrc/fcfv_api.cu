@@ -293,10 +293,16 @@ int copy_staged(fcfv_t* h, void* dev, void* host, size_t bytes, bool to_device) 
     for (int t = 0; t < kStageThreads; t++) {
         const size_t lo = t < nt ? std::min(bytes, per * t) : bytes, hi = t >= nt - 1 ? bytes : std::min(bytes, per * (t + 1));
         err[t] = cudaSuccess;
-        th[t] = std::thread([&, t, lo, hi]() { if (hi > lo) err[t] = stage_slice(h->device, S, t, (char*)dev, (char*)host, lo, hi, to_device);
-                                               else err[t] = cudaEventRecord(S.done[t], S.s[t]); });
+        auto work = [&, t, lo, hi]() { if (hi > lo) err[t] = stage_slice(h->device, S, t, (char*)dev, (char*)host, lo, hi, to_device);
+                                       else err[t] = cudaEventRecord(S.done[t], S.s[t]); };
+        try {
+            th[t] = std::thread(work);
+        } catch (...) {        // no thread to be had (resource limits): this slice runs here; nothing may cross the C boundary
+            work();
+        }
     }
-    for (int t = 0; t < kStageThreads; t++) th[t].join();
+    for (int t = 0; t < kStageThreads; t++)
+        if (th[t].joinable()) th[t].join();
     for (int t = 0; t < kStageThreads; t++)
         if (err[t] != cudaSuccess) return fail(h, FCFV_ERR_CUDA, "staged host copy failed: %s", cudaGetErrorString(err[t]));
     // ... and the handle's stream continues after them

@@ -1496,6 +1496,31 @@ int fcfv_get_mesh(fcfv_t* h, int64_t* e2f, int64_t* bc, double* Omega, double* n
     return sync(h);
 }
 
+int fcfv_numbering_locality(fcfv_t* h, double* element_span, double* face_offset) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_numbering_locality: no mesh set"));
+    CU(cudaSetDevice(h->device));
+    const int nblk = nblocks(h->nf);
+    DBuf part;
+    std::vector<double> host(3 * (size_t)nblk);
+    auto body = [&]() -> int {
+        TRY(ensure(h, part, sizeof(double) * 3 * nblk));
+        LAUNCH(h, k_locality, nblk, kBlock, P<int2>(h->f2e), (int)h->nf, (int)std::max<long long>(h->nel, 1), P<double>(part), nblk);
+        TRY(copy(h, host.data(), part.p, sizeof(double) * 3 * nblk));
+        return sync(h);
+    };
+    const int rc = body();
+    cudaStreamSynchronize(h->stream);
+    release(h, part);
+    if (rc != FCFV_OK) return rc;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int q = 0; q < 3; q++)
+        for (int b = 0; b < nblk; b++) s[q] += host[(size_t)q * nblk + b];
+    if (element_span) *element_span = s[2] > 0.0 ? s[0] / s[2] : 0.0;
+    if (face_offset) *face_offset = s[2] > 0.0 ? s[1] / s[2] : 0.0;
+    return FCFV_OK;
+}
+
 int fcfv_get_ownership(fcfv_t* h, uint8_t* elem_owned, uint8_t* face_owned, int64_t* nel_global, int64_t* nf_global) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_get_ownership: no mesh set"));

@@ -1090,6 +1090,29 @@ __global__ void k_fs_apply(const int* __restrict__ e2f, long long n3, const long
     if (k < n3) out[k] = new_of_old[e2f[k]];
 }
 
+// ---- numbering locality (diagnostic) ---------------------------------------------------------------------------
+// Per-block sums over the faces that have an element of |e_hi - e_lo| / nel (how far apart in memory the two
+// elements of a face are), |f/nf - e_lo/nel| (how far the face ids stray from the element order) and the count.
+__global__ void __launch_bounds__(kBlock)
+k_locality(const int2* __restrict__ f2e, int nf, int nel, double* __restrict__ partial, int nblk) {
+    __shared__ double sd[3 * (kBlock / 32)];
+    const int f = blockIdx.x * kBlock + threadIdx.x;
+    double t[3] = {0.0, 0.0, 0.0};
+    if (f < nf) {
+        const int2 pr = f2e[f];
+        if (pr.x >= 0) {
+            const int e0 = pr.x >> 2, e1 = pr.y >> 2;
+            t[0] = (double)(e1 > e0 ? e1 - e0 : e0 - e1) / (double)nel;
+            const double d = (double)f / (double)nf - (double)e0 / (double)nel;
+            t[1] = d < 0.0 ? -d : d;
+            t[2] = 1.0;
+        }
+    }
+    block_sums<3>(t, sd);
+    if (threadIdx.x == 0)
+        for (int q = 0; q < 3; q++) partial[(size_t)q * nblk + blockIdx.x] = t[q];
+}
+
 // ---- a9 Powell-Hestenes -------------------------------------------------------------------------
 // ru = (fu - Kuu*u) - Kup*p, one thread per row, products accumulated in ascending column order
 // (the order Julia's CSC mat-vec produces for each row), per-block sum of ru^2.

@@ -83,6 +83,7 @@ def load():
         "fcfv_schur": [vp, dbl, P(i64)],
         "fcfv_first_seen_faces": [vp, i64, i64, vp, vp, vp],
         "fcfv_hilbert_elements": [vp, i64, vp, vp, vp],
+        "fcfv_numbering_locality": [vp, P(dbl), P(dbl)],
         "fcfv_host_register": [vp, vp, i64],
         "fcfv_host_unregister": [vp, vp],
         "fcfv_run_pipeline": [vp, ci, ci, dbl, ci],

@@ -95,6 +95,12 @@ int fcfv_first_seen_faces(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f
  * e2f.  Stand-alone, does not need fcfv_set_mesh.  Meshes from Triangle and the generators here do not need it. */
 int fcfv_hilbert_elements(fcfv_t* h, int64_t nel, const double* xc, const double* yc, int64_t* old_of_new);
 
+/* Diagnostic for the two preparation calls above, on the mesh that is set: element_span = mean over the faces of
+ * |e_hi - e_lo| / nel (distance in memory between the two elements of a face; 0 for boundary faces), face_offset =
+ * mean of |f/nf - e_lo/nel| (how far the face ids stray from the element order).  Meshes from Triangle, the .dat
+ * fixtures and the generators give <= 0.01 for both; random numbering gives 1/3 and passes 3-7x slower. */
+int fcfv_numbering_locality(fcfv_t* h, double* element_span, double* face_offset);
+
 /* ---- a4: ComputeFCFV (src/DiscretisationFCFV_Stokes.jl:8-44) ---------------------------
  * Outputs alpha nel, beta nel x 2, Z nel x 2 x 2, tau nf (mesh.τ after the call: face f gets
  * τe of its highest-numbered adjacent element, faces without elements keep their value). */

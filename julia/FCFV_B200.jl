@@ -69,6 +69,13 @@ function handle_for(mesh)
     end
     h.nel, h.nf = mesh.nel, mesh.nf
     HANDLES[mesh] = h
+    if mesh.nel >= 100_000            # the gathers of the GPU passes rely on numbering locality
+        span, off = Ref{Float64}(0.0), Ref{Float64}(0.0)
+        check(h, ccall((:fcfv_numbering_locality, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h.ptr, span, off))
+        if span[] > 0.05 || off[] > 0.05
+            @warn "mesh numbering has little locality (element span $(round(span[], digits=2)), face offset $(round(off[], digits=2)) of the mesh): the GPU passes run 3-7x faster after FCFV_B200.PrepareNumbering!(mesh)"
+        end
+    end
     return h
 end
 

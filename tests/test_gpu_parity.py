@@ -613,6 +613,12 @@ def test_numbering_preparation_on_device(name, api):
     pf = perm[pf - 1]
     jump = np.hypot(np.diff(ms.xc), np.diff(ms.yc))
     assert np.median(jump) < 4.0 * np.sqrt(np.median(ms.Ω))
+    # the locality diagnostic tells the two numberings apart
+    hs = api.Handle(0); hs.set_mesh(ms); good = hs.numbering_locality(); hs.close()
+    mb, _ = cases.build(case)
+    M.renumber_elements(mb, rng.permutation(nel) + 1); M.renumber_faces(mb, rng.permutation(nf) + 1)
+    hb = api.Handle(0); hb.set_mesh(mb); bad = hb.numbering_locality(); hb.close()
+    assert good[0] < 0.08 and good[1] < 0.08 and bad[0] > 0.25 and bad[1] > 0.25, (good, bad)
 
     def faces(x):
         out = np.empty_like(x); out[pf - 1] = x; return out

@@ -2,6 +2,7 @@
 oracle on identical seeded inputs.  Contract (BASELINE.json north_star): CSR sparsity and face
 numbering bit-exact; matrix, RHS and residual values within 1e-12 relative.  Design goal checked
 here: alpha/beta/Z/tau/Kuu/Kup/Muu/fu/fp are BITWISE equal; residual norms within 1e-12."""
+import ctypes as C
 import hashlib
 import json
 import os
@@ -147,6 +148,11 @@ def test_edge_cases(api, oracle):
     h = api.Handle(0)
     with pytest.raises(L.FCFVError):
         h.run_local("Gradient")                       # no mesh
+    with pytest.raises(L.FCFVError):
+        h.numbering_locality()                        # no mesh either
+    x3, o3 = np.zeros(3), np.zeros(3, dtype=np.int64)
+    assert h.lib.fcfv_hilbert_elements(h._h, 3, x3.ctypes.data_as(C.c_void_p), None, o3.ctypes.data_as(C.c_void_p)) != 0   # null array
+    assert b"null array" in h.lib.fcfv_last_error(h._h)
     bad = cases.load_mesh("S6"); bad.e2f = bad.e2f.copy(); bad.e2f[0, 0] = bad.nf + 5
     with pytest.raises(L.FCFVError):
         h.set_mesh(bad)

@@ -5,5 +5,6 @@ residual evaluation) behind the C ABI of ``include/fcfv_b200.h``.
 ``lib``        ctypes binding of ``libfcfv_b200.so`` (built in-tree from ``csrc/``; there is no CPU fallback)
 ``mesh``       the mesh struct, fixture readers, numbering helpers
 ``partition``  element partitioner for one-process-per-GPU runs
+``solvers``    mirror of the consumer ``StokesSolvers!``: host factorisation (SciPy) around the GPU Powell-Hestenes lines
 """
 __version__ = "0.1.0"

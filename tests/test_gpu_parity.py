@@ -729,3 +729,28 @@ def test_staged_pageable_copies_give_identical_results(monkeypatch, api, oracle)
     h2 = api.handle_for(m)
     assert h2.staged_copies > 10 and np.array_equal(a, al0)
     h2.close()
+
+
+@pytest.mark.parametrize("solver", ["CoupledBackslash", "PowellHestenesLU"])
+def test_stokes_solvers_mirror(solver, api, oracle):
+    """solvers.StokesSolvers (mirror of StokesSolvers!, SolversFCFV_Stokes.jl:6-56) around the GPU lines: both solver
+    families give the same velocity field on LowRes and the matrix-free residuals of the solution vanish."""
+    from fcfv_nme23_b200 import solvers
+    case = cases.Case("LowRes", "inclusion", 0, "Gradient")
+    m, d = cases.build(case)
+    z, ze = np.zeros(m.nf), np.zeros(m.nel)
+    a, b, Z = api.ComputeFCFV(m, ze, ze, d["VxDir"], d["VyDir"], z, z, z, z, 2.0, case.form)
+    Kuu, Muu, Kup, fu, fp, _ = api.ElementAssemblyLoop(m, a, b, Z, d["VxDir"], d["VyDir"], z, z, z, z, case.form)
+    Vxh, Vyh, Pe = np.zeros(m.nf), np.zeros(m.nf), np.zeros(m.nel)
+    its = solvers.StokesSolvers(Vxh, Vyh, Pe, m, Kuu, Kup, fu, fp, Muu, solver, penalty=1e5, tol=1e-8, verbose=False)
+    assert its <= 6
+    n = api.ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, m, a, b, Z, ze, ze, d["VxDir"], d["VyDir"], z, z, z, z, case.form,
+                                           tau_mode="FACE", verbose=False)
+    assert np.all(n < 1e-7), n
+    dir_faces = m.bc == 1
+    assert np.allclose(Vxh[dir_faces], d["VxDir"][dir_faces], atol=1e-9)
+    if solver == "CoupledBackslash":
+        assert abs(Pe.mean()) < 1e-10
+    api.handle_for(m).close()
+    with pytest.raises(ValueError):
+        solvers.StokesSolvers(Vxh, Vyh, Pe, m, Kuu, Kup, fu, fp, Muu, "Jacobi")

@@ -20,7 +20,26 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fcfv_nme23_b200 import api, mesh as M   # noqa: E402
 
 
-def setup(n, η=(1.0, 1e-2), R=1.0 / 6.0):
+def analytic(x, y, rc, ηm, ηc, er=-1.0, gr=0.0):
+    """Velocity and pressure around a circular inclusion of radius rc and viscosity ηc in a matrix of viscosity ηm under
+    far-field pure shear er and simple shear gr (Schmid & Podladchikov 2003, complex-potential solution; the
+    reference evaluates the same formulas in src/EvalAnalDani.jl).  Coordinates relative to the inclusion centre."""
+    Z = np.asarray(x, dtype=float) + 1j * np.asarray(y, dtype=float)
+    A = ηm * (ηc - ηm) / (ηc + ηm)
+    far = 1j * gr + 2.0 * er
+    inside = np.abs(Z) <= rc
+    Zo = np.where(inside, 1.0, Z)                          # placeholder inside: avoids 1/0, masked below
+    V_in = (ηm / (ηc + ηm)) * far * np.conj(Z) - 0.5j * gr * Z
+    phi = -0.5j * ηm * gr * Zo - far * A * rc ** 2 / Zo
+    dphi = -0.5j * ηm * gr + far * A * rc ** 2 / Zo ** 2
+    psi = (1j * gr - 2.0 * er) * ηm * Zo - far * A * rc ** 4 / Zo ** 3
+    V_out = (phi - Zo * np.conj(dphi) - np.conj(psi)) / (2.0 * ηm)
+    P_out = -2.0 * ηm * (ηc - ηm) / (ηc + ηm) * np.real(rc ** 2 / Zo ** 2 * far)
+    V = np.where(inside, V_in, V_out)
+    return V.real, V.imag, np.where(inside, 0.0, P_out)
+
+
+def setup(n, η=(1.0, 1e-2), R=1.0 / 6.0, exact_bc=False):
     """Unit square, circular inclusion of viscosity η[1] (faces between phases tagged -1, README.md:24), pure shear
     on the boundary (v2.jl:103-108: Dirichlet values at face midpoints)."""
     m = M.MakeStructuredMesh(n, τr=1.0)                # geometry by the CUDA kernel
@@ -32,12 +51,16 @@ def setup(n, η=(1.0, 1e-2), R=1.0 / 6.0):
     for i in range(3):
         np.minimum.at(kmin, f[:, i], m.ke); np.maximum.at(kmax, f[:, i], m.ke)
     m.bc = np.where((m.bc == 0) & (kmin != kmax), -1, m.bc).astype(np.int64)
-    VxDir, VyDir = (m.xf - 0.5), -(m.yf - 0.5)
+    if exact_bc:        # the infinite-domain solution on the box boundary: it is then the exact solution inside
+        VxDir, VyDir, _ = analytic(m.xf - 0.5, m.yf - 0.5, R, η[0], η[1], er=0.5)
+    else:
+        VxDir, VyDir = (m.xf - 0.5), -(m.yf - 0.5)
     return m, VxDir, VyDir
 
 
-def solve(n=64, Formulation="SymmetricGradient", τr=2.0, γ=1e5, tol=1e-9, new_loop=False, verbose=True):
-    m, VxDir, VyDir = setup(n)
+def solve(n=64, Formulation="SymmetricGradient", τr=2.0, γ=1e5, tol=1e-9, new_loop=False, verbose=True, exact_bc=False,
+          η=(1.0, 1e-2), R=1.0 / 6.0):
+    m, VxDir, VyDir = setup(n, η, R, exact_bc)
     nel, nf = m.nel, m.nf
     m.τe = τr * np.ones(nel)
     z, ze = np.zeros(nf), np.zeros(nel)
@@ -68,8 +91,18 @@ def solve(n=64, Formulation="SymmetricGradient", τr=2.0, γ=1e5, tol=1e-9, new_
         print(f"nel = {nel}, nnz(Kuu) = {Kuu.nnz}, nnz(Kup) = {Kup.nnz}; set-up + assembly + export {t_asm:.3f} s "
               f"(device CSR build {tsparse * 1e3:.2f} ms), LU {t_fact:.3f} s, {its} Powell-Hestenes iterations")
         print(f"min/max Vx {Vxe.min():+.4f} {Vxe.max():+.4f}   min/max P {Pe.min():+.4f} {Pe.max():+.4f}")
-    return dict(mesh=m, norms=norms, iterations=its, Vxe=Vxe, Vye=Vye, Pe=Pe, Txxe=Txxe, Tyye=Tyye, Txye=Txye)
+    out = dict(mesh=m, norms=norms, iterations=its, Vxe=Vxe, Vye=Vye, Pe=Pe, Txxe=Txxe, Tyye=Tyye, Txye=Txye)
+    if exact_bc:        # L1 discretisation errors against the analytic solution (as ViscousInclusionFCFV_DiscretisationErrors.jl does)
+        vx, vy, pa = analytic(m.xc - 0.5, m.yc - 0.5, R, η[0], η[1], er=0.5)
+        w = m.Ω / m.Ω.sum()
+        pe = Pe - (w * Pe).sum()
+        pa = pa - (w * pa).sum()
+        out["errors"] = dict(Vx=float((w * np.abs(Vxe - vx)).sum()), Vy=float((w * np.abs(Vye - vy)).sum()),
+                             P=float((w * np.abs(pe - pa)).sum()))
+        if verbose:
+            print("L1 errors vs the analytic solution:", out["errors"])
+    return out
 
 
 if __name__ == "__main__":
-    solve(int(sys.argv[1]) if len(sys.argv) > 1 else 64)
+    solve(int(sys.argv[1]) if len(sys.argv) > 1 else 64, exact_bc="--exact-bc" in sys.argv)

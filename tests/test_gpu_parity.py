@@ -754,3 +754,22 @@ def test_stokes_solvers_mirror(solver, api, oracle):
     api.handle_for(m).close()
     with pytest.raises(ValueError):
         solvers.StokesSolvers(Vxh, Vyh, Pe, m, Kuu, Kup, fu, fp, Muu, "Jacobi")
+
+
+@pytest.mark.parametrize("eta", [(1.0, 1e-2), (1.0, 10.0)], ids=["weak-inclusion", "strong-inclusion"])
+def test_discretisation_error_converges_to_the_analytic_solution(eta):
+    """Known answer from outside the code base: the analytic solution of a circular inclusion under pure shear (Schmid &
+    Podladchikov 2003) imposed on the box boundary.  The GPU-assembled :SymmetricGradient system (host LU + PH lines)
+    approaches it at the scheme's first order in L1, velocity and pressure, on S(16), S(32), S(64) (the mesh is not
+    fitted to the circle); ElementAssemblyLoopNEW gives the same errors as ElementAssemblyLoop."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("viscous_inclusion", os.path.join(os.path.dirname(__file__), "..", "examples",
+                                                                                   "viscous_inclusion.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    errs = [ex.solve(n, Formulation="SymmetricGradient", verbose=False, exact_bc=True, η=eta, tol=1e-10)["errors"] for n in (16, 32, 64)]
+    for k in ("Vx", "Vy", "P"):
+        assert errs[0][k] / errs[1][k] > 1.4 and errs[1][k] / errs[2][k] > 1.4, (k, errs)
+    assert errs[2]["Vx"] < 1e-3 and errs[2]["P"] < 4e-2
+    new = ex.solve(32, Formulation="SymmetricGradient", new_loop=True, verbose=False, exact_bc=True, η=eta, tol=1e-10)["errors"]
+    assert all(abs(new[k] - errs[1][k]) <= 1e-5 * errs[1][k] for k in new), (new, errs[1])

@@ -246,3 +246,41 @@ def test_schur_against_scipy(case, oracle):
     assert rel_inf(S.data, R.data) <= 1e-14
     if case.form == "SymmetricGradient":   # the symmetric formulation gives a symmetric Schur complement (Cholesky branch)
         assert abs(S - S.T).max() <= 1e-12 * abs(S).max()
+
+
+@pytest.mark.parametrize("eta", [(1.0, 1e-2), (1.0, 10.0)], ids=["weak-inclusion", "strong-inclusion"])
+def test_oracle_converges_to_the_analytic_inclusion_solution(eta, oracle):
+    """Pins the oracle to something outside the code base: the analytic solution of a circular inclusion under pure
+    shear (Schmid & Podladchikov 2003; the reference evaluates the same formulas in src/EvalAnalDani.jl) imposed on
+    the boundary of S(n).  The oracle's :SymmetricGradient system (coupled SciPy solve), reconstructed with
+    ComputeElementValues, approaches it at the scheme's first order in L1 -- velocity and pressure -- on n = 16, 32, 64."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("viscous_inclusion", os.path.join(os.path.dirname(__file__), "..", "examples",
+                                                                                   "viscous_inclusion.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    form, R, errs = "SymmetricGradient", 1.0 / 6.0, []
+    for n in (16, 32, 64):
+        m = cases.load_mesh(f"S{n}")
+        nel, nf = m.nel, m.nf
+        inside = np.hypot(m.xc - 0.5, m.yc - 0.5) < R
+        m.ke = np.where(inside, eta[1], eta[0]); m.τe = 2.0 * np.ones(nel); m.τ = None
+        VxDir, VyDir, _ = ex.analytic(m.xf - 0.5, m.yf - 0.5, R, eta[0], eta[1], er=0.5)
+        z, ze = np.zeros(nf), np.zeros(nel)
+        a, b, Z = oracle.ComputeFCFV(m, ze, ze, VxDir, VyDir, z, z, z, z, 2.0, form)
+        Kuu, Muu, Kup, fu, fp, _, _ = oracle.ElementAssemblyLoop(m, a, b, Z, VxDir, VyDir, z, z, z, z, form)
+        K = oracle.csc_to_scipy(Kuu, (2 * nf, 2 * nf)); P = oracle.csc_to_scipy(Kup, (2 * nf, nel))
+        # coupled system [Kuu Kup; -Kup' 0] with the pressure of one element pinned (defined up to a constant)
+        S = sp.bmat([[K, P], [-P.T, None]], format="lil")
+        rhs = np.concatenate([fu.ravel(), fp])
+        S[2 * nf, :] = 0.0; S[2 * nf, 2 * nf] = 1.0; rhs[2 * nf] = 0.0
+        x = spla.spsolve(S.tocsc(), rhs)
+        Vxh, Vyh, Pe = x[:nf], x[nf:2 * nf], x[2 * nf:]
+        Vxe, Vye, *_ = oracle.ComputeElementValues(m, Vxh, Vyh, Pe, a, b, Z, VxDir, VyDir, form)
+        vx, vy, pa = ex.analytic(m.xc - 0.5, m.yc - 0.5, R, eta[0], eta[1], er=0.5)
+        w = m.Ω / m.Ω.sum()
+        errs.append(dict(Vx=(w * np.abs(Vxe - vx)).sum(), Vy=(w * np.abs(Vye - vy)).sum(),
+                         P=(w * np.abs((Pe - (w * Pe).sum()) - (pa - (w * pa).sum()))).sum()))
+    for k in ("Vx", "Vy", "P"):
+        assert errs[0][k] / errs[1][k] > 1.4 and errs[1][k] / errs[2][k] > 1.4, (k, errs)
+    assert errs[2]["Vx"] < 1e-3 and errs[2]["P"] < 4e-2, errs

@@ -248,39 +248,59 @@ def test_schur_against_scipy(case, oracle):
         assert abs(S - S.T).max() <= 1e-12 * abs(S).max()
 
 
-@pytest.mark.parametrize("eta", [(1.0, 1e-2), (1.0, 10.0)], ids=["weak-inclusion", "strong-inclusion"])
-def test_oracle_converges_to_the_analytic_inclusion_solution(eta, oracle):
-    """Pins the oracle to something outside the code base: the analytic solution of a circular inclusion under pure
-    shear (Schmid & Podladchikov 2003; the reference evaluates the same formulas in src/EvalAnalDani.jl) imposed on
-    the boundary of S(n).  The oracle's :SymmetricGradient system (coupled SciPy solve), reconstructed with
-    ComputeElementValues, approaches it at the scheme's first order in L1 -- velocity and pressure -- on n = 16, 32, 64."""
+def _analytic_module():
     import importlib.util
     spec = importlib.util.spec_from_file_location("viscous_inclusion", os.path.join(os.path.dirname(__file__), "..", "examples",
                                                                                    "viscous_inclusion.py"))
     ex = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ex)
+    return ex
+
+
+@pytest.mark.parametrize("neumann", [False, True], ids=["dirichlet", "neumann-south"])
+@pytest.mark.parametrize("eta", [(1.0, 1e-2), (1.0, 10.0)], ids=["weak-inclusion", "strong-inclusion"])
+def test_oracle_converges_to_the_analytic_inclusion_solution(eta, neumann, oracle):
+    """Pins the oracle to something outside the code base: the analytic solution of a circular inclusion under pure
+    shear (Schmid & Podladchikov 2003; the reference evaluates the same formulas in src/EvalAnalDani.jl) imposed on
+    the boundary of S(n).  The oracle's :SymmetricGradient system (coupled SciPy solve), reconstructed with
+    ComputeElementValues, approaches it at the scheme's first order in L1 -- velocity and pressure -- on n = 16, 32, 64.
+    neumann-south: the south boundary carries the analytic stress as a Neumann condition (bc = 2, README.md:24)
+    instead of the velocity, which also fixes the pressure level."""
+    ex = _analytic_module()
     form, R, errs = "SymmetricGradient", 1.0 / 6.0, []
+    sol = lambda x, y: ex.analytic(x - 0.5, y - 0.5, R, eta[0], eta[1], er=0.5)
     for n in (16, 32, 64):
         m = cases.load_mesh(f"S{n}")
         nel, nf = m.nel, m.nf
         inside = np.hypot(m.xc - 0.5, m.yc - 0.5) < R
         m.ke = np.where(inside, eta[1], eta[0]); m.τe = 2.0 * np.ones(nel); m.τ = None
-        VxDir, VyDir, _ = ex.analytic(m.xf - 0.5, m.yf - 0.5, R, eta[0], eta[1], er=0.5)
+        VxDir, VyDir, _ = sol(m.xf, m.yf)
         z, ze = np.zeros(nf), np.zeros(nel)
-        a, b, Z = oracle.ComputeFCFV(m, ze, ze, VxDir, VyDir, z, z, z, z, 2.0, form)
-        Kuu, Muu, Kup, fu, fp, _, _ = oracle.ElementAssemblyLoop(m, a, b, Z, VxDir, VyDir, z, z, z, z, form)
+        sxx, syy, sxy = z.copy(), z.copy(), z.copy()
+        if neumann:
+            south = (m.bc == 1) & (m.yf == 0.0)
+            m.bc = np.where(south, 2, m.bc).astype(np.int64)
+            h = 1e-6                                  # stress of the matrix from centred differences of the analytic velocity
+            x, y = m.xf[south], m.yf[south]
+            dvx_dx = (sol(x + h, y)[0] - sol(x - h, y)[0]) / (2 * h); dvx_dy = (sol(x, y + h)[0] - sol(x, y - h)[0]) / (2 * h)
+            dvy_dx = (sol(x + h, y)[1] - sol(x - h, y)[1]) / (2 * h); dvy_dy = (sol(x, y + h)[1] - sol(x, y - h)[1]) / (2 * h)
+            p = sol(x, y)[2]
+            sxx[south] = -p + 2.0 * eta[0] * dvx_dx; syy[south] = -p + 2.0 * eta[0] * dvy_dy
+            sxy[south] = eta[0] * (dvx_dy + dvy_dx)
+        a, b, Z = oracle.ComputeFCFV(m, ze, ze, VxDir, VyDir, sxx, syy, sxy, sxy, 2.0, form)
+        Kuu, Muu, Kup, fu, fp, _, _ = oracle.ElementAssemblyLoop(m, a, b, Z, VxDir, VyDir, sxx, syy, sxy, sxy, form)
         K = oracle.csc_to_scipy(Kuu, (2 * nf, 2 * nf)); P = oracle.csc_to_scipy(Kup, (2 * nf, nel))
-        # coupled system [Kuu Kup; -Kup' 0] with the pressure of one element pinned (defined up to a constant)
         S = sp.bmat([[K, P], [-P.T, None]], format="lil")
         rhs = np.concatenate([fu.ravel(), fp])
-        S[2 * nf, :] = 0.0; S[2 * nf, 2 * nf] = 1.0; rhs[2 * nf] = 0.0
+        if not neumann:     # all-Dirichlet: the pressure is defined up to a constant, pin one element
+            S[2 * nf, :] = 0.0; S[2 * nf, 2 * nf] = 1.0; rhs[2 * nf] = 0.0
         x = spla.spsolve(S.tocsc(), rhs)
         Vxh, Vyh, Pe = x[:nf], x[nf:2 * nf], x[2 * nf:]
         Vxe, Vye, *_ = oracle.ComputeElementValues(m, Vxh, Vyh, Pe, a, b, Z, VxDir, VyDir, form)
-        vx, vy, pa = ex.analytic(m.xc - 0.5, m.yc - 0.5, R, eta[0], eta[1], er=0.5)
+        vx, vy, pa = sol(m.xc, m.yc)
         w = m.Ω / m.Ω.sum()
-        errs.append(dict(Vx=(w * np.abs(Vxe - vx)).sum(), Vy=(w * np.abs(Vye - vy)).sum(),
-                         P=(w * np.abs((Pe - (w * Pe).sum()) - (pa - (w * pa).sum()))).sum()))
+        shift = 0.0 if neumann else (w * Pe).sum() - (w * pa).sum()
+        errs.append(dict(Vx=(w * np.abs(Vxe - vx)).sum(), Vy=(w * np.abs(Vye - vy)).sum(), P=(w * np.abs(Pe - shift - pa)).sum()))
     for k in ("Vx", "Vy", "P"):
         assert errs[0][k] / errs[1][k] > 1.4 and errs[1][k] / errs[2][k] > 1.4, (k, errs)
-    assert errs[2]["Vx"] < 1e-3 and errs[2]["P"] < 4e-2, errs
+    assert errs[2]["Vx"] < 2e-3 and errs[2]["P"] < 5e-2, errs

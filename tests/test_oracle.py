@@ -304,3 +304,41 @@ def test_oracle_converges_to_the_analytic_inclusion_solution(eta, neumann, oracl
     for k in ("Vx", "Vy", "P"):
         assert errs[0][k] / errs[1][k] > 1.4 and errs[1][k] / errs[2][k] > 1.4, (k, errs)
     assert errs[2]["Vx"] < 2e-3 and errs[2]["P"] < 5e-2, errs
+
+
+@pytest.mark.parametrize("form,loop", [("Gradient", "old"), ("SymmetricGradient", "old"), ("SymmetricGradient", "NEW"), ("Gradient", "NEW")])
+def test_oracle_on_the_shipped_inclusion_meshes_against_the_analytic_solution(form, loop, oracle):
+    """BASELINE config 1 as the reference's driver runs it (ViscousInclusionFCFV_v2.jl: [-3,3]^2, inclusion of radius 1
+    and viscosity 1e-2 fitted by the advancing-front meshes, interface faces tagged -1, analytic Dirichlet data with
+    er = -1): from LowRes (2 004 elements) to MedRes (8 130) the L1 errors of velocity and pressure drop by the mesh
+    ratio (first order) -- for :SymmetricGradient (both loops) and for :Gradient with its interface terms (old loop).
+    ElementAssemblyLoopNEW with :Gradient is the combination SURVEY Appendix A flags (values stored transposed, interface
+    terms dropped from the right-hand side; no driver of the reference uses it): its velocity still converges, its pressure
+    barely does -- recorded here as the reference's behaviour, which the kernels reproduce bit for bit."""
+    ex = _analytic_module()
+    errs = []
+    for name in ("LowRes", "MedRes"):
+        m = cases.load_mesh(name)
+        nel, nf = m.nel, m.nf
+        m.τe = 2.0 * np.ones(nel); m.τ = None
+        VxDir, VyDir, _ = ex.analytic(m.xf, m.yf, 1.0, 1.0, 1e-2, er=-1.0)
+        z, ze = np.zeros(nf), np.zeros(nel)
+        a, b, Z = oracle.ComputeFCFV(m, ze, ze, VxDir, VyDir, z, z, z, z, 2.0, form)
+        fn = oracle.ElementAssemblyLoop if loop == "old" else oracle.ElementAssemblyLoopNEW
+        Kuu, Muu, Kup, fu, fp, _, _ = fn(m, a, b, Z, VxDir, VyDir, z, z, z, z, form)
+        K = oracle.csc_to_scipy(Kuu, (2 * nf, 2 * nf)); P = oracle.csc_to_scipy(Kup, (2 * nf, nel))
+        S = sp.bmat([[K, P], [-P.T, None]], format="lil")
+        rhs = np.concatenate([fu.ravel(), fp])
+        S[2 * nf, :] = 0.0; S[2 * nf, 2 * nf] = 1.0; rhs[2 * nf] = 0.0
+        x = spla.spsolve(S.tocsc(), rhs)
+        Vxh, Vyh, Pe = x[:nf], x[nf:2 * nf], x[2 * nf:]
+        Vxe, Vye, *_ = oracle.ComputeElementValues(m, Vxh, Vyh, Pe, a, b, Z, VxDir, VyDir, form)
+        vx, vy, pa = ex.analytic(m.xc, m.yc, 1.0, 1.0, 1e-2, er=-1.0)
+        w = m.Ω / m.Ω.sum()
+        shift = (w * Pe).sum() - (w * pa).sum()
+        errs.append(dict(Vx=(w * np.abs(Vxe - vx)).sum(), Vy=(w * np.abs(Vye - vy)).sum(), P=(w * np.abs(Pe - shift - pa)).sum()))
+    if (form, loop) == ("Gradient", "NEW"):
+        assert errs[0]["Vx"] / errs[1]["Vx"] > 1.5 and 1.0 < errs[0]["P"] / errs[1]["P"] < 1.5, errs
+        return
+    for k in ("Vx", "Vy", "P"):
+        assert errs[0][k] / errs[1][k] > 1.5, (k, errs)

@@ -22,7 +22,7 @@ from . import lib as _L
 
 __all__ = [
     "Handle", "handle_for", "mesh_geometry", "ComputeFCFV", "ElementAssemblyLoop", "ElementAssemblyLoopNEW",
-    "ComputeResidualsFCFV_Stokes_o1", "ph_residual", "ph_update_p", "ph_fusc", "formulation_id",
+    "ComputeResidualsFCFV_Stokes_o1", "FusedPass", "ph_residual", "ph_update_p", "ph_fusc", "formulation_id",
 ]
 
 _FORMS = {"Gradient": _L.GRADIENT, "SymmetricGradient": _L.SYMMETRIC_GRADIENT}
@@ -409,6 +409,27 @@ def ElementAssemblyLoopNEW(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σx
                            want_muu=True, export=True):
     """src/DiscretisationFCFV_Stokes.jl:210-347 (+ Sparsify)."""
     return _assemble(_L.LOOP_NEW, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A, want_muu, export)
+
+
+def FusedPass(mesh, sex, sey, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Vxh, Vyh, Pe, Formulation, loop="old",
+              tau_mode="REFERENCE", A=A_DEFAULT, want_muu=False):
+    """``fcfv_pass``: ComputeFCFV + ElementAssemblyLoop[NEW] + ComputeResidualsFCFV_Stokes_o1 in one call, every host
+    array uploaded once and the download of α, β, Ζ, τ overlapped with the uploads.  Returns ``(α, β, Ζ, norms, nnz)``;
+    ``mesh.τ`` is set; the matrices stay on the GPU (``handle_for(mesh).export_scipy_csc(...)``, ``export_rhs()``)."""
+    h = handle_for(mesh)
+    _refresh(mesh, h)
+    nel, nf = h.nel, h.nf
+    a = _Arg()
+    α, β, Ζ = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")
+    τ, norms = np.empty(nf), np.zeros(6)
+    nnz = [C.c_int64(0) for _ in range(3)]
+    variant = _L.LOOP_NEW if str(loop).upper() == "NEW" else _L.LOOP_OLD
+    h.check(h.lib.fcfv_pass(h._h, variant, formulation_id(Formulation), float(A), _TAU_MODES[tau_mode], a.d(sex, nel), a.d(sey, nel),
+                            a.d(VxDir, nf), a.d(VyDir, nf), a.d(σxxNeu, nf), a.d(σyyNeu, nf), a.d(σxyNeu, nf), a.d(σyxNeu, nf),
+                            a.d(Vxh, nf), a.d(Vyh, nf), a.d(Pe, nel), _out(α), _out(β), _out(Ζ), _out(τ), int(bool(want_muu)),
+                            C.byref(nnz[0]), C.byref(nnz[1]), C.byref(nnz[2]), _out(norms)))
+    mesh.τ = τ
+    return α, β, Ζ, norms, tuple(int(v.value) for v in nnz)
 
 
 _RES_LINES = (

@@ -79,6 +79,8 @@ struct Stager {
 struct fcfv_handle {
     int device = 0;
     Stager stager;
+    cudaStream_t stream_out = nullptr;   // device-to-host copies of fcfv_pass, concurrent with its uploads
+    cudaEvent_t ev_out = nullptr;
     long long staged_copies = 0;      // copies that went through the Stager (diagnostics / tests)
     size_t staged_min_bytes = 8u << 20;
     cudaStream_t stream = nullptr;
@@ -473,6 +475,8 @@ int fcfv_destroy(fcfv_t* h) {
                    &h->Fg, &h->partial, &h->sumsq, &h->red_scratch, &h->red_tickets, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx, &h->coefs};
     for (DBuf* b : all) release(h, *b);
     stager_destroy(h);
+    if (h->stream_out) { cudaStreamSynchronize(h->stream_out); cudaStreamDestroy(h->stream_out); }
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     cudaEventDestroy(h->ev0);
@@ -1311,6 +1315,58 @@ int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, 
         TRY(sync(h));
     }
     return FCFV_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// The three calls of a driver (ComputeFCFV -> ElementAssemblyLoop[NEW] -> ComputeResidualsFCFV_Stokes_o1) as one:
+// every host array crosses PCIe once (the separate calls upload VxDir, VyDir three times, the Neumann arrays and the
+// sources twice) and the download of alpha / beta / Z / tau runs on a second stream while the remaining inputs are
+// still going up (page-locked or registered destinations; pageable ones are staged and complete before the uploads
+// continue).
+int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, const double* sex, const double* sey,
+              const double* VxDir, const double* VyDir, const double* sxxNeu, const double* syyNeu, const double* sxyNeu,
+              const double* syxNeu, const double* Vxh, const double* Vyh, const double* Pe, double* alpha, double* beta,
+              double* Z, double* tau, int want_muu, int64_t* nnz_uu, int64_t* nnz_up, int64_t* nnz_muu, double* norms) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_pass: no mesh set"));
+    if (!VxDir || !VyDir || !Vxh || !Vyh || !Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_pass: null input array");
+    CU(cudaSetDevice(h->device));
+    if (!h->stream_out) {
+        CU(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    }
+    const bool was_async = h->async;
+    h->async = true;
+    auto body = [&]() -> int {
+        TRY(fcfv_set_sources(h, sex, sey));
+        TRY(fcfv_set_face_data(h, VxDir, VyDir, nullptr, nullptr, nullptr, nullptr));
+        TRY(fcfv_run_local(h, formulation, A));
+        // outputs of the element kernel go down while the rest goes up
+        CU(cudaEventRecord(h->ev_out, h->stream));
+        CU(cudaStreamWaitEvent(h->stream_out, h->ev_out, 0));
+        struct Out { double* dst; const void* src; size_t bytes; } outs[4] = {
+            {alpha, h->alpha.p, sizeof(double) * (size_t)h->nel}, {beta, h->beta.p, sizeof(double) * 2 * (size_t)h->nel},
+            {Z, h->Z.p, sizeof(double) * 4 * (size_t)h->nel}, {tau, h->tau.p, sizeof(double) * (size_t)h->nf}};
+        for (const Out& o : outs) {
+            if (!o.dst || o.bytes == 0) continue;
+            if (is_pageable_host(o.dst)) TRY(copy(h, o.dst, o.src, o.bytes));
+            else CU(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToHost, h->stream_out));
+        }
+        TRY(fcfv_set_face_data(h, nullptr, nullptr, sxxNeu, syyNeu, sxyNeu, syxNeu));   // NULL = keep what is resident
+        TRY(fcfv_run_assemble(h, variant, formulation, A, want_muu));
+        TRY(fcfv_set_solution(h, Vxh, Vyh, Pe));
+        return FCFV_OK;
+    };
+    int rc = body();
+    h->async = was_async;
+    if (rc == FCFV_OK) {
+        double dummy[6];
+        rc = fcfv_run_residuals(h, formulation, tau_mode, nullptr, norms ? norms : dummy);   // synchronises the main stream
+    }
+    if (rc == FCFV_OK) rc = fcfv_get_nnz(h, nnz_uu, nnz_up, nnz_muu);
+    const cudaError_t e = cudaStreamSynchronize(h->stream_out);
+    if (rc == FCFV_OK && e != cudaSuccess) rc = fail(h, FCFV_ERR_CUDA, "fcfv_pass: %s", cudaGetErrorString(e));
+    return rc;
 }
 
 // -------------------------------------------------------------------------------------------------

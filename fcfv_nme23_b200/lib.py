@@ -83,6 +83,7 @@ def load():
         "fcfv_schur": [vp, dbl, P(i64)],
         "fcfv_first_seen_faces": [vp, i64, i64, vp, vp, vp],
         "fcfv_hilbert_elements": [vp, i64, vp, vp, vp],
+        "fcfv_pass": [vp, ci, ci, dbl, ci] + [vp] * 11 + [vp] * 4 + [ci, P(i64), P(i64), P(i64), vp],
         "fcfv_numbering_locality": [vp, P(dbl), P(dbl)],
         "fcfv_host_register": [vp, vp, i64],
         "fcfv_host_unregister": [vp, vp],

@@ -119,6 +119,17 @@ int fcfv_assemble(fcfv_t* h, int variant, int formulation, double A, const doubl
                   const double* syxNeu, int want_muu, int64_t* nnz_uu, int64_t* nnz_up,
                   int64_t* nnz_muu, double* seconds);
 
+/* ---- one pass through host buffers: fcfv_compute_local + fcfv_assemble + fcfv_residuals in one call -------------
+ * For drivers that can replace their three calls (ViscousInclusionFCFV_v2.jl:128,132,146) by one: every array crosses
+ * PCIe once (the separate calls take VxDir / VyDir three times, the Neumann arrays and the sources twice) and
+ * alpha / beta / Z / tau come down on a second stream while the remaining inputs go up.  Same results as the three
+ * calls.  Outputs may be NULL; the Neumann arrays may be NULL (zeros on first use, else what is resident); norms: 6. */
+int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, const double* sex, const double* sey,
+              const double* VxDir, const double* VyDir, const double* sxxNeu, const double* syyNeu,
+              const double* sxyNeu, const double* syxNeu, const double* Vxh, const double* Vyh, const double* Pe,
+              double* alpha, double* beta, double* Z, double* tau, int want_muu, int64_t* nnz_uu, int64_t* nnz_up,
+              int64_t* nnz_muu, double* norms);
+
 /* ---- Powell-Hestenes Schur complement, fused into the assembly (src/SolversFCFV_Stokes.jl:23-25)
  * Kuusc = Kuu .- Kup*(Kppi*Kpu) with Kppi = spdiagm(gamma .* ke ./ Ω), Kpu = -Kup': the same face-to-face
  * rows as Kuu with one extra term per adjacent element, so the fill pass writes it next to Kuu / Kup

@@ -773,3 +773,37 @@ def test_discretisation_error_converges_to_the_analytic_solution(eta):
     assert errs[2]["Vx"] < 1e-3 and errs[2]["P"] < 4e-2
     new = ex.solve(32, Formulation="SymmetricGradient", new_loop=True, verbose=False, exact_bc=True, η=eta, tol=1e-10)["errors"]
     assert all(abs(new[k] - errs[1][k]) <= 1e-5 * errs[1][k] for k in new), (new, errs[1])
+
+
+@pytest.mark.parametrize("case", [cases.Case("LowRes", "inclusion", 0, "Gradient", neumann=True), cases.Case("H2", "solkz", 1, "SymmetricGradient", tau_r=10.0)],
+                         ids=lambda c: c.name)
+def test_fused_pass_equals_the_three_calls(case, api):
+    """fcfv_pass (one call, every array uploaded once, outputs coming down while inputs go up) == fcfv_compute_local +
+    fcfv_assemble + fcfv_residuals, bit for bit, with pageable and with registered host arrays."""
+    from fcfv_nme23_b200 import lib as L
+    m, d = cases.build(case)
+    neu = d["neu"]
+    a, b, Z = api.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form)
+    fn = api.ElementAssemblyLoop if case.variant == 0 else api.ElementAssemblyLoopNEW
+    h, nnz, _ = fn(m, a, b, Z, d["VxDir"], d["VyDir"], *neu, case.form, want_muu=False, export=False)
+    ref = [h.export_csr(L.KUU), h.export_csr(L.KUP), h.export_rhs()]
+    n = api.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu,
+                                           case.form, verbose=False)
+    tau = m.τ.copy()
+    h.close()
+    for pinned in (False, True):
+        g, _ = cases.build(case)
+        hg = api.handle_for(g)
+        arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, d["Vxh"], d["Vyh"], d["Pe"])]
+        if pinned:
+            hg.host_register(*arrs)
+        a2, b2, Z2, n2, nnz2 = api.FusedPass(g, *arrs, case.form, loop="NEW" if case.variant else "old")
+        assert np.array_equal(a2, a) and np.array_equal(b2, b) and np.array_equal(Z2, Z) and np.array_equal(g.τ, tau)
+        assert nnz2[:2] == tuple(nnz)[:2] and np.array_equal(n2, n)
+        got = [hg.export_csr(L.KUU), hg.export_csr(L.KUP), hg.export_rhs()]
+        for x, y in zip(ref, got):
+            for p, q in zip(x, y):
+                assert np.array_equal(p, q)
+        if pinned:
+            hg.host_unregister(*arrs)
+        hg.close()

@@ -121,6 +121,59 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlClockSampler:
+    """Same quantities through NVML (pynvml), every 10 ms: the timed region of the default run is ~0.13 s, which
+    nvidia-smi's 100 ms loop covers with one to three rows.  Falls back to ClockSampler when NVML is not usable."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, index):
+        self.index, self.rows, self.fallback, self.stop_flag = index, [], None, threading.Event()
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(index)
+            try:
+                bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                self.dev = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            self.fallback = ClockSampler(index)
+
+    def _loop(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)), int(reasons_fn(self.dev))))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
+
+    def start(self):
+        if self.fallback:
+            return self.fallback.start()
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.fallback:
+            return self.fallback.stop()
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        mask = 0
+        for r in self.rows:
+            mask |= r[1]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, bit in self.REASONS if mask & bit], "samples": len(sm), "source": "nvml, 10 ms"}
+
+
 def measured_traffic(kernel, nel):
     """DRAM bytes per launch of `kernel` from the newest committed ncu capture taken at this mesh size
     (profiles/*traffic*.json, written by tools/ncu_traffic.py); None when there is none."""
@@ -289,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     h.set_timing(True)
     l0 = h.kernel_launches
-    sampler = ClockSampler(local_rank)
+    sampler = NvmlClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

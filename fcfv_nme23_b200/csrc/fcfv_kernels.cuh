@@ -859,8 +859,7 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
                                bc, tau, ux, uy, traction, r);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            Fg[(size_t)(2 * i) * nel + e] = r.Fg1[i][0];
-            Fg[(size_t)(2 * i + 1) * nel + e] = r.Fg1[i][1];
+            reinterpret_cast<double2*>(Fg)[(size_t)3 * e + i] = make_double2(r.Fg1[i][0], r.Fg1[i][1]);   // [e][i][comp]: 48 contiguous bytes per element
         }
         if (F_glob2_out) F_glob2_out[e] = r.Fg2;
         if (M.elem_owned == nullptr || M.elem_owned[e]) {
@@ -892,12 +891,14 @@ k_res_face(MeshView M, const double* __restrict__ Fg, double* __restrict__ parti
         const int2 pr = M.f2e[f];
         if (pr.x >= 0 && M.bc[f] != 1) {
             const int e0 = pr.x >> 2, i0 = pr.x & 3;
-            Fx = Fx + Fg[(size_t)(2 * i0) * nel + e0];
-            Fy = Fy + Fg[(size_t)(2 * i0 + 1) * nel + e0];
+            const double2 v0 = reinterpret_cast<const double2*>(Fg)[(size_t)3 * e0 + i0];
+            Fx = Fx + v0.x;
+            Fy = Fy + v0.y;
             if (pr.y != pr.x) {
                 const int e1 = pr.y >> 2, i1 = pr.y & 3;
-                Fx = Fx + Fg[(size_t)(2 * i1) * nel + e1];
-                Fy = Fy + Fg[(size_t)(2 * i1 + 1) * nel + e1];
+                const double2 v1 = reinterpret_cast<const double2*>(Fg)[(size_t)3 * e1 + i1];
+                Fx = Fx + v1.x;
+                Fy = Fy + v1.y;
             }
         }
         if (Fx_out) Fx_out[f] = Fx;

@@ -889,8 +889,12 @@ int launch_assemble(fcfv_t* h, double A, double gamma) {
     long long* chunk_tot = P<long long>(h->chunks);
     long long* chunk_base = chunk_tot + (size_t)kNumSums * nchunks;
     TLAUNCH(h, T_OTHER, k_asm_fp, nblocks((h->nf + 3) / 4, 256), 256, M, D, P<double>(h->fp));   // fp was zeroed by the caller
-    TLAUNCH(h, T_COEF, k_elem_coef<VARIANT>, nblocks(h->nel, 256), 256, M.nel, L.alpha, M.ke, M.dl, M.Om, gamma, (double*)Cf.ia,
-            (double*)Cf.c11, (double*)Cf.c12, (double*)Cf.c21, (double*)Cf.c22, (double*)Cf.cs);
+    if (!ANISO && EXTRA != kExtraSchur && (h->nel & 1) == 0 && h->nel > 0)
+        TLAUNCH(h, T_COEF, k_elem_coef2<VARIANT>, nblocks(h->nel / 2, 256), 256, (int)(h->nel / 2), (const double2*)L.alpha,
+                (const double2*)M.ke, (const double2*)M.Om, (double2*)Cf.ia, (double2*)Cf.c11);
+    else
+        TLAUNCH(h, T_COEF, k_elem_coef<VARIANT>, nblocks(h->nel, 256), 256, M.nel, L.alpha, M.ke, M.dl, M.Om, gamma, (double*)Cf.ia,
+                (double*)Cf.c11, (double*)Cf.c12, (double*)Cf.c21, (double*)Cf.c22, (double*)Cf.cs);
     TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, EXTRA, ANISO>), nblk, kAsmBlock, M, L, Cf, D, A, sums, nblk);
     TLAUNCH(h, T_SCAN, k_scan_local, dim3(nchunks, kNumSums), 1024, sums, local, nblk, nchunks, chunk_tot);
     Csr& X = EXTRA == kExtraSchur ? h->Kuusc : h->Muu;   // third block

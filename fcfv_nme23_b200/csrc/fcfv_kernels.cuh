@@ -502,6 +502,22 @@ k_elem_coef(int nel, const double* __restrict__ alpha, const double* __restrict_
     if (cs != nullptr) cs[e] = (gamma * ke[e]) / Om[e];   // penalty.*mesh.ke./mesh.Ω (SolversFCFV_Stokes.jl:23)
 }
 
+// delta == 1 everywhere, no Schur block, nel even: two elements per thread with 16-byte loads / stores
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+k_elem_coef2(int nel2, const double2* __restrict__ alpha, const double2* __restrict__ ke, const double2* __restrict__ Om,
+             double2* __restrict__ ia, double2* __restrict__ c11) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nel2) return;
+    const double2 a = alpha[k], e = ke[k], o = Om[k];
+    double2 ra, rc;
+    double d12, d21, d22;
+    element_coef<VARIANT>(a.x, e.x, 1.0, o.x, ra.x, rc.x, d12, d21, d22);
+    element_coef<VARIANT>(a.y, e.y, 1.0, o.y, ra.y, rc.y, d12, d21, d22);
+    ia[k] = ra;
+    c11[k] = rc;
+}
+
 // ---- a5/a6/a7 assembly --------------------------------------------------------------------------
 // A block owns a tile of kAsmFaces consecutive faces; a thread owns one face = CSR rows (f,x) and
 // (f,y).  It gathers the records of the <=2 adjacent elements (row face swapped to index 0, so
@@ -884,7 +900,6 @@ k_res_face(MeshView M, const double* __restrict__ Fg, double* __restrict__ parti
            double* __restrict__ Fx_out, double* __restrict__ Fy_out) {
     __shared__ double sd[2 * (kBlock / 32)];
     const int f = blockIdx.x * kBlock + threadIdx.x;
-    const int nel = M.nel;
     double sx = 0.0, sy = 0.0;
     if (f < M.nf) {
         double Fx = 0.0, Fy = 0.0;

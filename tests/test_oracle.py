@@ -435,3 +435,19 @@ def test_oracle_element_stresses_against_the_analytic_solution(form, oracle):
         assert min(bad) > 10.0          # the doubled Dirichlet part on the boundary elements
     else:
         assert max(bad) < 1.0
+
+
+def test_julia_golden_comparison_script(tmp_path):
+    """tests/golden/compare_julia_golden.py (the script that pins parity against julia/gen_golden.jl's dumps of the real
+    reference) reads and compares the dump format correctly: a self-written dump is identical, a perturbed one is not."""
+    import subprocess
+    import sys
+    script = os.path.join(cases.GOLDEN, "compare_julia_golden.py")
+    d = str(tmp_path / "dump")
+    assert subprocess.run([sys.executable, script, "--self-test", d]).returncode == 0
+    r = subprocess.run([sys.executable, script, d], capture_output=True, text=True)
+    assert r.returncode == 0 and "PARITY PINNED" in r.stdout, r.stdout + r.stderr
+    f = os.path.join(d, "LowRes_Gradient_0", "Kuu_nzval.bin")
+    v = np.fromfile(f); v[7] = np.nextafter(v[7], np.inf); v.tofile(f)
+    r = subprocess.run([sys.executable, script, d], capture_output=True, text=True)
+    assert r.returncode == 1 and "Kuu_nzval: 1 of" in r.stdout, r.stdout

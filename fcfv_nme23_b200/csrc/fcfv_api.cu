@@ -202,7 +202,11 @@ int ensure(fcfv_t* h, DBuf& b, size_t bytes) {
     if (bytes == 0) bytes = 8;
     if (b.cap >= bytes) return FCFV_OK;
     if (b.p) { CU(cudaFree(b.p)); h->bytes -= b.cap; b.p = nullptr; b.cap = 0; }
-    h->alloc_epoch++;
+    // only buffers the handle owns can be referenced by the captured pipeline graph; the temporaries of the
+    // export / geometry / renumbering calls live on the caller's stack and must not invalidate it
+    const char* hb = reinterpret_cast<const char*>(h);
+    const char* bb = reinterpret_cast<const char*>(&b);
+    if (bb >= hb && bb < hb + sizeof(*h)) h->alloc_epoch++;
     cudaError_t e = cudaMalloc(&b.p, bytes);
     if (e != cudaSuccess) {
         b.p = nullptr;
@@ -563,6 +567,9 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
         return fail(h, FCFV_ERR_INVALID, "fcfv_set_mesh: null mesh array");
     if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
     h->have_mesh = false; h->have_local = false;
+    // data arrays are sized for the mesh they were set on: a new mesh invalidates them (sources, face data and
+    // solution have to be set again; their buffers may be too small for the new nel / nf)
+    if (nel != h->nel || nf != h->nf) h->have_sources = h->have_face_data = h->have_solution = false;
     h->delta_dirty = true;
     h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = h->Kuusc.nnz = -1;
     h->nel = nel; h->nf = nf; h->nel_global = nel; h->nf_global = nf;

@@ -12,7 +12,7 @@ using SparseArrays, Printf
 
 export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
        SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!, RenumberFacesFirstSeen!,
-       RenumberElementsHilbert!, PrepareNumbering!, PinArrays, FusedPass
+       RenumberElementsHilbert!, PrepareNumbering!, PinArrays, FusedPass, release!
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
 
@@ -37,8 +37,15 @@ function Handle(device::Integer = 0)
     rc = ccall((:fcfv_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
     rc == 0 || error("fcfv_create failed with status $rc: no usable CUDA device (there is no CPU fallback)")
     h = Handle(r[], 0, 0)
-    finalizer(x -> ccall((:fcfv_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), h)
+    finalizer(destroy!, h)
     return h
+end
+
+# fcfv_destroy accepts NULL, so destroying twice (release! followed by the finalizer) is harmless
+function destroy!(h::Handle)
+    p, h.ptr = h.ptr, C_NULL
+    p == C_NULL || ccall((:fcfv_destroy, LIB), Cint, (Ptr{Cvoid},), p)
+    return nothing
 end
 
 function check(h::Handle, rc)
@@ -50,7 +57,19 @@ end
 form_id(F::Symbol) = F == :Gradient ? GRADIENT : F == :SymmetricGradient ? SYMMETRIC_GRADIENT :
                      error("Formulation must be :Gradient or :SymmetricGradient")
 
-const HANDLES = IdDict{Any,Handle}()     # one handle per mesh object
+# One handle per mesh object.  Weak keys (FCFV_Mesh is mutable): a mesh that is no longer referenced does not keep
+# its handle -- about 43 GB of device memory for 50 M elements -- alive; the handle's finalizer then frees it.
+const HANDLES = WeakKeyDict{Any,Handle}()
+
+"""    release!(mesh)
+
+Frees the device memory held for `mesh` now (drivers that loop over meshes, e.g.
+ViscousInclusionFCFV_DiscretisationErrors.jl).  The next call on `mesh` uploads it again."""
+function release!(mesh)
+    h = pop!(HANDLES, mesh, nothing)
+    h === nothing || destroy!(h)
+    return nothing
+end
 
 f64(x) = convert(Array{Float64}, x)
 i64(x) = convert(Array{Int64}, x)
@@ -271,7 +290,7 @@ function RenumberFacesFirstSeen!(mesh)
             b = similar(a); b[perm] = a; setfield!(mesh, name, b)
         end
     end
-    delete!(HANDLES, mesh)            # connectivity changed: upload again on next use
+    release!(mesh)                    # connectivity changed: free the device copy, upload again on next use
     return perm
 end
 
@@ -304,7 +323,7 @@ function RenumberElementsHilbert!(mesh)
         ismissing(a) && continue
         setfield!(mesh, name, map(e -> e > 0 ? new_of_old[e] : e, a))
     end
-    delete!(HANDLES, mesh)
+    release!(mesh)
     return order
 end
 

@@ -643,19 +643,19 @@ FCFV_HD void element_residual(double Om, double eta, double dl, double alpha, do
         }
         r.F2[0] = r.F2[0] + (G[i] * tau[i]) * ue[0];
         r.F2[1] = r.F2[1] + (G[i] * tau[i]) * ue[1];
-        const double un = u[0] * n[0] + u[1] * n[1];
-        r.Fg2 = r.Fg2 + G[i] * un;
+        // dAi * u'*n = (dAi*u')*n (:75, :82); dAi * n * u' = (dAi*n)*u' (:77); dAi * (n*u' .+ u*n') (:79)
+        const double un = (G[i] * u[0]) * n[0] + (G[i] * u[1]) * n[1];
+        r.Fg2 = r.Fg2 + un;
 #pragma unroll
         for (int a = 0; a < 2; a++)
 #pragma unroll
             for (int b = 0; b < 2; b++) {
-                double m = n[a] * u[b];
-                if (FORM == kSymmetricGradient) m = m + u[a] * n[b];
-                r.F1[a][b] = r.F1[a][b] + G[i] * m;
+                if (FORM == kSymmetricGradient) r.F1[a][b] = r.F1[a][b] + G[i] * (n[a] * u[b] + u[a] * n[b]);
+                else                            r.F1[a][b] = r.F1[a][b] + (G[i] * n[a]) * u[b];
             }
         r.F2[0] = r.F2[0] - (G[i] * tau[i]) * u[0];
         r.F2[1] = r.F2[1] - (G[i] * tau[i]) * u[1];
-        r.F3 = r.F3 + G[i] * un;
+        r.F3 = r.F3 + un;
     }
 }
 

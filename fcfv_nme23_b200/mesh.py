@@ -139,8 +139,15 @@ def LoadExternalMesh(res, η, mesh_dir=None) -> FCFV_Mesh:
 def read_dat(path):
     """Parses a ``square_TRI_H*.dat`` file: header ``nsd nel nv nextfaces``, ``nv`` coordinate
     rows, ``nel`` connectivity rows (1-based), boundary rows (ReadMeshesDat.jl:19-30)."""
-    with open(path) as fh:
-        tok = fh.read().split()
+    if not os.path.exists(path) and os.path.exists(path + ".gz"):      # the larger fixtures are stored compressed
+        path += ".gz"
+    if path.endswith(".gz"):
+        import gzip
+        with gzip.open(path, "rt") as fh:
+            tok = fh.read().split()
+    else:
+        with open(path) as fh:
+            tok = fh.read().split()
     nsd, nel, nv, next_ = (int(t) for t in tok[:4])
     if nsd != 2:
         raise ValueError("only 2-D meshes are supported")

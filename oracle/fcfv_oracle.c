@@ -6,14 +6,24 @@
  * (tests/, __graft_entry__.smoke()) and as the "port" CPU baseline timed by
  * bench.py.  Nothing under fcfv_nme23_b200/ may call into it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or expected
- * values for this path and Julia is not available in the build image, so this
- * restatement could not be compared against outputs of the real reference.
+ * PARITY: the reference ships no tests, golden vectors or expected values for
+ * this path and Julia is not available in the build image, so this file was
+ * never compared with a Julia run ("parity unpinned" in that strict sense).
+ * What pins it instead: tests/julia_transliteration.py reads the reference's
+ * own source text (src/DiscretisationFCFV_Stokes.jl, ComputeResidualsFCFV_
+ * Stokes.jl, the geometry loops of CreateMeshFCFV.jl, meshes/ReadMeshesDat.jl),
+ * rewrites it with a documented rule table and executes it with IEEE float64
+ * scalars; this oracle equals that run BIT FOR BIT for ComputeFCFV, both
+ * assembly loops + Sparsify, ComputeElementValues, the geometry and the face
+ * numbering, and to 1e-12 for the six residual norms, on 54 cases
+ * (tests/test_transliteration.py live, tests/golden/golden_reference.json
+ * committed).  Still resting on restatement alone: the Powell-Hestenes lines
+ * of SolversFCFV_Stokes.jl (sparse mat-vec, sparse `.-`) and whatever the rule
+ * table itself gets wrong about Julia semantics.
  * It follows the Julia sources statement by statement (file:line citations
- * are relative to the reference checkout), honours Julia's evaluation order
+ * are relative to the reference checkout) and honours Julia's evaluation order
  * (n-ary + and * fold left, x^-1 == inv(x), Bool*Float64 is a strong zero,
- * no FMA contraction) and is cross-checked in tests/ against an independent
- * NumPy/SciPy restatement and against discretisation identities.
+ * no FMA contraction).
  *
  * Build:  gcc -O2 -ffp-contract=off -fPIC -shared  (see oracle/Makefile).
  * -ffp-contract=off matters: Julia/LLVM never fuses a*b+c on its own, and the
@@ -545,16 +555,18 @@ int oracle_residuals(int formulation, int tau_mode, i64 nel, i64 nfaces,
             }
             Fe2[e] = Fe2[e] + (dAi * taui) * U(0);
             Fe2[n + e] = Fe2[n + e] + (dAi * taui) * U(1);
-            double un = u[0] * nn[0] + u[1] * nn[1];
-            Fg2[e] = Fg2[e] + dAi * un;
+            /* dAi * u'*n parses as (dAi*u')*n (:75, :82): the row is scaled first */
+            double un = (dAi * u[0]) * nn[0] + (dAi * u[1]) * nn[1];
+            Fg2[e] = Fg2[e] + un;
             for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) {
-                double m = nn[a] * u[b];
-                if (formulation == SYMMETRIC_GRADIENT) m = m + u[a] * nn[b];
-                F1(a, b) = F1(a, b) + dAi * m;
+                if (formulation == SYMMETRIC_GRADIENT)      /* dAi * (n*u' .+ u*n') (:79) */
+                    F1(a, b) = F1(a, b) + dAi * (nn[a] * u[b] + u[a] * nn[b]);
+                else                                        /* dAi * n * u' = (dAi*n)*u' (:77) */
+                    F1(a, b) = F1(a, b) + (dAi * nn[a]) * u[b];
             }
             Fe2[e] = Fe2[e] - (dAi * taui) * u[0];
             Fe2[n + e] = Fe2[n + e] - (dAi * taui) * u[1];
-            Fe3[e] = Fe3[e] + dAi * un;
+            Fe3[e] = Fe3[e] + un;
         }
     }
     /* pass C :88-100 */

@@ -1,8 +1,8 @@
 """ctypes front-end of the CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
-import this module.  PARITY UNPINNED (see the header of ``fcfv_oracle.c``): the reference
-has no golden vectors and Julia is not available here.
+import this module.  Parity: never compared with a Julia run (none is possible here); pinned bit for bit against
+the reference's own source text executed through tests/julia_transliteration.py (see the header of ``fcfv_oracle.c``).
 
 Function names and argument order follow the reference's Julia functions; meshes are any
 object with the ``FCFV_Mesh`` attribute names (``nel, nf, e2f, bc, Ω, Γ, n_x, n_y, ke, δ, τ, τe``).

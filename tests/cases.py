@@ -44,6 +44,13 @@ def all_cases(mesh_dir=GOLDEN, small_only=False):
     return out
 
 
+def large_cases():
+    """BASELINE config 2 beyond H2: SolKz on square_TRI_H3 / H4 (the largest meshes the reference ships; H5 is missing)."""
+    out = [Case("H3", "solkz", v, f, tau_r=10.0) for v in (0, 1) for f in ("Gradient", "SymmetricGradient")]
+    out += [Case("H4", "solkz", 1, "SymmetricGradient", tau_r=10.0), Case("H4", "solkz", 0, "Gradient", tau_r=10.0)]
+    return out
+
+
 _mesh_cache = {}
 
 

@@ -3,7 +3,8 @@
     python tests/golden/make_fixtures.py
 
 1. Mesh inputs converted from the reference's shipped meshes (data, not source):
-   MeshAdvancingFront{Low,Med}Res.mat -> .npz with the same keys; square_TRI_H{1,2}.dat copied.
+   MeshAdvancingFront{Low,Med}Res.mat -> .npz with the same keys; square_TRI_H{1,2}.dat copied,
+   square_TRI_H{3,4}.dat gzip-compressed.
 2. golden_oracle.json: SHA-256 digests + sizes of the ORACLE's outputs on those meshes.
    The reference has no golden vectors and Julia is not available here (parity unpinned), so
    these digests pin the oracle itself (regression) -- the GPU path is compared with the oracle
@@ -31,6 +32,11 @@ def convert_meshes():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
     for name in ("square_TRI_H1", "square_TRI_H2"):
         shutil.copyfile(os.path.join(REF, "meshes", name + ".dat"), os.path.join(HERE, name + ".dat"))
+    import gzip
+    for name in ("square_TRI_H3", "square_TRI_H4"):      # 0.7 / 2.8 MB of text: stored gzip-compressed (byte-exact)
+        with open(os.path.join(REF, "meshes", name + ".dat"), "rb") as src, \
+                gzip.GzipFile(os.path.join(HERE, name + ".dat.gz"), "wb", compresslevel=9, mtime=0) as dst:
+            shutil.copyfileobj(src, dst)
 
 
 def digest(*arrays):

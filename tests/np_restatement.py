@@ -201,13 +201,15 @@ def residual_arrays(mesh, Vxh, Vyh, Pe, ae, be, ze, sex, sey, VxDir, VyDir, Sxx,
             acc = acc + Ji[:, None] * np.einsum("ea,eba->eb", n[:, i], DL)
         Fg1 = G[:, i, None] * acc
         F2 = F2 + (G[:, i] * tau[:, i])[:, None] * ue - (G[:, i] * tau[:, i])[:, None] * u
-        un = np.einsum("ea,ea->e", u, n[:, i])
-        Fg2 = Fg2 + G[:, i] * un
-        M = n[:, i, :, None] * u[:, None, :]
+        # dAi * u'*n = (dAi*u')*n (:75, :82); dAi * n * u' = (dAi*n)*u' (:77); dAi * (n*u' .+ u*n') (:79)
+        Gu = G[:, i, None] * u
+        un = Gu[:, 0] * n[:, i, 0] + Gu[:, 1] * n[:, i, 1]
+        Fg2 = Fg2 + un
         if formulation == "SymmetricGradient":
-            M = M + u[:, :, None] * n[:, i, None, :]
-        F1 = F1 + G[:, i, None, None] * M
-        F3 = F3 + G[:, i] * un
+            F1 = F1 + G[:, i, None, None] * (n[:, i, :, None] * u[:, None, :] + u[:, :, None] * n[:, i, None, :])
+        else:
+            F1 = F1 + (G[:, i, None] * n[:, i])[:, :, None] * u[:, None, :]
+        F3 = F3 + un
         w = nd[:, i]
         np.add.at(Fnx, fi[w], Fg1[w, 0])
         np.add.at(Fny, fi[w], Fg1[w, 1])

@@ -98,3 +98,43 @@ def test_cuda_path_reproduces_the_reference(name):
                                             d["VyDir"], *neu, case.form, tau_mode="REFERENCE", verbose=False)
     assert _norms_close(gn, gold["norms_reference"])
     h.close()
+
+
+# ---- BASELINE config 3 size (1 M elements): CUDA path against the oracle, bit for bit ---------------------------
+C3_CASES = [cases.Case("S500", "solkz", 1, "SymmetricGradient", tau_r=10.0),                  # what SolKzFCFV.jl runs
+            cases.Case("S500", "inclusion", 0, "Gradient", neumann=True),                     # bc = -1 interface, bc = 2 south
+            cases.Case("S500", "inclusion", 1, "SymmetricGradient", neumann=True)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", C3_CASES, ids=lambda c: c.name)
+def test_config3_size_bitwise(case, oracle):
+    from fcfv_nme23_b200 import api, lib as L
+    from helpers import assert_csr_equal, csc_triple_to_csr
+    m, d = cases.build(case)
+    g, _ = cases.build(case)
+    nel, nf, neu = m.nel, m.nf, d["neu"]
+    assert nel == 1_000_000 and nf == 1_501_000
+    if case.setting == "inclusion":
+        assert (m.bc == -1).sum() > 0 and (m.bc == 2).sum() == 500
+    a, b, Z = oracle.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form)
+    ga, gb, gZ = api.ComputeFCFV(g, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *neu, case.tau_r, case.form)
+    assert np.array_equal(ga, a) and np.array_equal(gb, b) and np.array_equal(gZ, Z) and np.array_equal(g.τ, m.τ)
+    ofn = oracle.ElementAssemblyLoop if case.variant == 0 else oracle.ElementAssemblyLoopNEW
+    gfn = api.ElementAssemblyLoop if case.variant == 0 else api.ElementAssemblyLoopNEW
+    Kuu, Muu, Kup, fu, fp, _, _ = ofn(m, a, b, Z, d["VxDir"], d["VyDir"], *neu, case.form)
+    gKuu, gMuu, gKup, gfu, gfp, _ = gfn(g, ga, gb, gZ, d["VxDir"], d["VyDir"], *neu, case.form)
+    h = api.handle_for(g)
+    for blk, ref, shape, what in ((L.KUU, Kuu, (2 * nf, 2 * nf), "Kuu"), (L.KUP, Kup, (2 * nf, nel), "Kup"),
+                                  (L.MUU, Muu, (2 * nf, 2 * nf), "Muu")):
+        assert_csr_equal(h.export_csr(blk), csc_triple_to_csr(ref, shape), what)
+        cp, rv, v = h.export_csc(blk)
+        assert np.array_equal(cp, ref[0]) and np.array_equal(rv, ref[1]) and np.array_equal(v, ref[2]), what + " CSC"
+    assert np.array_equal(gfu.ravel(), np.asarray(fu).ravel()) and np.array_equal(gfp, fp)
+    for tau_mode in ("REFERENCE", "FACE"):
+        n = oracle.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], m, a, b, Z, d["sex"], d["sey"], d["VxDir"],
+                                                  d["VyDir"], *neu, case.form, tau_mode=tau_mode)
+        gn = api.ComputeResidualsFCFV_Stokes_o1(d["Vxh"], d["Vyh"], d["Pe"], g, ga, gb, gZ, d["sex"], d["sey"], d["VxDir"],
+                                                d["VyDir"], *neu, case.form, tau_mode=tau_mode, verbose=False)
+        assert _norms_close(gn, n), (tau_mode, gn, n)
+    h.close()

@@ -110,7 +110,7 @@ struct fcfv_handle {
     int last_variant = -1, last_form = -1;   // parameters of the last assembly (fcfv_schur reuses them)
     double last_A = 1.0;
     DBuf fu, fp, sums, bases, chunks, totals;
-    long long totals_host[9] = {0};
+    long long totals_host[10] = {0};
     bool totals_valid = false;
     // residual
     DBuf Fg, partial, sumsq, red_scratch, red_tickets;
@@ -910,12 +910,12 @@ int launch_assemble(fcfv_t* h, double A, double gamma) {
     CsrOut oex{X.rowptr.p, P<int>(X.col), P<double>(X.val)};
     if (h->rp64) {
         TLAUNCH(h, T_SCAN, k_scan_chunks<long long>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals),
-                (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)oex.rowptr, M.nf, (int)(EXTRA != kExtraNone));
+                (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)oex.rowptr, M.nf, (int)(EXTRA != kExtraNone), EXTRA == kExtraSchur ? 9 : 8);
         TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, EXTRA, ANISO, long long>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk,
                 nchunks, ouu, oup, oex, P<double>(h->fu));
     } else {
         TLAUNCH(h, T_SCAN, k_scan_chunks<int>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals), (int*)ouu.rowptr,
-                (int*)oup.rowptr, (int*)oex.rowptr, M.nf, (int)(EXTRA != kExtraNone));
+                (int*)oup.rowptr, (int*)oex.rowptr, M.nf, (int)(EXTRA != kExtraNone), EXTRA == kExtraSchur ? 9 : 8);
         TLAUNCH(h, T_FILL, (k_asm_fill<VARIANT, FORM, EXTRA, ANISO, int>), nblk, kAsmBlock, M, L, Cf, D, A, local, chunk_base, nblk, nchunks,
                 ouu, oup, oex, P<double>(h->fu));
     }
@@ -937,12 +937,12 @@ int launch_assemble_x(fcfv_t* h, double A, int extra, double gamma) {
 
 int fetch_totals(fcfv_t* h) {
     if (h->totals_valid) return FCFV_OK;
-    CU(cudaMemcpyAsync(h->totals_host, h->totals.p, sizeof(long long) * 9, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->totals_host, h->totals.p, sizeof(long long) * 10, cudaMemcpyDeviceToHost, h->stream));
     TRY(sync(h));
     h->Kuu.nnz = h->totals_host[6];
     h->Kup.nnz = h->totals_host[7];
     if (h->Muu.nnz == -2) h->Muu.nnz = h->totals_host[8];
-    if (h->Kuusc.nnz == -2) h->Kuusc.nnz = h->totals_host[8];
+    if (h->Kuusc.nnz == -2) h->Kuusc.nnz = h->totals_host[9];
     h->totals_valid = true;
     return FCFV_OK;
 }

@@ -647,12 +647,12 @@ k_scan_local(const int* __restrict__ sums, int* __restrict__ local, int nblk, in
 }
 
 // one block: exclusive scan of the chunk totals per quantity; y-row bases are offset by the x-row
-// total of the same matrix.  totals[0..5] per quantity, totals[6..8] nnz of Kuu/Kup/Muu; also writes
+// total of the same matrix.  totals[0..5] per quantity, totals[6..9] nnz of Kuu/Kup/Muu/Kuusc; also writes
 // the last row pointer of each CSR.
 template <typename RP>
 __global__ void k_scan_chunks(const long long* __restrict__ chunk_tot, long long* __restrict__ chunk_base, int nchunks,
                               long long* __restrict__ totals, RP* __restrict__ rp_uu, RP* __restrict__ rp_up,
-                              RP* __restrict__ rp_mu, int nf, int want_m) {
+                              RP* __restrict__ rp_mu, int nf, int want_m, int slot_m) {
     __shared__ long long tot[kNumSums];
     const int q = threadIdx.x;
     if (q < kNumSums) {
@@ -665,7 +665,9 @@ __global__ void k_scan_chunks(const long long* __restrict__ chunk_tot, long long
     if (q < kNumSums && (q & 1))
         for (int c = 0; c < nchunks; c++) chunk_base[(size_t)q * nchunks + c] += tot[q - 1];
     if (q == 0) {
-        totals[6] = tot[0] + tot[1]; totals[7] = tot[2] + tot[3]; totals[8] = tot[4] + tot[5];
+        totals[6] = tot[0] + tot[1]; totals[7] = tot[2] + tot[3];
+        if (want_m) totals[slot_m] = tot[4] + tot[5];      // 8: Muu, 9: Schur complement (separate slots: an unfetched
+                                                           // Muu count survives a later fcfv_schur)
         rp_uu[2 * (size_t)nf] = (RP)(tot[0] + tot[1]);
         rp_up[2 * (size_t)nf] = (RP)(tot[2] + tot[3]);
         if (want_m) rp_mu[2 * (size_t)nf] = (RP)(tot[4] + tot[5]);

@@ -807,3 +807,32 @@ def test_fused_pass_equals_the_three_calls(case, api):
         if pinned:
             hg.host_unregister(*arrs)
         hg.close()
+
+
+def test_async_muu_then_schur_keeps_both_counts(api):
+    """fcfv_run_assemble(want_muu) followed by fcfv_schur without fetching the counts in between: Muu and the Schur
+    block report their own sizes (separate count slots) and a second fcfv_set_mesh with another size invalidates
+    the data set for the first mesh."""
+    import ctypes as C
+    from fcfv_nme23_b200 import lib as L
+    h = api.Handle(0)
+    h.generate_structured(24, setting="inclusion", tau_r=2.0)
+    form = "SymmetricGradient"
+    h.run_local(form); h.run_assemble(L.LOOP_OLD, form, want_muu=True)
+    nnz_ref = h.get_nnz()
+    h.set_async(True)
+    h.run_assemble(L.LOOP_OLD, form, want_muu=True)             # counts not fetched
+    nsc = C.c_int64(0)
+    h.check(h.lib.fcfv_schur(h._h, C.c_double(1.0e4), C.byref(nsc)))
+    h.set_async(False)
+    assert h.block_size(L.MUU)[2] == nnz_ref[2] > 0
+    assert h.block_size(L.KUUSC)[2] == nsc.value > nnz_ref[2]
+    rp, ci, v = h.export_csr(L.MUU)
+    assert rp[-1] == nnz_ref[2] and len(v) == nnz_ref[2]
+    # a mesh of another size: the residual must refuse to run on the old data
+    m = cases.load_mesh("S6")
+    m.τe = np.ones(m.nel); m.ke = np.ones(m.nel)
+    h.set_mesh(m)
+    rc = h.lib.fcfv_run_local(h._h, L.FORMULATIONS[form] if hasattr(L, "FORMULATIONS") else 1, C.c_double(1.0))
+    assert rc != 0 and b"not set" in h.lib.fcfv_last_error(h._h)
+    h.close()

@@ -75,6 +75,22 @@ def algorithmic_bytes(nel, nf, nnz_uu, nnz_up, rpw):
     return dict(local=local, assembly=assembly, residual=residual, total=local + assembly + residual)
 
 
+def kernel_algorithmic_bytes(nel, nf, nnz_uu, nnz_up, rpw):
+    """Bytes each hot kernel itself has to move once (its own inputs read once + its own outputs written once; face
+    data that is only read on boundary faces is left out).  The fill kernel's figure is what ncu measures for it
+    (29.9 GB at 50 M elements, profiles/*traffic*): its traffic is at the algorithmic minimum."""
+    rec = 72 + 16 + 48            # per element: G, nx, ny | 1/alpha, c11 | beta, Z
+    conn = 8 + 16 + 4 + 8         # per face: f2e, fconn, fbc, tau
+    return {
+        "k_local": nel * (12 + 4 + 72 + 32) + nel * 56 + nf * 8,
+        "k_elem_coef": nel * 40,
+        "k_asm_count": nel * rec + nf * conn,
+        "k_asm_fill": nel * rec + nf * conn + 12 * (nnz_uu + nnz_up) + 2 * rpw * (2 * nf + 1) + nf * 16,
+        "k_res_elem": nel * (12 + 4 + 72 + 24 + 56 + 16 + 8) + nf * (8 + 16) + nel * 48,
+        "k_res_face": nf * (8 + 1) + nel * 48,
+    }
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -200,15 +216,19 @@ def measured_peak():
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_port_throughput(mesh_arrays, data, reps=1):
+def cpu_port_throughput(mesh_arrays, data, reps=1, workspace=None):
     """Times the oracle port (C restatement of the reference's algorithm incl. its dense COO
-    intermediates and sparse()/dropzeros, 1 thread) on host arrays.  Returns Melements/s."""
+    intermediates and sparse()/dropzeros, 1 thread) on host arrays.  Returns Melements/s.
+    The ctypes wrapper's output arrays come from `workspace` (allocated by the caller, outside the timed
+    region): only the C code's own allocations -- the reference's `zeros(...)` / `sparse` -- are timed."""
     from oracle import oracle as O
     from fcfv_nme23_b200.mesh import FCFV_Mesh
     O.lib()
     m = FCFV_Mesh(nel=int(mesh_arrays["Ω"].size), nf=int(mesh_arrays["bc"].size), nf_el=3)
     for k, v in mesh_arrays.items():
         setattr(m, k, v)
+    if workspace is None:
+        workspace = O.assembly_workspace(m.nel, m.nf)
     neu = [data["sxx"], data["syy"], data["sxy"], data["syx"]]
     best = None
     for _ in range(reps):
@@ -217,7 +237,7 @@ def cpu_port_throughput(mesh_arrays, data, reps=1):
         a, b, Z = O.ComputeFCFV(m, data["sex"], data["sey"], data["VxDir"], data["VyDir"], *neu, 10.0, FORM)
         t1 = time.perf_counter()
         fn = O.ElementAssemblyLoopNEW if VARIANT == 1 else O.ElementAssemblyLoop
-        out = fn(m, a, b, Z, data["VxDir"], data["VyDir"], *neu, FORM)
+        out = fn(m, a, b, Z, data["VxDir"], data["VyDir"], *neu, FORM, workspace=workspace)
         t2 = time.perf_counter()
         O.ComputeResidualsFCFV_Stokes_o1(data["Vxh"], data["Vyh"], data["Pe"], m, a, b, Z, data["sex"], data["sey"],
                                          data["VxDir"], data["VyDir"], *neu, FORM, tau_mode="FACE")
@@ -229,14 +249,81 @@ def cpu_port_throughput(mesh_arrays, data, reps=1):
     return m.nel / best[0] / 1e6, best
 
 
-def sample_inputs(n):
-    """Host copies of S(n) and its SolKz data, produced by the device generator (setup, not timed)."""
-    from fcfv_nme23_b200 import api
-    h = api.Handle(0)
-    h.generate_structured(n, setting="solkz", tau_r=10.0)
-    mesh_arrays, data = h.get_mesh(), h.get_data()
-    h.close()
+def host_sample(n):
+    """S(n) and its SolKz data built on the HOST (numpy + the oracle's geometry): the CPU arm never maps the
+    product library.  Same fields as the device generator (tests/cases.py, checked against it in the GPU tests)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    m, d = cases.build(cases.Case(f"S{n}", "solkz", VARIANT, FORM, tau_r=10.0))
+    mesh_arrays = {k: getattr(m, k) for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe")}
+    data = dict(sex=d["sex"], sey=d["sey"], VxDir=d["VxDir"], VyDir=d["VyDir"], sxx=d["neu"][0], syy=d["neu"][1],
+                sxy=d["neu"][2], syx=d["neu"][3], Vxh=d["Vxh"], Vyh=d["Vyh"], Pe=d["Pe"])
     return mesh_arrays, data
+
+
+# --------------------------------------------------------------------------------------------
+def multi_gpu_parity(rank, world, local_rank, n=40):
+    """Value proof for the N > 1 path, inside the bench run: a small S(n) mesh is split over the ranks of THIS
+    job by the element partitioner (ghost elements replicated, face owner = rank of the highest adjacent element),
+    every rank runs ComputeFCFV + assembly + residuals on its part with the library's NCCL all-reduce, and compares
+    with the whole mesh on one GPU: every owned row of Kuu / Kup / fu and every owned fp entry bit for bit, the
+    all-reduced sums of squares to 1e-12.  Returns the record for the JSON line (identical on all ranks)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fcfv_nme23_b200 import api, lib as L
+    from fcfv_nme23_b200.mesh import FCFV_Mesh
+    from fcfv_nme23_b200.partition import partition_mesh
+    full = api.Handle(local_rank)
+    full.generate_structured(n, setting="solkz", tau_r=10.0)
+    full.run_local(FORM); full.run_assemble(VARIANT, FORM)
+    ss_full, _ = full.run_residuals(FORM, "FACE")
+    grp, gci, gv = full.export_csr(L.KUU)
+    grpp, gcip, gvp = full.export_csr(L.KUP)
+    gfu, gfp = full.export_rhs()
+    ma, d = full.get_mesh(), full.get_data()
+    full.close()
+    gm = FCFV_Mesh(nel=int(ma["Ω"].size), nf=int(ma["bc"].size), nf_el=3)
+    for k, v in ma.items():
+        setattr(gm, k, v)
+    P = partition_mesh(gm, world, rank)
+    h = api.Handle(local_rank)
+    h.set_mesh(P.mesh)                                   # uploads the ownership masks as well
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(h.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    h.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    sf, se = P.scatter_face, P.scatter_elem
+    h.set_sources(se(d["sex"]), se(d["sey"]))
+    h.set_face_data(sf(d["VxDir"]), sf(d["VyDir"]), sf(d["sxx"]), sf(d["syy"]), sf(d["sxy"]), sf(d["syx"]))
+    h.set_solution(sf(d["Vxh"]), sf(d["Vyh"]), se(d["Pe"]))
+    h.run_local(FORM); h.run_assemble(VARIANT, FORM)
+    ss, _ = h.run_residuals(FORM, "FACE")               # all-reduced by the library (NCCL)
+    rp, ci, v = h.export_csr(L.KUU)
+    rpp, cip, vp = h.export_csr(L.KUP)
+    fu, fp = h.export_rhs()
+    h.close()
+    ok, rows = True, 0
+    for lr, gr in zip(P.local_rows(), P.owned_rows()):
+        ok &= np.array_equal(P.global_columns(ci[rp[lr]:rp[lr + 1]]), gci[grp[gr]:grp[gr + 1]])
+        ok &= np.array_equal(v[rp[lr]:rp[lr + 1]], gv[grp[gr]:grp[gr + 1]])
+        ok &= np.array_equal(P.global_columns(cip[rpp[lr]:rpp[lr + 1]], "up"), gcip[grpp[gr]:grpp[gr + 1]])
+        ok &= np.array_equal(vp[rpp[lr]:rpp[lr + 1]], gvp[grpp[gr]:grpp[gr + 1]])
+        ok &= fu[lr] == gfu[gr]
+        rows += 1
+    ok &= bool(np.array_equal(fp[P.elem_owned], gfp[P.elem_global[P.elem_owned]]))
+    rel = float(np.max(np.abs(ss - ss_full) / np.maximum(np.abs(ss_full), 1e-300)))
+    t = torch.tensor([1.0 if ok else 0.0, -rel], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    cnt = torch.tensor([rows, int(P.elem_owned.sum())], dtype=torch.int64, device="cuda")
+    dist.all_reduce(cnt)
+    used = np.zeros(gm.nf, bool); used[np.asarray(gm.e2f).ravel() - 1] = True
+    complete = int(cnt[0].item()) == 2 * int(used.sum()) and int(cnt[1].item()) == gm.nel
+    return {"mesh": f"S({n}), {gm.nel} elements over {world} ranks (host partitioner, ghost replication)",
+            "bitwise_rows": bool(t[0].item() == 1.0 and complete), "rows_checked": int(cnt[0].item()),
+            "max_rel": float(-t[1].item()), "tolerance": 1e-12,
+            "checked": "Kuu/Kup rows (columns + values), fu, fp bit for bit vs the single-GPU run; 6 all-reduced sums of squares"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -260,25 +347,14 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     n = args.cpu_n
-    try:
-        import torch
-        have_gpu = torch.cuda.is_available()
-    except Exception:
-        have_gpu = False
-    if have_gpu:
-        mesh_arrays, data = sample_inputs(n)
-    else:   # no GPU: build the sample on the host (slow path, tests only)
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import cases
-        m, d = cases.build(cases.Case(f"S{n}", "solkz", VARIANT, FORM, tau_r=10.0))
-        mesh_arrays = {k: getattr(m, k) for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe")}
-        data = dict(sex=d["sex"], sey=d["sey"], VxDir=d["VxDir"], VyDir=d["VyDir"], sxx=d["neu"][0], syy=d["neu"][1],
-                    sxy=d["neu"][2], syx=d["neu"][3], Vxh=d["Vxh"], Vyh=d["Vyh"], Pe=d["Pe"])
+    mesh_arrays, data = host_sample(n)
+    from oracle import oracle as O
+    ws = O.assembly_workspace(int(mesh_arrays["Ω"].size), int(mesh_arrays["bc"].size))
     for _ in range(min(args.warmup, 1)):
-        cpu_port_throughput(mesh_arrays, data)
+        cpu_port_throughput(mesh_arrays, data, workspace=ws)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_throughput(mesh_arrays, data)
+        cpu_port_throughput(mesh_arrays, data, workspace=ws)
     dt = time.perf_counter() - t0
     nel = int(mesh_arrays["Ω"].size)
     val = nel * args.steps / dt / 1e6
@@ -325,11 +401,15 @@ def run_ours(args, rank, world, local_rank):
         h.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
     st = torch.cuda.ExternalStream(h.stream)
     h.set_async(True)
+    # Residual tau mode of the headline: FACE (the face value of tau, what is consistent with the assembled system and
+    # what a partitioned mesh can evaluate locally).  The reference function's literal tau[e] (Residuals:17,54: the
+    # FACE array indexed by the ELEMENT id) is timed beside it at N = 1 (`tau_modes`).
+    TAU = "FACE"
 
-    def step():
+    def step(tau_mode=TAU):
         h.run_local(FORM)
         h.run_assemble(VARIANT, FORM)
-        h.run_residuals(FORM, "FACE", fetch=False)
+        h.run_residuals(FORM, tau_mode, fetch=False)
 
     def barrier():
         h.sync()
@@ -337,64 +417,95 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
+    def timed(fn, reps):
+        """ms for `reps` calls of fn: CUDA events on the library's stream, barrier + synchronize on both sides,
+        max over ranks."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(st)
+        for _ in range(reps):
+            fn()
+        e1.record(st)
+        barrier()
+        t = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return t
+
     for _ in range(args.warmup):
         step()
     barrier()
-    h.set_timing(True)
+    # ---- headline: K steps, per-kernel timers OFF
     l0 = h.kernel_launches
     sampler = NvmlClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(st)
-    for _ in range(args.steps):
-        step()
-    e1.record(st)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = h.kernel_launches - l0
-    timers = h.get_timers()
-    h.set_timing(False)
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(lt)
         launches = int(lt.item())
-    ss, norms = h.run_residuals(FORM, "FACE")
-    nnz_uu, nnz_up, _ = h.get_nnz()
     value = total_el * args.steps / (ms * 1e-3) / 1e6
+    # ---- per-kernel device times: a second, separate repetition with an event pair around every launch
+    h.set_timing(True)
+    ksteps = max(1, min(args.steps, 5))
+    for _ in range(ksteps):
+        step()
+    h.sync()
+    timers = h.get_timers()
+    h.set_timing(False)
+    # ---- the same step with the reference's literal tau[e] in the residual
+    ms_ref = timed(lambda: step("REFERENCE"), ksteps) / ksteps if world == 1 else None
+    ss, norms = h.run_residuals(FORM, TAU)
+    nnz_uu, nnz_up, _ = h.get_nnz()
 
     # ---- roofline of the dominant kernel -----------------------------------------------------
     rpw = h.lib.fcfv_index_width(h._h)
     ab = algorithmic_bytes(h.nel, h.nf, nnz_uu, nnz_up, rpw)
+    kab = kernel_algorithmic_bytes(h.nel, h.nf, nnz_uu, nnz_up, rpw)
     peak, peak_src = measured_peak()
-    dom = max((k for k in timers if timers[k][1] > 0), key=lambda k: timers[k][0])
-    dom_ms = timers[dom][0] / timers[dom][1]
-    phase_of = {"k_asm_fill": "assembly", "k_asm_count": "assembly", "k_res_elem": "residual", "k_local": "local"}
-    dom_bytes = ab[phase_of.get(dom, "assembly")]
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    kms = {k: v[0] / v[1] for k, v in timers.items() if v[1] > 0}          # ms per launch
+    dom = max(kms, key=lambda k: kms[k])
+    dom_ms = kms[dom]
+    dom_bytes = kab.get(dom)
     traffic = measured_traffic(dom, h.nel)
+    if dom_bytes is None:
+        dom_bytes = traffic[0] if traffic else ab["assembly"]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    step_ms = ms / args.steps
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                "basis": "bytes this kernel itself has to read and write once (kernel_algorithmic_bytes) / its CUDA-event time",
                 "kernel_ms": dom_ms,
-                "pipeline": {"algorithmic_bytes_per_step": ab["total"], "achieved": ab["total"] * args.steps / (ms * 1e-3) / 1e9,
-                             "frac": ab["total"] * args.steps / (ms * 1e-3) / 1e9 / peak,
+                "pipeline": {"algorithmic_bytes_per_step": ab["total"], "achieved": ab["total"] / (step_ms * 1e-3) / 1e9,
+                             "frac": ab["total"] / (step_ms * 1e-3) / 1e9 / peak,
                              "bytes_per_element": ab["total"] / h.nel},
-                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timers.items() if v[1] > 0}}
-    # the same algorithmic bytes against every kernel of the assembly phase (coefficients, count pass, scans, fill),
-    # and the fill kernel's own measured DRAM traffic against its duration
-    asm_ms = sum(timers[k][0] for k in ("k_elem_coef", "k_asm_count", "k_scan", "k_asm_fill") if k in timers) / args.steps
-    if asm_ms > 0:
-        roofline["assembly_phase"] = {"ms_per_step": asm_ms, "achieved": ab["assembly"] / (asm_ms * 1e-3) / 1e9,
-                                      "frac": ab["assembly"] / (asm_ms * 1e-3) / 1e9 / peak}
+                "kernel_ms_per_step": {k: v[0] / ksteps for k, v in timers.items() if v[1] > 0},
+                "kernel_timing": f"separate repetition of {ksteps} steps with per-kernel events; the headline loop runs without them"}
+    # SURVEY 8(d) bytes of each phase against ALL kernels of the phase
+    phases = {"local": ("k_local",), "assembly": ("k_elem_coef", "k_asm_count", "k_scan", "k_asm_fill", "other"),
+              "residual": ("k_res_elem", "k_res_face", "k_reduce_partials")}
+    for ph, ks in phases.items():
+        pms = sum(timers[k][0] for k in ks if k in timers) / ksteps
+        if pms > 0:
+            roofline[ph + "_phase"] = {"ms_per_step": pms, "algorithmic_bytes": ab[ph], "achieved": ab[ph] / (pms * 1e-3) / 1e9,
+                                       "frac": ab[ph] / (pms * 1e-3) / 1e9 / peak}
+    # the SURVEY 8(d) attribution of round 1 (whole assembly phase's bytes over the fill kernel alone), kept for comparison
+    if "k_asm_fill" in kms:
+        roofline["frac_algorithmic_phase_bytes"] = ab["assembly"] / (kms["k_asm_fill"] * 1e-3) / 1e9 / peak
     if traffic:
         roofline["traffic_rate"] = {"achieved": traffic[0] / (dom_ms * 1e-3) / 1e9, "frac": traffic[0] / (dom_ms * 1e-3) / 1e9 / peak}
+    tau_modes = {"FACE": {"ms_per_step": step_ms, "value": value}}
+    if ms_ref is not None:
+        tau_modes["REFERENCE"] = {"ms_per_step": ms_ref, "value": total_el / (ms_ref * 1e-3) / 1e6}
 
+    # ---- N > 1: value proof on the same communicator ------------------------------------------
+    parity = multi_gpu_parity(rank, world, local_rank) if world > 1 else None
     # ---- e2e through the host-buffer C ABI ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -402,7 +513,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        mesh_arrays, data = sample_inputs(args.cpu_n)
+        mesh_arrays, data = host_sample(args.cpu_n)
         val, parts = cpu_port_throughput(mesh_arrays, data, reps=2)
         cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "host_cpu": host_cpu()[0], "host_cores": host_cpu()[1],
                "sample": f"S({args.cpu_n}) = {int(mesh_arrays['Ω'].size)} elements (BASELINE config 3 size), best of 2; "
@@ -416,8 +527,11 @@ def run_ours(args, rank, world, local_rank):
                            "elements_per_rank": owned_el, "partition": f"{world} strips of quad rows + ghost rows" if world > 1 else "none",
                            "l2": "inputs (>40 GB per rank at the default size) exceed the 126 MB L2; no flush needed",
                            "nnz_uu_rank0": nnz_uu, "nnz_up_rank0": nnz_up, "rowptr_bytes": rpw,
-                           "residual_norms": [float(x) for x in norms]},
+                           "residual_tau_mode": TAU, "residual_norms": [float(x) for x in norms]},
+                "tau_modes": tau_modes,
                 "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:

@@ -15,6 +15,7 @@ with ``ccall``.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -79,17 +80,32 @@ def _out(a):
 
 
 class Handle:
-    """One GPU, one stream, all device-resident state (``fcfv_t``)."""
+    """One GPU (``Handle(device)``) or several behind one handle (``Handle(ngpus=N)``: devices 0..N-1 of this
+    process, the mesh is partitioned inside ``fcfv_set_mesh``; arguments and results stay the global arrays),
+    its stream(s) and all device-resident state (``fcfv_t``)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, ngpus=1):
         self.lib = _L.load()
         self._h = C.c_void_p()
-        rc = self.lib.fcfv_create(C.byref(self._h), int(device))
+        self.ngpus = int(ngpus)
+        if self.ngpus > 1:
+            rc = self.lib.fcfv_create_multi(C.byref(self._h), self.ngpus)
+        else:
+            rc = self.lib.fcfv_create(C.byref(self._h), int(device))
         if rc != _L.FCFV_OK:
-            raise _L.FCFVError(f"fcfv_create(device={device}) failed with status {rc}: no usable CUDA device "
+            raise _L.FCFVError(f"fcfv_create(device={device}, ngpus={ngpus}) failed with status {rc}: no usable CUDA device "
                                "(this library has no CPU fallback)")
         self.device = int(device)
         self.nel = self.nf = 0
+
+    def partition_info(self):
+        """Per part of a multi-GPU handle: (nel_local, nf_local, nel_owned, nf_owned); and the partitioner's host seconds."""
+        out, sec = [], C.c_double(0.0)
+        for p in range(self.lib.fcfv_num_devices(self._h)):
+            v = [C.c_int64(0) for _ in range(4)]
+            self.check(self.lib.fcfv_partition_info(self._h, p, *[C.byref(x) for x in v], C.byref(sec)))
+            out.append(tuple(x.value for x in v))
+        return out, sec.value
 
     # -- plumbing ---------------------------------------------------------------------------
     def close(self):
@@ -322,13 +338,43 @@ class Handle:
 # ---------------------------------------------------------------------------------------------
 # handle cache: one handle per mesh object, created on first use
 # ---------------------------------------------------------------------------------------------
+# GPUs a mesh is spread over when its handle is created (the reference's functions have no such argument):
+# ``mesh.ngpus`` if set, else this default (environment FCFV_NGPUS, use_gpus(n)).
+DEFAULT_GPUS = int(os.environ.get("FCFV_NGPUS", "1"))
+
+
+def use_gpus(n):
+    global DEFAULT_GPUS
+    DEFAULT_GPUS = int(n)
+
+
+def partition_part(e2f, nf, nparts, part):
+    """Host-only: (elem_global, face_global, elem_owned, face_owned) of part `part` of `nparts` -- the partition a
+    multi-GPU handle uses (1-based ascending global ids = the part's local numbering).  Needs no GPU."""
+    lib = _L.load()
+    e2f = np.asfortranarray(np.asarray(e2f, dtype=np.int64))
+    nel = int(e2f.shape[0])
+    ne, nfl = C.c_int64(0), C.c_int64(0)
+    args = (nel, int(nf), C.c_void_p(e2f.ctypes.data), int(nparts), int(part))
+    rc = lib.fcfv_partition_part(*args, C.byref(ne), C.byref(nfl), None, None, None, None)
+    if rc != _L.FCFV_OK:
+        raise _L.FCFVError(f"fcfv_partition_part failed with status {rc}")
+    eg, fg = np.empty(ne.value, dtype=np.int64), np.empty(nfl.value, dtype=np.int64)
+    eo, fo = np.empty(ne.value, dtype=np.uint8), np.empty(nfl.value, dtype=np.uint8)
+    rc = lib.fcfv_partition_part(*args, C.byref(ne), C.byref(nfl), _out(eg), _out(fg), _out(eo), _out(fo))
+    if rc != _L.FCFV_OK:
+        raise _L.FCFVError(f"fcfv_partition_part failed with status {rc}")
+    return eg, fg, eo, fo
+
+
 def handle_for(mesh, device=None) -> Handle:
     h = getattr(mesh, "_fcfv_handle", None)
     if h is None:
-        h = Handle(0 if device is None else device)
+        ngpus = int(getattr(mesh, "ngpus", None) or DEFAULT_GPUS)
+        h = Handle(0 if device is None else device, ngpus=ngpus)
         h.set_mesh(mesh)
         mesh._fcfv_handle = h
-        if h.nel >= 100_000 and getattr(mesh, "elem_owned", None) is None:
+        if ngpus == 1 and h.nel >= 100_000 and getattr(mesh, "elem_owned", None) is None:
             span, off = h.numbering_locality()
             if span > 0.05 or off > 0.05:
                 import warnings

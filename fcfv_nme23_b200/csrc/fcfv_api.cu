@@ -12,6 +12,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <initializer_list>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -76,7 +78,10 @@ struct Stager {
     cudaEvent_t begin = nullptr;
 };
 
+struct fcfv_multi;
+
 struct fcfv_handle {
+    fcfv_multi* multi = nullptr;    // non-null: a multi-GPU handle (fcfv_create_multi, fcfv_multi.inl); the device state below is unused
     int device = 0;
     Stager stager;
     cudaStream_t stream_out = nullptr;   // device-to-host copies of fcfv_pass, concurrent with its uploads
@@ -134,6 +139,28 @@ struct fcfv_handle {
 };
 
 namespace {
+
+// multi-GPU layer (fcfv_multi.inl): the same entry points on the global arrays, scattered over the parts
+int multi_sync(fcfv_t* h);
+void multi_destroy(fcfv_t* h);
+int multi_set_mesh(fcfv_t*, int64_t, int64_t, const int64_t*, const int64_t*, const double*, const double*, const double*, const double*,
+                   const double*, const double*, const double*, int64_t);
+int multi_update_fields(fcfv_t*, const double*, const double*, const double*, int64_t, const double*);
+int multi_set_sources(fcfv_t*, const double*, const double*);
+int multi_set_face_data(fcfv_t*, const double*, const double*, const double*, const double*, const double*, const double*);
+int multi_set_solution(fcfv_t*, const double*, const double*, const double*);
+int multi_set_local(fcfv_t*, const double*, const double*, const double*);
+int multi_run_local(fcfv_t*, int, double);
+int multi_get_local(fcfv_t*, double*, double*, double*, double*);
+int multi_run_assemble(fcfv_t*, int, int, double, int, double);
+int multi_fetch_totals(fcfv_t*);
+int multi_export(fcfv_t*, int, int, void*, void*, double*);
+int multi_export_rhs(fcfv_t*, double*, double*);
+int multi_run_residuals(fcfv_t*, int, int, double*, double*);
+int multi_unsupported(fcfv_t*, const char*);
+double multi_asm_seconds(fcfv_t*);
+fcfv_t* multi_part0(fcfv_t*);
+template <typename F> void multi_each(fcfv_t* h, F&& fn);
 
 int fail(fcfv_t* h, int code, const char* fmt, ...) {
     char buf[512];
@@ -468,6 +495,7 @@ int fcfv_create(fcfv_t** out, int device) {
 
 int fcfv_destroy(fcfv_t* h) {
     if (!h) return FCFV_OK;
+    if (h->multi) { multi_destroy(h); delete h; return FCFV_OK; }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
@@ -500,6 +528,7 @@ int fcfv_set_async(fcfv_t* h, int async) {
 
 int fcfv_sync(fcfv_t* h) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_sync(h);
     return sync(h);
 }
 
@@ -529,6 +558,7 @@ int fcfv_host_unregister(fcfv_t* h, void* ptr) {
 
 int fcfv_set_timing(fcfv_t* h, int on) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) { int rc = FCFV_OK; multi_each(h, [&](fcfv_t* q) { if (!rc) rc = fcfv_set_timing(q, on); }); return rc; }
     TRY(sync(h));
     resolve_timers(h);
     h->timing = on != 0;
@@ -541,6 +571,20 @@ const char* fcfv_timer_name(int k) { return (k >= 0 && k < kNumTimers) ? kTimerN
 
 int fcfv_get_timers(fcfv_t* h, double* ms, int64_t* calls) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) {      // per kernel: the slowest device's time, the first device's launch count
+        int rc = FCFV_OK;
+        bool first = true;
+        multi_each(h, [&](fcfv_t* q) {
+            double m[kNumTimers]; int64_t c[kNumTimers];
+            if (rc || (rc = fcfv_get_timers(q, m, c))) return;
+            for (int k = 0; k < kNumTimers; k++) {
+                if (ms) ms[k] = first ? m[k] : std::max(ms[k], m[k]);
+                if (calls && first) calls[k] = c[k];
+            }
+            first = false;
+        });
+        return rc;
+    }
     TRY(sync(h));
     resolve_timers(h);
     for (int k = 0; k < kNumTimers; k++) {
@@ -550,16 +594,32 @@ int fcfv_get_timers(fcfv_t* h, double* ms, int64_t* calls) {
     return FCFV_OK;
 }
 
-void* fcfv_stream(fcfv_t* h) { return h ? (void*)h->stream : nullptr; }
-int64_t fcfv_kernel_launches(fcfv_t* h) { return h ? h->launches : 0; }
-int64_t fcfv_staged_copies(fcfv_t* h) { return h ? h->staged_copies : 0; }
-int64_t fcfv_device_bytes(fcfv_t* h) { return h ? (int64_t)h->bytes : 0; }
+void* fcfv_stream(fcfv_t* h) { return !h ? nullptr : (void*)(h->multi ? multi_part0(h)->stream : h->stream); }
+int64_t fcfv_kernel_launches(fcfv_t* h) {
+    if (!h) return 0;
+    int64_t n = h->launches;
+    if (h->multi) multi_each(h, [&](fcfv_t* q) { n += q->launches; });
+    return n;
+}
+int64_t fcfv_staged_copies(fcfv_t* h) {
+    if (!h) return 0;
+    int64_t n = h->staged_copies;
+    if (h->multi) multi_each(h, [&](fcfv_t* q) { n += q->staged_copies; });
+    return n;
+}
+int64_t fcfv_device_bytes(fcfv_t* h) {
+    if (!h) return 0;
+    int64_t n = (int64_t)h->bytes;
+    if (h->multi) multi_each(h, [&](fcfv_t* q) { n += (int64_t)q->bytes; });
+    return n;
+}
 
 // -------------------------------------------------------------------------------------------------
 int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const int64_t* bc, const double* Omega,
                   const double* nx, const double* ny, const double* Gamma, const double* ke, const double* delta,
                   const double* taue, int64_t ntaue) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_set_mesh(h, nel, nf, e2f, bc, Omega, nx, ny, Gamma, ke, delta, taue, ntaue);
     CU(cudaSetDevice(h->device));
     if (nel < 0 || nf < 0 || nel >= (1LL << 29) || nf >= (1LL << 30))
         return fail(h, FCFV_ERR_INVALID, "mesh size out of range (nel=%lld < 2^29, nf=%lld < 2^30 required)", (long long)nel, (long long)nf);
@@ -609,6 +669,7 @@ int fcfv_update_fields(fcfv_t* h, const double* ke, const double* delta, const d
                        const double* tau) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_update_fields: no mesh set"));
+    if (h->multi) return multi_update_fields(h, ke, delta, taue, ntaue, tau);
     CU(cudaSetDevice(h->device));
     if (taue && ntaue < h->nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel", (long long)ntaue);
     if (ke) TRY(copy(h, h->ke.p, ke, sizeof(double) * h->nel));
@@ -621,6 +682,7 @@ int fcfv_update_fields(fcfv_t* h, const double* ke, const double* delta, const d
 int fcfv_set_ownership(fcfv_t* h, const uint8_t* elem_owned, const uint8_t* face_owned, int64_t nel_global,
                        int64_t nf_global, const double* tau_ref) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_set_ownership");
     TRY(need(h, h->have_mesh, "fcfv_set_ownership: no mesh set"));
     CU(cudaSetDevice(h->device));
     h->have_elem_owned = elem_owned != nullptr;
@@ -639,6 +701,11 @@ int fcfv_geometry(fcfv_t* h, int64_t nel, int64_t nf, int64_t nv, const int64_t*
                   const double* xv, const double* yv, const double* xf, const double* yf, int numbering, double tau_r,
                   double* Omega, double* xc, double* yc, double* nx, double* ny, double* Gamma, double* tau) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) {      // stateless utility: runs on the first device
+        const int rc = fcfv_geometry(multi_part0(h), nel, nf, nv, e2v, e2f, xv, yv, xf, yf, numbering, tau_r, Omega, xc, yc, nx, ny, Gamma, tau);
+        if (rc) h->err = multi_part0(h)->err;
+        return rc;
+    }
     CU(cudaSetDevice(h->device));
     if (nel < 0 || nf < 0 || nv < 0 || nel >= (1LL << 29) || nf >= (1LL << 30) || nv >= (1LL << 31))
         return fail(h, FCFV_ERR_INVALID, "fcfv_geometry: size out of range");
@@ -702,6 +769,11 @@ int scan64_ranks(fcfv_t* h, unsigned long long* a, long long n, DBuf& chunks) {
 
 int fcfv_first_seen_faces(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, int64_t* new_of_old, int64_t* e2f_new) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) {
+        const int rc = fcfv_first_seen_faces(multi_part0(h), nel, nf, e2f, new_of_old, e2f_new);
+        if (rc) h->err = multi_part0(h)->err;
+        return rc;
+    }
     CU(cudaSetDevice(h->device));
     if (nel < 0 || nf < 0 || nel >= (1LL << 29) || nf >= (1LL << 30)) return fail(h, FCFV_ERR_INVALID, "fcfv_first_seen_faces: size out of range");
     if (!e2f) return fail(h, FCFV_ERR_INVALID, "fcfv_first_seen_faces: null e2f");
@@ -750,6 +822,11 @@ int fcfv_first_seen_faces(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f
 
 int fcfv_hilbert_elements(fcfv_t* h, int64_t nel, const double* xc, const double* yc, int64_t* old_of_new) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) {
+        const int rc = fcfv_hilbert_elements(multi_part0(h), nel, xc, yc, old_of_new);
+        if (rc) h->err = multi_part0(h)->err;
+        return rc;
+    }
     CU(cudaSetDevice(h->device));
     if (nel < 0 || nel >= (1LL << 31)) return fail(h, FCFV_ERR_INVALID, "fcfv_hilbert_elements: size out of range");
     if (!xc || !yc || !old_of_new) return fail(h, FCFV_ERR_INVALID, "fcfv_hilbert_elements: null array");
@@ -775,6 +852,7 @@ int fcfv_hilbert_elements(fcfv_t* h, int64_t nel, const double* xc, const double
 int fcfv_set_sources(fcfv_t* h, const double* sex, const double* sey) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_set_sources: no mesh set"));
+    if (h->multi) return multi_set_sources(h, sex, sey);
     CU(cudaSetDevice(h->device));
     if (!sex || !sey) return fail(h, FCFV_ERR_INVALID, "fcfv_set_sources: null array");
     TRY(upload(h, h->sex, sex, sizeof(double) * h->nel));
@@ -787,6 +865,7 @@ int fcfv_set_face_data(fcfv_t* h, const double* VxDir, const double* VyDir, cons
                        const double* sxyNeu, const double* syxNeu) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_set_face_data: no mesh set"));
+    if (h->multi) return multi_set_face_data(h, VxDir, VyDir, sxxNeu, syyNeu, sxyNeu, syxNeu);
     CU(cudaSetDevice(h->device));
     const size_t b = sizeof(double) * h->nf;
     DBuf* dst[6] = {&h->VxDir, &h->VyDir, &h->sxx, &h->syy, &h->sxy, &h->syx};
@@ -804,6 +883,7 @@ int fcfv_set_face_data(fcfv_t* h, const double* VxDir, const double* VyDir, cons
 int fcfv_set_solution(fcfv_t* h, const double* Vxh, const double* Vyh, const double* Pe) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_set_solution: no mesh set"));
+    if (h->multi) return multi_set_solution(h, Vxh, Vyh, Pe);
     CU(cudaSetDevice(h->device));
     if (!Vxh || !Vyh || !Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_set_solution: null array");
     TRY(upload(h, h->Vxh, Vxh, sizeof(double) * h->nf));
@@ -816,6 +896,7 @@ int fcfv_set_solution(fcfv_t* h, const double* Vxh, const double* Vyh, const dou
 int fcfv_set_local(fcfv_t* h, const double* alpha, const double* beta, const double* Z) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_set_local: no mesh set"));
+    if (h->multi) return multi_set_local(h, alpha, beta, Z);
     CU(cudaSetDevice(h->device));
     if (!alpha || !beta || !Z) return fail(h, FCFV_ERR_INVALID, "fcfv_set_local: null array");
     TRY(copy(h, h->alpha.p, alpha, sizeof(double) * h->nel));
@@ -829,6 +910,7 @@ int fcfv_set_local(fcfv_t* h, const double* alpha, const double* beta, const dou
 int fcfv_run_local(fcfv_t* h, int formulation, double A) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(check_form(h, formulation));
+    if (h->multi) return multi_run_local(h, formulation, A);
     TRY(need(h, h->have_mesh, "fcfv_run_local: no mesh set"));
     TRY(need(h, h->have_sources && h->have_face_data, "fcfv_run_local: sources / face data not set"));
     CU(cudaSetDevice(h->device));
@@ -847,6 +929,7 @@ int fcfv_run_local(fcfv_t* h, int formulation, double A) {
 
 int fcfv_get_local(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_get_local(h, alpha, beta, Z, tau);
     TRY(need(h, h->have_local, "fcfv_get_local: local coefficients not computed"));
     CU(cudaSetDevice(h->device));
     if (alpha) TRY(copy(h, alpha, h->alpha.p, sizeof(double) * h->nel));
@@ -936,6 +1019,7 @@ int launch_assemble_x(fcfv_t* h, double A, int extra, double gamma) {
 }
 
 int fetch_totals(fcfv_t* h) {
+    if (h->multi) return multi_fetch_totals(h);
     if (h->totals_valid) return FCFV_OK;
     CU(cudaMemcpyAsync(h->totals_host, h->totals.p, sizeof(long long) * 10, cudaMemcpyDeviceToHost, h->stream));
     TRY(sync(h));
@@ -952,6 +1036,7 @@ int run_assemble_impl(fcfv_t* h, int variant, int formulation, double A, int ext
     TRY(check_form(h, formulation));
     if (variant != FCFV_LOOP_OLD && variant != FCFV_LOOP_NEW)
         return fail(h, FCFV_ERR_INVALID, "variant must be FCFV_LOOP_OLD or FCFV_LOOP_NEW (got %d)", variant);
+    if (h->multi) return multi_run_assemble(h, variant, formulation, A, extra, gamma);
     TRY(need(h, h->have_mesh, "fcfv_run_assemble: no mesh set"));
     TRY(need(h, h->have_local, "fcfv_run_assemble: local coefficients missing (fcfv_compute_local / fcfv_set_local)"));
     TRY(need(h, h->have_face_data, "fcfv_run_assemble: face data not set"));
@@ -1047,7 +1132,7 @@ int fcfv_schur(fcfv_t* h, double gamma, int64_t* nnz_sc) {
 int fcfv_get_nnz(fcfv_t* h, int64_t* nnz_uu, int64_t* nnz_up, int64_t* nnz_muu) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_get_nnz: nothing assembled"));
-    CU(cudaSetDevice(h->device));
+    if (!h->multi) CU(cudaSetDevice(h->device));
     TRY(fetch_totals(h));
     if (nnz_uu) *nnz_uu = h->Kuu.nnz;
     if (nnz_up) *nnz_up = h->Kup.nnz;
@@ -1069,7 +1154,9 @@ int fcfv_assemble(fcfv_t* h, int variant, int formulation, double A, const doubl
     h->async = was_async;
     if (rc) return rc;
     TRY(fcfv_get_nnz(h, nnz_uu, nnz_up, nnz_muu));   // synchronises
-    if (seconds) {
+    if (seconds && h->multi) {
+        *seconds = multi_asm_seconds(h);       // host clock around the launches on all devices and their completion
+    } else if (seconds) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         *seconds = 1e-3 * ms;
@@ -1096,7 +1183,7 @@ int fcfv_block_size(fcfv_t* h, int block, int64_t* nrows, int64_t* ncols, int64_
     Csr* c = block_of(h, block);
     if (!c) return fail(h, FCFV_ERR_INVALID, "unknown block %d", block);
     TRY(need(h, c->nnz != -1, "fcfv_block_size: block not assembled"));
-    CU(cudaSetDevice(h->device));
+    if (!h->multi) CU(cudaSetDevice(h->device));
     TRY(fetch_totals(h));
     if (nrows) *nrows = c->nrows;
     if (ncols) *ncols = c->ncols;
@@ -1106,6 +1193,7 @@ int fcfv_block_size(fcfv_t* h, int block, int64_t* nrows, int64_t* ncols, int64_
 
 int fcfv_export(fcfv_t* h, int block, int layout, void* ptr, void* idx, double* val) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_export(h, block, layout, ptr, idx, val);
     Csr* c = block_of(h, block);
     if (!c) return fail(h, FCFV_ERR_INVALID, "unknown block %d", block);
     TRY(need(h, c->nnz != -1, "fcfv_export: block not assembled"));
@@ -1160,6 +1248,7 @@ int fcfv_export(fcfv_t* h, int block, int layout, void* ptr, void* idx, double* 
 
 int fcfv_export_rhs(fcfv_t* h, double* fu, double* fp) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_export_rhs(h, fu, fp);
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_export_rhs: nothing assembled"));
     CU(cudaSetDevice(h->device));
     if (fu) TRY(copy(h, fu, h->fu.p, sizeof(double) * 2 * h->nf));
@@ -1169,6 +1258,7 @@ int fcfv_export_rhs(fcfv_t* h, double* fu, double* fp) {
 
 int fcfv_device_csr(fcfv_t* h, int block, void** rowptr, void** colidx, void** val) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_device_csr (the rows live on several devices)");
     Csr* c = block_of(h, block);
     if (!c) return fail(h, FCFV_ERR_INVALID, "unknown block %d", block);
     TRY(need(h, c->nnz != -1, "fcfv_device_csr: block not assembled"));
@@ -1180,6 +1270,7 @@ int fcfv_device_csr(fcfv_t* h, int block, void** rowptr, void** colidx, void** v
 
 int fcfv_device_rhs(fcfv_t* h, void** fu, void** fp) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_device_rhs");
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_device_rhs: nothing assembled"));
     if (fu) *fu = h->fu.p;
     if (fp) *fp = h->fp.p;
@@ -1189,6 +1280,7 @@ int fcfv_device_rhs(fcfv_t* h, void** fu, void** fp) {
 // -------------------------------------------------------------------------------------------------
 int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, double* norms) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_run_residuals(h, formulation, tau_mode, sumsq, norms);
     TRY(check_form(h, formulation));
     if (tau_mode != FCFV_TAU_REFERENCE && tau_mode != FCFV_TAU_FACE)
         return fail(h, FCFV_ERR_INVALID, "tau_mode must be FCFV_TAU_REFERENCE or FCFV_TAU_FACE (got %d)", tau_mode);
@@ -1249,6 +1341,7 @@ int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau
         h->async = was_async;
         return rc;
     };
+    if (h->multi) { TRY(direct()); return multi_sync(h) ? FCFV_ERR_CUDA : FCFV_OK; }
     if (h->comm || h->timing) { TRY(direct()); return finish(h); }
     long long abits;
     memcpy(&abits, &A, sizeof abits);
@@ -1304,6 +1397,7 @@ int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, 
     if (rc) return rc;
     double dummy[6];
     TRY(fcfv_run_residuals(h, formulation, tau_mode, nullptr, norms ? norms : dummy));
+    if ((F_nodes_x || F_nodes_y || F_glob2) && h->multi) return multi_unsupported(h, "fcfv_residuals with F_nodes / F_glob2 outputs");
     if (F_nodes_x || F_nodes_y || F_glob2) {
         // optional arrays: rerun the two kernels with output pointers (device scratch), then copy out
         const long long nel = h->nel, nf = h->nf;
@@ -1341,6 +1435,13 @@ int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, c
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_pass: no mesh set"));
     if (!VxDir || !VyDir || !Vxh || !Vyh || !Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_pass: null input array");
+    if (h->multi) {      // the three calls one after the other (each array is scattered once per call)
+        TRY(fcfv_compute_local(h, formulation, A, sex, sey, VxDir, VyDir, alpha, beta, Z, tau));
+        TRY(fcfv_assemble(h, variant, formulation, A, nullptr, nullptr, nullptr, VxDir, VyDir, sxxNeu, syyNeu, sxyNeu, syxNeu, want_muu, nnz_uu,
+                          nnz_up, nnz_muu, nullptr));
+        return fcfv_residuals(h, formulation, tau_mode, Vxh, Vyh, Pe, nullptr, nullptr, nullptr, sex, sey, VxDir, VyDir, sxxNeu, syyNeu, sxyNeu,
+                              syxNeu, norms, nullptr, nullptr, nullptr);
+    }
     CU(cudaSetDevice(h->device));
     if (!h->stream_out) {
         CU(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
@@ -1384,6 +1485,7 @@ int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, c
 int fcfv_element_values(fcfv_t* h, const double* Vxh, const double* Vyh, const double* alpha, const double* beta,
                         const double* Z, double* Vxe, double* Vye, double* Txxe, double* Tyye, double* Txye) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_element_values");
     TRY(need(h, h->have_mesh, "fcfv_element_values: no mesh set"));
     CU(cudaSetDevice(h->device));
     const long long nel = h->nel, nf = h->nf;
@@ -1428,6 +1530,7 @@ int ph_inputs(fcfv_t* h, const double* u, const double* p, double** du, double**
 
 int fcfv_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, double* rp, double* nrm) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_ph_residual");
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_residual: nothing assembled"));
     if (!u || !p) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_residual: null u or p");
     CU(cudaSetDevice(h->device));
@@ -1464,6 +1567,7 @@ int fcfv_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, do
 
 int fcfv_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_ph_update_p");
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_update_p: nothing assembled"));
     if (!u || !p) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_update_p: null u or p");
     CU(cudaSetDevice(h->device));
@@ -1478,6 +1582,7 @@ int fcfv_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p) {
 
 int fcfv_center_pressure(fcfv_t* h, double* Pe, double* mean) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_center_pressure");
     TRY(need(h, h->have_mesh, "fcfv_center_pressure: no mesh set"));
     if (!Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_center_pressure: null Pe");
     CU(cudaSetDevice(h->device));
@@ -1504,6 +1609,7 @@ int fcfv_center_pressure(fcfv_t* h, double* Pe, double* mean) {
 
 int fcfv_ph_fusc(fcfv_t* h, double gamma, const double* p, double* fusc) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_ph_fusc");
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_fusc: nothing assembled"));
     if (!p || !fusc) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_fusc: null p or fusc");
     CU(cudaSetDevice(h->device));
@@ -1537,6 +1643,7 @@ int fcfv_mesh_size(fcfv_t* h, int64_t* nel, int64_t* nf) {
 int fcfv_get_mesh(fcfv_t* h, int64_t* e2f, int64_t* bc, double* Omega, double* nx, double* ny, double* Gamma,
                   double* ke, double* delta, double* taue, double* tau) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_get_mesh");
     TRY(need(h, h->have_mesh, "fcfv_get_mesh: no mesh set"));
     CU(cudaSetDevice(h->device));
     const long long nel = h->nel, nf = h->nf;
@@ -1565,6 +1672,7 @@ int fcfv_get_mesh(fcfv_t* h, int64_t* e2f, int64_t* bc, double* Omega, double* n
 
 int fcfv_numbering_locality(fcfv_t* h, double* element_span, double* face_offset) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_numbering_locality");
     TRY(need(h, h->have_mesh, "fcfv_numbering_locality: no mesh set"));
     CU(cudaSetDevice(h->device));
     const int nblk = nblocks(h->nf);
@@ -1590,6 +1698,7 @@ int fcfv_numbering_locality(fcfv_t* h, double* element_span, double* face_offset
 
 int fcfv_get_ownership(fcfv_t* h, uint8_t* elem_owned, uint8_t* face_owned, int64_t* nel_global, int64_t* nf_global) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_get_ownership");
     TRY(need(h, h->have_mesh, "fcfv_get_ownership: no mesh set"));
     CU(cudaSetDevice(h->device));
     if (elem_owned) {
@@ -1608,6 +1717,7 @@ int fcfv_get_ownership(fcfv_t* h, uint8_t* elem_owned, uint8_t* face_owned, int6
 int fcfv_get_data(fcfv_t* h, double* sex, double* sey, double* VxDir, double* VyDir, double* sxxNeu, double* syyNeu,
                   double* sxyNeu, double* syxNeu, double* Vxh, double* Vyh, double* Pe) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_get_data");
     TRY(need(h, h->have_mesh && h->have_sources && h->have_face_data && h->have_solution, "fcfv_get_data: data not set"));
     CU(cudaSetDevice(h->device));
     const size_t be = sizeof(double) * h->nel, bf = sizeof(double) * h->nf;
@@ -1629,6 +1739,7 @@ int fcfv_get_data(fcfv_t* h, double* sex, double* sey, double* VxDir, double* Vy
 int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, int ghost_below, int setting,
                              double tau_r, double eta_incl, int neumann_south) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_generate_structured");
     CU(cudaSetDevice(h->device));
     if (n < 1 || row0 < 0 || row1 > n || row0 >= row1) return fail(h, FCFV_ERR_INVALID, "fcfv_generate_structured: bad row range");
     if (setting != 0 && setting != 1) return fail(h, FCFV_ERR_INVALID, "fcfv_generate_structured: setting must be 0 or 1");
@@ -1710,6 +1821,7 @@ int nccl_fail(fcfv_t* h, const char* what, int rc) {
 
 int fcfv_comm_unique_id(fcfv_t* h, void* id128) {
     if (!h || !id128) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_comm_unique_id (the handle owns its communicators)");
     TRY(load_nccl(h));
     const int rc = h->nccl.GetUniqueId(id128);
     if (rc) return nccl_fail(h, "ncclGetUniqueId", rc);
@@ -1718,6 +1830,7 @@ int fcfv_comm_unique_id(fcfv_t* h, void* id128) {
 
 int fcfv_comm_init(fcfv_t* h, const void* id128, int rank, int nranks) {
     if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_comm_init");
     CU(cudaSetDevice(h->device));
     TRY(load_nccl(h));
     Id128 id;
@@ -1730,6 +1843,7 @@ int fcfv_comm_init(fcfv_t* h, const void* id128, int rank, int nranks) {
 
 int fcfv_comm_allreduce_sum(fcfv_t* h, double* data, int n) {
     if (!h || !data || n < 0) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_unsupported(h, "fcfv_comm_allreduce_sum");
     if (!h->comm) return FCFV_OK;   // single rank: identity
     CU(cudaSetDevice(h->device));
     cudaPointerAttributes at;
@@ -1750,3 +1864,6 @@ int fcfv_comm_allreduce_sum(fcfv_t* h, double* data, int n) {
     }
     return FCFV_OK;
 }
+
+// =================================================================================================
+#include "fcfv_multi.inl"

@@ -61,6 +61,10 @@ def load():
     P = C.POINTER
     sig = {
         "fcfv_create": [P(vp), ci],
+        "fcfv_create_multi": [P(vp), ci],
+        "fcfv_num_devices": [vp],
+        "fcfv_partition_info": [vp, ci, P(i64), P(i64), P(i64), P(i64), P(dbl)],
+        "fcfv_partition_part": [i64, i64, vp, ci, ci, P(i64), P(i64), vp, vp, vp, vp],
         "fcfv_destroy": [vp],
         "fcfv_version": [],
         "fcfv_set_mesh": [vp, i64, i64] + [vp] * 9 + [i64],

@@ -17,7 +17,8 @@
  *  - Every array pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer of the
  *    handle's GPU; the library detects which (cudaPointerGetAttributes).  Pointers are borrowed
  *    for the duration of the call only.  Output arrays are caller-allocated; NULL skips them.
- *  - A handle owns one GPU, one stream and all device-resident state.  It is not thread-safe.
+ *  - A handle owns one GPU (fcfv_create) or several (fcfv_create_multi), one stream per GPU and all device-resident
+ *    state.  It is not thread-safe.
  *    Calls return after the stream has been synchronised unless stated otherwise.
  *  - Assembled blocks stay on the device as CSR: 0-based, int32 column indices, row pointers
  *    int32 when 20*nf < 2^31 and int64 otherwise (fcfv_index_width).  Within a row columns are
@@ -44,6 +45,26 @@ enum { FCFV_CSR0 = 0, FCFV_CSC1_INT64 = 1 };               /* export layouts */
 
 /* ---- life cycle ---------------------------------------------------------------------- */
 int fcfv_create(fcfv_t** h, int device);
+/* Several GPUs behind ONE handle, for the reference's single-process drivers (examples/ViscousInclusionFCFV_v2.jl:60-154,
+ * examples/SolKzFCFV.jl:50-215): devices 0..ngpus-1 of this process.  Every entry point keeps its meaning and takes / returns
+ * the GLOBAL arrays of the unpartitioned mesh (host pointers only).  fcfv_set_mesh splits the mesh by element (contiguous
+ * ranges; a face belongs to the part of its highest adjacent element, the element whose tau_e DiscretisationFCFV_Stokes.jl:40
+ * leaves in mesh.tau; one layer of ghost elements is replicated) and scatters the arrays; each part assembles the rows of its
+ * faces with no data-path communication, bit-identical to the single-GPU rows; fcfv_export concatenates them into the global
+ * CSR / Julia CSC.  One NCCL communicator per device (ncclCommInitAll), used for one grouped all-reduce of the six residual
+ * sums per evaluation.  Supported: set_mesh, update_fields, set_* / run_* / get_local / get_nnz, compute_local, assemble,
+ * schur, export (CSR0, CSC1_INT64), export_rhs, residuals (norms), run_pipeline, pass, geometry / first_seen_faces /
+ * hilbert_elements (first device).  Everything else returns FCFV_ERR_STATE.  ngpus == 1 gives a plain single-GPU handle. */
+int fcfv_create_multi(fcfv_t** h, int ngpus);
+int fcfv_num_devices(fcfv_t* h);
+/* What part `part` of a multi-GPU handle holds after fcfv_set_mesh: local / owned element and face counts (local - owned =
+ * replicated ghosts) and the host seconds the partitioner took. */
+int fcfv_partition_info(fcfv_t* h, int part, int64_t* nel_local, int64_t* nf_local, int64_t* nel_owned, int64_t* nf_owned,
+                        double* seconds);
+/* The same partition computed on the host alone (no GPU, no handle): global ids (1-based, ascending = the part's local
+ * numbering) and ownership masks of part `part` of `nparts`.  Call with the arrays NULL for the sizes first. */
+int fcfv_partition_part(int64_t nel, int64_t nf, const int64_t* e2f, int nparts, int part, int64_t* nel_local, int64_t* nf_local,
+                        int64_t* elem_global, int64_t* face_global, uint8_t* elem_owned, uint8_t* face_owned);
 int fcfv_destroy(fcfv_t* h);
 const char* fcfv_last_error(fcfv_t* h);
 int fcfv_version(void);

@@ -12,7 +12,7 @@ using SparseArrays, Printf
 
 export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
        SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!, RenumberFacesFirstSeen!,
-       RenumberElementsHilbert!, PrepareNumbering!, PinArrays, FusedPass, release!
+       RenumberElementsHilbert!, PrepareNumbering!, PinArrays, FusedPass, release!, NGPUS
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
 
@@ -32,9 +32,16 @@ mutable struct Handle
     nf::Int
 end
 
-function Handle(device::Integer = 0)
+# GPUs a mesh is spread over when its handle is created.  The reference's functions have no such argument and its
+# drivers are single-process scripts, so the choice is made here: FCFV_B200.NGPUS[] = 8 (or ENV["FCFV_NGPUS"]) before
+# the first call on a mesh.  With more than one GPU the handle partitions the mesh inside fcfv_set_mesh; every
+# function below keeps taking and returning the global arrays.
+const NGPUS = Ref(parse(Int, get(ENV, "FCFV_NGPUS", "1")))
+
+function Handle(device::Integer = 0; ngpus::Integer = NGPUS[])
     r = Ref{Ptr{Cvoid}}(C_NULL)
-    rc = ccall((:fcfv_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
+    rc = ngpus > 1 ? ccall((:fcfv_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, ngpus) :
+                     ccall((:fcfv_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
     rc == 0 || error("fcfv_create failed with status $rc: no usable CUDA device (there is no CPU fallback)")
     h = Handle(r[], 0, 0)
     finalizer(destroy!, h)

@@ -88,14 +88,35 @@ def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τ
     return al, be.reshape((nel, 2), order="F"), Z.reshape((nel, 2, 2), order="F")
 
 
-def _assemble(variant, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A=1.0):
-    nel, nf = mesh.nel, mesh.nf
+def assembly_workspace(nel, nf):
+    """Output arrays of one assembly at their capacity (Kuu/Muu 36*nel, Kup 6*nel entries).  bench.py's CPU legs
+    allocate them once, OUTSIDE the timed region, and pass them as ``workspace=``: the wrapper's own allocations and
+    trim copies are not part of the reference's algorithm and must not be charged to it."""
     cap_uu, cap_up = 36 * nel, 6 * nel
-    uu = (np.zeros(2 * nf + 1, np.int64), np.zeros(cap_uu, np.int64), np.zeros(cap_uu))
-    mu = (np.zeros(2 * nf + 1, np.int64), np.zeros(cap_uu, np.int64), np.zeros(cap_uu))
-    up = (np.zeros(nel + 1, np.int64), np.zeros(cap_up, np.int64), np.zeros(cap_up))
+    ws = dict(uu=(np.zeros(2 * nf + 1, np.int64), np.zeros(cap_uu, np.int64), np.zeros(cap_uu)),
+              mu=(np.zeros(2 * nf + 1, np.int64), np.zeros(cap_uu, np.int64), np.zeros(cap_uu)),
+              up=(np.zeros(nel + 1, np.int64), np.zeros(cap_up, np.int64), np.zeros(cap_up)),
+              fu=np.zeros(2 * nf), fp=np.zeros(nel), nel=nel, nf=nf)
+    for t in (ws["uu"], ws["mu"], ws["up"]):     # touch every page now (np.zeros maps them lazily)
+        for x in t:
+            x.fill(0)
+    return ws
+
+
+def _assemble(variant, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A=1.0, workspace=None):
+    nel, nf = mesh.nel, mesh.nf
+    ws = workspace if workspace is not None else None
+    if ws is not None:
+        assert ws["nel"] == nel and ws["nf"] == nf
+        uu, mu, up, fu, fp = ws["uu"], ws["mu"], ws["up"], ws["fu"], ws["fp"]
+    else:
+        cap_uu, cap_up = 36 * nel, 6 * nel
+        uu = (np.zeros(2 * nf + 1, np.int64), np.zeros(cap_uu, np.int64), np.zeros(cap_uu))
+        mu = (np.zeros(2 * nf + 1, np.int64), np.zeros(cap_uu, np.int64), np.zeros(cap_uu))
+        up = (np.zeros(nel + 1, np.int64), np.zeros(cap_up, np.int64), np.zeros(cap_up))
+        fu, fp = np.zeros(2 * nf), np.zeros(nel)
     nnz = [C.c_int64(0) for _ in range(3)]
-    fu, fp, times = np.zeros(2 * nf), np.zeros(nel), np.zeros(2)
+    times = np.zeros(2)
     a = [_i(mesh.e2f), _i(mesh.bc), _d(mesh.Ω), _d(mesh.Γ), _d(mesh.n_x), _d(mesh.n_y), _d(mesh.ke), _d(mesh.δ),
          _d(mesh.τ), _d(α), _d(β), _d(Ζ), _d(VxDir), _d(VyDir), _d(σxxNeu), _d(σyyNeu), _d(σxyNeu), _d(σyxNeu)]
     rc = lib().oracle_assemble(
@@ -105,19 +126,22 @@ def _assemble(variant, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu
         _p(up[0]), _p(up[1]), _p(up[2]), C.byref(nnz[2]),
         _p(fu), _p(fp), _p(times))
     assert rc == 0
-    trim = lambda t, n: (t[0], t[1][:n].copy(), t[2][:n].copy())
+    if ws is not None:      # views into the workspace: valid until its next use
+        trim = lambda t, n: (t[0], t[1][:n], t[2][:n])
+    else:
+        trim = lambda t, n: (t[0], t[1][:n].copy(), t[2][:n].copy())
     Kuu, Muu, Kup = trim(uu, nnz[0].value), trim(mu, nnz[1].value), trim(up, nnz[2].value)
     return Kuu, Muu, Kup, fu.reshape(-1, 1), fp, float(times[1]), float(times[0])
 
 
-def ElementAssemblyLoop(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A=1.0):
+def ElementAssemblyLoop(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A=1.0, workspace=None):
     """a5+a7 -- returns Kuu, Muu, Kup (CSC triples), fu (2nf x 1), fp (nel), tsparse, tloop."""
-    return _assemble(0, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A)
+    return _assemble(0, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A, workspace)
 
 
-def ElementAssemblyLoopNEW(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A=1.0):
+def ElementAssemblyLoopNEW(mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A=1.0, workspace=None):
     """a6+a7."""
-    return _assemble(1, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A)
+    return _assemble(1, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu, σyxNeu, Formulation, A, workspace)
 
 
 def ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu,

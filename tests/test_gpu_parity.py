@@ -833,6 +833,6 @@ def test_async_muu_then_schur_keeps_both_counts(api):
     m = cases.load_mesh("S6")
     m.τe = np.ones(m.nel); m.ke = np.ones(m.nel)
     h.set_mesh(m)
-    rc = h.lib.fcfv_run_local(h._h, L.FORMULATIONS[form] if hasattr(L, "FORMULATIONS") else 1, C.c_double(1.0))
+    rc = h.lib.fcfv_run_local(h._h, api.formulation_id(form), C.c_double(1.0))
     assert rc != 0 and b"not set" in h.lib.fcfv_last_error(h._h)
     h.close()

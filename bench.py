@@ -44,6 +44,15 @@ N_DEFAULT = 3536       # S(3536): 50,013,184 elements (BASELINE config 4)
 CPU_SAMPLE_N = 500     # S(500): 1,000,000 elements (BASELINE config 3) -- bounded CPU sample
 
 
+_T0 = time.time()
+
+
+def progress(msg):
+    """Phase marker on stderr (rank 0): locates a stall in the driver's log."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def workload_name(n1, world, scaling):
     """Name of the workload both arms are quoted on (n1 = quads per side of the single-GPU mesh)."""
     n = int(round(n1 * world ** 0.5)) if scaling == "weak" else n1
@@ -86,8 +95,8 @@ def kernel_algorithmic_bytes(nel, nf, nnz_uu, nnz_up, rpw):
         "k_elem_coef": nel * 40,
         "k_asm_count": nel * rec + nf * conn,
         "k_asm_fill": nel * rec + nf * conn + 12 * (nnz_uu + nnz_up) + 2 * rpw * (2 * nf + 1) + nf * 16,
-        "k_res_elem": nel * (12 + 4 + 72 + 24 + 56 + 16 + 8) + nf * (8 + 16) + nel * 48,
-        "k_res_face": nf * (8 + 1) + nel * 48,
+        "k_res_elem": nel * (12 + 4 + 4 + 72 + 24 + 56 + 16 + 8) + nf * (8 + 16),
+        "k_res_late": nf * 4,
     }
 
 
@@ -406,10 +415,10 @@ def run_ours(args, rank, world, local_rank):
     # FACE array indexed by the ELEMENT id) is timed beside it at N = 1 (`tau_modes`).
     TAU = "FACE"
 
-    def step(tau_mode=TAU):
-        h.run_local(FORM)
-        h.run_assemble(VARIANT, FORM)
-        h.run_residuals(FORM, tau_mode, fetch=False)
+    def step(tau_mode=TAU, hh=None):
+        # one pass = local coefficients -> assembly -> residual sums (+ NCCL all-reduce at N > 1); fcfv_run_pipeline
+        # issues exactly the launches of run_local + run_assemble + run_residuals, replayed as one CUDA graph
+        (hh or h).run_pipeline(VARIANT, FORM, tau_mode)
 
     def barrier():
         h.sync()
@@ -434,9 +443,11 @@ def run_ours(args, rank, world, local_rank):
             t = float(tt.item())
         return t
 
+    progress(f"mesh generated ({h.nel} elements per rank), warm-up")
     for _ in range(args.warmup):
         step()
     barrier()
+    progress("headline loop")
     # ---- headline: K steps, per-kernel timers OFF
     l0 = h.kernel_launches
     sampler = NvmlClockSampler(local_rank)
@@ -451,6 +462,7 @@ def run_ours(args, rank, world, local_rank):
         launches = int(lt.item())
     value = total_el * args.steps / (ms * 1e-3) / 1e6
     # ---- per-kernel device times: a second, separate repetition with an event pair around every launch
+    progress("per-kernel timers")
     h.set_timing(True)
     ksteps = max(1, min(args.steps, 5))
     for _ in range(ksteps):
@@ -489,7 +501,7 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_timing": f"separate repetition of {ksteps} steps with per-kernel events; the headline loop runs without them"}
     # SURVEY 8(d) bytes of each phase against ALL kernels of the phase
     phases = {"local": ("k_local",), "assembly": ("k_elem_coef", "k_asm_count", "k_scan", "k_asm_fill", "other"),
-              "residual": ("k_res_elem", "k_res_face", "k_reduce_partials")}
+              "residual": ("k_res_elem", "k_res_late", "k_reduce_partials")}
     for ph, ks in phases.items():
         pms = sum(timers[k][0] for k in ks if k in timers) / ksteps
         if pms > 0:
@@ -504,7 +516,37 @@ def run_ours(args, rank, world, local_rank):
     if ms_ref is not None:
         tau_modes["REFERENCE"] = {"ms_per_step": ms_ref, "value": total_el / (ms_ref * 1e-3) / 1e6}
 
+    # ---- N > 1: strong scaling of the single-GPU workload S(n1) in the same run ------------------
+    strong = None
+    if world > 1 and args.scaling == "weak":
+        progress("strong-scaling point")
+        hs = api.Handle(local_rank)
+        hs.generate_structured(n1, rank * n1 // world, (rank + 1) * n1 // world, setting="solkz", tau_r=10.0)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(hs.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        hs.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        hs.set_async(True)
+        sts = torch.cuda.ExternalStream(hs.stream)
+        for _ in range(max(3, args.warmup)):
+            step(TAU, hs)
+        hs.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); hs.sync(); dist.barrier()
+        e0.record(sts)
+        for _ in range(args.steps):
+            step(TAU, hs)
+        e1.record(sts)
+        hs.sync(); barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_s = float(tt.item()) / args.steps
+        strong = {"workload": workload_name(n1, 1, "strong"), "ms_per_step": ms_s, "value": 4 * n1 * n1 / (ms_s * 1e-3) / 1e6,
+                  "unit": UNIT, "note": "the N = 1 mesh split over the N ranks (value / the N = 1 value / N = strong-scaling efficiency)"}
+        hs.close()
     # ---- N > 1: value proof on the same communicator ------------------------------------------
+    progress("multi-GPU parity record" if world > 1 else "e2e")
     parity = multi_gpu_parity(rank, world, local_rank) if world > 1 else None
     # ---- e2e through the host-buffer C ABI ---------------------------------------------------
     e2e = None
@@ -530,6 +572,8 @@ def run_ours(args, rank, world, local_rank):
                            "residual_tau_mode": TAU, "residual_norms": [float(x) for x in norms]},
                 "tau_modes": tau_modes,
                 "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+        if strong is not None:
+            line["strong"] = strong
         if parity is not None:
             line["multi_gpu_parity"] = parity
         if e2e is not None:
@@ -543,8 +587,16 @@ def run_ours(args, rank, world, local_rank):
 
 
 def run_e2e(args, hdev, rank, world, total_el, barrier):
-    """Same step through fcfv_set_mesh / fcfv_compute_local / fcfv_assemble / fcfv_residuals with
-    pinned HOST buffers (what the Julia shim calls), H2D and D2H inside the timed region."""
+    """The same step through the reference-facing host-buffer calls, exactly as the shims (julia/FCFV_B200.jl,
+    fcfv_nme23_b200/api.py) issue them for the three calls of a driver (SolKzFCFV.jl:150,155,205):
+
+        ComputeFCFV            -> [first call on a mesh: fcfv_set_mesh | later: fcfv_new_epoch], fcfv_update_fields(ke, delta,
+                                  tau_e, tau), fcfv_compute_local_ex
+        ElementAssemblyLoopNEW -> fcfv_update_fields(...), fcfv_assemble(alpha, beta, Z, VDir, sigmaNeu)
+        ComputeResiduals..._o1 -> fcfv_update_fields(...), fcfv_residuals(Vh, Pe, alpha, beta, Z, sources, VDir, sigmaNeu)
+
+    with pinned HOST buffers, H2D and D2H inside the timed region; the handle's upload cache is on, as in the shims
+    (an array the device already mirrors is not sent again).  Byte counts are the library's own transfer counters."""
     import ctypes as C
     import numpy as np
     import torch
@@ -561,8 +613,9 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
     P = {k: pin(v) for k, v in mesh_arrays.items()}
     P["eo"], P["fo"] = pin(eo), pin(fo)
     Dd = {k: pin(v) for k, v in data.items()}
+    del mesh_arrays, data
     out = {"alpha": torch.empty(nel, dtype=torch.float64).pin_memory(), "beta": torch.empty(2 * nel, dtype=torch.float64).pin_memory(),
-           "Z": torch.empty(4 * nel, dtype=torch.float64).pin_memory(), "tau": torch.empty(nf, dtype=torch.float64).pin_memory()}
+           "Z": torch.empty(4 * nel, dtype=torch.float64).pin_memory(), "tau": torch.zeros(nf, dtype=torch.float64).pin_memory()}
     ptr = lambda t: C.c_void_p(t.data_ptr())
     h = hdev   # reuse the handle (its buffers are already sized); ownership/comm state is kept
     lib = h.lib
@@ -571,90 +624,136 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
     nnz = [C.c_int64(0) for _ in range(3)]
     sec = C.c_double(0.0)
 
-    def step(with_mesh=True):
-        if with_mesh:
-            h.check(lib.fcfv_set_mesh(h._h, nel, nf, ptr(P["e2f"]), ptr(P["bc"]), ptr(P["Ω"]), ptr(P["n_x"]), ptr(P["n_y"]),
+    def three_calls(h, P, Dd, out, nel, with_mesh=True, ownership=True, cached=True):
+        def refresh():
+            h.check(lib.fcfv_update_fields(h._h, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, ptr(out["tau"])))
+        if with_mesh:       # first call on an FCFV_Mesh object (or a driver that rebuilds its mesh): the mesh goes up
+            h.check(lib.fcfv_set_mesh(h._h, nel, P["bc"].numel(), ptr(P["e2f"]), ptr(P["bc"]), ptr(P["Ω"]), ptr(P["n_x"]), ptr(P["n_y"]),
                                       ptr(P["Γ"]), ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel))
-            if world > 1:
+            if world > 1 and ownership:
                 h.check(lib.fcfv_set_ownership(h._h, ptr(P["eo"]), ptr(P["fo"]), nel_g, nf_g, None))
-        else:   # what the shim does on a mesh it has already uploaded: refresh the mutable fields only
-            h.check(lib.fcfv_update_fields(h._h, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, None))
-        h.check(lib.fcfv_compute_local(h._h, form, 1.0, ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]),
-                                       ptr(out["alpha"]), ptr(out["beta"]), ptr(out["Z"]), ptr(out["tau"])))
-        h.check(lib.fcfv_assemble(h._h, VARIANT, form, 1.0, None, None, None, ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), ptr(Dd["sxx"]),
-                                  ptr(Dd["syy"]), ptr(Dd["sxy"]), ptr(Dd["syx"]), 0, C.byref(nnz[0]), C.byref(nnz[1]),
-                                  C.byref(nnz[2]), C.byref(sec)))
-        h.check(lib.fcfv_residuals(h._h, form, L.TAU_FACE, ptr(Dd["Vxh"]), ptr(Dd["Vyh"]), ptr(Dd["Pe"]), None, None, None,
-                                   ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), ptr(Dd["sxx"]),
-                                   ptr(Dd["syy"]), ptr(Dd["sxy"]), ptr(Dd["syx"]), C.c_void_p(norms.ctypes.data), None, None, None))
+        sig = [ptr(Dd[k]) for k in ("sxx", "syy", "sxy", "syx")]
+        loc = [ptr(out[k]) for k in ("alpha", "beta", "Z")]
+        # ComputeFCFV
+        if cached and not with_mesh:      # the shims skip this right after they have uploaded the mesh themselves
+            h.check(lib.fcfv_new_epoch(h._h))
+        refresh()
+        h.check(lib.fcfv_compute_local_ex(h._h, form, 1.0, ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), *sig,
+                                          *loc, ptr(out["tau"])))
+        # ElementAssemblyLoopNEW
+        refresh()
+        h.check(lib.fcfv_assemble(h._h, VARIANT, form, 1.0, *loc, ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), *sig, 0, C.byref(nnz[0]),
+                                  C.byref(nnz[1]), C.byref(nnz[2]), C.byref(sec)))
+        # ComputeResidualsFCFV_Stokes_o1
+        refresh()
+        h.check(lib.fcfv_residuals(h._h, form, L.TAU_FACE, ptr(Dd["Vxh"]), ptr(Dd["Vyh"]), ptr(Dd["Pe"]), *loc, ptr(Dd["sex"]),
+                                   ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), *sig, C.c_void_p(norms.ctypes.data), None, None, None))
+
+    def step(with_mesh=True, cached=True):
+        three_calls(h, P, Dd, out, nel, with_mesh, True, cached)
+
+    def timed_host(fn, reps):
+        fn()
+        barrier()
+        h.transfer_stats(reset=True)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        h.sync()
+        dt = time.perf_counter() - t0
+        up, down, hit = h.transfer_stats(reset=True)
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            b = torch.tensor([up, down, hit], dtype=torch.int64, device="cuda")
+            dist.all_reduce(b)                      # whole job: bytes of all ranks
+            up, down, hit = (int(x) for x in b.tolist())
+        return dt / reps, up // reps, down // reps, hit // reps
 
     h.set_async(False)
-    # set_mesh 128 nel + 8 nf | compute_local 16 nel + 16 nf | assemble 48 nf | residuals 24 nel + 64 nf
-    h2d = 168 * nel + 136 * nf + ((nel + nf) if world > 1 else 0)
-    d2h = 8 * (7 * nel + nf) + 72 + 48 + 4     # alpha/beta/Z/tau + nnz totals + norms + validation flag
+    h.upload_cache(True)
     steps = max(1, min(args.steps, 3))
-    step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    h.sync()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    # same pass on a mesh that is already resident (second and later calls on one FCFV_Mesh object)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step(with_mesh=False)
-    h.sync()
-    dt2 = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt2], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt2 = float(t.item())
-    # the same pass through the single-call entry fcfv_pass (a driver that replaces its three calls by one): every array
-    # uploaded once, alpha/beta/Z/tau downloaded on a second stream while the remaining inputs go up
+    progress("e2e: three calls with set_mesh")
+    dt, h2d, d2h, hit = timed_host(step, steps)
+    # same pass on a mesh that is already resident (second and later passes on one FCFV_Mesh object)
+    progress("e2e: three calls, mesh resident")
+    dt2, h2d2, d2h2, hit2 = timed_host(lambda: step(with_mesh=False), steps)
+    # the three calls with the upload cache off (every call sends everything it is given: what round 1 measured,
+    # with alpha / beta / Z now also going back up as the shims pass them)
+    h.upload_cache(False)
+    progress("e2e: three calls, cache off")
+    dt3, h2d3, d2h3, _ = timed_host(lambda: step(cached=False), 1)
+    h.upload_cache(True)
+    # the same pass through the single-call entry fcfv_pass (a driver that replaces its three calls by one)
     def fused(with_mesh=True):
         if with_mesh:
             h.check(lib.fcfv_set_mesh(h._h, nel, nf, ptr(P["e2f"]), ptr(P["bc"]), ptr(P["Ω"]), ptr(P["n_x"]), ptr(P["n_y"]),
                                       ptr(P["Γ"]), ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel))
             if world > 1:
                 h.check(lib.fcfv_set_ownership(h._h, ptr(P["eo"]), ptr(P["fo"]), nel_g, nf_g, None))
-        else:
-            h.check(lib.fcfv_update_fields(h._h, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, None))
+        h.check(lib.fcfv_new_epoch(h._h))
+        h.check(lib.fcfv_update_fields(h._h, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, None))
         h.check(lib.fcfv_pass(h._h, VARIANT, form, 1.0, L.TAU_FACE, ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]),
                               ptr(Dd["sxx"]), ptr(Dd["syy"]), ptr(Dd["sxy"]), ptr(Dd["syx"]), ptr(Dd["Vxh"]), ptr(Dd["Vyh"]), ptr(Dd["Pe"]),
                               ptr(out["alpha"]), ptr(out["beta"]), ptr(out["Z"]), ptr(out["tau"]), 0, C.byref(nnz[0]), C.byref(nnz[1]),
                               C.byref(nnz[2]), C.c_void_p(norms.ctypes.data)))
     fused_res = {}
     for tag, wm in (("with_mesh", True), ("mesh_resident", False)):
-        fused(wm)
+        progress(f"e2e: fcfv_pass {tag}")
+        dtf, upf, downf, _ = timed_host(lambda: fused(wm), steps)
+        fused_res[tag] = {"value": total_el / dtf / 1e6, "ms_per_step": 1e3 * dtf, "h2d_bytes_per_step": int(upf), "d2h_bytes_per_step": int(downf)}
+    fused_res["note"] = ("fcfv_pass: one call instead of three; not the headline because a driver has to change three lines to use it")
+    # N > 1: the same three calls through ONE multi-GPU handle (fcfv_create_multi) in one process -- what a single-process
+    # driver of the reference gets.  Rank 0 drives all GPUs of the box on a stand-alone S(1000) mesh (4 M elements: the
+    # host-side partitioning and scatter of one process bound this figure, not the GPUs); the other ranks wait on a
+    # host-side (gloo) barrier so that their GPUs are idle.  Partitioning and scatter are inside the timed region.
+    single = None
+    if world > 1:
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            fused(wm)
-        h.sync()
-        dtf = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dtf], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dtf = float(t.item())
-        fused_res[tag] = {"value": total_el * steps / dtf / 1e6, "ms_per_step": 1e3 * dtf / steps}
-    fused_h2d = 24 * nel + 64 * nf
-    fused_res["with_mesh"]["h2d_bytes_per_step"] = int(fused_h2d + 128 * nel + 8 * nf + ((nel + nf) if world > 1 else 0))
-    fused_res["mesh_resident"]["h2d_bytes_per_step"] = int(fused_h2d + 24 * nel)
-    fused_res["note"] = ("fcfv_pass: one call instead of three, each array uploaded once, D2H of alpha/beta/Z/tau concurrent with the "
-                         "uploads; not the headline because a driver has to change three lines to use it")
-    return {"value": total_el * steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        gl = dist.new_group(backend="gloo")
+        if rank == 0:
+            progress("e2e: one multi-GPU handle in one process")
+            try:
+                ns = min(1000, args.n or N_DEFAULT)
+                hsm = api.Handle(0)
+                hsm.generate_structured(ns, 0, ns, setting="solkz", tau_r=10.0)
+                Ps = {k: pin(v) for k, v in hsm.get_mesh().items()}
+                Ds = {k: pin(v) for k, v in hsm.get_data().items()}
+                nels, nfs = hsm.nel, hsm.nf
+                hsm.close()
+                outs = {"alpha": torch.empty(nels, dtype=torch.float64).pin_memory(), "beta": torch.empty(2 * nels, dtype=torch.float64).pin_memory(),
+                        "Z": torch.empty(4 * nels, dtype=torch.float64).pin_memory(), "tau": torch.zeros(nfs, dtype=torch.float64).pin_memory()}
+                hm = api.Handle(ngpus=world)
+                three_calls(hm, Ps, Ds, outs, nels, True, False, False)
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    three_calls(hm, Ps, Ds, outs, nels, True, False, False)
+                hm.sync()
+                dts = (time.perf_counter() - t0) / 2
+                info, psec = hm.partition_info()
+                single = {"value": nels / dts / 1e6, "unit": UNIT, "ms_per_step": 1e3 * dts, "elements": int(nels), "gpus": world,
+                          "partition_seconds": psec, "ghost_elements": int(sum(i[0] - i[2] for i in info)),
+                          "note": "one process, one handle over all GPUs: fcfv_set_mesh partitions on the host (C++), every call "
+                                  "scatters its global arrays; bound by the host-side gather and PCIe of one process"}
+                hm.close()
+            except Exception as ex:      # reported, not fatal: the per-rank figures above stand on their own
+                single = {"error": str(ex)[:300]}
+        dist.barrier(group=gl)
+        barrier()
+    return {"value": total_el / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "upload_cache_hit_bytes_per_step": int(hit), "steps": steps, "ms_per_step": 1e3 * dt,
+            "mesh_resident": {"value": total_el / dt2 / 1e6, "ms_per_step": 1e3 * dt2, "h2d_bytes_per_step": int(h2d2),
+                              "d2h_bytes_per_step": int(d2h2), "upload_cache_hit_bytes_per_step": int(hit2),
+                              "note": "no fcfv_set_mesh (mesh uploaded once per FCFV_Mesh object)"},
+            "cache_off": {"value": total_el / dt3 / 1e6, "ms_per_step": 1e3 * dt3, "h2d_bytes_per_step": int(h2d3), "d2h_bytes_per_step": int(d2h3),
+                          "note": "same calls with fcfv_upload_cache(0): every call sends every array it is given"},
+            "single_process_multi_gpu_handle": single,
             "fused_pass": fused_res,
-            "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "mesh_resident": {"value": total_el * steps / dt2 / 1e6, "ms_per_step": 1e3 * dt2 / steps,
-                              "h2d_bytes_per_step": int(h2d - (128 * nel + 8 * nf) + 24 * nel - ((nel + nf) if world > 1 else 0)),
-                              "note": "fcfv_update_fields instead of fcfv_set_mesh (mesh uploaded once per FCFV_Mesh object)"},
-            "api": "fcfv_set_mesh + fcfv_compute_local + fcfv_assemble + fcfv_residuals, pinned host buffers, CSR left device-resident"}
+            "api": "per pass: fcfv_set_mesh, then what the shims issue for ComputeFCFV / ElementAssemblyLoopNEW / ComputeResidualsFCFV_Stokes_o1 "
+                   "(fcfv_new_epoch + fcfv_update_fields + fcfv_compute_local_ex | fcfv_update_fields + fcfv_assemble | fcfv_update_fields + "
+                   "fcfv_residuals) with pinned host buffers and the upload cache on; byte counts from fcfv_transfer_stats (all ranks); "
+                   "CSR left device-resident"}
 
 
 _RESULT_FD = None

@@ -43,6 +43,12 @@ class _Arg:
 
     def __init__(self):
         self.keep = []
+        self.temp = False         # some argument had to be converted / copied: its address means nothing after the call
+
+    def done(self, h):
+        """After the call: temporaries die here, so the library's upload cache must not remember their addresses."""
+        if self.temp:
+            h.new_epoch()
 
     def d(self, a, n=None):       # float64 input
         return self._conv(a, np.float64, n)
@@ -71,6 +77,8 @@ class _Arg:
             flat = np.ascontiguousarray(arr)
         if n is not None and flat.size < n:
             raise ValueError(f"array has {flat.size} entries, need {n}")
+        if not (isinstance(a, np.ndarray) and np.shares_memory(flat, a)):
+            self.temp = True
         self.keep.append(flat)
         return C.c_void_p(flat.ctypes.data)
 
@@ -195,6 +203,22 @@ class Handle:
         nt = 0 if taue is None else int(np.size(taue))
         self.check(self.lib.fcfv_update_fields(self._h, a.d(ke, self.nel), a.d(delta, self.nel), a.d(taue, self.nel),
                                                nt, a.d(tau, self.nf)))
+        a.done(self)
+
+    # -- upload cache / transfer counters ---------------------------------------------------------
+    def upload_cache(self, on=True):
+        """See ``fcfv_upload_cache``: skip uploads of host arrays the device already mirrors (same address, size, epoch
+        and sampled fingerprint)."""
+        self.check(self.lib.fcfv_upload_cache(self._h, int(bool(on))))
+
+    def new_epoch(self):
+        self.check(self.lib.fcfv_new_epoch(self._h))
+
+    def transfer_stats(self, reset=False):
+        """(h2d_bytes, d2h_bytes, cache_hit_bytes) moved / saved by this handle so far."""
+        v = [C.c_int64(0) for _ in range(3)]
+        self.check(self.lib.fcfv_transfer_stats(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), int(bool(reset))))
+        return tuple(x.value for x in v)
 
     def set_ownership(self, elem_owned, face_owned, nel_global=0, nf_global=0, tau_ref=None):
         a = _Arg()
@@ -340,6 +364,11 @@ class Handle:
 # ---------------------------------------------------------------------------------------------
 # GPUs a mesh is spread over when its handle is created (the reference's functions have no such argument):
 # ``mesh.ngpus`` if set, else this default (environment FCFV_NGPUS, use_gpus(n)).
+# The reference's drivers pass the same arrays to ComputeFCFV, ElementAssemblyLoop[NEW] and the residual function; with
+# this switch on (default) a handle made by handle_for() skips uploads of arrays the GPU already mirrors.  A new epoch
+# starts at every ComputeFCFV; arrays modified IN PLACE between ComputeFCFV and the calls that follow it need
+# ``handle_for(mesh).new_epoch()`` (no driver of the reference does that).
+CACHE_INPUTS = True
 DEFAULT_GPUS = int(os.environ.get("FCFV_NGPUS", "1"))
 
 
@@ -372,6 +401,7 @@ def handle_for(mesh, device=None) -> Handle:
     if h is None:
         ngpus = int(getattr(mesh, "ngpus", None) or DEFAULT_GPUS)
         h = Handle(0 if device is None else device, ngpus=ngpus)
+        h.upload_cache(CACHE_INPUTS)
         h.set_mesh(mesh)
         mesh._fcfv_handle = h
         if ngpus == 1 and h.nel >= 100_000 and getattr(mesh, "elem_owned", None) is None:
@@ -410,14 +440,20 @@ def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τ
     arrays and τr are accepted and unused, as in the reference."""
     if mesh.τ is None:
         mesh.τ = np.zeros(mesh.nf)
+    fresh = getattr(mesh, "_fcfv_handle", None) is None
     h = handle_for(mesh)
+    if not fresh:            # first call of a driver pass: whatever the caller changed since the last one goes up again
+        h.new_epoch()        # (a handle made just now has uploaded the mesh fields in this very call)
     _refresh(mesh, h)
     nel, nf = h.nel, h.nf
     a = _Arg()
     al, be, Z = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")
     tau = np.empty(nf)
-    h.check(h.lib.fcfv_compute_local(h._h, formulation_id(Formulation), float(A), a.d(sex, nel), a.d(sey, nel),
-                                     a.d(VxDir, nf), a.d(VyDir, nf), _out(al), _out(be), _out(Z), _out(tau)))
+    # the Neumann arrays the reference's ComputeFCFV receives and ignores go up while the results come down
+    h.check(h.lib.fcfv_compute_local_ex(h._h, formulation_id(Formulation), float(A), a.d(sex, nel), a.d(sey, nel),
+                                        a.d(VxDir, nf), a.d(VyDir, nf), a.d(SxxNeu, nf), a.d(SyyNeu, nf), a.d(SxyNeu, nf),
+                                        a.d(SyxNeu, nf), _out(al), _out(be), _out(Z), _out(tau)))
+    a.done(h)
     mesh.τ = tau
     return al, be, Z
 
@@ -433,6 +469,7 @@ def _assemble(variant, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNeu, σxyNeu
                                 a.d(Ζ, 4 * nel), a.d(VxDir, nf), a.d(VyDir, nf), a.d(σxxNeu, nf), a.d(σyyNeu, nf),
                                 a.d(σxyNeu, nf), a.d(σyxNeu, nf), int(bool(want_muu)), C.byref(nnz[0]), C.byref(nnz[1]),
                                 C.byref(nnz[2]), C.byref(sec)))
+    a.done(h)
     if not export:   # result stays on the device (fcfv_device_csr / Handle.export_*)
         return h, tuple(x.value for x in nnz), sec.value
     Kuu = h.export_scipy_csc(_L.KUU)
@@ -506,6 +543,7 @@ def ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey, VxD
                                  a.d(Pe, nel), a.d(ae, nel), a.d(be, 2 * nel), a.d(ze, 4 * nel), a.d(sex, nel), a.d(sey, nel),
                                  a.d(VxDir, nf), a.d(VyDir, nf), a.d(SxxNeu, nf), a.d(SyyNeu, nf), a.d(SxyNeu, nf),
                                  a.d(SyxNeu, nf), _out(norms), _out(Fx), _out(Fy), _out(Fg2)))
+    a.done(h)
     if verbose:
         for line, v in zip(_RES_LINES, norms):
             print(line % v)

@@ -28,14 +28,24 @@ struct Id128 { char b[128]; };   // ncclUniqueId
 
 enum { T_LOCAL = 0, T_COEF, T_COUNT, T_SCAN, T_FILL, T_RES_ELEM, T_RES_FACE, T_REDUCE, T_PH, T_OTHER, kNumTimers };
 static const char* const kTimerNames[kNumTimers] = {"k_local", "k_elem_coef", "k_asm_count", "k_scan", "k_asm_fill",
-                                                    "k_res_elem", "k_res_face", "k_reduce_partials", "k_ph", "other"};
+                                                    "k_res_elem", "k_res_late", "k_reduce_partials", "k_ph", "other"};
 struct TimerRec { int id; cudaEvent_t a, b; };
 
 namespace {
 
+// The host array a device buffer currently mirrors (upload cache, fcfv_upload_cache): address, size, a sampled
+// fingerprint of the contents and the epoch the record was made in.
+struct HostMirror {
+    const void* ptr = nullptr;
+    size_t bytes = 0;
+    uint64_t fp = 0;
+    long long epoch = -1;
+};
+
 struct DBuf {   // device buffer that only grows
     void* p = nullptr;
     size_t cap = 0;
+    HostMirror hm;
 };
 
 struct Csr {
@@ -102,7 +112,7 @@ struct fcfv_handle {
     bool have_elem_owned = false, have_face_owned = false, have_tau_ref = false;
 
     // mesh
-    DBuf e2f, bc, f2e, fconn, fbc, ebc, Om, G, nx, ny, ke, dl, taue, tau, elem_owned, face_owned, tau_ref;
+    DBuf e2f, bc, f2e, fconn, fbc, ebc, eadj, Om, G, nx, ny, ke, dl, taue, tau, elem_owned, face_owned, tau_ref;
     // data
     DBuf sex, sey, VxDir, VyDir, sxx, syy, sxy, syx, Vxh, Vyh, Pe;
     // local coefficients
@@ -130,8 +140,13 @@ struct fcfv_handle {
     long long timer_calls[kNumTimers] = {0};
     // CUDA graph of one pass (fcfv_run_pipeline): replayed while nothing it captured has changed
     cudaGraphExec_t graph_exec = nullptr;
+    bool graph_disabled = false;          // capture failed with a communicator attached: run directly
     long long graph_key[7] = {-1, -1, -1, -1, -1, -1, -1};   // variant, formulation, tau_mode + flags, alloc epoch, nel, nf, bits of A
     long long alloc_epoch = 0;                           // bumped whenever a device buffer is (re)allocated
+    // upload cache (fcfv_upload_cache / fcfv_new_epoch) and transfer counters (fcfv_transfer_stats)
+    bool cache_on = false;
+    long long epoch = 0;
+    long long h2d_bytes = 0, d2h_bytes = 0, cache_hit_bytes = 0, cache_hits = 0;
     // nccl
     NcclApi nccl;
     void* comm = nullptr;
@@ -361,9 +376,12 @@ bool is_device(const void* p) {
 // side when the call returns.
 int copy(fcfv_t* h, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return FCFV_OK;
+    const bool dd = is_device(dst), sd = is_device(src);
+    if (dd && !sd) h->h2d_bytes += (long long)bytes;       // what actually crosses PCIe (fcfv_transfer_stats)
+    if (sd && !dd) h->d2h_bytes += (long long)bytes;
     if (bytes >= h->staged_min_bytes) {
-        if (is_pageable_host(src) && is_device(dst)) return copy_staged(h, dst, const_cast<void*>(src), bytes, true);
-        if (is_pageable_host(dst) && is_device(src)) return copy_staged(h, const_cast<void*>(src), dst, bytes, false);
+        if (dd && is_pageable_host(src)) return copy_staged(h, dst, const_cast<void*>(src), bytes, true);
+        if (sd && is_pageable_host(dst)) return copy_staged(h, const_cast<void*>(src), dst, bytes, false);
     }
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream));
     return FCFV_OK;
@@ -371,8 +389,57 @@ int copy(fcfv_t* h, void* dst, const void* src, size_t bytes) {
 
 int upload(fcfv_t* h, DBuf& b, const void* src, size_t bytes) {
     TRY(ensure(h, b, bytes));
+    b.hm.epoch = -1;
     return copy(h, b.p, src, bytes);
 }
+
+// ---- upload cache -------------------------------------------------------------------------------
+// A driver of the reference hands the same arrays to ComputeFCFV, ElementAssemblyLoop[NEW] and
+// ComputeResidualsFCFV_Stokes_o1 (VxDir / VyDir three times, the Neumann arrays and the sources twice, and alpha /
+// beta / Z come back as arguments after they were returned, SolKzFCFV.jl:150-205).  With the cache on, a device
+// buffer remembers which host array it mirrors; an upload of the same address and size inside the same epoch is
+// skipped when a sampled fingerprint of the host contents still matches.  The caller vouches for "not modified in
+// place inside an epoch" (fcfv_new_epoch starts a new one; fcfv_set_mesh does so implicitly); the fingerprint is a
+// safety net that catches wholesale changes, not a proof.  Off by default.
+uint64_t fingerprint(const void* p, size_t bytes) {
+    const unsigned char* c = static_cast<const unsigned char*>(p);
+    uint64_t hsh = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
+    auto mix = [&](uint64_t v) { hsh ^= v + 0x9E3779B97F4A7C15ull + (hsh << 6) + (hsh >> 2); hsh *= 0xFF51AFD7ED558CCDull; hsh ^= hsh >> 33; };
+    const size_t nw = bytes / 8;
+    auto word = [&](size_t k) { uint64_t v; memcpy(&v, c + 8 * k, 8); return v; };
+    if (nw <= 8192) {
+        for (size_t k = 0; k < nw; k++) mix(word(k));
+    } else {
+        for (size_t k = 0; k < 256; k++) { mix(word(k)); mix(word(nw - 1 - k)); }
+        const size_t stride = nw / 4096;
+        for (size_t k = 0; k < 4096; k++) mix(word(k * stride + (k * 7) % stride));     // one word per 1/4096th, at varying offsets
+    }
+    for (size_t k = 8 * nw; k < bytes; k++) mix(c[k]);
+    return hsh;
+}
+
+bool cache_hit(fcfv_t* h, const DBuf& b, const void* src, size_t bytes) {
+    return h->cache_on && b.hm.epoch == h->epoch && b.hm.ptr == src && b.hm.bytes == bytes && b.cap >= bytes && !is_device(src) &&
+           fingerprint(src, bytes) == b.hm.fp;
+}
+
+// host -> device copy of a caller's array into a handle-owned buffer, skipped when the buffer already mirrors it
+int upload_cached(fcfv_t* h, DBuf& b, const void* src, size_t bytes) {
+    if (bytes == 0) return ensure(h, b, bytes);
+    if (cache_hit(h, b, src, bytes)) { h->cache_hits++; h->cache_hit_bytes += (long long)bytes; return FCFV_OK; }
+    TRY(ensure(h, b, bytes));
+    b.hm.epoch = -1;
+    TRY(copy(h, b.p, src, bytes));
+    if (h->cache_on && !is_device(src)) b.hm = HostMirror{src, bytes, fingerprint(src, bytes), h->epoch};
+    return FCFV_OK;
+}
+
+// after a COMPLETED device -> host copy of a whole buffer: the destination is a mirror of it
+void mirror_download(fcfv_t* h, DBuf& b, const void* dst, size_t bytes) {
+    if (h->cache_on && dst && bytes && !is_device(dst)) b.hm = HostMirror{dst, bytes, fingerprint(dst, bytes), h->epoch};
+}
+
+void new_epoch(fcfv_t* h) { h->epoch++; }
 
 int sync(fcfv_t* h) {
     CU(cudaStreamSynchronize(h->stream));
@@ -389,7 +456,7 @@ MeshView mesh_view(fcfv_t* h) {
     MeshView M;
     M.nel = (int)h->nel; M.nf = (int)h->nf;
     M.e2f = P<int>(h->e2f); M.bc = P<int8_t>(h->bc); M.f2e = P<int2>(h->f2e);
-    M.fconn = P<int4>(h->fconn); M.fbc = P<int>(h->fbc); M.ebc = P<int>(h->ebc);
+    M.fconn = P<int4>(h->fconn); M.fbc = P<int>(h->fbc); M.ebc = P<int>(h->ebc); M.eadj = P<int>(h->eadj);
     M.Om = P<double>(h->Om); M.G = P<double>(h->G); M.nx = P<double>(h->nx); M.ny = P<double>(h->ny);
     M.ke = P<double>(h->ke); M.dl = P<double>(h->dl); M.taue = P<double>(h->taue); M.tau = P<double>(h->tau);
     M.elem_owned = h->have_elem_owned ? P<uint8_t>(h->elem_owned) : nullptr;
@@ -435,7 +502,8 @@ int build_fconn(fcfv_t* h) {
     LAUNCH(h, k_fconn, nblocks(nf, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), P<int2>(h->f2e), (int)nel, (int)nf, P<int4>(h->fconn),
            P<int>(h->fbc));
     TRY(ensure(h, h->ebc, sizeof(int) * nel));
-    LAUNCH(h, k_ebc, nblocks(nel, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), P<int2>(h->f2e), (int)nel, P<int>(h->ebc));
+    TRY(ensure(h, h->eadj, sizeof(int) * nel));
+    LAUNCH(h, k_ebc, nblocks(nel, 256), 256, P<int>(h->e2f), P<int8_t>(h->bc), P<int2>(h->f2e), (int)nel, P<int>(h->ebc), P<int>(h->eadj));
     return FCFV_OK;
 }
 
@@ -499,7 +567,7 @@ int fcfv_destroy(fcfv_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
-    DBuf* all[] = {&h->e2f, &h->bc, &h->f2e, &h->fconn, &h->fbc, &h->ebc, &h->Om, &h->G, &h->nx, &h->ny, &h->ke, &h->dl, &h->taue, &h->tau,
+    DBuf* all[] = {&h->e2f, &h->bc, &h->f2e, &h->fconn, &h->fbc, &h->ebc, &h->eadj, &h->Om, &h->G, &h->nx, &h->ny, &h->ke, &h->dl, &h->taue, &h->tau,
                    &h->elem_owned, &h->face_owned, &h->tau_ref, &h->sex, &h->sey, &h->VxDir, &h->VyDir, &h->sxx,
                    &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
                    &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,
@@ -530,6 +598,33 @@ int fcfv_sync(fcfv_t* h) {
     if (!h) return FCFV_ERR_INVALID;
     if (h->multi) return multi_sync(h);
     return sync(h);
+}
+
+int fcfv_upload_cache(fcfv_t* h, int on) {
+    if (!h) return FCFV_ERR_INVALID;
+    h->cache_on = on != 0;
+    new_epoch(h);
+    return FCFV_OK;
+}
+
+int fcfv_new_epoch(fcfv_t* h) {
+    if (!h) return FCFV_ERR_INVALID;
+    new_epoch(h);
+    return FCFV_OK;
+}
+
+int fcfv_transfer_stats(fcfv_t* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* cache_hit_bytes, int reset) {
+    if (!h) return FCFV_ERR_INVALID;
+    long long up = h->h2d_bytes, down = h->d2h_bytes, hit = h->cache_hit_bytes;
+    if (h->multi) multi_each(h, [&](fcfv_t* q) { up += q->h2d_bytes; down += q->d2h_bytes; hit += q->cache_hit_bytes; });
+    if (h2d_bytes) *h2d_bytes = up;
+    if (d2h_bytes) *d2h_bytes = down;
+    if (cache_hit_bytes) *cache_hit_bytes = hit;
+    if (reset) {
+        h->h2d_bytes = h->d2h_bytes = h->cache_hit_bytes = 0;
+        if (h->multi) multi_each(h, [&](fcfv_t* q) { q->h2d_bytes = q->d2h_bytes = q->cache_hit_bytes = 0; });
+    }
+    return FCFV_OK;
 }
 
 int fcfv_host_register(fcfv_t* h, void* ptr, int64_t bytes) {
@@ -627,6 +722,7 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
         return fail(h, FCFV_ERR_INVALID, "fcfv_set_mesh: null mesh array");
     if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
     h->have_mesh = false; h->have_local = false;
+    new_epoch(h);        // a new mesh: nothing that is resident mirrors a host array any more
     // data arrays are sized for the mesh they were set on: a new mesh invalidates them (sources, face data and
     // solution have to be set again; their buffers may be too small for the new nel / nf)
     if (nel != h->nel || nf != h->nf) h->have_sources = h->have_face_data = h->have_solution = false;
@@ -647,11 +743,13 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     TRY(upload(h, h->nx, nx, sizeof(double) * 3 * nel));
     TRY(upload(h, h->ny, ny, sizeof(double) * 3 * nel));
     TRY(upload(h, h->G, Gamma, sizeof(double) * 3 * nel));
-    TRY(upload(h, h->ke, ke, sizeof(double) * nel));
-    TRY(upload(h, h->dl, delta, sizeof(double) * nel));
+    // the mutable fields are remembered by the upload cache: the field refresh of the first ComputeFCFV on this mesh
+    // (fcfv_update_fields in the same epoch) does not send them a second time
+    TRY(upload_cached(h, h->ke, ke, sizeof(double) * nel));
+    TRY(upload_cached(h, h->dl, delta, sizeof(double) * nel));
     TRY(ensure(h, h->taue, sizeof(double) * nel));
-    if (taue) TRY(copy(h, h->taue.p, taue, sizeof(double) * nel));
-    else CU(cudaMemsetAsync(h->taue.p, 0, sizeof(double) * nel, h->stream));
+    if (taue) TRY(upload_cached(h, h->taue, taue, sizeof(double) * nel));
+    else { h->taue.hm.epoch = -1; CU(cudaMemsetAsync(h->taue.p, 0, sizeof(double) * nel, h->stream)); }
     TRY(alloc_mesh_dependent(h));
     CU(cudaMemsetAsync(h->tau.p, 0, sizeof(double) * nf, h->stream));
     TRY(build_f2e(h));
@@ -672,10 +770,14 @@ int fcfv_update_fields(fcfv_t* h, const double* ke, const double* delta, const d
     if (h->multi) return multi_update_fields(h, ke, delta, taue, ntaue, tau);
     CU(cudaSetDevice(h->device));
     if (taue && ntaue < h->nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel", (long long)ntaue);
-    if (ke) TRY(copy(h, h->ke.p, ke, sizeof(double) * h->nel));
-    if (delta) { TRY(copy(h, h->dl.p, delta, sizeof(double) * h->nel)); h->delta_dirty = true; }
-    if (taue) TRY(copy(h, h->taue.p, taue, sizeof(double) * h->nel));
-    if (tau) TRY(copy(h, h->tau.p, tau, sizeof(double) * h->nf));
+    if (ke) TRY(upload_cached(h, h->ke, ke, sizeof(double) * h->nel));
+    if (delta) {
+        const long long hits = h->cache_hits;
+        TRY(upload_cached(h, h->dl, delta, sizeof(double) * h->nel));
+        if (h->cache_hits == hits) h->delta_dirty = true;
+    }
+    if (taue) TRY(upload_cached(h, h->taue, taue, sizeof(double) * h->nel));
+    if (tau) TRY(upload_cached(h, h->tau, tau, sizeof(double) * h->nf));
     return finish(h);
 }
 
@@ -693,6 +795,11 @@ int fcfv_set_ownership(fcfv_t* h, const uint8_t* elem_owned, const uint8_t* face
     if (tau_ref) TRY(upload(h, h->tau_ref, tau_ref, sizeof(double) * h->nel));
     h->nel_global = nel_global > 0 ? nel_global : h->nel;
     h->nf_global = nf_global > 0 ? nf_global : h->nf;
+    // the kernels read the masks from the tag words they load anyway
+    LAUNCH(h, k_pack_owned, nblocks(h->nel, 256), 256, (int)h->nel, elem_owned ? P<uint8_t>(h->elem_owned) : nullptr, kOwnedElem, P<int>(h->ebc));
+    LAUNCH(h, k_pack_owned, nblocks(h->nf, 256), 256, (int)h->nf, face_owned ? P<uint8_t>(h->face_owned) : nullptr, kOwnedFace, P<int>(h->fbc));
+    LAUNCH(h, k_pack_face_owned, nblocks(h->nel, 256), 256, (int)h->nel, P<int>(h->e2f), face_owned ? P<uint8_t>(h->face_owned) : nullptr, P<int>(h->eadj));
+    CU(cudaGetLastError());
     return finish(h);
 }
 
@@ -855,8 +962,8 @@ int fcfv_set_sources(fcfv_t* h, const double* sex, const double* sey) {
     if (h->multi) return multi_set_sources(h, sex, sey);
     CU(cudaSetDevice(h->device));
     if (!sex || !sey) return fail(h, FCFV_ERR_INVALID, "fcfv_set_sources: null array");
-    TRY(upload(h, h->sex, sex, sizeof(double) * h->nel));
-    TRY(upload(h, h->sey, sey, sizeof(double) * h->nel));
+    TRY(upload_cached(h, h->sex, sex, sizeof(double) * h->nel));
+    TRY(upload_cached(h, h->sey, sey, sizeof(double) * h->nel));
     h->have_sources = true;
     return finish(h);
 }
@@ -873,8 +980,8 @@ int fcfv_set_face_data(fcfv_t* h, const double* VxDir, const double* VyDir, cons
     for (int k = 0; k < 6; k++) {
         const bool fresh = dst[k]->cap < b;
         TRY(ensure(h, *dst[k], b));
-        if (src[k]) TRY(copy(h, dst[k]->p, src[k], b));
-        else if (fresh || !h->have_face_data) CU(cudaMemsetAsync(dst[k]->p, 0, b, h->stream));
+        if (src[k]) TRY(upload_cached(h, *dst[k], src[k], b));
+        else if (fresh || !h->have_face_data) { dst[k]->hm.epoch = -1; CU(cudaMemsetAsync(dst[k]->p, 0, b, h->stream)); }
     }
     h->have_face_data = true;
     return finish(h);
@@ -886,9 +993,9 @@ int fcfv_set_solution(fcfv_t* h, const double* Vxh, const double* Vyh, const dou
     if (h->multi) return multi_set_solution(h, Vxh, Vyh, Pe);
     CU(cudaSetDevice(h->device));
     if (!Vxh || !Vyh || !Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_set_solution: null array");
-    TRY(upload(h, h->Vxh, Vxh, sizeof(double) * h->nf));
-    TRY(upload(h, h->Vyh, Vyh, sizeof(double) * h->nf));
-    TRY(upload(h, h->Pe, Pe, sizeof(double) * h->nel));
+    TRY(upload_cached(h, h->Vxh, Vxh, sizeof(double) * h->nf));
+    TRY(upload_cached(h, h->Vyh, Vyh, sizeof(double) * h->nf));
+    TRY(upload_cached(h, h->Pe, Pe, sizeof(double) * h->nel));
     h->have_solution = true;
     return finish(h);
 }
@@ -899,9 +1006,9 @@ int fcfv_set_local(fcfv_t* h, const double* alpha, const double* beta, const dou
     if (h->multi) return multi_set_local(h, alpha, beta, Z);
     CU(cudaSetDevice(h->device));
     if (!alpha || !beta || !Z) return fail(h, FCFV_ERR_INVALID, "fcfv_set_local: null array");
-    TRY(copy(h, h->alpha.p, alpha, sizeof(double) * h->nel));
-    TRY(copy(h, h->beta.p, beta, sizeof(double) * 2 * h->nel));
-    TRY(copy(h, h->Z.p, Z, sizeof(double) * 4 * h->nel));
+    TRY(upload_cached(h, h->alpha, alpha, sizeof(double) * h->nel));
+    TRY(upload_cached(h, h->beta, beta, sizeof(double) * 2 * h->nel));
+    TRY(upload_cached(h, h->Z, Z, sizeof(double) * 4 * h->nel));
     h->have_local = true;
     return finish(h);
 }
@@ -923,6 +1030,7 @@ int fcfv_run_local(fcfv_t* h, int formulation, double A) {
         TLAUNCH(h, T_LOCAL, k_local<kSymmetricGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey),
                P<double>(h->VxDir), P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z), P<double>(h->tau));
     CU(cudaGetLastError());
+    h->alpha.hm.epoch = h->beta.hm.epoch = h->Z.hm.epoch = h->tau.hm.epoch = -1;     // rewritten on the device
     h->have_local = true;
     return finish(h);
 }
@@ -936,11 +1044,62 @@ int fcfv_get_local(fcfv_t* h, double* alpha, double* beta, double* Z, double* ta
     if (beta) TRY(copy(h, beta, h->beta.p, sizeof(double) * 2 * h->nel));
     if (Z) TRY(copy(h, Z, h->Z.p, sizeof(double) * 4 * h->nel));
     if (tau) TRY(copy(h, tau, h->tau.p, sizeof(double) * h->nf));
-    return sync(h);
+    TRY(sync(h));
+    // the caller's arrays now mirror the device buffers: handing them back (ElementAssemblyLoop(mesh, ae, be, ze, ...),
+    // mesh.τ in the field refresh) costs no upload
+    mirror_download(h, h->alpha, alpha, sizeof(double) * h->nel);
+    mirror_download(h, h->beta, beta, sizeof(double) * 2 * h->nel);
+    mirror_download(h, h->Z, Z, sizeof(double) * 4 * h->nel);
+    mirror_download(h, h->tau, tau, sizeof(double) * h->nf);
+    return FCFV_OK;
 }
 
 int fcfv_compute_local(fcfv_t* h, int formulation, double A, const double* sex, const double* sey, const double* VxDir,
                        const double* VyDir, double* alpha, double* beta, double* Z, double* tau) {
+    return fcfv_compute_local_ex(h, formulation, A, sex, sey, VxDir, VyDir, nullptr, nullptr, nullptr, nullptr, alpha, beta, Z, tau);
+}
+
+namespace {
+// alpha / beta / Z / tau leave on the handle's second stream (after everything queued on the main stream so far), so
+// that uploads issued on the main stream afterwards run concurrently: PCIe is full duplex.  Pageable destinations go
+// through the staged path instead (complete on return).  fcfv_local_downloaded() closes the transfer.
+int download_local_async(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau) {
+    if (!h->stream_out) {
+        CU(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(h->ev_out, h->stream));
+    CU(cudaStreamWaitEvent(h->stream_out, h->ev_out, 0));
+    struct Out { double* dst; const void* src; size_t bytes; } outs[4] = {
+        {alpha, h->alpha.p, sizeof(double) * (size_t)h->nel}, {beta, h->beta.p, sizeof(double) * 2 * (size_t)h->nel},
+        {Z, h->Z.p, sizeof(double) * 4 * (size_t)h->nel}, {tau, h->tau.p, sizeof(double) * (size_t)h->nf}};
+    for (const Out& o : outs) {
+        if (!o.dst || o.bytes == 0) continue;
+        if (is_device(o.dst) || is_pageable_host(o.dst)) { TRY(copy(h, o.dst, o.src, o.bytes)); continue; }
+        CU(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToHost, h->stream_out));
+        h->d2h_bytes += (long long)o.bytes;
+    }
+    return FCFV_OK;
+}
+
+int local_downloaded(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau) {
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->stream_out));
+    mirror_download(h, h->alpha, alpha, sizeof(double) * h->nel);
+    mirror_download(h, h->beta, beta, sizeof(double) * 2 * h->nel);
+    mirror_download(h, h->Z, Z, sizeof(double) * 4 * h->nel);
+    mirror_download(h, h->tau, tau, sizeof(double) * h->nf);
+    return FCFV_OK;
+}
+}  // namespace
+
+// ComputeFCFV with the reference's full argument list (DiscretisationFCFV_Stokes.jl:8 also receives the four Neumann
+// arrays and never reads them).  Here they are put to use: while alpha / beta / Z / tau come down, the Neumann arrays
+// go up on the other direction of the link, and the assembly / residual calls that follow find them resident
+// (upload cache on) -- the download costs no wall time beyond what the later uploads would have taken anyway.
+int fcfv_compute_local_ex(fcfv_t* h, int formulation, double A, const double* sex, const double* sey, const double* VxDir,
+                          const double* VyDir, const double* sxxNeu, const double* syyNeu, const double* sxyNeu, const double* syxNeu,
+                          double* alpha, double* beta, double* Z, double* tau) {
     if (!h) return FCFV_ERR_INVALID;
     const bool was_async = h->async;
     h->async = true;
@@ -950,9 +1109,21 @@ int fcfv_compute_local(fcfv_t* h, int formulation, double A, const double* sex, 
         else rc = fcfv_set_face_data(h, VxDir, VyDir, nullptr, nullptr, nullptr, nullptr);
     }
     if (!rc) rc = fcfv_run_local(h, formulation, A);
+    if (rc || h->multi) {
+        h->async = was_async;
+        if (rc) return rc;
+        return fcfv_get_local(h, alpha, beta, Z, tau);
+    }
+    auto tail = [&]() -> int {
+        TRY(download_local_async(h, alpha, beta, Z, tau));
+        // without the cache the later calls would send them again anyway: nothing to gain
+        if (h->cache_on && (sxxNeu || syyNeu || sxyNeu || syxNeu)) TRY(fcfv_set_face_data(h, nullptr, nullptr, sxxNeu, syyNeu, sxyNeu, syxNeu));
+        return FCFV_OK;
+    };
+    rc = tail();
     h->async = was_async;
-    if (rc) return rc;
-    return fcfv_get_local(h, alpha, beta, Z, tau);
+    const int rc2 = local_downloaded(h, alpha, beta, Z, tau);     // both streams are drained whatever happened above
+    return rc ? rc : rc2;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1291,22 +1462,23 @@ int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, 
         return fail(h, FCFV_ERR_INVALID, "FCFV_TAU_REFERENCE reads tau[e] for e <= nel but nf < nel");
     CU(cudaSetDevice(h->device));
     const long long nel = h->nel, nf = h->nf;
-    const int nbe = nblocks(nel), nbf = nblocks(nf);
-    const int stride = std::max(nbe, nbf);
+    // element blocks (which also form F_nodes of the faces inside their tile) + blocks of the late-face kernel (4 faces per thread)
+    const int nbe = nblocks(nel), nbl = nblocks((nf + 3) / 4);
+    const int stride = nbe + nbl;
     TRY(ensure(h, h->Fg, sizeof(double) * 6 * nel));
     TRY(ensure(h, h->partial, sizeof(double) * 6 * stride));
     const MeshView M = mesh_view(h);
     double* part = P<double>(h->partial);
     if (formulation == FCFV_GRADIENT)
         TLAUNCH(h, T_RES_ELEM, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
-               P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr);
+               P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr, (double*)nullptr, (double*)nullptr);
     else
         TLAUNCH(h, T_RES_ELEM, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
-               P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr);
-    TLAUNCH(h, T_RES_FACE, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, (double*)nullptr, (double*)nullptr);
+               P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr, (double*)nullptr, (double*)nullptr);
+    TLAUNCH(h, T_RES_FACE, k_res_late, nbl, kBlock, M, P<double>(h->Fg), part, stride, nbe, (double*)nullptr, (double*)nullptr);
     // sumsq order = print order: F_eq1, F_eq2, F_eq3, F_nodes_x, F_nodes_y, F_glob2
     double* ss = P<double>(h->sumsq);
-    TLAUNCH(h, T_REDUCE, k_reduce_residuals, dim3(kRedSlices, 6), 256, part, nbe, nbf, stride, P<double>(h->red_scratch),
+    TLAUNCH(h, T_REDUCE, k_reduce_residuals, dim3(kRedSlices, 6), 256, part, nbe, nbe + nbl, stride, P<double>(h->red_scratch),
             P<unsigned int>(h->red_tickets), ss);
     CU(cudaGetLastError());
     if (h->comm) TRY(fcfv_comm_allreduce_sum(h, ss, 6));
@@ -1329,7 +1501,8 @@ int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, 
 // meshes the pass is bound by launch latency (ten kernels of a few microseconds), a replayed graph removes it.
 // The graph is rebuilt when its key changes: loop / formulation / tau mode / A, the mesh size, or any device
 // buffer was reallocated (alloc_epoch); ownership / ghost flags and the anisotropy switch are re-checked through
-// the direct pass that precedes every capture.  With a communicator or per-kernel timing the pass runs directly.
+// the direct pass that precedes every capture.  The NCCL all-reduce of a partitioned mesh is captured with the kernels;
+// with per-kernel timing the pass runs directly.
 int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau_mode) {
     if (!h) return FCFV_ERR_INVALID;
     auto direct = [&]() -> int {
@@ -1342,7 +1515,7 @@ int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau
         return rc;
     };
     if (h->multi) { TRY(direct()); return multi_sync(h) ? FCFV_ERR_CUDA : FCFV_OK; }
-    if (h->comm || h->timing) { TRY(direct()); return finish(h); }
+    if (h->timing || h->graph_disabled) { TRY(direct()); return finish(h); }
     long long abits;
     memcpy(&abits, &A, sizeof abits);
     const long long flags = (h->have_elem_owned ? 1 : 0) | (h->have_face_owned ? 2 : 0) | (h->have_tau_ref ? 4 : 0) | (h->aniso ? 8 : 0);
@@ -1371,12 +1544,21 @@ int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau
     if (rc || ce != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
+        if (h->comm) {      // a collective that cannot be captured (old NCCL): passes run directly from now on; this call's
+            h->graph_disabled = true;      // result was produced by the direct pass above
+            return finish(h);
+        }
         if (rc) return rc;
         return fail(h, FCFV_ERR_CUDA, "fcfv_run_pipeline: stream capture failed: %s", cudaGetErrorString(ce));
     }
     ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) { h->graph_exec = nullptr; return fail(h, FCFV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+    if (ce != cudaSuccess) {
+        h->graph_exec = nullptr;
+        cudaGetLastError();
+        if (h->comm) { h->graph_disabled = true; return finish(h); }
+        return fail(h, FCFV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    }
     memcpy(h->graph_key, key2, sizeof key2);
     return finish(h);   // the direct pass above already produced this call's result
 }
@@ -1403,16 +1585,16 @@ int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, 
         const long long nel = h->nel, nf = h->nf;
         TRY(ensure(h, h->tmp, sizeof(double) * (2 * nf + nel)));
         double* t = P<double>(h->tmp);
-        const int nbe = nblocks(nel), nbf = nblocks(nf), stride = std::max(nbe, nbf);
+        const int nbe = nblocks(nel), nbl = nblocks((nf + 3) / 4), stride = nbe + nbl;
         const MeshView M = mesh_view(h);
         double* part = P<double>(h->partial);
         if (formulation == FCFV_GRADIENT)
             TLAUNCH(h, T_RES_ELEM, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
-                   P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf);
+                   P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf, t, t + nf);
         else
             TLAUNCH(h, T_RES_ELEM, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h),
-                   P<double>(h->sex), P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf);
-        TLAUNCH(h, T_RES_FACE, k_res_face, nbf, kBlock, M, P<double>(h->Fg), part + 4 * (size_t)stride, stride, t, t + nf);
+                   P<double>(h->sex), P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf, t, t + nf);
+        TLAUNCH(h, T_RES_FACE, k_res_late, nbl, kBlock, M, P<double>(h->Fg), part, stride, nbe, t, t + nf);
         CU(cudaGetLastError());
         if (F_nodes_x) TRY(copy(h, F_nodes_x, t, sizeof(double) * nf));
         if (F_nodes_y) TRY(copy(h, F_nodes_y, t + nf, sizeof(double) * nf));
@@ -1443,10 +1625,6 @@ int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, c
                               syxNeu, norms, nullptr, nullptr, nullptr);
     }
     CU(cudaSetDevice(h->device));
-    if (!h->stream_out) {
-        CU(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
-    }
     const bool was_async = h->async;
     h->async = true;
     auto body = [&]() -> int {
@@ -1454,16 +1632,7 @@ int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, c
         TRY(fcfv_set_face_data(h, VxDir, VyDir, nullptr, nullptr, nullptr, nullptr));
         TRY(fcfv_run_local(h, formulation, A));
         // outputs of the element kernel go down while the rest goes up
-        CU(cudaEventRecord(h->ev_out, h->stream));
-        CU(cudaStreamWaitEvent(h->stream_out, h->ev_out, 0));
-        struct Out { double* dst; const void* src; size_t bytes; } outs[4] = {
-            {alpha, h->alpha.p, sizeof(double) * (size_t)h->nel}, {beta, h->beta.p, sizeof(double) * 2 * (size_t)h->nel},
-            {Z, h->Z.p, sizeof(double) * 4 * (size_t)h->nel}, {tau, h->tau.p, sizeof(double) * (size_t)h->nf}};
-        for (const Out& o : outs) {
-            if (!o.dst || o.bytes == 0) continue;
-            if (is_pageable_host(o.dst)) TRY(copy(h, o.dst, o.src, o.bytes));
-            else CU(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToHost, h->stream_out));
-        }
+        TRY(download_local_async(h, alpha, beta, Z, tau));
         TRY(fcfv_set_face_data(h, nullptr, nullptr, sxxNeu, syyNeu, sxyNeu, syxNeu));   // NULL = keep what is resident
         TRY(fcfv_run_assemble(h, variant, formulation, A, want_muu));
         TRY(fcfv_set_solution(h, Vxh, Vyh, Pe));
@@ -1476,8 +1645,10 @@ int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, c
         rc = fcfv_run_residuals(h, formulation, tau_mode, nullptr, norms ? norms : dummy);   // synchronises the main stream
     }
     if (rc == FCFV_OK) rc = fcfv_get_nnz(h, nnz_uu, nnz_up, nnz_muu);
-    const cudaError_t e = cudaStreamSynchronize(h->stream_out);
-    if (rc == FCFV_OK && e != cudaSuccess) rc = fail(h, FCFV_ERR_CUDA, "fcfv_pass: %s", cudaGetErrorString(e));
+    if (h->stream_out) {
+        const int rc2 = local_downloaded(h, alpha, beta, Z, tau);
+        if (rc == FCFV_OK) rc = rc2;
+    }
     return rc;
 }
 
@@ -1493,7 +1664,7 @@ int fcfv_element_values(fcfv_t* h, const double* Vxh, const double* Vyh, const d
     if (Vxh) {
         TRY(upload(h, h->Vxh, Vxh, sizeof(double) * nf));
         TRY(upload(h, h->Vyh, Vyh, sizeof(double) * nf));
-        if (!h->have_solution) { TRY(ensure(h, h->Pe, sizeof(double) * nel)); CU(cudaMemsetAsync(h->Pe.p, 0, sizeof(double) * nel, h->stream)); }
+        if (!h->have_solution) { TRY(ensure(h, h->Pe, sizeof(double) * nel)); h->Pe.hm.epoch = -1; CU(cudaMemsetAsync(h->Pe.p, 0, sizeof(double) * nel, h->stream)); }
         h->have_solution = true;
     }
     if (alpha || beta || Z) {
@@ -1593,7 +1764,7 @@ int fcfv_center_pressure(fcfv_t* h, double* Pe, double* mean) {
     double* dp = P<double>(h->tmp);
     double* ss = P<double>(h->sumsq);
     TRY(copy(h, dp, Pe, sizeof(double) * nel));
-    LAUNCH(h, k_sum_owned, nbe, kBlock, (int)nel, dp, h->have_elem_owned ? P<uint8_t>(h->elem_owned) : nullptr, P<double>(h->partial));
+    LAUNCH(h, k_sum_owned, nbe, kBlock, (int)nel, dp, P<int>(h->ebc), P<double>(h->partial));
     LAUNCH(h, k_reduce_partials, 1, 1024, P<double>(h->partial), nbe, nbe, ss + 7);
     CU(cudaGetLastError());
     if (h->comm) TRY(fcfv_comm_allreduce_sum(h, ss + 7, 1));
@@ -1754,6 +1925,7 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     h->nel_global = 4 * n * n; h->nf_global = 6 * n * n + 2 * n;
     TRY(ensure(h, h->e2f, sizeof(int) * 3 * nel));
     TRY(ensure(h, h->bc, (size_t)nf));
+    new_epoch(h);        // every data buffer is rewritten on the device
     for (DBuf* b : {&h->Om, &h->ke, &h->dl, &h->taue, &h->sex, &h->sey, &h->Pe}) TRY(ensure(h, *b, sizeof(double) * nel));
     for (DBuf* b : {&h->nx, &h->ny, &h->G}) TRY(ensure(h, *b, sizeof(double) * 3 * nel));
     for (DBuf* b : {&h->VxDir, &h->VyDir, &h->sxx, &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh}) TRY(ensure(h, *b, sizeof(double) * nf));
@@ -1785,6 +1957,12 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     TRY(read_err_flag(h, &flag));
     if (flag) return fail(h, FCFV_ERR_STATE, "fcfv_generate_structured: generated connectivity failed validation (%d)", flag);
     TRY(build_fconn(h));
+    if (partitioned) {
+        LAUNCH(h, k_pack_owned, nblocks(nel, 256), 256, (int)nel, P<uint8_t>(h->elem_owned), kOwnedElem, P<int>(h->ebc));
+        LAUNCH(h, k_pack_owned, nblocks(nf, 256), 256, (int)nf, P<uint8_t>(h->face_owned), kOwnedFace, P<int>(h->fbc));
+        LAUNCH(h, k_pack_face_owned, nblocks(nel, 256), 256, (int)nel, P<int>(h->e2f), P<uint8_t>(h->face_owned), P<int>(h->eadj));
+        CU(cudaGetLastError());
+    }
     TRY(sync(h));
     h->have_mesh = h->have_sources = h->have_face_data = h->have_solution = true;
     h->delta_dirty = false; h->aniso = false;   // the generator sets delta = 1 everywhere

@@ -33,15 +33,29 @@ struct MeshView {
     const int8_t* bc;
     const int2* f2e;
     const int4* fconn;           // per face: the other two faces of the lower (x, y) and higher (z, w) element, -1 when absent
-    const int* fbc;              // per face: bc tags of (f, x, y, z, w) packed 4 bits each (tag + 1)
-    const int* ebc;              // per element: bc tags of its three faces packed 4 bits each (tag + 1)
+    const int* fbc;              // per face: bc tags of (f, x, y, z, w) packed 4 bits each (tag + 1); bit 20: this rank owns the face
+    const int* ebc;              // per element: bc tags of its three faces packed 4 bits each (tag + 1); bits 12..14: highest
+                                 // adjacent element of local face j; bit 15: this rank owns the element
+    const int* eadj;             // per element: where the residual kernel finds the flux of the element across local face j
+                                 // (9 bits each, see k_ebc) + bits 27..29: this rank owns local face j
     const double *Om, *G, *nx, *ny, *ke, *dl, *taue;
     const double* tau;
-    const uint8_t* elem_owned;   // nullable
-    const uint8_t* face_owned;   // nullable
+    const uint8_t* elem_owned;   // nullable; the kernels read the copies packed into ebc / fbc (kOwnedElem / kOwnedFace), which
+    const uint8_t* face_owned;   // are loaded anyway: a partitioned mesh costs no extra dependent loads
     const double* tau_ref;       // nullable (REFERENCE tau mode on a partition)
 };
 
+constexpr int kOwnedFace = 1 << 20;   // in fbc
+constexpr int kOwnedElem = 1 << 15;   // in ebc
+constexpr int kLateFace = 1 << 21;    // in fbc: F_nodes of this face is not formed inside k_res_elem (its two elements sit in
+                                      // different 128-element tiles, or no element references it): k_res_late does it
+// eadj slot of local face j (bits 9j .. 9j+8): (thread of the neighbour in this element's 128-element tile) << 2 | (its local
+// index of the shared face); local index 3 = no neighbour in the tile: thread field kAdjBoundary = boundary face (the
+// element is the face's only one), 0 = the neighbour lives in another tile
+constexpr int kAdjNone = 3;
+
+constexpr int kAdjBoundary = 127;
+constexpr int kAdjOwnedShift = 27;
 struct LocalView { const double *alpha, *beta, *Z; };
 // per-element assembly coefficients (k_elem_coef): 1/alpha, c11 (old: eta/Omega, NEW: D11) and, only
 // when some delta != 1 (c12 != nullptr), the other three entries of D
@@ -238,6 +252,7 @@ FCFV_HD void asm_face(const FaceDataView& D, double A, int f, int2 pr, const Fac
 // kernels
 // =============================================================================================
 constexpr int kBlock = 128;          // threads per block for element / face kernels
+static_assert(kBlock == 128, "eadj slots and kLateFace are built for 128-element tiles");
 #ifndef FCFV_ASM_BLOCK
 #define FCFV_ASM_BLOCK 128
 #endif
@@ -396,7 +411,9 @@ __global__ void k_fconn(const int* __restrict__ e2f, const int8_t* __restrict__ 
     int4 o; int p;
     face_conn_of(e2f, bc, nel, f, f2e[f], o, p);
     fconn[f] = o;
-    fbc[f] = p;
+    const int2 pr = f2e[f];
+    const bool late = pr.x < 0 || (pr.y != pr.x && ((pr.x >> 2) >> 7) != ((pr.y >> 2) >> 7));
+    fbc[f] = p | kOwnedFace | (late ? kLateFace : 0);        // everything is owned until fcfv_set_ownership says otherwise (k_pack_owned)
 }
 
 // per-element copy of the bc tags of its faces (static per mesh): the element kernels know the tags
@@ -404,17 +421,47 @@ __global__ void k_fconn(const int* __restrict__ e2f, const int8_t* __restrict__ 
 // highest-numbered one adjacent to its local face j, i.e. the last writer of mesh.τ[face]
 // (Discretisation:40), so that ComputeFCFV can set τ from the element side.
 __global__ void k_ebc(const int* __restrict__ e2f, const int8_t* __restrict__ bc, const int2* __restrict__ f2e, int nel,
-                      int* __restrict__ ebc) {
+                      int* __restrict__ ebc, int* __restrict__ eadj) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nel) return;
-    int p = 0;
+    int p = 0, a = 7 << kAdjOwnedShift;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         const int f = e2f[j * nel + e];
+        const int2 pr = f2e[f];
         p |= (((int)bc[f] + 1) & 15) << (4 * j);
-        p |= ((f2e[f].y >> 2) == e ? 1 : 0) << (12 + j);
+        p |= ((pr.y >> 2) == e ? 1 : 0) << (12 + j);
+        // the element on the other side of face j, as seen from the residual kernel's 128-element tile
+        int slot;
+        if (pr.x == pr.y) slot = (kAdjBoundary << 2) | kAdjNone;
+        else {
+            const int other = pr.x == 4 * e + j ? pr.y : pr.x;
+            const int oe = other >> 2;
+            slot = (oe >> 7) == (e >> 7) ? (((oe & 127) << 2) | (other & 3)) : kAdjNone;
+        }
+        a |= slot << (9 * j);
     }
-    ebc[e] = p;
+    ebc[e] = p | kOwnedElem;
+    eadj[e] = a;
+}
+
+// face ownership of a partitioned mesh as seen from the elements: bits 27..29 of eadj (nullptr: everything owned)
+__global__ void k_pack_face_owned(int nel, const int* __restrict__ e2f, const uint8_t* __restrict__ face_owned, int* __restrict__ eadj) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nel) return;
+    int a = eadj[e] & ~(7 << kAdjOwnedShift);
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        if (face_owned == nullptr || face_owned[e2f[j * nel + e]]) a |= 1 << (kAdjOwnedShift + j);
+    eadj[e] = a;
+}
+
+// ownership masks of a partitioned mesh -> bit kOwnedFace of fbc / kOwnedElem of ebc (nullptr: everything owned)
+__global__ void k_pack_owned(int n, const uint8_t* __restrict__ owned, int bit, int* __restrict__ packed) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int v = packed[k] & ~bit;
+    packed[k] = (owned == nullptr || owned[k]) ? (v | bit) : v;
 }
 
 // ---- a2 geometry -------------------------------------------------------------------------------
@@ -536,8 +583,9 @@ __device__ __forceinline__ void tile_face_rows(const MeshView& M, const LocalVie
     inrange = f < M.nf;
     const int2 pr = inrange ? M.f2e[f] : make_int2(-1, -1);
     FaceConn C;
-    unpack_conn(f, inrange ? M.fconn[f] : make_int4(-1, -1, -1, -1), inrange ? M.fbc[f] : 0x11111, C);
-    const bool owned = inrange && (M.face_owned == nullptr || M.face_owned[f]);
+    const int tags = inrange ? M.fbc[f] : 0x11111;
+    unpack_conn(f, inrange ? M.fconn[f] : make_int4(-1, -1, -1, -1), tags, C);
+    const bool owned = inrange && (tags & kOwnedFace) != 0;
     auto load = [&](bool second, int e, int i, FaceElem& F) { load_face_elem<VARIANT, ANISO, EXTRA, NATURAL>(M, L, Cf, C, second, e, i, F); };
     asm_face<VARIANT, FORM, EXTRA>(D, A, f, pr, C, owned, load, sink, R);
 }
@@ -563,7 +611,7 @@ k_asm_fp(MeshView M, FaceDataView D, double* __restrict__ fp) {
             if (s2 == 1 && pr.y == pr.x) break;
             const int code = s2 == 0 ? pr.x : pr.y;
             const int e = code >> 2, i = code & 3;
-            if (M.elem_owned != nullptr && !M.elem_owned[e]) continue;
+            if (!(M.ebc[e] & kOwnedElem)) continue;
             double v;
             if (face_fp(M, D, e, i, v)) fp[e] = v;
         }
@@ -838,23 +886,32 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
 }
 
 // ---- a8 residuals ------------------------------------------------------------------------------
-// Element kernel: ue, Le, the three face fluxes F_glob1[e,i,:] (stored for the face kernel), and
-// the sums of squares of F_eq1, F_eq2, F_eq3, F_glob2 reduced per block (warp shuffles, fixed order).
-// partial[q*nblk + b], q = 0:F_eq1 1:F_eq2 2:F_eq3 3:F_glob2.
+// Element kernel: ue, Le, the three face fluxes F_glob1[e,i,:] and the sums of squares of F_eq1, F_eq2, F_eq3, F_glob2
+// reduced per block (warp shuffles, fixed order).  Pass C of the reference (:88-100, F_nodes[f] = sum of the fluxes of
+// the <= 2 elements of a non-Dirichlet face) is formed HERE for every face whose elements sit in the same 128-element
+// tile: the fluxes are exchanged through shared memory, the face's highest element adds them (lower element first, like
+// the reference's element loop) and squares the result.  Only the fluxes of faces cut by a tile boundary go to memory
+// (Fg, [element][face][component]) for k_res_late.  On a locality-numbered mesh that is one face in six.
+// partial[q*stride + b]: q = 0 F_eq1, 1 F_eq2, 2 F_eq3, 3 F_glob2, 4 / 5 F_nodes x / y (this kernel's blocks first, then
+// those of k_res_late).
 template <int FORM>
 __global__ void __launch_bounds__(kBlock, FCFV_RES_MINBLOCKS)
 k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double* __restrict__ sex,
            const double* __restrict__ sey, int tau_mode, double* __restrict__ Fg, double* __restrict__ partial,
-           int nblk, double* __restrict__ F_glob2_out) {
-    __shared__ double sd[4 * (kBlock / 32)];
+           int stride, double* __restrict__ F_glob2_out, double* __restrict__ Fx_out, double* __restrict__ Fy_out) {
+    __shared__ double sd[6 * (kBlock / 32)];
+    __shared__ double2 sF[3 * kBlock];
     const int e = blockIdx.x * kBlock + threadIdx.x;
     const int nel = M.nel;
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, sx = 0.0, sy = 0.0;
+    int fid[3] = {0, 0, 0};
+    int tags = 0, adj = 0;
     if (e < nel) {
         double G[3], nx[3], ny[3], tau[3], ux[3], uy[3];
-        int bc[3], fid[3];
+        int bc[3];
         const double tau_e = (tau_mode == 0) ? (M.tau_ref ? M.tau_ref[e] : M.tau[e < M.nf ? e : 0]) : 0.0;
-        const int tags = M.ebc[e];
+        tags = M.ebc[e];
+        adj = M.eadj[e];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int f = M.e2f[i * nel + e];
@@ -877,56 +934,85 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
                                bc, tau, ux, uy, traction, r);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            reinterpret_cast<double2*>(Fg)[(size_t)3 * e + i] = make_double2(r.Fg1[i][0], r.Fg1[i][1]);   // [e][i][comp]: 48 contiguous bytes per element
+            const double2 v = make_double2(r.Fg1[i][0], r.Fg1[i][1]);
+            sF[3 * threadIdx.x + i] = v;
+            if (((adj >> (9 * i)) & 511) == kAdjNone) reinterpret_cast<double2*>(Fg)[(size_t)3 * e + i] = v;   // cut face
         }
         if (F_glob2_out) F_glob2_out[e] = r.Fg2;
-        if (M.elem_owned == nullptr || M.elem_owned[e]) {
+        if (tags & kOwnedElem) {
             s1 = ((r.F1[0][0] * r.F1[0][0] + r.F1[1][0] * r.F1[1][0]) + r.F1[0][1] * r.F1[0][1]) + r.F1[1][1] * r.F1[1][1];
             s2 = r.F2[0] * r.F2[0] + r.F2[1] * r.F2[1];
             s3 = r.F3 * r.F3;
             s4 = r.Fg2 * r.Fg2;
         }
     }
-    double t[4] = {s1, s2, s3, s4};
-    block_sums<4>(t, sd);
+    __syncthreads();
+    if (e < nel) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int slot = (adj >> (9 * i)) & 511;
+            if (slot == kAdjNone || !((tags >> (12 + i)) & 1)) continue;       // cut face, or the other element forms the sum
+            double Fx = 0.0, Fy = 0.0;
+            if ((((tags >> (4 * i)) & 15) - 1) != 1) {                           // :89 Dirichlet faces stay zero
+                if ((slot & 3) != kAdjNone) {                                    // lower element first
+                    const double2 lo = sF[3 * (slot >> 2) + (slot & 3)];
+                    Fx = Fx + lo.x; Fy = Fy + lo.y;
+                }
+                const double2 me = sF[3 * threadIdx.x + i];
+                Fx = Fx + me.x; Fy = Fy + me.y;
+            }
+            if (Fx_out) Fx_out[fid[i]] = Fx;
+            if (Fy_out) Fy_out[fid[i]] = Fy;
+            if ((adj >> (kAdjOwnedShift + i)) & 1) { sx = sx + Fx * Fx; sy = sy + Fy * Fy; }
+        }
+    }
+    double t[6] = {s1, s2, s3, s4, sx, sy};
+    block_sums<6>(t, sd);
     if (threadIdx.x == 0) {
         const int b = blockIdx.x;
-        partial[0 * (size_t)nblk + b] = t[0]; partial[1 * (size_t)nblk + b] = t[1];
-        partial[2 * (size_t)nblk + b] = t[2]; partial[3 * (size_t)nblk + b] = t[3];
+#pragma unroll
+        for (int q = 0; q < 6; q++) partial[q * (size_t)stride + b] = t[q];
     }
 }
 
-// Face kernel (pass C :88-100): F_nodes[f] = sum of the <=2 element fluxes (non-Dirichlet faces).
+// Faces k_res_elem leaves out (kLateFace: cut by a tile boundary, or referenced by no element): one thread per four faces,
+// one 16-byte load of the packed tags, the gathers only where there is work.  partial rows 4 / 5 from block offset `b0`.
 __global__ void __launch_bounds__(kBlock)
-k_res_face(MeshView M, const double* __restrict__ Fg, double* __restrict__ partial, int nblk,
+k_res_late(MeshView M, const double* __restrict__ Fg, double* __restrict__ partial, int stride, int b0,
            double* __restrict__ Fx_out, double* __restrict__ Fy_out) {
     __shared__ double sd[2 * (kBlock / 32)];
-    const int f = blockIdx.x * kBlock + threadIdx.x;
+    const int f0 = 4 * (blockIdx.x * kBlock + threadIdx.x);
     double sx = 0.0, sy = 0.0;
-    if (f < M.nf) {
-        double Fx = 0.0, Fy = 0.0;
-        const int2 pr = M.f2e[f];
-        if (pr.x >= 0 && M.bc[f] != 1) {
-            const int e0 = pr.x >> 2, i0 = pr.x & 3;
-            const double2 v0 = reinterpret_cast<const double2*>(Fg)[(size_t)3 * e0 + i0];
-            Fx = Fx + v0.x;
-            Fy = Fy + v0.y;
-            if (pr.y != pr.x) {
-                const int e1 = pr.y >> 2, i1 = pr.y & 3;
-                const double2 v1 = reinterpret_cast<const double2*>(Fg)[(size_t)3 * e1 + i1];
-                Fx = Fx + v1.x;
-                Fy = Fy + v1.y;
-            }
+    if (f0 < M.nf) {
+        int tags[4] = {0, 0, 0, 0};
+        if (f0 + 3 < M.nf) {
+            const int4 t = *reinterpret_cast<const int4*>(M.fbc + f0);
+            tags[0] = t.x; tags[1] = t.y; tags[2] = t.z; tags[3] = t.w;
+        } else {
+            for (int q = 0; q < 4 && f0 + q < M.nf; q++) tags[q] = M.fbc[f0 + q];
         }
-        if (Fx_out) Fx_out[f] = Fx;
-        if (Fy_out) Fy_out[f] = Fy;
-        if (M.face_owned == nullptr || M.face_owned[f]) { sx = Fx * Fx; sy = Fy * Fy; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (!(tags[q] & kLateFace)) continue;
+            const int f = f0 + q;
+            double Fx = 0.0, Fy = 0.0;
+            const int2 pr = M.f2e[f];
+            if (pr.x >= 0 && ((tags[q] & 15) - 1) != 1) {
+                const double2 v0 = reinterpret_cast<const double2*>(Fg)[(size_t)3 * (pr.x >> 2) + (pr.x & 3)];
+                const double2 v1 = reinterpret_cast<const double2*>(Fg)[(size_t)3 * (pr.y >> 2) + (pr.y & 3)];
+                Fx = Fx + v0.x; Fy = Fy + v0.y;
+                Fx = Fx + v1.x; Fy = Fy + v1.y;
+            }
+            if (Fx_out) Fx_out[f] = Fx;
+            if (Fy_out) Fy_out[f] = Fy;
+            if (tags[q] & kOwnedFace) { sx = sx + Fx * Fx; sy = sy + Fy * Fy; }
+        }
     }
     double t[2] = {sx, sy};
     block_sums<2>(t, sd);
     if (threadIdx.x == 0) {
-        partial[0 * (size_t)nblk + blockIdx.x] = t[0];
-        partial[1 * (size_t)nblk + blockIdx.x] = t[1];
+        partial[4 * (size_t)stride + b0 + blockIdx.x] = t[0];
+        partial[5 * (size_t)stride + b0 + blockIdx.x] = t[1];
     }
 }
 
@@ -1187,7 +1273,7 @@ k_ph_rp(MeshView M, const double* __restrict__ fp, const double* __restrict__ u,
     double sq = 0.0;
     if (e < M.nel) {
         const double v = fp[e] - kpu_dot_u(M, e, u);
-        if (mode == 0) { if (rp) rp[e] = v; sq = (M.elem_owned == nullptr || M.elem_owned[e]) ? v * v : 0.0; }   // ghosts are counted by their owner
+        if (mode == 0) { if (rp) rp[e] = v; sq = (M.ebc[e] & kOwnedElem) ? v * v : 0.0; }   // ghosts are counted by their owner
         else { const double coef = (gamma * M.ke[e]) / M.Om[e]; p[e] = p[e] + coef * v; }
     }
     if (mode == 0) {
@@ -1198,10 +1284,10 @@ k_ph_rp(MeshView M, const double* __restrict__ fp, const double* __restrict__ u,
 
 // Pe .-= mean(Pe) (SolversFCFV_Stokes.jl:20): per-block sums over owned elements, then p[e] -= sum / n
 __global__ void __launch_bounds__(kBlock)
-k_sum_owned(int nel, const double* __restrict__ p, const uint8_t* __restrict__ owned, double* __restrict__ partial) {
+k_sum_owned(int nel, const double* __restrict__ p, const int* __restrict__ ebc, double* __restrict__ partial) {
     __shared__ double sd[kBlock / 32];
     const int e = blockIdx.x * kBlock + threadIdx.x;
-    const double v = (e < nel && (owned == nullptr || owned[e])) ? p[e] : 0.0;
+    const double v = (e < nel && (ebc[e] & kOwnedElem)) ? p[e] : 0.0;
     const double t = block_sum(v, sd);
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }

@@ -89,6 +89,10 @@ def load():
         "fcfv_hilbert_elements": [vp, i64, vp, vp, vp],
         "fcfv_pass": [vp, ci, ci, dbl, ci] + [vp] * 11 + [vp] * 4 + [ci, P(i64), P(i64), P(i64), vp],
         "fcfv_numbering_locality": [vp, P(dbl), P(dbl)],
+        "fcfv_compute_local_ex": [vp, ci, dbl] + [vp] * 12,
+        "fcfv_upload_cache": [vp, ci],
+        "fcfv_new_epoch": [vp],
+        "fcfv_transfer_stats": [vp, P(i64), P(i64), P(i64), ci],
         "fcfv_host_register": [vp, vp, i64],
         "fcfv_host_unregister": [vp, vp],
         "fcfv_run_pipeline": [vp, ci, ci, dbl, ci],

@@ -129,6 +129,30 @@ int fcfv_compute_local(fcfv_t* h, int formulation, double A, const double* sex, 
                        const double* VxDir, const double* VyDir, double* alpha, double* beta,
                        double* Z, double* tau);
 
+/* The same with the reference's full argument list: ComputeFCFV (DiscretisationFCFV_Stokes.jl:8) also receives the four
+ * Neumann arrays (and never reads them).  Any that are non-NULL are uploaded while alpha / beta / Z / tau come down --
+ * the two directions of the link run concurrently -- so that fcfv_assemble / fcfv_residuals find them resident when
+ * the upload cache is on.  Results identical to fcfv_compute_local. */
+int fcfv_compute_local_ex(fcfv_t* h, int formulation, double A, const double* sex, const double* sey,
+                          const double* VxDir, const double* VyDir, const double* sxxNeu, const double* syyNeu,
+                          const double* sxyNeu, const double* syxNeu, double* alpha, double* beta, double* Z,
+                          double* tau);
+
+/* ---- upload cache ---------------------------------------------------------------------------------
+ * A driver hands the same host arrays to ComputeFCFV, ElementAssemblyLoop[NEW] and ComputeResidualsFCFV_Stokes_o1
+ * (examples/SolKzFCFV.jl:150,155,205: VxDir / VyDir three times, the Neumann arrays and the sources twice, and
+ * alpha / beta / Z go back in after they came out).  With the cache on, every device buffer remembers the host array
+ * it mirrors -- uploaded from, or downloaded to (alpha, beta, Z, tau) --; a later upload of the same address and size
+ * in the same epoch is skipped if a sampled fingerprint of the host contents (768 words at both ends + 4096 spread
+ * over the array) still matches.  The caller vouches that arrays are not modified in place inside an epoch;
+ * fcfv_new_epoch starts a new one (the shims do so at the top of every ComputeFCFV, i.e. once per driver pass),
+ * fcfv_set_mesh and fcfv_generate_structured too.  fcfv_set_mesh itself always uploads.  Off by default. */
+int fcfv_upload_cache(fcfv_t* h, int on);
+int fcfv_new_epoch(fcfv_t* h);
+/* Bytes this handle has moved host -> device / device -> host so far and bytes the upload cache saved; reset != 0
+ * zeroes the counters after reading.  Any pointer may be NULL. */
+int fcfv_transfer_stats(fcfv_t* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* cache_hit_bytes, int reset);
+
 /* ---- a5/a6/a7: ElementAssemblyLoop[NEW] + Sparsify (Discretisation:102-202,210-347,355-364)
  * alpha/beta/Z: NULL = use the device-resident result of the last fcfv_compute_local.
  * Uses mesh.τ as resident (fcfv_compute_local / fcfv_update_fields).  Result: device CSR of

@@ -12,7 +12,7 @@ using SparseArrays, Printf
 
 export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
        SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!, RenumberFacesFirstSeen!,
-       RenumberElementsHilbert!, PrepareNumbering!, PinArrays, FusedPass, release!, NGPUS
+       RenumberElementsHilbert!, PrepareNumbering!, PinArrays, FusedPass, release!, NGPUS, CACHE_INPUTS, new_epoch!
 
 const LIB = get(ENV, "FCFV_LIB", joinpath(@__DIR__, "..", "fcfv_nme23_b200", "libfcfv_b200.so"))
 
@@ -37,6 +37,18 @@ end
 # the first call on a mesh.  With more than one GPU the handle partitions the mesh inside fcfv_set_mesh; every
 # function below keeps taking and returning the global arrays.
 const NGPUS = Ref(parse(Int, get(ENV, "FCFV_NGPUS", "1")))
+
+# Upload cache (fcfv_upload_cache): the drivers pass the same arrays to ComputeFCFV, ElementAssemblyLoop[NEW] and
+# ComputeResidualsFCFV_Stokes_o1 (SolKzFCFV.jl:150,155,205); with the cache on an array the GPU already mirrors -- same
+# address, size, epoch and sampled fingerprint -- is not uploaded again, and α, β, Ζ, mesh.τ returned by ComputeFCFV cost
+# nothing when they come back as arguments.  A new epoch starts at every ComputeFCFV.  A driver that modifies an input
+# array IN PLACE between ComputeFCFV and the calls that follow it (none of the reference's does) calls
+# FCFV_B200.new_epoch!(mesh) afterwards, or sets FCFV_B200.CACHE_INPUTS[] = false before the first call on the mesh.
+const CACHE_INPUTS = Ref(true)
+new_epoch!(h::Handle) = (ccall((:fcfv_new_epoch, LIB), Cint, (Ptr{Cvoid},), h.ptr); nothing)
+new_epoch!(mesh) = haskey(HANDLES, mesh) ? new_epoch!(HANDLES[mesh]) : nothing
+# converted copies die with the call: the cache must not remember their addresses
+forget_temps!(h, pairs...) = (any(p -> !(p[1] === p[2]), pairs) && new_epoch!(h); nothing)
 
 function Handle(device::Integer = 0; ngpus::Integer = NGPUS[])
     r = Ref{Ptr{Cvoid}}(C_NULL)
@@ -84,6 +96,7 @@ i64(x) = convert(Array{Int64}, x)
 function handle_for(mesh)
     haskey(HANDLES, mesh) && return HANDLES[mesh]
     h = Handle()
+    check(h, ccall((:fcfv_upload_cache, LIB), Cint, (Ptr{Cvoid}, Cint), h.ptr, CACHE_INPUTS[] ? 1 : 0))
     e2f, bc = i64(mesh.e2f), i64(mesh.bc)
     Ω, nx, ny, Γ, ke, δ = f64(mesh.Ω), f64(mesh.n_x), f64(mesh.n_y), f64(mesh.Γ), f64(mesh.ke), f64(mesh.δ)
     τe = ismissing(mesh.τe) ? zeros(mesh.nel) : f64(mesh.τe)       # may have nf entries (v2.jl:127)
@@ -116,6 +129,7 @@ function refresh!(h::Handle, mesh)
             (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
             h.ptr, ke, δ, τe, length(τe), isempty(τ) ? C_NULL : pointer(τ)))
     end
+    forget_temps!(h, (mesh.ke, ke), (mesh.δ, δ), (mesh.τe, τe), (ismissing(mesh.τ) ? τ : mesh.τ, τ))
 end
 
 """Ω, centroids, outward normals, Γ (and τ .= τr) from xv, yv, e2v, e2f, xf, yf -- the loops of
@@ -142,16 +156,22 @@ end
 """src/DiscretisationFCFV_Stokes.jl:8-44"""
 function ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τr, Formulation)
     ismissing(mesh.τ) && (mesh.τ = zeros(mesh.nf))      # LoadExternalMesh leaves τ missing
-    h = handle_for(mesh); refresh!(h, mesh)
+    fresh = !haskey(HANDLES, mesh)
+    h = handle_for(mesh)
+    fresh || new_epoch!(h)              # first call of a driver pass: everything the driver may have changed goes up again
+    refresh!(h, mesh)                   # (a handle made just now has uploaded the mesh fields in this very call)
     nel, nf = mesh.nel, mesh.nf
     α, β, Ζ, τ = zeros(nel), zeros(nel, 2), zeros(nel, 2, 2), zeros(nf)
     sx, sy, vx, vy = f64(sex), f64(sey), f64(VxDir), f64(VyDir)
-    GC.@preserve sx sy vx vy α β Ζ τ begin
-        check(h, ccall((:fcfv_compute_local, LIB), Cint,
+    sxx, syy, sxy, syx = f64(SxxNeu), f64(SyyNeu), f64(SxyNeu), f64(SyxNeu)
+    # the Neumann arrays (received and ignored by the reference) go up while α, β, Ζ, τ come down
+    GC.@preserve sx sy vx vy sxx syy sxy syx α β Ζ τ begin
+        check(h, ccall((:fcfv_compute_local_ex, LIB), Cint,
             (Ptr{Cvoid}, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-             Ptr{Float64}, Ptr{Float64}),
-            h.ptr, form_id(Formulation), A, sx, sy, vx, vy, α, β, Ζ, τ))
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h.ptr, form_id(Formulation), A, sx, sy, vx, vy, sxx, syy, sxy, syx, α, β, Ζ, τ))
     end
+    forget_temps!(h, (sex, sx), (sey, sy), (VxDir, vx), (VyDir, vy), (SxxNeu, sxx), (SyyNeu, syy), (SxyNeu, sxy), (SyxNeu, syx))
     mesh.τ = τ
     return α, β, Ζ
 end
@@ -179,6 +199,7 @@ function assemble(variant::Cint, mesh, α, β, Ζ, VxDir, VyDir, σxxNeu, σyyNe
              Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
             h.ptr, variant, form_id(Formulation), A, a, b, z, vx, vy, sxx, syy, sxy, syx, WANT_MUU[] ? 1 : 0, n1, n2, n3, sec))
     end
+    forget_temps!(h, (α, a), (β, b), (Ζ, z), (VxDir, vx), (VyDir, vy), (σxxNeu, sxx), (σyyNeu, syy), (σxyNeu, sxy), (σyxNeu, syx))
     Kuu, Kup = export_csc(h, KUU), export_csc(h, KUP)
     Muu = WANT_MUU[] ? export_csc(h, MUU) : spzeros(2nf, 2nf)
     fu, fp = zeros(2nf, 1), zeros(nel)                  # fu is a 2nf x 1 Matrix in the reference
@@ -211,6 +232,8 @@ function ComputeResidualsFCFV_Stokes_o1(Vxh, Vyh, Pe, mesh, ae, be, ze, sex, sey
             h.ptr, form_id(Formulation), tau_mode == :Face ? TAU_FACE : TAU_REFERENCE, vxh, vyh, pe, a, b, z, sx, sy, vx, vy,
             sxx, syy, sxy, syx, norms, C_NULL, C_NULL, C_NULL))
     end
+    forget_temps!(h, (Vxh, vxh), (Vyh, vyh), (Pe, pe), (ae, a), (be, b), (ze, z), (sex, sx), (sey, sy), (VxDir, vx), (VyDir, vy),
+                  (SxxNeu, sxx), (SyyNeu, syy), (SxyNeu, sxy), (SyxNeu, syx))
     @printf("Residual of local  equation 20a: %2.2e\n", norms[1])
     @printf("Residual of local  equation 20b: %2.2e\n", norms[2])
     @printf("Residual of local  equation 20c: %2.2e\n", norms[3])

@@ -53,11 +53,36 @@ def progress(msg):
         print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
+# BASELINE.json configs the bench can run: c4 (headline: SolKz, 50 M elements per GPU) and c5 (AnisoViscousInclusion-style:
+# circular inclusion eta = [1, 1e-2] with interface faces tagged -1, south side Neumann, anisotropy factor delta != 1
+# inside the inclusion -- the full 2x2 rheology path of ElementAssemblyLoopNEW --, tau_r = 2, 12.5 M elements per GPU,
+# i.e. 100 M elements on 8 GPUs; examples/AnisoViscousInclusionFCFV_v0.jl:76-78,154-164)
+CONFIGS = {
+    "c4": dict(n1=N_DEFAULT, setting="solkz", tau_r=10.0, gen={}, delta_incl=None,
+               name="SolKz S({n}) criss-cross triangulation, {nel} elements, ElementAssemblyLoopNEW :SymmetricGradient, tau_e=10*max(ke,1)"),
+    "c5": dict(n1=1768, setting="inclusion", tau_r=2.0, gen=dict(eta_incl=1e-2, neumann_south=True), delta_incl=2.0,
+               name="AnisoViscousInclusion-style S({n}) criss-cross triangulation, {nel} elements, eta=[1,1e-2], delta=2 in the inclusion, "
+                    "interface faces bc=-1, south Neumann, ElementAssemblyLoopNEW :SymmetricGradient, tau_e=2"),
+}
+CONFIG = "c4"
+
+
 def workload_name(n1, world, scaling):
     """Name of the workload both arms are quoted on (n1 = quads per side of the single-GPU mesh)."""
     n = int(round(n1 * world ** 0.5)) if scaling == "weak" else n1
-    return (f"SolKz S({n}) criss-cross triangulation, {4 * n * n} elements, ElementAssemblyLoopNEW :SymmetricGradient, "
-            "tau_e=10*max(ke,1)")
+    return CONFIGS[CONFIG]["name"].format(n=n, nel=4 * n * n)
+
+
+def generate(h, n, row0, row1):
+    """The rank's strip of the configured workload, generated on its GPU."""
+    import numpy as np
+    cfg = CONFIGS[CONFIG]
+    h.generate_structured(n, row0, row1, setting=cfg["setting"], tau_r=cfg["tau_r"], **cfg["gen"])
+    if cfg["delta_incl"] is not None:       # anisotropy factor inside the inclusion (the generator leaves delta = 1)
+        import ctypes as C
+        ke = np.empty(h.nel)
+        h.check(h.lib.fcfv_get_mesh(h._h, None, None, None, None, None, None, C.c_void_p(ke.ctypes.data), None, None, None))
+        h.update_fields(delta=np.where(ke != 1.0, cfg["delta_incl"], 1.0))
 
 
 def parse():
@@ -68,6 +93,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh-n", dest="n", type=int, default=None, help="quads per side of the per-rank-equivalent mesh (default 3536)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS), help="BASELINE.json config: c4 (headline) or c5")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=CPU_SAMPLE_N)
@@ -391,14 +417,18 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n1 = args.n or N_DEFAULT
+    global CONFIG
+    CONFIG = args.config
+    if CONFIG != "c4":
+        args.no_cpu = True           # the CPU arm is quoted on the headline workload only
+    n1 = args.n or CONFIGS[CONFIG]["n1"]
     if args.scaling == "weak":
         n = int(round(n1 * world ** 0.5))       # world * (4 n1^2) elements in total
     else:
         n = n1
     row0, row1 = rank * n // world, (rank + 1) * n // world
     h = api.Handle(local_rank)
-    h.generate_structured(n, row0, row1, setting="solkz", tau_r=10.0)
+    generate(h, n, row0, row1)
     owned_el = 4 * n * (row1 - row0)
     total_el = 4 * n * n
     if world > 1:
@@ -521,7 +551,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1 and args.scaling == "weak":
         progress("strong-scaling point")
         hs = api.Handle(local_rank)
-        hs.generate_structured(n1, rank * n1 // world, (rank + 1) * n1 // world, setting="solkz", tau_r=10.0)
+        generate(hs, n1, rank * n1 // world, (rank + 1) * n1 // world)
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(hs.comm_unique_id()), dtype=torch.uint8))
@@ -725,10 +755,11 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
                 outs = {"alpha": torch.empty(nels, dtype=torch.float64).pin_memory(), "beta": torch.empty(2 * nels, dtype=torch.float64).pin_memory(),
                         "Z": torch.empty(4 * nels, dtype=torch.float64).pin_memory(), "tau": torch.zeros(nfs, dtype=torch.float64).pin_memory()}
                 hm = api.Handle(ngpus=world)
-                three_calls(hm, Ps, Ds, outs, nels, True, False, False)
+                hm.upload_cache(True)
+                three_calls(hm, Ps, Ds, outs, nels, True, False, True)
                 t0 = time.perf_counter()
                 for _ in range(2):
-                    three_calls(hm, Ps, Ds, outs, nels, True, False, False)
+                    three_calls(hm, Ps, Ds, outs, nels, True, False, True)
                 hm.sync()
                 dts = (time.perf_counter() - t0) / 2
                 info, psec = hm.partition_info()

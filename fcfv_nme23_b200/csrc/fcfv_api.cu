@@ -120,6 +120,7 @@ struct fcfv_handle {
     // per-element assembly coefficients (k_elem_coef): ia, c11 and, when some delta != 1, c12 c21 c22
     DBuf coef, coefx, coefs;
     bool delta_dirty = true, aniso = false;
+    int coef_variant = -1;       // loop whose 1/alpha, c11 in `coef` match the resident alpha / ke (written by k_local in the pipeline), -1: none
     // assembly
     Csr Kuu, Kup, Muu, Kuusc;
     int last_variant = -1, last_form = -1;   // parameters of the last assembly (fcfv_schur reuses them)
@@ -140,6 +141,7 @@ struct fcfv_handle {
     long long timer_calls[kNumTimers] = {0};
     // CUDA graph of one pass (fcfv_run_pipeline): replayed while nothing it captured has changed
     cudaGraphExec_t graph_exec = nullptr;
+    long long graph_launches = 0;
     bool graph_disabled = false;          // capture failed with a communicator attached: run directly
     long long graph_key[7] = {-1, -1, -1, -1, -1, -1, -1};   // variant, formulation, tau_mode + flags, alloc epoch, nel, nf, bits of A
     long long alloc_epoch = 0;                           // bumped whenever a device buffer is (re)allocated
@@ -566,6 +568,9 @@ int fcfv_destroy(fcfv_t* h) {
     if (h->multi) { multi_destroy(h); delete h; return FCFV_OK; }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    // the pipeline graph may hold captured NCCL work: a communicator is only released once every graph that captured
+    // its operations is gone (ncclCommDestroy waits for that), so the graph goes first
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; cudaStreamSynchronize(h->stream); }
     if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
     DBuf* all[] = {&h->e2f, &h->bc, &h->f2e, &h->fconn, &h->fbc, &h->ebc, &h->eadj, &h->Om, &h->G, &h->nx, &h->ny, &h->ke, &h->dl, &h->taue, &h->tau,
                    &h->elem_owned, &h->face_owned, &h->tau_ref, &h->sex, &h->sey, &h->VxDir, &h->VyDir, &h->sxx,
@@ -578,7 +583,6 @@ int fcfv_destroy(fcfv_t* h) {
     if (h->stream_out) { cudaStreamSynchronize(h->stream_out); cudaStreamDestroy(h->stream_out); }
     if (h->ev_out) cudaEventDestroy(h->ev_out);
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -723,6 +727,7 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
     h->have_mesh = false; h->have_local = false;
     new_epoch(h);        // a new mesh: nothing that is resident mirrors a host array any more
+    h->coef_variant = -1;
     // data arrays are sized for the mesh they were set on: a new mesh invalidates them (sources, face data and
     // solution have to be set again; their buffers may be too small for the new nel / nf)
     if (nel != h->nel || nf != h->nf) h->have_sources = h->have_face_data = h->have_solution = false;
@@ -770,6 +775,7 @@ int fcfv_update_fields(fcfv_t* h, const double* ke, const double* delta, const d
     if (h->multi) return multi_update_fields(h, ke, delta, taue, ntaue, tau);
     CU(cudaSetDevice(h->device));
     if (taue && ntaue < h->nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel", (long long)ntaue);
+    h->coef_variant = -1;
     if (ke) TRY(upload_cached(h, h->ke, ke, sizeof(double) * h->nel));
     if (delta) {
         const long long hits = h->cache_hits;
@@ -1009,26 +1015,45 @@ int fcfv_set_local(fcfv_t* h, const double* alpha, const double* beta, const dou
     TRY(upload_cached(h, h->alpha, alpha, sizeof(double) * h->nel));
     TRY(upload_cached(h, h->beta, beta, sizeof(double) * 2 * h->nel));
     TRY(upload_cached(h, h->Z, Z, sizeof(double) * 4 * h->nel));
+    h->coef_variant = -1;
     h->have_local = true;
     return finish(h);
 }
 
 // -------------------------------------------------------------------------------------------------
+namespace {
+template <int FORM, int COEF>
+void launch_local(fcfv_t* h, double A) {
+    const MeshView M = mesh_view(h);
+    double* c = P<double>(h->coef);
+    // mesh.τ is set by the element kernel (one writer per face: its highest adjacent element)
+    TLAUNCH(h, T_LOCAL, (k_local<FORM, COEF>), nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey), P<double>(h->VxDir),
+            P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z), P<double>(h->tau), COEF >= 0 ? c : nullptr,
+            COEF >= 0 ? c + (size_t)h->nel : nullptr);
+}
+
+// coef_variant: FCFV_LOOP_OLD / FCFV_LOOP_NEW = the assembly of that loop follows (fcfv_run_pipeline): the element kernel
+// writes its per-element coefficients as well, which saves the coefficient pass; -1 = plain ComputeFCFV
+int run_local_impl(fcfv_t* h, int formulation, double A, int coef_variant) {
+    TRY(check_form(h, formulation));
+    TRY(need(h, h->have_mesh, "fcfv_run_local: no mesh set"));
+    TRY(need(h, h->have_sources && h->have_face_data, "fcfv_run_local: sources / face data not set"));
+    CU(cudaSetDevice(h->device));
+    if (coef_variant >= 0 && (h->delta_dirty || h->aniso || h->coef.cap < sizeof(double) * 2 * (size_t)h->nel)) coef_variant = -1;
+    const bool g = formulation == FCFV_GRADIENT;
+    if (coef_variant == FCFV_LOOP_OLD) g ? launch_local<kGradient, kLoopOld>(h, A) : launch_local<kSymmetricGradient, kLoopOld>(h, A);
+    else if (coef_variant == FCFV_LOOP_NEW) g ? launch_local<kGradient, kLoopNew>(h, A) : launch_local<kSymmetricGradient, kLoopNew>(h, A);
+    else g ? launch_local<kGradient, -1>(h, A) : launch_local<kSymmetricGradient, -1>(h, A);
+    h->coef_variant = coef_variant;
+    return FCFV_OK;
+}
+}  // namespace
+
 int fcfv_run_local(fcfv_t* h, int formulation, double A) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(check_form(h, formulation));
     if (h->multi) return multi_run_local(h, formulation, A);
-    TRY(need(h, h->have_mesh, "fcfv_run_local: no mesh set"));
-    TRY(need(h, h->have_sources && h->have_face_data, "fcfv_run_local: sources / face data not set"));
-    CU(cudaSetDevice(h->device));
-    const MeshView M = mesh_view(h);
-    // mesh.τ is set by the element kernel (one writer per face: its highest adjacent element)
-    if (formulation == FCFV_GRADIENT)
-        TLAUNCH(h, T_LOCAL, k_local<kGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey), P<double>(h->VxDir),
-               P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z), P<double>(h->tau));
-    else
-        TLAUNCH(h, T_LOCAL, k_local<kSymmetricGradient>, nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey),
-               P<double>(h->VxDir), P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z), P<double>(h->tau));
+    TRY(run_local_impl(h, formulation, A, -1));
     CU(cudaGetLastError());
     h->alpha.hm.epoch = h->beta.hm.epoch = h->Z.hm.epoch = h->tau.hm.epoch = -1;     // rewritten on the device
     h->have_local = true;
@@ -1150,12 +1175,15 @@ int launch_assemble(fcfv_t* h, double A, double gamma) {
     long long* chunk_tot = P<long long>(h->chunks);
     long long* chunk_base = chunk_tot + (size_t)kNumSums * nchunks;
     TLAUNCH(h, T_OTHER, k_asm_fp, nblocks((h->nf + 3) / 4, 256), 256, M, D, P<double>(h->fp));   // fp was zeroed by the caller
-    if (!ANISO && EXTRA != kExtraSchur && (h->nel & 1) == 0 && h->nel > 0)
+    if (!ANISO && EXTRA != kExtraSchur && h->coef_variant == VARIANT) {
+        // 1/alpha and c11 were written by the element kernel of this pass (fcfv_run_pipeline)
+    } else if (!ANISO && EXTRA != kExtraSchur && (h->nel & 1) == 0 && h->nel > 0)
         TLAUNCH(h, T_COEF, k_elem_coef2<VARIANT>, nblocks(h->nel / 2, 256), 256, (int)(h->nel / 2), (const double2*)L.alpha,
                 (const double2*)M.ke, (const double2*)M.Om, (double2*)Cf.ia, (double2*)Cf.c11);
     else
         TLAUNCH(h, T_COEF, k_elem_coef<VARIANT>, nblocks(h->nel, 256), 256, M.nel, L.alpha, M.ke, M.dl, M.Om, gamma, (double*)Cf.ia,
                 (double*)Cf.c11, (double*)Cf.c12, (double*)Cf.c21, (double*)Cf.c22, (double*)Cf.cs);
+    h->coef_variant = (!ANISO && EXTRA != kExtraSchur) ? VARIANT : -1;      // what `coef` now holds for the resident alpha / ke
     TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, EXTRA, ANISO>), nblk, kAsmBlock, M, L, Cf, D, A, sums, nblk);
     TLAUNCH(h, T_SCAN, k_scan_local, dim3(nchunks, kNumSums), 1024, sums, local, nblk, nchunks, chunk_tot);
     Csr& X = EXTRA == kExtraSchur ? h->Kuusc : h->Muu;   // third block
@@ -1463,19 +1491,19 @@ int fcfv_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq, 
     CU(cudaSetDevice(h->device));
     const long long nel = h->nel, nf = h->nf;
     // element blocks (which also form F_nodes of the faces inside their tile) + blocks of the late-face kernel (4 faces per thread)
-    const int nbe = nblocks(nel), nbl = nblocks((nf + 3) / 4);
+    const int nbe = nblocks(nel), nbl = nblocks((nf + kLateFaces - 1) / kLateFaces, kLateBlock);
     const int stride = nbe + nbl;
-    TRY(ensure(h, h->Fg, sizeof(double) * 6 * nel));
+    TRY(ensure(h, h->Fg, sizeof(double) * 4 * nf));        // [face][side][component], only cut faces are touched
     TRY(ensure(h, h->partial, sizeof(double) * 6 * stride));
     const MeshView M = mesh_view(h);
     double* part = P<double>(h->partial);
     if (formulation == FCFV_GRADIENT)
-        TLAUNCH(h, T_RES_ELEM, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+        TLAUNCH(h, T_RES_ELEM, (k_res_elem<kGradient, false>), nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
                P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr, (double*)nullptr, (double*)nullptr);
     else
-        TLAUNCH(h, T_RES_ELEM, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+        TLAUNCH(h, T_RES_ELEM, (k_res_elem<kSymmetricGradient, false>), nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
                P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, (double*)nullptr, (double*)nullptr, (double*)nullptr);
-    TLAUNCH(h, T_RES_FACE, k_res_late, nbl, kBlock, M, P<double>(h->Fg), part, stride, nbe, (double*)nullptr, (double*)nullptr);
+    TLAUNCH(h, T_RES_FACE, k_res_late, nbl, kLateBlock, M, P<double>(h->Fg), part, stride, nbe, (double*)nullptr, (double*)nullptr);
     // sumsq order = print order: F_eq1, F_eq2, F_eq3, F_nodes_x, F_nodes_y, F_glob2
     double* ss = P<double>(h->sumsq);
     TLAUNCH(h, T_REDUCE, k_reduce_residuals, dim3(kRedSlices, 6), 256, part, nbe, nbe + nbl, stride, P<double>(h->red_scratch),
@@ -1508,7 +1536,8 @@ int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau
     auto direct = [&]() -> int {
         const bool was_async = h->async;
         h->async = true;
-        int rc = fcfv_run_local(h, formulation, A);
+        int rc = run_local_impl(h, formulation, A, variant);
+        if (!rc) { h->alpha.hm.epoch = h->beta.hm.epoch = h->Z.hm.epoch = h->tau.hm.epoch = -1; h->have_local = true; }
         if (!rc) rc = fcfv_run_assemble(h, variant, formulation, A, 0);
         if (!rc) rc = fcfv_run_residuals(h, formulation, tau_mode, nullptr, nullptr);
         h->async = was_async;
@@ -1523,7 +1552,9 @@ int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau
     if (h->graph_exec && !h->delta_dirty && memcmp(key, h->graph_key, sizeof key) == 0) {
         CU(cudaSetDevice(h->device));
         CU(cudaGraphLaunch(h->graph_exec, h->stream));
-        h->launches += 10;
+        h->launches += h->graph_launches;
+        h->coef_variant = h->aniso ? -1 : variant;
+        h->alpha.hm.epoch = h->beta.hm.epoch = h->Z.hm.epoch = h->tau.hm.epoch = -1;
         h->have_local = true;
         h->Kuu.nnz = h->Kup.nnz = -2; h->Muu.nnz = -1; h->Kuusc.nnz = -1;
         h->totals_valid = false;
@@ -1539,6 +1570,7 @@ int fcfv_run_pipeline(fcfv_t* h, int variant, int formulation, double A, int tau
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     const long long launches0 = h->launches;
     const int rc = direct();
+    h->graph_launches = h->launches - launches0;   // kernels one replay launches
     h->launches = launches0;                       // captured, not launched
     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
     if (rc || ce != cudaSuccess || !graph) {
@@ -1585,16 +1617,16 @@ int fcfv_residuals(fcfv_t* h, int formulation, int tau_mode, const double* Vxh, 
         const long long nel = h->nel, nf = h->nf;
         TRY(ensure(h, h->tmp, sizeof(double) * (2 * nf + nel)));
         double* t = P<double>(h->tmp);
-        const int nbe = nblocks(nel), nbl = nblocks((nf + 3) / 4), stride = nbe + nbl;
+        const int nbe = nblocks(nel), nbl = nblocks((nf + kLateFaces - 1) / kLateFaces, kLateBlock), stride = nbe + nbl;
         const MeshView M = mesh_view(h);
         double* part = P<double>(h->partial);
         if (formulation == FCFV_GRADIENT)
-            TLAUNCH(h, T_RES_ELEM, k_res_elem<kGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
+            TLAUNCH(h, T_RES_ELEM, (k_res_elem<kGradient, true>), nbe, kBlock, M, local_view(h), face_view(h), sol_view(h), P<double>(h->sex),
                    P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf, t, t + nf);
         else
-            TLAUNCH(h, T_RES_ELEM, k_res_elem<kSymmetricGradient>, nbe, kBlock, M, local_view(h), face_view(h), sol_view(h),
+            TLAUNCH(h, T_RES_ELEM, (k_res_elem<kSymmetricGradient, true>), nbe, kBlock, M, local_view(h), face_view(h), sol_view(h),
                    P<double>(h->sex), P<double>(h->sey), tau_mode, P<double>(h->Fg), part, stride, t + 2 * nf, t, t + nf);
-        TLAUNCH(h, T_RES_FACE, k_res_late, nbl, kBlock, M, P<double>(h->Fg), part, stride, nbe, t, t + nf);
+        TLAUNCH(h, T_RES_FACE, k_res_late, nbl, kLateBlock, M, P<double>(h->Fg), part, stride, nbe, t, t + nf);
         CU(cudaGetLastError());
         if (F_nodes_x) TRY(copy(h, F_nodes_x, t, sizeof(double) * nf));
         if (F_nodes_y) TRY(copy(h, F_nodes_y, t + nf, sizeof(double) * nf));
@@ -1926,6 +1958,7 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     TRY(ensure(h, h->e2f, sizeof(int) * 3 * nel));
     TRY(ensure(h, h->bc, (size_t)nf));
     new_epoch(h);        // every data buffer is rewritten on the device
+    h->coef_variant = -1;
     for (DBuf* b : {&h->Om, &h->ke, &h->dl, &h->taue, &h->sex, &h->sey, &h->Pe}) TRY(ensure(h, *b, sizeof(double) * nel));
     for (DBuf* b : {&h->nx, &h->ny, &h->G}) TRY(ensure(h, *b, sizeof(double) * 3 * nel));
     for (DBuf* b : {&h->VxDir, &h->VyDir, &h->sxx, &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh}) TRY(ensure(h, *b, sizeof(double) * nf));

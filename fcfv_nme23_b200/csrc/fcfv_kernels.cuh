@@ -49,6 +49,7 @@ constexpr int kOwnedFace = 1 << 20;   // in fbc
 constexpr int kOwnedElem = 1 << 15;   // in ebc
 constexpr int kLateFace = 1 << 21;    // in fbc: F_nodes of this face is not formed inside k_res_elem (its two elements sit in
                                       // different 128-element tiles, or no element references it): k_res_late does it
+constexpr int kOrphanFace = 1 << 22;  // in fbc: no element references the face
 // eadj slot of local face j (bits 9j .. 9j+8): (thread of the neighbour in this element's 128-element tile) << 2 | (its local
 // index of the shared face); local index 3 = no neighbour in the tile: thread field kAdjBoundary = boundary face (the
 // element is the face's only one), 0 = the neighbour lives in another tile
@@ -413,7 +414,7 @@ __global__ void k_fconn(const int* __restrict__ e2f, const int8_t* __restrict__ 
     fconn[f] = o;
     const int2 pr = f2e[f];
     const bool late = pr.x < 0 || (pr.y != pr.x && ((pr.x >> 2) >> 7) != ((pr.y >> 2) >> 7));
-    fbc[f] = p | kOwnedFace | (late ? kLateFace : 0);        // everything is owned until fcfv_set_ownership says otherwise (k_pack_owned)
+    fbc[f] = p | kOwnedFace | (late ? kLateFace : 0) | (pr.x < 0 ? kOrphanFace : 0);        // everything is owned until fcfv_set_ownership says otherwise (k_pack_owned)
 }
 
 // per-element copy of the bc tags of its faces (static per mesh): the element kernels know the tags
@@ -495,11 +496,14 @@ __global__ void k_geometry(int nel, const int* __restrict__ e2v, const int* __re
 }
 
 // ---- a4 ComputeFCFV --------------------------------------------------------------------------
-template <int FORM>
+// COEF: kLoopOld / kLoopNew = also write the per-element assembly coefficients 1/alpha and c11 of that loop (what
+// k_elem_coef would compute from alpha in a pass of its own; delta == 1 everywhere), -1 = alpha / beta / Z only.
+template <int FORM, int COEF>
 __global__ void __launch_bounds__(kBlock)
 k_local(MeshView M, const double* __restrict__ sex, const double* __restrict__ sey,
         const double* __restrict__ VxDir, const double* __restrict__ VyDir, double A, double* __restrict__ alpha,
-        double* __restrict__ beta, double* __restrict__ Z, double* __restrict__ tau) {
+        double* __restrict__ beta, double* __restrict__ Z, double* __restrict__ tau, double* __restrict__ ia,
+        double* __restrict__ c11) {
     const int e = blockIdx.x * kBlock + threadIdx.x;
     const int nel = M.nel;
     if (e >= nel) return;
@@ -522,7 +526,13 @@ k_local(MeshView M, const double* __restrict__ sex, const double* __restrict__ s
     for (int i = 0; i < 3; i++)
         if ((tags >> (12 + i)) & 1) tau[fid[i]] = te;
     ElemLocal o;
-    element_local<FORM>(M.Om[e], te, sex[e], sey[e], G, nx, ny, dir, vx, vy, A, o);
+    const double Om = M.Om[e];
+    element_local<FORM>(Om, te, sex[e], sey[e], G, nx, ny, dir, vx, vy, A, o);
+    if (COEF >= 0) {
+        double a, d11, d12, d21, d22;
+        element_coef<COEF < 0 ? kLoopOld : COEF>(o.alpha, M.ke[e], 1.0, Om, a, d11, d12, d21, d22);
+        ia[e] = a; c11[e] = d11;
+    }
     alpha[e] = o.alpha;
     beta[e] = o.b1; beta[nel + e] = o.b2;
     Z[e] = o.Z11; Z[nel + e] = o.Z21; Z[2 * nel + e] = o.Z12; Z[3 * nel + e] = o.Z22;
@@ -891,10 +901,12 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
 // the <= 2 elements of a non-Dirichlet face) is formed HERE for every face whose elements sit in the same 128-element
 // tile: the fluxes are exchanged through shared memory, the face's highest element adds them (lower element first, like
 // the reference's element loop) and squares the result.  Only the fluxes of faces cut by a tile boundary go to memory
-// (Fg, [element][face][component]) for k_res_late.  On a locality-numbered mesh that is one face in six.
+// (Fg, [face][side: lower / higher element][component] -- the two contributions of a face share one 32-byte sector) for
+// k_res_late.  On a locality-numbered mesh that is one face in six.
 // partial[q*stride + b]: q = 0 F_eq1, 1 F_eq2, 2 F_eq3, 3 F_glob2, 4 / 5 F_nodes x / y (this kernel's blocks first, then
 // those of k_res_late).
-template <int FORM>
+// OUT: the optional arrays F_glob2 / F_nodes are written (second, rare launch); the hot variant carries no face ids.
+template <int FORM, bool OUT>
 __global__ void __launch_bounds__(kBlock, FCFV_RES_MINBLOCKS)
 k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double* __restrict__ sex,
            const double* __restrict__ sey, int tau_mode, double* __restrict__ Fg, double* __restrict__ partial,
@@ -936,9 +948,10 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
         for (int i = 0; i < 3; i++) {
             const double2 v = make_double2(r.Fg1[i][0], r.Fg1[i][1]);
             sF[3 * threadIdx.x + i] = v;
-            if (((adj >> (9 * i)) & 511) == kAdjNone) reinterpret_cast<double2*>(Fg)[(size_t)3 * e + i] = v;   // cut face
+            if (((adj >> (9 * i)) & 511) == kAdjNone)          // cut face: slot of this side (the highest element is side 1)
+                reinterpret_cast<double2*>(Fg)[(size_t)2 * fid[i] + ((tags >> (12 + i)) & 1)] = v;
         }
-        if (F_glob2_out) F_glob2_out[e] = r.Fg2;
+        if (OUT && F_glob2_out) F_glob2_out[e] = r.Fg2;
         if (tags & kOwnedElem) {
             s1 = ((r.F1[0][0] * r.F1[0][0] + r.F1[1][0] * r.F1[1][0]) + r.F1[0][1] * r.F1[0][1]) + r.F1[1][1] * r.F1[1][1];
             s2 = r.F2[0] * r.F2[0] + r.F2[1] * r.F2[1];
@@ -961,8 +974,8 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
                 const double2 me = sF[3 * threadIdx.x + i];
                 Fx = Fx + me.x; Fy = Fy + me.y;
             }
-            if (Fx_out) Fx_out[fid[i]] = Fx;
-            if (Fy_out) Fy_out[fid[i]] = Fy;
+            if (OUT && Fx_out) Fx_out[fid[i]] = Fx;
+            if (OUT && Fy_out) Fy_out[fid[i]] = Fy;
             if ((adj >> (kAdjOwnedShift + i)) & 1) { sx = sx + Fx * Fx; sy = sy + Fy * Fy; }
         }
     }
@@ -976,31 +989,33 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
 }
 
 // Faces k_res_elem leaves out (kLateFace: cut by a tile boundary, or referenced by no element): one thread per four faces,
-// one 16-byte load of the packed tags, the gathers only where there is work.  partial rows 4 / 5 from block offset `b0`.
-__global__ void __launch_bounds__(kBlock)
+// one 16-byte load of the packed tags, then one 32-byte sector per cut face (both fluxes).  partial rows 4 / 5 from block
+// offset `b0`.
+constexpr int kLateBlock = 128;
+constexpr int kLateFaces = 4;
+__global__ void __launch_bounds__(kLateBlock)
 k_res_late(MeshView M, const double* __restrict__ Fg, double* __restrict__ partial, int stride, int b0,
            double* __restrict__ Fx_out, double* __restrict__ Fy_out) {
-    __shared__ double sd[2 * (kBlock / 32)];
-    const int f0 = 4 * (blockIdx.x * kBlock + threadIdx.x);
+    __shared__ double sd[2 * (kLateBlock / 32)];
+    const long long f0 = (long long)kLateFaces * (blockIdx.x * kLateBlock + threadIdx.x);
     double sx = 0.0, sy = 0.0;
     if (f0 < M.nf) {
-        int tags[4] = {0, 0, 0, 0};
-        if (f0 + 3 < M.nf) {
+        int tags[kLateFaces] = {0, 0, 0, 0};
+        if (f0 + kLateFaces <= M.nf) {
             const int4 t = *reinterpret_cast<const int4*>(M.fbc + f0);
             tags[0] = t.x; tags[1] = t.y; tags[2] = t.z; tags[3] = t.w;
         } else {
-            for (int q = 0; q < 4 && f0 + q < M.nf; q++) tags[q] = M.fbc[f0 + q];
+            for (int q = 0; q < kLateFaces && f0 + q < M.nf; q++) tags[q] = M.fbc[f0 + q];
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < kLateFaces; q++) {
             if (!(tags[q] & kLateFace)) continue;
-            const int f = f0 + q;
+            const long long f = f0 + q;
             double Fx = 0.0, Fy = 0.0;
-            const int2 pr = M.f2e[f];
-            if (pr.x >= 0 && ((tags[q] & 15) - 1) != 1) {
-                const double2 v0 = reinterpret_cast<const double2*>(Fg)[(size_t)3 * (pr.x >> 2) + (pr.x & 3)];
-                const double2 v1 = reinterpret_cast<const double2*>(Fg)[(size_t)3 * (pr.y >> 2) + (pr.y & 3)];
-                Fx = Fx + v0.x; Fy = Fy + v0.y;
+            if (!(tags[q] & kOrphanFace) && ((tags[q] & 15) - 1) != 1) {      // :89 Dirichlet faces stay zero
+                const double2 v0 = reinterpret_cast<const double2*>(Fg)[2 * f];
+                const double2 v1 = reinterpret_cast<const double2*>(Fg)[2 * f + 1];
+                Fx = Fx + v0.x; Fy = Fy + v0.y;       // lower element first
                 Fx = Fx + v1.x; Fy = Fy + v1.y;
             }
             if (Fx_out) Fx_out[f] = Fx;

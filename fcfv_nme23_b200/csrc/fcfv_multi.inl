@@ -81,23 +81,40 @@ int multi_sync(fcfv_t* h) {
 int multi_finish(fcfv_t* h) { return h->async ? FCFV_OK : multi_sync(h); }
 
 // out[c * n + i] = g[c * ld + idx[i]]  (columns of a column-major global array restricted to local ids)
+// temporaries of the gather / scatter: a vector that does not zero its storage (every entry is written before it is read)
 template <typename T>
-void take(const T* g, int64_t ld, const std::vector<int64_t>& idx, int ncol, std::vector<T>& out) {
+struct no_init_alloc : std::allocator<T> {
+    template <typename U> struct rebind { using other = no_init_alloc<U>; };
+    template <typename U, typename... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
+template <typename T> using uvec = std::vector<T, no_init_alloc<T>>;
+
+// out[c * n + i] = g[c * ld + idx[i]].  Local ids ascend with the global ids and a part is a few contiguous id ranges (its
+// own range plus ghost layers), so the gather runs as one memcpy per run of consecutive ids.
+template <typename T, typename V>
+void take(const T* g, int64_t ld, const std::vector<int64_t>& idx, int ncol, V& out) {
     const size_t n = idx.size();
     out.resize(n * (size_t)ncol);
-    for (int c = 0; c < ncol; c++) {
-        const T* src = g + (size_t)c * ld;
-        T* dst = out.data() + (size_t)c * n;
-        for (size_t i = 0; i < n; i++) dst[i] = src[idx[i]];
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        while (j < n && idx[j] == idx[j - 1] + 1) j++;
+        for (int c = 0; c < ncol; c++) memcpy(out.data() + (size_t)c * n + i, g + (size_t)c * ld + idx[i], (j - i) * sizeof(T));
+        i = j;
     }
 }
 
-// g[c * ld + idx[own[k]]] = loc[c * n + own[k]]  (owned entries of a local array back into the global one)
+// g[c * ld + idx[own[k]]] = loc[c * n + own[k]]  (owned entries of a local array back into the global one), by runs
 template <typename T>
 void put_owned(T* g, int64_t ld, const std::vector<int64_t>& idx, const std::vector<int64_t>& own, int ncol, const T* loc) {
-    const size_t n = idx.size();
-    for (int c = 0; c < ncol; c++)
-        for (int64_t k : own) g[(size_t)c * ld + idx[k]] = loc[(size_t)c * n + k];
+    const size_t n = idx.size(), m = own.size();
+    for (size_t a = 0; a < m;) {
+        size_t b = a + 1;
+        while (b < m && own[b] == own[b - 1] + 1 && idx[own[b]] == idx[own[b - 1]] + 1) b++;
+        for (int c = 0; c < ncol; c++) memcpy(g + (size_t)c * ld + idx[own[a]], loc + (size_t)c * n + own[a], (b - a) * sizeof(T));
+        a = b;
+    }
 }
 
 // ---- the partitioner (C++ port of what one rank of a torchrun job does in fcfv_nme23_b200/partition.py) ------------
@@ -115,40 +132,65 @@ bool face_adjacency(int64_t nel, int64_t nf, const int64_t* e2f, std::vector<int
     return true;
 }
 
-void sort_unique(std::vector<int64_t>& v) {
-    std::sort(v.begin(), v.end());
-    v.erase(std::unique(v.begin(), v.end()), v.end());
+// ascending ids with a mark in [lo, hi]
+void collect_marked(const std::vector<uint8_t>& mark, int64_t lo, int64_t hi, std::vector<int64_t>& out) {
+    size_t n = 0;
+    for (int64_t k = lo; k <= hi; k++) n += mark[k];
+    out.clear();
+    out.reserve(n);
+    for (int64_t k = lo; k <= hi; k++)
+        if (mark[k]) out.push_back(k);
 }
 
 // Part `p` of `np`: owned elements [e0, e1); (A) the lower neighbours of its owned faces; (B) the tau donors: the
 // highest neighbour of every face of an owned / A element, so that the local last-writer rule reproduces the
-// global mesh.tau on every column the owned rows touch.
+// global mesh.tau on every column the owned rows touch.  Sets are kept as byte marks over the id range they span
+// (no sorting: the ids come out ascending from a scan).
 void build_part(int64_t nel, int64_t nf, const int64_t* e2f, const std::vector<int64_t>& lo, const std::vector<int64_t>& hi,
                 int p, int np, Part& P) {
     const int64_t e0 = (int64_t)p * nel / np, e1 = (int64_t)(p + 1) * nel / np;
     auto in_range = [&](int64_t e) { return e >= e0 && e < e1; };
-    std::vector<int64_t> core;
-    core.reserve((size_t)(e1 - e0) + 1024);
-    for (int64_t e = e0; e < e1; e++) core.push_back(e);
+    std::vector<uint8_t> em((size_t)nel, 0);
+    int64_t emin = e0, emax = e1 - 1;
+    std::vector<int64_t> ghostA;
     // owned faces are found among the faces of the owned elements (hi[f] in range implies f is a face of hi[f])
-    for (int64_t e = e0; e < e1; e++)
+    for (int64_t e = e0; e < e1; e++) {
+        em[e] = 1;
         for (int i = 0; i < 3; i++) {
             const int64_t f = e2f[(size_t)i * nel + e] - 1;
-            if (hi[f] == e && !in_range(lo[f])) core.push_back(lo[f]);       // (A)
+            const int64_t l = lo[f];
+            if (hi[f] == e && !in_range(l) && !em[l]) { em[l] = 1; ghostA.push_back(l); }       // (A)
         }
-    sort_unique(core);
-    std::vector<int64_t> elems = core;
-    for (int64_t e : core)
+    }
+    auto donors = [&](int64_t e) {
         for (int i = 0; i < 3; i++) {
             const int64_t d = hi[e2f[(size_t)i * nel + e] - 1];
-            if (!in_range(d)) elems.push_back(d);                            // (B) (duplicates of A are removed below)
+            if (!in_range(d)) em[d] |= 2;                                    // (B)
         }
-    sort_unique(elems);
-    std::vector<int64_t> faces;
-    faces.reserve(elems.size() * 2);
+    };
+    for (int64_t e = e0; e < e1; e++) donors(e);
+    for (int64_t e : ghostA) donors(e);
+    for (int64_t e : ghostA) { emin = std::min(emin, e); emax = std::max(emax, e); }
+    // B elements can lie anywhere: find their span while collecting
+    if (e1 > e0) {
+        for (int64_t e = 0; e < e0; e++) if (em[e]) { emin = std::min(emin, e); break; }
+        for (int64_t e = nel - 1; e >= e1; e--) if (em[e]) { emax = std::max(emax, e); break; }
+    } else {
+        emin = 0; emax = nel - 1;
+    }
+    std::vector<int64_t> elems;
+    if (nel > 0) collect_marked(em, std::max<int64_t>(emin, 0), std::min(emax, nel - 1), elems);
+    std::vector<uint8_t>().swap(em);
+    std::vector<uint8_t> fm((size_t)nf, 0);
+    int64_t fmin = nf, fmax = -1;
     for (int64_t e : elems)
-        for (int i = 0; i < 3; i++) faces.push_back(e2f[(size_t)i * nel + e] - 1);
-    sort_unique(faces);
+        for (int i = 0; i < 3; i++) {
+            const int64_t f = e2f[(size_t)i * nel + e] - 1;
+            fm[f] = 1;
+            fmin = std::min(fmin, f); fmax = std::max(fmax, f);
+        }
+    std::vector<int64_t> faces;
+    if (fmax >= fmin) collect_marked(fm, fmin, fmax, faces);
     P.elems.swap(elems);
     P.faces.swap(faces);
     P.eown.resize(P.elems.size());
@@ -163,6 +205,9 @@ void build_part(int64_t nel, int64_t nf, const int64_t* e2f, const std::vector<i
         if (P.fown[k]) P.own_f.push_back((int64_t)k);
     }
 }
+
+bool multi_hit(fcfv_t* h, const DBuf& rec, const void* src, size_t bytes);
+void multi_note(fcfv_t* h, DBuf& rec, const void* src, size_t bytes);
 
 int multi_load_nccl(fcfv_t* h) {
     fcfv_multi& M = *h->multi;
@@ -226,6 +271,7 @@ int multi_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const
                           (const void*)ke, (const void*)delta, (const void*)taue})
         if (p && is_device(p)) return fail(h, FCFV_ERR_INVALID, "a multi-GPU handle takes host arrays (it scatters them over its devices)");
     h->have_mesh = false; h->have_local = false;
+    new_epoch(h);
     if (nel != h->nel || nf != h->nf) h->have_sources = h->have_face_data = h->have_solution = false;
     h->nel = nel; h->nf = nf; h->nel_global = nel; h->nf_global = nf;
     h->rp64 = 20 * nf >= (1LL << 31);
@@ -244,14 +290,16 @@ int multi_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const
     M.partition_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     TRY(for_parts(h, [&](int, Part& Pt) -> int {
         const int64_t ne = (int64_t)Pt.elems.size(), nfl = (int64_t)Pt.faces.size();
-        std::vector<int64_t> le2f((size_t)3 * ne), lbc;
-        for (int i = 0; i < 3; i++)
-            for (int64_t k = 0; k < ne; k++) {
-                const int64_t f = e2f[(size_t)i * nel + Pt.elems[k]] - 1;
-                le2f[(size_t)i * ne + k] = (std::lower_bound(Pt.faces.begin(), Pt.faces.end(), f) - Pt.faces.begin()) + 1;
-            }
+        uvec<int64_t> le2f((size_t)3 * ne), lbc;
+        {   // global -> local face ids through a dense map over the span of the part's faces
+            const int64_t fmin = nfl ? Pt.faces.front() : 0, fspan = nfl ? Pt.faces.back() - fmin + 1 : 0;
+            uvec<int32_t> fl((size_t)fspan);
+            for (int64_t k = 0; k < nfl; k++) fl[(size_t)(Pt.faces[k] - fmin)] = (int32_t)(k + 1);
+            for (int i = 0; i < 3; i++)
+                for (int64_t k = 0; k < ne; k++) le2f[(size_t)i * ne + k] = fl[(size_t)(e2f[(size_t)i * nel + Pt.elems[k]] - 1 - fmin)];
+        }
         take(bc, nf, Pt.faces, 1, lbc);
-        std::vector<double> lOm, lnx, lny, lG, lke, ldl, lte;
+        uvec<double> lOm, lnx, lny, lG, lke, ldl, lte;
         take(Omega, nel, Pt.elems, 1, lOm); take(nx, nel, Pt.elems, 3, lnx); take(ny, nel, Pt.elems, 3, lny);
         take(Gamma, nel, Pt.elems, 3, lG); take(ke, nel, Pt.elems, 1, lke); take(delta, nel, Pt.elems, 1, ldl);
         if (taue) take(taue, ntaue, Pt.elems, 1, lte);
@@ -261,19 +309,47 @@ int multi_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const
     }));
     M.tau_ref_stale = true;
     h->have_mesh = true;
+    // the field refresh of the first ComputeFCFV on this mesh (same epoch) does not scatter them a second time
+    multi_note(h, h->ke, ke, sizeof(double) * (size_t)nel);
+    multi_note(h, h->dl, delta, sizeof(double) * (size_t)nel);
+    multi_note(h, h->taue, taue, sizeof(double) * (size_t)nel);
     return FCFV_OK;
 }
 
 // one call of a part-level setter with arrays restricted to the part: kind 'e' (per element) / 'f' (per face)
-struct Field { const double* g; char kind; int ncol; };
+// rec: the top-level handle's (otherwise unused) buffer record of the same name -- the upload cache of a multi-GPU handle
+// works on the GLOBAL arrays: when every array of a call is one the parts already mirror (same address, size, epoch and
+// fingerprint), the whole gather / scatter is skipped
+struct Field { const double* g; char kind; int ncol; DBuf* rec; };
+
+bool multi_hit(fcfv_t* h, const DBuf& rec, const void* src, size_t bytes) {
+    return h->cache_on && rec.hm.epoch == h->epoch && rec.hm.ptr == src && rec.hm.bytes == bytes && fingerprint(src, bytes) == rec.hm.fp;
+}
+void multi_note(fcfv_t* h, DBuf& rec, const void* src, size_t bytes) {
+    if (h->cache_on && src) rec.hm = HostMirror{src, bytes, fingerprint(src, bytes), h->epoch};
+    else rec.hm.epoch = -1;
+}
 
 template <typename Call>
 int multi_scatter(fcfv_t* h, std::initializer_list<Field> fields, Call&& call) {
     const std::vector<Field> fl(fields);
     for (const Field& f : fl)
         if (f.g && is_device(f.g)) return fail(h, FCFV_ERR_INVALID, "a multi-GPU handle takes host arrays");
+    auto bytes_of = [&](const Field& f) { return sizeof(double) * (size_t)f.ncol * (size_t)(f.kind == 'e' ? h->nel : h->nf); };
+    if (h->cache_on) {
+        bool all = true, any = false;
+        for (const Field& f : fl)
+            if (f.g) { any = true; all = all && f.rec && multi_hit(h, *f.rec, f.g, bytes_of(f)); }
+        if (any && all) {
+            for (const Field& f : fl)
+                if (f.g) { h->cache_hits++; h->cache_hit_bytes += (long long)bytes_of(f); }
+            return FCFV_OK;
+        }
+    }
+    for (const Field& f : fl)
+        if (f.rec) f.rec->hm.epoch = -1;
     TRY(for_parts(h, [&](int, Part& Pt) -> int {
-        std::vector<std::vector<double>> loc(fl.size());
+        std::vector<uvec<double>> loc(fl.size());
         std::vector<const double*> ptr(fl.size(), nullptr);
         for (size_t k = 0; k < fl.size(); k++) {
             if (!fl[k].g) continue;
@@ -287,19 +363,25 @@ int multi_scatter(fcfv_t* h, std::initializer_list<Field> fields, Call&& call) {
         Pt.h->async = was;
         return rc;
     }));
+    for (const Field& f : fl)
+        if (f.g && f.rec) multi_note(h, *f.rec, f.g, bytes_of(f));
     return FCFV_OK;
 }
 
 int multi_update_fields(fcfv_t* h, const double* ke, const double* delta, const double* taue, int64_t ntaue, const double* tau) {
     if (taue && ntaue < h->nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel", (long long)ntaue);
-    if (ke || delta || tau) {
-        TRY(multi_scatter(h, {{ke, 'e', 1}, {delta, 'e', 1}, {tau, 'f', 1}}, [&](fcfv_t* q, const std::vector<const double*>& a) {
-            return fcfv_update_fields(q, a[0], a[1], nullptr, 0, a[2]);
-        }));
+    if (ke) TRY(multi_scatter(h, {{ke, 'e', 1, &h->ke}}, [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_update_fields(q, a[0], nullptr, nullptr, 0, nullptr); }));
+    if (delta) TRY(multi_scatter(h, {{delta, 'e', 1, &h->dl}}, [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_update_fields(q, nullptr, a[0], nullptr, 0, nullptr); }));
+    const bool tau_hit = tau && multi_hit(h, h->tau, tau, sizeof(double) * (size_t)h->nf);
+    if (tau) TRY(multi_scatter(h, {{tau, 'f', 1, &h->tau}}, [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_update_fields(q, nullptr, nullptr, nullptr, 0, a[0]); }));
+    if (tau_hit) tau = nullptr;       // the parts already hold it: nothing below has anything new to do
+    if (taue && multi_hit(h, h->taue, taue, sizeof(double) * (size_t)h->nel)) {
+        h->cache_hits++; h->cache_hit_bytes += (long long)(sizeof(double) * (size_t)h->nel);
+        taue = nullptr;
     }
     if (taue) {     // may have more than nel entries (ViscousInclusionFCFV_v2.jl:127): only [0, nel) is read
         TRY(for_parts(h, [&](int, Part& Pt) -> int {
-            std::vector<double> lte;
+            uvec<double> lte;
             take(taue, ntaue, Pt.elems, 1, lte);
             const bool was = Pt.h->async;
             Pt.h->async = false;
@@ -307,6 +389,7 @@ int multi_update_fields(fcfv_t* h, const double* ke, const double* delta, const 
             Pt.h->async = was;
             return rc;
         }));
+        multi_note(h, h->taue, taue, sizeof(double) * (size_t)h->nel);
     }
     if (tau)
         for (size_t k = 0; k < h->multi->unref.size(); k++) h->multi->unref_tau[k] = tau[h->multi->unref[k]];
@@ -324,22 +407,28 @@ int multi_update_fields(fcfv_t* h, const double* ke, const double* delta, const 
 
 int multi_set_sources(fcfv_t* h, const double* sex, const double* sey) {
     if (!sex || !sey) return fail(h, FCFV_ERR_INVALID, "fcfv_set_sources: null array");
-    TRY(multi_scatter(h, {{sex, 'e', 1}, {sey, 'e', 1}}, [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_set_sources(q, a[0], a[1]); }));
+    TRY(multi_scatter(h, {{sex, 'e', 1, &h->sex}, {sey, 'e', 1, &h->sey}}, [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_set_sources(q, a[0], a[1]); }));
     h->have_sources = true;
     return FCFV_OK;
 }
 
 int multi_set_face_data(fcfv_t* h, const double* VxDir, const double* VyDir, const double* sxx, const double* syy, const double* sxy,
                         const double* syx) {
-    TRY(multi_scatter(h, {{VxDir, 'f', 1}, {VyDir, 'f', 1}, {sxx, 'f', 1}, {syy, 'f', 1}, {sxy, 'f', 1}, {syx, 'f', 1}},
-                      [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_set_face_data(q, a[0], a[1], a[2], a[3], a[4], a[5]); }));
+    // NULL = keep what is resident, so the Dirichlet pair and the Neumann quadruple are scattered (or skipped) separately
+    const bool first = !h->have_face_data;
+    if (first || VxDir || VyDir)
+        TRY(multi_scatter(h, {{VxDir, 'f', 1, &h->VxDir}, {VyDir, 'f', 1, &h->VyDir}},
+                          [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_set_face_data(q, a[0], a[1], nullptr, nullptr, nullptr, nullptr); }));
+    if (sxx || syy || sxy || syx)
+        TRY(multi_scatter(h, {{sxx, 'f', 1, &h->sxx}, {syy, 'f', 1, &h->syy}, {sxy, 'f', 1, &h->sxy}, {syx, 'f', 1, &h->syx}},
+                          [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_set_face_data(q, nullptr, nullptr, a[0], a[1], a[2], a[3]); }));
     h->have_face_data = true;
     return FCFV_OK;
 }
 
 int multi_set_solution(fcfv_t* h, const double* Vxh, const double* Vyh, const double* Pe) {
     if (!Vxh || !Vyh || !Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_set_solution: null array");
-    TRY(multi_scatter(h, {{Vxh, 'f', 1}, {Vyh, 'f', 1}, {Pe, 'e', 1}},
+    TRY(multi_scatter(h, {{Vxh, 'f', 1, &h->Vxh}, {Vyh, 'f', 1, &h->Vyh}, {Pe, 'e', 1, &h->Pe}},
                       [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_set_solution(q, a[0], a[1], a[2]); }));
     h->have_solution = true;
     return FCFV_OK;
@@ -347,7 +436,7 @@ int multi_set_solution(fcfv_t* h, const double* Vxh, const double* Vyh, const do
 
 int multi_set_local(fcfv_t* h, const double* alpha, const double* beta, const double* Z) {
     if (!alpha || !beta || !Z) return fail(h, FCFV_ERR_INVALID, "fcfv_set_local: null array");
-    TRY(multi_scatter(h, {{alpha, 'e', 1}, {beta, 'e', 2}, {Z, 'e', 4}},
+    TRY(multi_scatter(h, {{alpha, 'e', 1, &h->alpha}, {beta, 'e', 2, &h->beta}, {Z, 'e', 4, &h->Z}},
                       [&](fcfv_t* q, const std::vector<const double*>& a) { return fcfv_set_local(q, a[0], a[1], a[2]); }));
     h->have_local = true;
     return FCFV_OK;
@@ -366,10 +455,13 @@ int multi_run(fcfv_t* h, Call&& call) {
     return FCFV_OK;
 }
 
+int multi_get_local_parts(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau);
+
 int multi_run_local(fcfv_t* h, int formulation, double A) {
     TRY(need(h, h->have_mesh, "fcfv_run_local: no mesh set"));
     TRY(need(h, h->have_sources && h->have_face_data, "fcfv_run_local: sources / face data not set"));
     TRY(multi_run(h, [&](fcfv_t* q) { return fcfv_run_local(q, formulation, A); }));
+    h->alpha.hm.epoch = h->beta.hm.epoch = h->Z.hm.epoch = h->tau.hm.epoch = -1;      // rewritten on the devices
     h->have_local = true;
     h->multi->tau_ref_stale = true;
     return multi_finish(h);
@@ -379,9 +471,19 @@ int multi_get_local(fcfv_t* h, double* alpha, double* beta, double* Z, double* t
     TRY(need(h, h->have_local, "fcfv_get_local: local coefficients not computed"));
     if (tau)
         for (size_t k = 0; k < h->multi->unref.size(); k++) tau[h->multi->unref[k]] = h->multi->unref_tau[k];
+    TRY(multi_get_local_parts(h, alpha, beta, Z, tau));
+    // the caller's arrays now mirror what the parts hold
+    multi_note(h, h->alpha, alpha, sizeof(double) * (size_t)h->nel);
+    multi_note(h, h->beta, beta, sizeof(double) * 2 * (size_t)h->nel);
+    multi_note(h, h->Z, Z, sizeof(double) * 4 * (size_t)h->nel);
+    if (h->multi->unref.empty()) multi_note(h, h->tau, tau, sizeof(double) * (size_t)h->nf);
+    return FCFV_OK;
+}
+
+int multi_get_local_parts(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau) {
     return for_parts(h, [&](int, Part& Pt) -> int {
         const size_t ne = Pt.elems.size(), nfl = Pt.faces.size();
-        std::vector<double> a(alpha ? ne : 0), b(beta ? 2 * ne : 0), z(Z ? 4 * ne : 0), t(tau ? nfl : 0);
+        uvec<double> a(alpha ? ne : 0), b(beta ? 2 * ne : 0), z(Z ? 4 * ne : 0), t(tau ? nfl : 0);
         TRY(fcfv_get_local(Pt.h, alpha ? a.data() : nullptr, beta ? b.data() : nullptr, Z ? z.data() : nullptr, tau ? t.data() : nullptr));
         if (alpha) put_owned(alpha, h->nel, Pt.elems, Pt.own_e, 1, a.data());
         if (beta) put_owned(beta, h->nel, Pt.elems, Pt.own_e, 2, b.data());

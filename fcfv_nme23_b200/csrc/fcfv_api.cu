@@ -377,7 +377,7 @@ bool is_device(const void* p) {
 // pageable host memory go through the Stager; like the driver's own pageable path they have completed on the host
 // side when the call returns.
 int copy(fcfv_t* h, void* dst, const void* src, size_t bytes) {
-    if (bytes == 0) return FCFV_OK;
+    if (bytes == 0 || dst == src) return FCFV_OK;       // dst == src: the data is already where it belongs (multi-GPU scatter)
     const bool dd = is_device(dst), sd = is_device(src);
     if (dd && !sd) h->h2d_bytes += (long long)bytes;       // what actually crosses PCIe (fcfv_transfer_stats)
     if (sd && !dd) h->d2h_bytes += (long long)bytes;

@@ -20,6 +20,8 @@ struct Part {
     std::vector<int64_t> elems, faces;      // local -> global (0-based), ascending
     std::vector<int64_t> own_e, own_f;      // local ids of the owned elements / faces, ascending
     std::vector<uint8_t> eown, fown;
+    std::vector<std::pair<int64_t, int64_t>> erun, frun;   // (first local id, length) of every run of consecutive global ids
+    std::vector<std::pair<int64_t, int64_t>> oerun, ofrun; // the same for the OWNED elements / faces only
 };
 
 }  // namespace
@@ -105,6 +107,51 @@ void take(const T* g, int64_t ld, const std::vector<int64_t>& idx, int ncol, V& 
     }
 }
 
+void make_runs(const std::vector<int64_t>& idx, std::vector<std::pair<int64_t, int64_t>>& runs) {
+    runs.clear();
+    const size_t n = idx.size();
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        while (j < n && idx[j] == idx[j - 1] + 1) j++;
+        runs.emplace_back((int64_t)i, (int64_t)(j - i));
+        i = j;
+    }
+}
+
+// A part of a range partition is a handful of runs (its own id range plus ghost layers): its restriction of a global array
+// then goes straight from the caller's memory into the part's device buffer, one copy per run and column -- no gather into
+// a temporary, no extra pass over host memory (a copy costs a few microseconds).  Beyond this many runs (scattered ghosts of an unordered mesh) the gather
+// into a temporary is cheaper than that many small copies.
+size_t max_direct_runs() {      // FCFV_MULTI_MAX_RUNS overrides (0 forces the gather path: test hook)
+    const char* e = getenv("FCFV_MULTI_MAX_RUNS");
+    return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)16384;
+}
+
+template <typename T>
+int upload_runs(fcfv_t* q, DBuf& b, const T* g, int64_t ld, const std::vector<int64_t>& idx,
+                const std::vector<std::pair<int64_t, int64_t>>& runs, int ncol) {
+    const size_t n = idx.size();
+    TRY(ensure(q, b, sizeof(T) * n * (size_t)ncol));
+    b.hm.epoch = -1;
+    fcfv_t* h = q;      // for the CU / TRY macros
+    for (const auto& r : runs)
+        for (int c = 0; c < ncol; c++)
+            TRY(copy(h, static_cast<T*>(b.p) + (size_t)c * n + r.first, g + (size_t)c * ld + idx[(size_t)r.first], (size_t)r.second * sizeof(T)));
+    return FCFV_OK;
+}
+
+// owned entries of a part's device array straight into the caller's global array, one copy per run and column
+template <typename T>
+int download_runs(fcfv_t* q, const T* dev, T* g, int64_t ld, const std::vector<int64_t>& idx,
+                  const std::vector<std::pair<int64_t, int64_t>>& runs, int ncol) {
+    const size_t n = idx.size();
+    fcfv_t* h = q;
+    for (const auto& r : runs)
+        for (int c = 0; c < ncol; c++)
+            TRY(copy(h, g + (size_t)c * ld + idx[(size_t)r.first], dev + (size_t)c * n + r.first, (size_t)r.second * sizeof(T)));
+    return FCFV_OK;
+}
+
 // g[c * ld + idx[own[k]]] = loc[c * n + own[k]]  (owned entries of a local array back into the global one), by runs
 template <typename T>
 void put_owned(T* g, int64_t ld, const std::vector<int64_t>& idx, const std::vector<int64_t>& own, int ncol, const T* loc) {
@@ -120,15 +167,40 @@ void put_owned(T* g, int64_t ld, const std::vector<int64_t>& idx, const std::vec
 // ---- the partitioner (C++ port of what one rank of a torchrun job does in fcfv_nme23_b200/partition.py) ------------
 // lo / hi: lowest / highest adjacent element of every face (-1: none).  Returns false on an out-of-range face id.
 bool face_adjacency(int64_t nel, int64_t nf, const int64_t* e2f, std::vector<int64_t>& lo, std::vector<int64_t>& hi) {
-    lo.assign(nf, -1);
-    hi.assign(nf, -1);
-    for (int i = 0; i < 3; i++)
-        for (int64_t e = 0; e < nel; e++) {
-            const int64_t f = e2f[(size_t)i * nel + e] - 1;
-            if (f < 0 || f >= nf) return false;
-            if (lo[f] < 0 || e < lo[f]) lo[f] = e;
-            if (e > hi[f]) hi[f] = e;
+    lo.resize((size_t)nf);
+    hi.resize((size_t)nf);
+    // element ranges on several threads; a face is touched by at most two elements, so the compare-and-swap loops below
+    // almost never retry
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)(hw ? hw : 1u), 16, nel / 65536 + 1}));
+    std::vector<int> bad(nt, 0);
+    auto fill = [&](int t) {
+        const int64_t f0 = nf * t / nt, f1 = nf * (t + 1) / nt;
+        for (int64_t f = f0; f < f1; f++) { lo[f] = -1; hi[f] = -1; }
+    };
+    auto scan = [&](int t) {
+        const int64_t a = nel * t / nt, b = nel * (t + 1) / nt;
+        for (int64_t e = a; e < b; e++)
+            for (int i = 0; i < 3; i++) {
+                const int64_t f = e2f[(size_t)i * nel + e] - 1;
+                if (f < 0 || f >= nf) { bad[t] = 1; return; }
+                int64_t o = __atomic_load_n(&lo[f], __ATOMIC_RELAXED);
+                while ((o < 0 || e < o) && !__atomic_compare_exchange_n(&lo[f], &o, e, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+                o = __atomic_load_n(&hi[f], __ATOMIC_RELAXED);
+                while (e > o && !__atomic_compare_exchange_n(&hi[f], &o, e, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+            }
+    };
+    auto run = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) {
+            try { th.emplace_back(fn, t); } catch (...) { fn(t); }
         }
+        fn(0);
+        for (auto& x : th) x.join();
+    };
+    run(fill);
+    run(scan);
+    for (int b : bad) if (b) return false;
     return true;
 }
 
@@ -204,6 +276,20 @@ void build_part(int64_t nel, int64_t nf, const int64_t* e2f, const std::vector<i
         P.fown[k] = in_range(hi[P.faces[k]]) ? 1 : 0;
         if (P.fown[k]) P.own_f.push_back((int64_t)k);
     }
+    make_runs(P.elems, P.erun);
+    make_runs(P.faces, P.frun);
+    auto owned_runs = [](const std::vector<int64_t>& idx, const std::vector<int64_t>& own, std::vector<std::pair<int64_t, int64_t>>& runs) {
+        runs.clear();
+        const size_t m = own.size();
+        for (size_t a = 0; a < m;) {
+            size_t b = a + 1;
+            while (b < m && own[b] == own[b - 1] + 1 && idx[own[b]] == idx[own[b - 1]] + 1) b++;
+            runs.emplace_back(own[a], (int64_t)(b - a));
+            a = b;
+        }
+    };
+    owned_runs(P.elems, P.own_e, P.oerun);
+    owned_runs(P.faces, P.own_f, P.ofrun);
 }
 
 bool multi_hit(fcfv_t* h, const DBuf& rec, const void* src, size_t bytes);
@@ -299,12 +385,24 @@ int multi_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const
                 for (int64_t k = 0; k < ne; k++) le2f[(size_t)i * ne + k] = fl[(size_t)(e2f[(size_t)i * nel + Pt.elems[k]] - 1 - fmin)];
         }
         take(bc, nf, Pt.faces, 1, lbc);
-        uvec<double> lOm, lnx, lny, lG, lke, ldl, lte;
-        take(Omega, nel, Pt.elems, 1, lOm); take(nx, nel, Pt.elems, 3, lnx); take(ny, nel, Pt.elems, 3, lny);
-        take(Gamma, nel, Pt.elems, 3, lG); take(ke, nel, Pt.elems, 1, lke); take(delta, nel, Pt.elems, 1, ldl);
-        if (taue) take(taue, ntaue, Pt.elems, 1, lte);
-        TRY(fcfv_set_mesh(Pt.h, ne, nfl, le2f.data(), lbc.data(), lOm.data(), lnx.data(), lny.data(), lG.data(), lke.data(), ldl.data(),
-                          taue ? lte.data() : nullptr, ne));
+        fcfv_t* q = Pt.h;
+        if (Pt.erun.size() <= max_direct_runs()) {
+            // the floating-point fields go from the caller's arrays into the part's own buffers; fcfv_set_mesh then finds
+            // them in place (device pointers of its own buffers: nothing is copied twice)
+            TRY(upload_runs(q, q->Om, Omega, nel, Pt.elems, Pt.erun, 1)); TRY(upload_runs(q, q->nx, nx, nel, Pt.elems, Pt.erun, 3));
+            TRY(upload_runs(q, q->ny, ny, nel, Pt.elems, Pt.erun, 3)); TRY(upload_runs(q, q->G, Gamma, nel, Pt.elems, Pt.erun, 3));
+            TRY(upload_runs(q, q->ke, ke, nel, Pt.elems, Pt.erun, 1)); TRY(upload_runs(q, q->dl, delta, nel, Pt.elems, Pt.erun, 1));
+            if (taue) TRY(upload_runs(q, q->taue, taue, ntaue, Pt.elems, Pt.erun, 1));
+            TRY(fcfv_set_mesh(q, ne, nfl, le2f.data(), lbc.data(), P<double>(q->Om), P<double>(q->nx), P<double>(q->ny), P<double>(q->G),
+                              P<double>(q->ke), P<double>(q->dl), taue ? P<double>(q->taue) : nullptr, ne));
+        } else {
+            uvec<double> lOm, lnx, lny, lG, lke, ldl, lte;
+            take(Omega, nel, Pt.elems, 1, lOm); take(nx, nel, Pt.elems, 3, lnx); take(ny, nel, Pt.elems, 3, lny);
+            take(Gamma, nel, Pt.elems, 3, lG); take(ke, nel, Pt.elems, 1, lke); take(delta, nel, Pt.elems, 1, ldl);
+            if (taue) take(taue, ntaue, Pt.elems, 1, lte);
+            TRY(fcfv_set_mesh(q, ne, nfl, le2f.data(), lbc.data(), lOm.data(), lnx.data(), lny.data(), lG.data(), lke.data(), ldl.data(),
+                              taue ? lte.data() : nullptr, ne));
+        }
         return fcfv_set_ownership(Pt.h, Pt.eown.data(), Pt.fown.data(), nel, nf, nullptr);
     }));
     M.tau_ref_stale = true;
@@ -353,7 +451,16 @@ int multi_scatter(fcfv_t* h, std::initializer_list<Field> fields, Call&& call) {
         std::vector<const double*> ptr(fl.size(), nullptr);
         for (size_t k = 0; k < fl.size(); k++) {
             if (!fl[k].g) continue;
-            if (fl[k].kind == 'e') take(fl[k].g, h->nel, Pt.elems, fl[k].ncol, loc[k]);
+            const bool el = fl[k].kind == 'e';
+            const auto& runs = el ? Pt.erun : Pt.frun;
+            if (fl[k].rec && runs.size() <= max_direct_runs()) {
+                // straight into the part's buffer of the same name; the setter below is handed that device pointer
+                DBuf& pb = *reinterpret_cast<DBuf*>(reinterpret_cast<char*>(Pt.h) + (reinterpret_cast<char*>(fl[k].rec) - reinterpret_cast<char*>(h)));
+                TRY(upload_runs(Pt.h, pb, fl[k].g, el ? h->nel : h->nf, el ? Pt.elems : Pt.faces, runs, fl[k].ncol));
+                ptr[k] = P<double>(pb);
+                continue;
+            }
+            if (el) take(fl[k].g, h->nel, Pt.elems, fl[k].ncol, loc[k]);
             else take(fl[k].g, h->nf, Pt.faces, fl[k].ncol, loc[k]);
             ptr[k] = loc[k].data();
         }
@@ -380,16 +487,9 @@ int multi_update_fields(fcfv_t* h, const double* ke, const double* delta, const 
         taue = nullptr;
     }
     if (taue) {     // may have more than nel entries (ViscousInclusionFCFV_v2.jl:127): only [0, nel) is read
-        TRY(for_parts(h, [&](int, Part& Pt) -> int {
-            uvec<double> lte;
-            take(taue, ntaue, Pt.elems, 1, lte);
-            const bool was = Pt.h->async;
-            Pt.h->async = false;
-            const int rc = fcfv_update_fields(Pt.h, nullptr, nullptr, lte.data(), (int64_t)lte.size(), nullptr);
-            Pt.h->async = was;
-            return rc;
+        TRY(multi_scatter(h, {{taue, 'e', 1, &h->taue}}, [&](fcfv_t* q, const std::vector<const double*>& a) {
+            return fcfv_update_fields(q, nullptr, nullptr, a[0], q->nel, nullptr);
         }));
-        multi_note(h, h->taue, taue, sizeof(double) * (size_t)h->nel);
     }
     if (tau)
         for (size_t k = 0; k < h->multi->unref.size(); k++) h->multi->unref_tau[k] = tau[h->multi->unref[k]];
@@ -483,6 +583,15 @@ int multi_get_local(fcfv_t* h, double* alpha, double* beta, double* Z, double* t
 int multi_get_local_parts(fcfv_t* h, double* alpha, double* beta, double* Z, double* tau) {
     return for_parts(h, [&](int, Part& Pt) -> int {
         const size_t ne = Pt.elems.size(), nfl = Pt.faces.size();
+        if (Pt.oerun.size() <= max_direct_runs() && Pt.ofrun.size() <= max_direct_runs()) {
+            fcfv_t* q = Pt.h;
+            TRY(need(q, q->have_local, "fcfv_get_local: local coefficients not computed"));
+            if (alpha) TRY(download_runs(q, P<double>(q->alpha), alpha, h->nel, Pt.elems, Pt.oerun, 1));
+            if (beta) TRY(download_runs(q, P<double>(q->beta), beta, h->nel, Pt.elems, Pt.oerun, 2));
+            if (Z) TRY(download_runs(q, P<double>(q->Z), Z, h->nel, Pt.elems, Pt.oerun, 4));
+            if (tau) TRY(download_runs(q, P<double>(q->tau), tau, h->nf, Pt.faces, Pt.ofrun, 1));
+            return sync(q);
+        }
         uvec<double> a(alpha ? ne : 0), b(beta ? 2 * ne : 0), z(Z ? 4 * ne : 0), t(tau ? nfl : 0);
         TRY(fcfv_get_local(Pt.h, alpha ? a.data() : nullptr, beta ? b.data() : nullptr, Z ? z.data() : nullptr, tau ? t.data() : nullptr));
         if (alpha) put_owned(alpha, h->nel, Pt.elems, Pt.own_e, 1, a.data());

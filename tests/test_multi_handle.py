@@ -92,6 +92,25 @@ def test_multi_handle_random_mesh(ngpus, monkeypatch):
             assert np.array_equal(x, y), k
 
 
+@pytest.mark.parametrize("max_runs", ["0", "3"])
+def test_multi_handle_gather_path(max_runs, monkeypatch):
+    """The scatter goes straight from the caller's arrays when a part is a few runs of consecutive ids, and through a
+    gathered temporary otherwise: both give the single-GPU result (FCFV_MULTI_MAX_RUNS forces the choice)."""
+    if _ngpus() < 2:
+        monkeypatch.setenv("FCFV_MULTI_OVERSUBSCRIBE", "1")
+    case = CASES[1]
+    ref = _run(case, 1)
+    monkeypatch.setenv("FCFV_MULTI_MAX_RUNS", max_runs)
+    got = _run(case, 2)
+    for k in ("a", "b", "Z", "tau", "fu", "fp"):
+        assert np.array_equal(got[k], ref[k]), k
+    for k in ("Kuu", "Kup", "Muu", "Kuusc"):
+        for x, y in zip(got[k], ref[k]):
+            assert np.array_equal(x, y), k
+    n, r = got["norms"]["FACE"], ref["norms"]["FACE"]
+    assert np.all(np.abs(n - r) <= TOL * r.max())
+
+
 def test_multi_handle_rejects_what_it_cannot_do(monkeypatch):
     import ctypes as C
     from fcfv_nme23_b200 import api, lib as L

@@ -34,6 +34,22 @@ def test_cpp_partition_equals_numpy_partition(name, mesh, nparts):
     assert np.all(owned_e == 1) and np.all(owned_f[used] == 1) and np.all(owned_f[~used] == 0)    # ownership is a partition
 
 
+def test_cpp_partition_threaded_adjacency_on_a_larger_mesh():
+    """Above 65 536 elements the face adjacency is built by several threads (compare-and-swap min / max): S(200) has
+    160 000 elements, and a shuffled element order makes the ghost sets large."""
+    from fcfv_nme23_b200 import mesh as M
+    m = M.MakeStructuredMesh(200, geometry=False)
+    rng = np.random.default_rng(1)
+    for shuffled in (False, True):
+        if shuffled:
+            m.e2f = np.asfortranarray(np.asarray(m.e2f)[rng.permutation(m.nel)])
+        for nparts, part in ((4, 0), (4, 2), (7, 6)):
+            P = partition_mesh(m, nparts, part)
+            eg, fg, eo, fo = api.partition_part(m.e2f, m.nf, nparts, part)
+            assert np.array_equal(eg, P.elem_global + 1) and np.array_equal(fg, P.face_global + 1)
+            assert np.array_equal(eo.astype(bool), P.elem_owned) and np.array_equal(fo.astype(bool), P.face_owned)
+
+
 def test_cpp_partition_rejects_bad_face_ids():
     from fcfv_nme23_b200 import lib as L
     e2f = np.asfortranarray(np.array([[1, 2, 9]], dtype=np.int64))

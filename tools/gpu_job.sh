@@ -26,6 +26,6 @@ fi
 if [ "$WHAT" = all ] || [ "$WHAT" = traffic ]; then
   # DRAM bytes of the hot kernels at the bench's own size (50M elements), one step
   timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-      -k regex:'k_asm_fill|k_asm_count|k_res_elem|k_local|k_elem_coef|k_res_face|k_face_tau' -s 7 -c 7 \
+      -k regex:'k_asm_fill|k_asm_count|k_res_elem|k_local|k_elem_coef|k_res_late' -s 7 -c 7 \
       -o $OUT/${TAG}_traffic50M -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/${TAG}_ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
 fi

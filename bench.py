@@ -655,8 +655,8 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
     sec = C.c_double(0.0)
 
     def three_calls(h, P, Dd, out, nel, with_mesh=True, ownership=True, cached=True):
-        def refresh():
-            h.check(lib.fcfv_update_fields(h._h, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, ptr(out["tau"])))
+        def refresh(tau=True):
+            h.check(lib.fcfv_update_fields(h._h, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, ptr(out["tau"]) if tau else None))
         if with_mesh:       # first call on an FCFV_Mesh object (or a driver that rebuilds its mesh): the mesh goes up
             h.check(lib.fcfv_set_mesh(h._h, nel, P["bc"].numel(), ptr(P["e2f"]), ptr(P["bc"]), ptr(P["Ω"]), ptr(P["n_x"]), ptr(P["n_y"]),
                                       ptr(P["Γ"]), ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel))
@@ -665,9 +665,13 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
         sig = [ptr(Dd[k]) for k in ("sxx", "syy", "sxy", "syx")]
         loc = [ptr(out[k]) for k in ("alpha", "beta", "Z")]
         # ComputeFCFV
+        if with_mesh:                     # handle creation in the shims: mesh.tau goes up once with the mesh
+            refresh(True)
         if cached and not with_mesh:      # the shims skip this right after they have uploaded the mesh themselves
             h.check(lib.fcfv_new_epoch(h._h))
-        refresh()
+        orph = C.c_int(1)
+        h.check(lib.fcfv_has_orphan_faces(h._h, C.byref(orph)))
+        refresh(bool(orph.value))         # ComputeFCFV overwrites tau on every face that has an element
         h.check(lib.fcfv_compute_local_ex(h._h, form, 1.0, ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), *sig,
                                           *loc, ptr(out["tau"])))
         # ElementAssemblyLoopNEW

@@ -192,6 +192,9 @@ class Handle:
             self._h, nel, nf, a.i(mesh.e2f, 3 * nel), a.i(mesh.bc, nf), a.d(mesh.Ω, nel), a.d(mesh.n_x, 3 * nel),
             a.d(mesh.n_y, 3 * nel), a.d(mesh.Γ, 3 * nel), a.d(mesh.ke, nel), a.d(mesh.δ, nel), a.d(taue, nel), ntaue))
         self.nel, self.nf = nel, nf
+        flag = C.c_int(0)
+        self.check(self.lib.fcfv_has_orphan_faces(self._h, C.byref(flag)))
+        self.has_orphans = bool(flag.value)      # faces no element references keep the tau the caller gave them
         if mesh.τ is not None:
             self.update_fields(tau=mesh.τ)
         if getattr(mesh, "elem_owned", None) is not None or getattr(mesh, "face_owned", None) is not None:
@@ -414,11 +417,12 @@ def handle_for(mesh, device=None) -> Handle:
     return h
 
 
-def _refresh(mesh, h):
+def _refresh(mesh, h, tau=True):
     """The drivers mutate ke, δ, τe, τ after mesh creation (ViscousInclusionFCFV_v2.jl:44,127;
-    SolKzFCFV.jl:25,149): re-upload those vectors at the top of every entry point."""
+    SolKzFCFV.jl:25,149): re-upload those vectors at the top of every entry point.  ``tau=False``: in front of
+    ComputeFCFV, which overwrites mesh.τ on every face that has an element (Discretisation:40)."""
     taue = mesh.τe if mesh.τe is not None else None
-    h.update_fields(ke=mesh.ke, delta=mesh.δ, taue=taue, tau=mesh.τ)
+    h.update_fields(ke=mesh.ke, delta=mesh.δ, taue=taue, tau=mesh.τ if tau else None)
 
 
 def mesh_geometry(mesh, τr, device=0):
@@ -444,7 +448,7 @@ def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τ
     h = handle_for(mesh)
     if not fresh:            # first call of a driver pass: whatever the caller changed since the last one goes up again
         h.new_epoch()        # (a handle made just now has uploaded the mesh fields in this very call)
-    _refresh(mesh, h)
+    _refresh(mesh, h, tau=getattr(h, "has_orphans", True))
     nel, nf = h.nel, h.nf
     a = _Arg()
     al, be, Z = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")

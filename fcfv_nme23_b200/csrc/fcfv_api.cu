@@ -109,6 +109,7 @@ struct fcfv_handle {
     long long nel_global = 0, nf_global = 0;
     bool have_mesh = false, have_local = false, have_face_data = false, have_sources = false, have_solution = false;
     bool rp64 = false;
+    bool has_orphans = false;         // some face is referenced by no element
     bool have_elem_owned = false, have_face_owned = false, have_tau_ref = false;
 
     // mesh
@@ -175,6 +176,7 @@ int multi_export(fcfv_t*, int, int, void*, void*, double*);
 int multi_export_rhs(fcfv_t*, double*, double*);
 int multi_run_residuals(fcfv_t*, int, int, double*, double*);
 int multi_unsupported(fcfv_t*, const char*);
+int multi_has_orphans(fcfv_t*);
 double multi_asm_seconds(fcfv_t*);
 fcfv_t* multi_part0(fcfv_t*);
 template <typename F> void multi_each(fcfv_t* h, F&& fn);
@@ -760,6 +762,8 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     TRY(build_f2e(h));
     int flag = 0;
     TRY(read_err_flag(h, &flag));
+    h->has_orphans = (flag & 8) != 0;        // faces no element references: their tau is only ever what the caller uploads
+    flag &= 7;
     if (!flag) { TRY(build_fconn(h)); TRY(sync(h)); }
     if (flag & 1) return fail(h, FCFV_ERR_INVALID, "e2f contains a face id outside 1..nf");
     if (flag & 2) return fail(h, FCFV_ERR_INVALID, "a face is referenced by more than two (element, local face) pairs");
@@ -1835,6 +1839,13 @@ int fcfv_ph_fusc(fcfv_t* h, double gamma, const double* p, double* fusc) {
 }
 
 // -------------------------------------------------------------------------------------------------
+int fcfv_has_orphan_faces(fcfv_t* h, int* flag) {
+    if (!h || !flag) return FCFV_ERR_INVALID;
+    TRY(need(h, h->have_mesh, "fcfv_has_orphan_faces: no mesh set"));
+    *flag = h->multi ? multi_has_orphans(h) : (h->has_orphans ? 1 : 0);
+    return FCFV_OK;
+}
+
 int fcfv_mesh_size(fcfv_t* h, int64_t* nel, int64_t* nf) {
     if (!h) return FCFV_ERR_INVALID;
     TRY(need(h, h->have_mesh, "fcfv_mesh_size: no mesh set"));
@@ -1988,6 +1999,8 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     }
     int flag = 0;
     TRY(read_err_flag(h, &flag));
+    h->has_orphans = (flag & 8) != 0;
+    flag &= 7;
     if (flag) return fail(h, FCFV_ERR_STATE, "fcfv_generate_structured: generated connectivity failed validation (%d)", flag);
     TRY(build_fconn(h));
     if (partitioned) {

@@ -387,7 +387,7 @@ __global__ void k_f2e_check(int2* __restrict__ f2e, const int* __restrict__ cnt,
     if (f >= nf) return;
     const int c = cnt[f];
     if (c > 2) atomicOr(err, 2);
-    if (c == 0) f2e[f] = make_int2(-1, -1);
+    if (c == 0) { f2e[f] = make_int2(-1, -1); atomicOr(err, 8); }      // bit 8: not an error, the mesh has faces without elements
     if (c == 2) {
         const int2 pr = f2e[f];
         const int e0 = pr.x >> 2, e1 = pr.y >> 2;

@@ -785,6 +785,7 @@ int multi_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq,
 }
 
 double multi_asm_seconds(fcfv_t* h) { return h->multi->asm_seconds; }
+int multi_has_orphans(fcfv_t* h) { return h->multi->unref.empty() ? 0 : 1; }
 fcfv_t* multi_part0(fcfv_t* h) { return h->multi->parts[0].h; }
 template <typename F>
 void multi_each(fcfv_t* h, F&& fn) {

@@ -91,6 +91,7 @@ def load():
         "fcfv_numbering_locality": [vp, P(dbl), P(dbl)],
         "fcfv_compute_local_ex": [vp, ci, dbl] + [vp] * 12,
         "fcfv_upload_cache": [vp, ci],
+        "fcfv_has_orphan_faces": [vp, P(ci)],
         "fcfv_new_epoch": [vp],
         "fcfv_transfer_stats": [vp, P(i64), P(i64), P(i64), ci],
         "fcfv_host_register": [vp, vp, i64],

@@ -147,6 +147,9 @@ int fcfv_compute_local_ex(fcfv_t* h, int formulation, double A, const double* se
  * over the array) still matches.  The caller vouches that arrays are not modified in place inside an epoch;
  * fcfv_new_epoch starts a new one (the shims do so at the top of every ComputeFCFV, i.e. once per driver pass),
  * fcfv_set_mesh and fcfv_generate_structured too.  fcfv_set_mesh itself always uploads.  Off by default. */
+/* *flag = 1 when the resident mesh has faces no element references.  Without such faces ComputeFCFV overwrites every
+ * entry of mesh.tau (DiscretisationFCFV_Stokes.jl:40), so the shims do not upload mesh.tau in front of it. */
+int fcfv_has_orphan_faces(fcfv_t* h, int* flag);
 int fcfv_upload_cache(fcfv_t* h, int on);
 int fcfv_new_epoch(fcfv_t* h);
 /* Bytes this handle has moved host -> device / device -> host so far and bytes the upload cache saved; reset != 0

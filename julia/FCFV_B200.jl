@@ -30,6 +30,7 @@ mutable struct Handle
     ptr::Ptr{Cvoid}
     nel::Int
     nf::Int
+    orphans::Bool        # the mesh has faces no element references (their τ is only ever what the caller gives them)
 end
 
 # GPUs a mesh is spread over when its handle is created.  The reference's functions have no such argument and its
@@ -55,7 +56,7 @@ function Handle(device::Integer = 0; ngpus::Integer = NGPUS[])
     rc = ngpus > 1 ? ccall((:fcfv_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, ngpus) :
                      ccall((:fcfv_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
     rc == 0 || error("fcfv_create failed with status $rc: no usable CUDA device (there is no CPU fallback)")
-    h = Handle(r[], 0, 0)
+    h = Handle(r[], 0, 0, true)
     finalizer(destroy!, h)
     return h
 end
@@ -107,6 +108,9 @@ function handle_for(mesh)
             h.ptr, mesh.nel, mesh.nf, e2f, bc, Ω, nx, ny, Γ, ke, δ, τe, length(τe)))
     end
     h.nel, h.nf = mesh.nel, mesh.nf
+    orph = Ref{Cint}(1)
+    check(h, ccall((:fcfv_has_orphan_faces, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}), h.ptr, orph))
+    h.orphans = orph[] != 0
     HANDLES[mesh] = h
     if mesh.nel >= 100_000            # the gathers of the GPU passes rely on numbering locality
         span, off = Ref{Float64}(0.0), Ref{Float64}(0.0)
@@ -120,16 +124,17 @@ end
 
 # The drivers mutate mesh.ke / δ / τe / τ after the mesh is built (v2.jl:44,127; SolKzFCFV.jl:25,149):
 # refresh those vectors at the top of every entry point.
-function refresh!(h::Handle, mesh)
+# `tau = false`: in front of ComputeFCFV, which overwrites mesh.τ on every face that has an element (Discretisation:40).
+function refresh!(h::Handle, mesh; tau::Bool = true)
     ke, δ = f64(mesh.ke), f64(mesh.δ)
     τe = ismissing(mesh.τe) ? zeros(mesh.nel) : f64(mesh.τe)
-    τ = ismissing(mesh.τ) ? Float64[] : f64(mesh.τ)
+    τ = (ismissing(mesh.τ) || !tau) ? Float64[] : f64(mesh.τ)
     GC.@preserve ke δ τe τ begin
         check(h, ccall((:fcfv_update_fields, LIB), Cint,
             (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
             h.ptr, ke, δ, τe, length(τe), isempty(τ) ? C_NULL : pointer(τ)))
     end
-    forget_temps!(h, (mesh.ke, ke), (mesh.δ, δ), (mesh.τe, τe), (ismissing(mesh.τ) ? τ : mesh.τ, τ))
+    forget_temps!(h, (mesh.ke, ke), (mesh.δ, δ), (mesh.τe, τe), ((ismissing(mesh.τ) || !tau) ? τ : mesh.τ, τ))
 end
 
 """Ω, centroids, outward normals, Γ (and τ .= τr) from xv, yv, e2v, e2f, xf, yf -- the loops of
@@ -159,7 +164,7 @@ function ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNe
     fresh = !haskey(HANDLES, mesh)
     h = handle_for(mesh)
     fresh || new_epoch!(h)              # first call of a driver pass: everything the driver may have changed goes up again
-    refresh!(h, mesh)                   # (a handle made just now has uploaded the mesh fields in this very call)
+    refresh!(h, mesh; tau = h.orphans)  # (a handle made just now has uploaded the mesh fields in this very call)
     nel, nf = mesh.nel, mesh.nf
     α, β, Ζ, τ = zeros(nel), zeros(nel, 2), zeros(nel, 2, 2), zeros(nf)
     sx, sy, vx, vy = f64(sex), f64(sey), f64(VxDir), f64(VyDir)

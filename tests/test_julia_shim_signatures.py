@@ -17,6 +17,7 @@ C2J = {
     "double": {"Float64"},
     "double*": {"Ptr{Float64}", "Ref{Float64}", "Ptr{Cvoid}"},
     "int64_t*": {"Ptr{Int64}", "Ref{Int64}", "Ptr{Cvoid}"},
+    "int*": {"Ref{Cint}", "Ptr{Cint}"},
     "uint8_t*": {"Ptr{UInt8}", "Ptr{Cvoid}"},
     "void*": {"Ptr{Cvoid}", "Ptr{Float64}", "Ptr{Int64}"},
     "void**": {"Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"},

@@ -248,6 +248,7 @@ int ensure(fcfv_t* h, DBuf& b, size_t bytes) {
     if (bytes == 0) bytes = 8;
     if (b.cap >= bytes) return FCFV_OK;
     if (b.p) { CU(cudaFree(b.p)); h->bytes -= b.cap; b.p = nullptr; b.cap = 0; }
+    b.hm.epoch = -1;        // fresh storage mirrors nothing
     // only buffers the handle owns can be referenced by the captured pipeline graph; the temporaries of the
     // export / geometry / renumbering calls live on the caller's stack and must not invalidate it
     const char* hb = reinterpret_cast<const char*>(h);

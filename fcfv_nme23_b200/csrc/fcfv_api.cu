@@ -464,8 +464,6 @@ MeshView mesh_view(fcfv_t* h) {
     M.fconn = P<int4>(h->fconn); M.fbc = P<int>(h->fbc); M.ebc = P<int>(h->ebc); M.eadj = P<int>(h->eadj);
     M.Om = P<double>(h->Om); M.G = P<double>(h->G); M.nx = P<double>(h->nx); M.ny = P<double>(h->ny);
     M.ke = P<double>(h->ke); M.dl = P<double>(h->dl); M.taue = P<double>(h->taue); M.tau = P<double>(h->tau);
-    M.elem_owned = h->have_elem_owned ? P<uint8_t>(h->elem_owned) : nullptr;
-    M.face_owned = h->have_face_owned ? P<uint8_t>(h->face_owned) : nullptr;
     M.tau_ref = h->have_tau_ref ? P<double>(h->tau_ref) : nullptr;
     return M;
 }

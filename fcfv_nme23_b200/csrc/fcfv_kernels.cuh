@@ -40,8 +40,8 @@ struct MeshView {
                                  // (9 bits each, see k_ebc) + bits 27..29: this rank owns local face j
     const double *Om, *G, *nx, *ny, *ke, *dl, *taue;
     const double* tau;
-    const uint8_t* elem_owned;   // nullable; the kernels read the copies packed into ebc / fbc (kOwnedElem / kOwnedFace), which
-    const uint8_t* face_owned;   // are loaded anyway: a partitioned mesh costs no extra dependent loads
+    // ownership of a partitioned mesh lives in the tag words above (kOwnedFace, kOwnedElem, eadj bits 27..29), which the kernels
+    // load anyway: no separate masks, no extra dependent loads
     const double* tau_ref;       // nullable (REFERENCE tau mode on a partition)
 };
 

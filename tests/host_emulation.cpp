@@ -47,7 +47,7 @@ void build_mesh(HostMesh& H, long long nel, long long nf, const long long* e2f, 
     MeshView& M = H.view;
     M.nel = (int)nel; M.nf = (int)nf; M.e2f = H.e2f.data(); M.bc = H.bc.data(); M.f2e = H.f2e.data(); M.fconn = H.fconn.data(); M.fbc = H.fbc.data(); M.ebc = H.ebc.data();
     M.Om = Om; M.G = G; M.nx = nx; M.ny = ny; M.ke = ke; M.dl = dl; M.taue = taue; M.tau = tau;
-    M.elem_owned = nullptr; M.face_owned = nullptr; M.tau_ref = nullptr;
+    M.tau_ref = nullptr;
 }
 
 // Serial stand-in for k_asm_count / k_asm_fill: thread = face becomes a loop iteration, the block

@@ -665,13 +665,12 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
         sig = [ptr(Dd[k]) for k in ("sxx", "syy", "sxy", "syx")]
         loc = [ptr(out[k]) for k in ("alpha", "beta", "Z")]
         # ComputeFCFV
-        if with_mesh:                     # handle creation in the shims: mesh.tau goes up once with the mesh
-            refresh(True)
         if cached and not with_mesh:      # the shims skip this right after they have uploaded the mesh themselves
             h.check(lib.fcfv_new_epoch(h._h))
         orph = C.c_int(1)
         h.check(lib.fcfv_has_orphan_faces(h._h, C.byref(orph)))
-        refresh(bool(orph.value))         # ComputeFCFV overwrites tau on every face that has an element
+        refresh(bool(orph.value))         # ComputeFCFV overwrites tau on every face that has an element: mesh.tau only goes up
+                                          # in front of it when the mesh has faces without elements
         h.check(lib.fcfv_compute_local_ex(h._h, form, 1.0, ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), *sig,
                                           *loc, ptr(out["tau"])))
         # ElementAssemblyLoopNEW

@@ -183,7 +183,9 @@ class Handle:
                 self.check(self.lib.fcfv_host_unregister(self._h, C.c_void_p(a.ctypes.data)))
 
     # -- mesh ---------------------------------------------------------------------------------
-    def set_mesh(self, mesh):
+    def set_mesh(self, mesh, tau=True):
+        """``tau=False``: the caller is ComputeFCFV, which overwrites mesh.τ on every face that has an element -- mesh.τ then
+        only goes up when the mesh has faces without elements."""
         a = _Arg()
         nel, nf = int(mesh.nel), int(mesh.nf)
         taue = mesh.τe if mesh.τe is not None else np.zeros(nel)
@@ -195,7 +197,7 @@ class Handle:
         flag = C.c_int(0)
         self.check(self.lib.fcfv_has_orphan_faces(self._h, C.byref(flag)))
         self.has_orphans = bool(flag.value)      # faces no element references keep the tau the caller gave them
-        if mesh.τ is not None:
+        if mesh.τ is not None and (tau or self.has_orphans):
             self.update_fields(tau=mesh.τ)
         if getattr(mesh, "elem_owned", None) is not None or getattr(mesh, "face_owned", None) is not None:
             self.set_ownership(mesh.elem_owned, mesh.face_owned, getattr(mesh, "nel_global", 0),
@@ -399,13 +401,13 @@ def partition_part(e2f, nf, nparts, part):
     return eg, fg, eo, fo
 
 
-def handle_for(mesh, device=None) -> Handle:
+def handle_for(mesh, device=None, tau=True) -> Handle:
     h = getattr(mesh, "_fcfv_handle", None)
     if h is None:
         ngpus = int(getattr(mesh, "ngpus", None) or DEFAULT_GPUS)
         h = Handle(0 if device is None else device, ngpus=ngpus)
         h.upload_cache(CACHE_INPUTS)
-        h.set_mesh(mesh)
+        h.set_mesh(mesh, tau=tau)
         mesh._fcfv_handle = h
         if ngpus == 1 and h.nel >= 100_000 and getattr(mesh, "elem_owned", None) is None:
             span, off = h.numbering_locality()
@@ -445,7 +447,7 @@ def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τ
     if mesh.τ is None:
         mesh.τ = np.zeros(mesh.nf)
     fresh = getattr(mesh, "_fcfv_handle", None) is None
-    h = handle_for(mesh)
+    h = handle_for(mesh, tau=False)
     if not fresh:            # first call of a driver pass: whatever the caller changed since the last one goes up again
         h.new_epoch()        # (a handle made just now has uploaded the mesh fields in this very call)
     _refresh(mesh, h, tau=getattr(h, "has_orphans", True))

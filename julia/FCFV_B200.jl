@@ -111,7 +111,7 @@ function handle_for(mesh)
     orph = Ref{Cint}(1)
     check(h, ccall((:fcfv_has_orphan_faces, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}), h.ptr, orph))
     h.orphans = orph[] != 0
-    HANDLES[mesh] = h
+    HANDLES[mesh] = h          # mesh.τ goes up with the field refresh of the entry point that asked for the handle
     if mesh.nel >= 100_000            # the gathers of the GPU passes rely on numbering locality
         span, off = Ref{Float64}(0.0), Ref{Float64}(0.0)
         check(h, ccall((:fcfv_numbering_locality, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), h.ptr, span, off))

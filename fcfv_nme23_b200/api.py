@@ -225,6 +225,18 @@ class Handle:
         self.check(self.lib.fcfv_transfer_stats(self._h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), int(bool(reset))))
         return tuple(x.value for x in v)
 
+    def sparse_face_data(self, mode=1):
+        """See ``fcfv_sparse_face_data``: 0 = whole per-face boundary arrays go up, 1 (default) = only their values on
+        the Dirichlet / Neumann faces when those are few, 2 = always."""
+        self.check(self.lib.fcfv_sparse_face_data(self._h, int(mode)))
+
+    def sparse_face_info(self):
+        """(active, n_dirichlet, n_neumann, list_uploads) of the resident mesh."""
+        act = C.c_int(0)
+        v = [C.c_int64(0) for _ in range(3)]
+        self.check(self.lib.fcfv_sparse_face_info(self._h, C.byref(act), C.byref(v[0]), C.byref(v[1]), C.byref(v[2])))
+        return bool(act.value), v[0].value, v[1].value, v[2].value
+
     def set_ownership(self, elem_owned, face_owned, nel_global=0, nf_global=0, tau_ref=None):
         a = _Arg()
         self.check(self.lib.fcfv_set_ownership(self._h, a.u8(elem_owned, self.nel), a.u8(face_owned, self.nf),

@@ -150,6 +150,18 @@ struct fcfv_handle {
     bool cache_on = false;
     long long epoch = 0;
     long long h2d_bytes = 0, d2h_bytes = 0, cache_hit_bytes = 0, cache_hits = 0;
+    // boundary-face lists (fcfv_sparse_face_data): VxDir / VyDir are only ever read on Dirichlet faces and the four Neumann
+    // arrays on Neumann faces (Bool factors in the reference: Discretisation:17,31,167-178, Residuals:59-66), so a host array
+    // of nf values crosses PCIe as the few values on those faces
+    int sparse_mode = 1;              // 0 dense uploads, 1 lists when they are short (auto), 2 always lists
+    bool sparse_faces = false;        // the lists below describe the resident mesh
+    DBuf dir_idx, neu_idx, face_counts, fpack;
+    std::vector<int> dir_list, neu_list;
+    double* fstage = nullptr;         // page-locked, 6 slots of fstage_cap values
+    size_t fstage_cap = 0;
+    cudaEvent_t fstage_ev[6] = {};
+    bool fstage_busy[6] = {};
+    long long sparse_uploads = 0;
     // nccl
     NcclApi nccl;
     void* comm = nullptr;
@@ -166,6 +178,7 @@ int multi_set_mesh(fcfv_t*, int64_t, int64_t, const int64_t*, const int64_t*, co
 int multi_update_fields(fcfv_t*, const double*, const double*, const double*, int64_t, const double*);
 int multi_set_sources(fcfv_t*, const double*, const double*);
 int multi_set_face_data(fcfv_t*, const double*, const double*, const double*, const double*, const double*, const double*);
+int set_face_data_listed(fcfv_t* h, const double* const src[6], const int64_t* faces);
 int multi_set_solution(fcfv_t*, const double*, const double*, const double*);
 int multi_set_local(fcfv_t*, const double*, const double*, const double*);
 int multi_run_local(fcfv_t*, int, double);
@@ -510,6 +523,76 @@ int build_fconn(fcfv_t* h) {
     return FCFV_OK;
 }
 
+// Lists of the Dirichlet / Neumann faces of the resident mesh (device bc).  They are short on every mesh of the reference
+// (boundary faces: O(sqrt(nf))); when one of them is not (more than nf/16 or 2^18 faces in auto mode) the per-face data
+// keeps going up whole.
+int build_face_lists(fcfv_t* h) {
+    h->sparse_faces = false;
+    h->dir_list.clear(); h->neu_list.clear();
+    const long long nf = h->nf;
+    if (h->sparse_mode == 0 || nf == 0) return FCFV_OK;
+    const long long cap = h->sparse_mode == 2 ? nf : std::min<long long>(nf / 16, 1LL << 18);
+    if (cap < 1) return FCFV_OK;
+    TRY(ensure(h, h->dir_idx, sizeof(int) * cap));
+    TRY(ensure(h, h->neu_idx, sizeof(int) * cap));
+    TRY(ensure(h, h->face_counts, sizeof(int) * 2));
+    CU(cudaMemsetAsync(h->face_counts.p, 0, sizeof(int) * 2, h->stream));
+    LAUNCH(h, k_bc_face_lists, nblocks(nf, 256), 256, (int)nf, P<int8_t>(h->bc), (int)cap, P<int>(h->dir_idx), P<int>(h->neu_idx),
+           P<int>(h->face_counts));
+    int cnt[2] = {0, 0};
+    CU(cudaMemcpyAsync(cnt, h->face_counts.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+    TRY(sync(h));
+    if (cnt[0] > cap || cnt[1] > cap) return FCFV_OK;
+    struct L { std::vector<int>* v; DBuf* d; int n; } lists[2] = {{&h->dir_list, &h->dir_idx, cnt[0]}, {&h->neu_list, &h->neu_idx, cnt[1]}};
+    for (L& l : lists) {
+        l.v->resize((size_t)l.n);
+        if (l.n == 0) continue;
+        CU(cudaMemcpyAsync(l.v->data(), l.d->p, sizeof(int) * (size_t)l.n, cudaMemcpyDeviceToHost, h->stream));
+        TRY(sync(h));
+        std::sort(l.v->begin(), l.v->end());        // ascending ids: a deterministic list and a forward walk over the host arrays
+        CU(cudaMemcpyAsync(l.d->p, l.v->data(), sizeof(int) * (size_t)l.n, cudaMemcpyHostToDevice, h->stream));
+        TRY(sync(h));
+    }
+    const size_t need = (size_t)std::max(1, std::max(cnt[0], cnt[1]));
+    if (need > h->fstage_cap) {
+        for (int k = 0; k < 6; k++)
+            if (h->fstage_busy[k]) { CU(cudaEventSynchronize(h->fstage_ev[k])); h->fstage_busy[k] = false; }
+        if (h->fstage) { CU(cudaFreeHost(h->fstage)); h->fstage = nullptr; h->fstage_cap = 0; }
+        const size_t cap2 = need + need / 2 + 64;
+        CU(cudaHostAlloc((void**)&h->fstage, sizeof(double) * 6 * cap2, cudaHostAllocDefault));
+        h->fstage_cap = cap2;
+    }
+    TRY(ensure(h, h->fpack, sizeof(double) * 6 * h->fstage_cap));
+    for (int k = 0; k < 6; k++)
+        if (!h->fstage_ev[k]) CU(cudaEventCreateWithFlags(&h->fstage_ev[k], cudaEventDisableTiming));
+    h->sparse_faces = true;
+    return FCFV_OK;
+}
+
+// Array `which` (0 VxDir, 1 VyDir, 2..5 sxx, syy, sxy, syx) of the per-face data from a HOST array through the list of the
+// faces it is read on: gather into a page-locked slot, one small copy, scatter on the device.  The rest of the device
+// array keeps what it held (zeros after allocation); no kernel reads it.
+// map: local -> global face id when src is the GLOBAL array of a multi-GPU handle (this handle is one of its parts).
+int upload_listed(fcfv_t* h, DBuf& b, const double* src, int which, const int64_t* map = nullptr) {
+    const std::vector<int>& list = which < 2 ? h->dir_list : h->neu_list;
+    const DBuf& idx = which < 2 ? h->dir_idx : h->neu_idx;
+    b.hm.epoch = -1;
+    const size_t n = list.size();
+    h->sparse_uploads++;
+    if (n == 0) return FCFV_OK;
+    double* slot = h->fstage + (size_t)which * h->fstage_cap;
+    if (h->fstage_busy[which]) { CU(cudaEventSynchronize(h->fstage_ev[which])); h->fstage_busy[which] = false; }
+    if (map) for (size_t k = 0; k < n; k++) slot[k] = src[map[list[k]]];
+    else     for (size_t k = 0; k < n; k++) slot[k] = src[list[k]];
+    double* pack = P<double>(h->fpack) + (size_t)which * h->fstage_cap;
+    CU(cudaMemcpyAsync(pack, slot, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    h->h2d_bytes += (long long)(sizeof(double) * n);
+    CU(cudaEventRecord(h->fstage_ev[which], h->stream));
+    h->fstage_busy[which] = true;
+    LAUNCH(h, k_scatter_faces, nblocks((long long)n, 256), 256, (int)n, P<int>(idx), pack, P<double>(b));
+    return FCFV_OK;
+}
+
 int alloc_mesh_dependent(fcfv_t* h) {
     const long long nel = h->nel, nf = h->nf;
     TRY(ensure(h, h->tau, sizeof(double) * nf));
@@ -547,6 +630,8 @@ int fcfv_create(fcfv_t** out, int device) {
     h->device = device;
     if (const char* v = getenv("FCFV_STAGED_MIN_BYTES")) h->staged_min_bytes = (size_t)strtoull(v, nullptr, 10);   // 0 = never
     if (h->staged_min_bytes == 0) h->staged_min_bytes = ~(size_t)0;
+    if (const char* v = getenv("FCFV_SPARSE_FACE_DATA"))                      // initial fcfv_sparse_face_data mode (test hook)
+        if (v[0] >= '0' && v[0] <= '2' && v[1] == 0) h->sparse_mode = v[0] - '0';
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
         delete h;
@@ -578,8 +663,12 @@ int fcfv_destroy(fcfv_t* h) {
                    &h->syy, &h->sxy, &h->syx, &h->Vxh, &h->Vyh, &h->Pe, &h->alpha, &h->beta, &h->Z,
                    &h->Kuu.rowptr, &h->Kuu.col, &h->Kuu.val, &h->Kup.rowptr, &h->Kup.col, &h->Kup.val,
                    &h->Muu.rowptr, &h->Muu.col, &h->Muu.val, &h->Kuusc.rowptr, &h->Kuusc.col, &h->Kuusc.val, &h->fu, &h->fp, &h->sums, &h->bases, &h->chunks, &h->totals,
-                   &h->Fg, &h->partial, &h->sumsq, &h->red_scratch, &h->red_tickets, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx, &h->coefs};
+                   &h->Fg, &h->partial, &h->sumsq, &h->red_scratch, &h->red_tickets, &h->tmp, &h->tmp2, &h->err_flag, &h->phw, &h->coef, &h->coefx, &h->coefs,
+                   &h->dir_idx, &h->neu_idx, &h->face_counts, &h->fpack};
     for (DBuf* b : all) release(h, *b);
+    if (h->fstage) cudaFreeHost(h->fstage);
+    for (cudaEvent_t e : h->fstage_ev)
+        if (e) cudaEventDestroy(e);
     stager_destroy(h);
     if (h->stream_out) { cudaStreamSynchronize(h->stream_out); cudaStreamDestroy(h->stream_out); }
     if (h->ev_out) cudaEventDestroy(h->ev_out);
@@ -609,6 +698,24 @@ int fcfv_upload_cache(fcfv_t* h, int on) {
     if (!h) return FCFV_ERR_INVALID;
     h->cache_on = on != 0;
     new_epoch(h);
+    return FCFV_OK;
+}
+
+int fcfv_sparse_face_data(fcfv_t* h, int mode) {
+    if (!h) return FCFV_ERR_INVALID;
+    if (mode < 0 || mode > 2) return fail(h, FCFV_ERR_INVALID, "fcfv_sparse_face_data: mode must be 0 (off), 1 (auto) or 2 (always)");
+    h->sparse_mode = mode;
+    if (h->multi) { multi_each(h, [&](fcfv_t* q) { q->sparse_mode = mode; }); return FCFV_OK; }
+    if (h->have_mesh) { CU(cudaSetDevice(h->device)); TRY(build_face_lists(h)); }
+    return FCFV_OK;
+}
+
+int fcfv_sparse_face_info(fcfv_t* h, int* active, int64_t* n_dirichlet, int64_t* n_neumann, int64_t* uploads) {
+    if (!h) return FCFV_ERR_INVALID;
+    if (active) *active = h->sparse_faces ? 1 : 0;
+    if (n_dirichlet) *n_dirichlet = h->sparse_faces ? (int64_t)h->dir_list.size() : -1;
+    if (n_neumann) *n_neumann = h->sparse_faces ? (int64_t)h->neu_list.size() : -1;
+    if (uploads) *uploads = h->sparse_uploads;
     return FCFV_OK;
 }
 
@@ -763,7 +870,7 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     TRY(read_err_flag(h, &flag));
     h->has_orphans = (flag & 8) != 0;        // faces no element references: their tau is only ever what the caller uploads
     flag &= 7;
-    if (!flag) { TRY(build_fconn(h)); TRY(sync(h)); }
+    if (!flag) { TRY(build_fconn(h)); TRY(build_face_lists(h)); TRY(sync(h)); }
     if (flag & 1) return fail(h, FCFV_ERR_INVALID, "e2f contains a face id outside 1..nf");
     if (flag & 2) return fail(h, FCFV_ERR_INVALID, "a face is referenced by more than two (element, local face) pairs");
     if (flag & 4) return fail(h, FCFV_ERR_INVALID, "two elements share more than one face (or an element lists a face twice)");
@@ -989,12 +1096,34 @@ int fcfv_set_face_data(fcfv_t* h, const double* VxDir, const double* VyDir, cons
     for (int k = 0; k < 6; k++) {
         const bool fresh = dst[k]->cap < b;
         TRY(ensure(h, *dst[k], b));
-        if (src[k]) TRY(upload_cached(h, *dst[k], src[k], b));
+        if (src[k] && h->sparse_faces && !is_device(src[k])) {
+            // only the faces the array is read on (Dirichlet / Neumann) cross the link
+            if (fresh || !h->have_face_data) CU(cudaMemsetAsync(dst[k]->p, 0, b, h->stream));
+            TRY(upload_listed(h, *dst[k], src[k], k));
+        } else if (src[k]) TRY(upload_cached(h, *dst[k], src[k], b));
         else if (fresh || !h->have_face_data) { dst[k]->hm.epoch = -1; CU(cudaMemsetAsync(dst[k]->p, 0, b, h->stream)); }
     }
     h->have_face_data = true;
     return finish(h);
 }
+
+namespace {
+// fcfv_set_face_data of one part of a multi-GPU handle straight from the caller's GLOBAL arrays (faces: local -> global ids):
+// only possible when the part lists its boundary faces (sparse_faces); NULL = keep what is resident
+int set_face_data_listed(fcfv_t* h, const double* const src[6], const int64_t* faces) {
+    CU(cudaSetDevice(h->device));
+    const size_t b = sizeof(double) * h->nf;
+    DBuf* dst[6] = {&h->VxDir, &h->VyDir, &h->sxx, &h->syy, &h->sxy, &h->syx};
+    for (int k = 0; k < 6; k++) {
+        const bool fresh = dst[k]->cap < b;
+        TRY(ensure(h, *dst[k], b));
+        if (fresh || !h->have_face_data) { dst[k]->hm.epoch = -1; CU(cudaMemsetAsync(dst[k]->p, 0, b, h->stream)); }
+        if (src[k]) TRY(upload_listed(h, *dst[k], src[k], k, faces));
+    }
+    h->have_face_data = true;
+    return finish(h);
+}
+}  // namespace
 
 int fcfv_set_solution(fcfv_t* h, const double* Vxh, const double* Vyh, const double* Pe) {
     if (!h) return FCFV_ERR_INVALID;
@@ -2002,6 +2131,7 @@ int fcfv_generate_structured(fcfv_t* h, int64_t n, int64_t row0, int64_t row1, i
     flag &= 7;
     if (flag) return fail(h, FCFV_ERR_STATE, "fcfv_generate_structured: generated connectivity failed validation (%d)", flag);
     TRY(build_fconn(h));
+    TRY(build_face_lists(h));
     if (partitioned) {
         LAUNCH(h, k_pack_owned, nblocks(nel, 256), 256, (int)nel, P<uint8_t>(h->elem_owned), kOwnedElem, P<int>(h->ebc));
         LAUNCH(h, k_pack_owned, nblocks(nf, 256), 256, (int)nf, P<uint8_t>(h->face_owned), kOwnedFace, P<int>(h->fbc));

@@ -359,6 +359,23 @@ __global__ void k_convert_bc(const long long* __restrict__ in, int8_t* __restric
     out[f] = (v == 1 || v == 2 || v == -1) ? (int8_t)v : (int8_t)0;   // other tags behave as interior
 }
 
+// Ids of the Dirichlet (bc == 1) and Neumann (bc == 2) faces, appended in any order (the host sorts the short lists);
+// counts[0..1] keep counting past `cap`, which tells the host that a list did not fit.
+__global__ void k_bc_face_lists(int nf, const int8_t* __restrict__ bc, int cap, int* __restrict__ dir_idx, int* __restrict__ neu_idx,
+                                int* __restrict__ counts) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int t = bc[f];
+    if (t == 1) { const int k = atomicAdd(&counts[0], 1); if (k < cap) dir_idx[k] = f; }
+    else if (t == 2) { const int k = atomicAdd(&counts[1], 1); if (k < cap) neu_idx[k] = f; }
+}
+
+// dst[idx[k]] = packed[k]: the values of a per-face array on the listed faces
+__global__ void k_scatter_faces(int n, const int* __restrict__ idx, const double* __restrict__ packed, double* __restrict__ dst) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[idx[k]] = packed[k];
+}
+
 __global__ void k_f2e_init(int2* __restrict__ f2e, int* __restrict__ cnt, int nf) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;

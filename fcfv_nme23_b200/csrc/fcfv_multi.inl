@@ -514,6 +514,19 @@ int multi_set_sources(fcfv_t* h, const double* sex, const double* sey) {
 
 int multi_set_face_data(fcfv_t* h, const double* VxDir, const double* VyDir, const double* sxx, const double* syy, const double* sxy,
                         const double* syx) {
+    // every part lists its Dirichlet / Neumann faces: the values on those faces go from the global arrays to the parts and
+    // nothing else (fcfv_sparse_face_data); no nf-sized array is scattered
+    bool listed = true;
+    for (const Part& Pt : h->multi->parts) listed = listed && Pt.h->sparse_faces;
+    const double* const src[6] = {VxDir, VyDir, sxx, syy, sxy, syx};
+    for (const double* p : src)
+        if (p && is_device(p)) return fail(h, FCFV_ERR_INVALID, "a multi-GPU handle takes host arrays");
+    if (listed) {
+        for (DBuf* rec : {&h->VxDir, &h->VyDir, &h->sxx, &h->syy, &h->sxy, &h->syx}) rec->hm.epoch = -1;
+        TRY(for_parts(h, [&](int, Part& Pt) -> int { return set_face_data_listed(Pt.h, src, Pt.faces.data()); }));
+        h->have_face_data = true;
+        return FCFV_OK;
+    }
     // NULL = keep what is resident, so the Dirichlet pair and the Neumann quadruple are scattered (or skipped) separately
     const bool first = !h->have_face_data;
     if (first || VxDir || VyDir)

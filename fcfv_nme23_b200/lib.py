@@ -94,6 +94,8 @@ def load():
         "fcfv_has_orphan_faces": [vp, P(ci)],
         "fcfv_new_epoch": [vp],
         "fcfv_transfer_stats": [vp, P(i64), P(i64), P(i64), ci],
+        "fcfv_sparse_face_data": [vp, ci],
+        "fcfv_sparse_face_info": [vp, P(ci), P(i64), P(i64), P(i64)],
         "fcfv_host_register": [vp, vp, i64],
         "fcfv_host_unregister": [vp, vp],
         "fcfv_run_pipeline": [vp, ci, ci, dbl, ci],

@@ -156,6 +156,22 @@ int fcfv_new_epoch(fcfv_t* h);
  * zeroes the counters after reading.  Any pointer may be NULL. */
 int fcfv_transfer_stats(fcfv_t* h, int64_t* h2d_bytes, int64_t* d2h_bytes, int64_t* cache_hit_bytes, int reset);
 
+/* ---- per-face boundary data through face lists ------------------------------------------------------
+ * The reference reads VxDir / VyDir only behind the Bool factor (bc==1) (DiscretisationFCFV_Stokes.jl:27-37,191-194,
+ * 321-325; ComputeResidualsFCFV_Stokes.jl:62-66) and the four Neumann arrays only through t*Xi with Xi = (bc==2)
+ * (Discretisation:167-169,177-178; Residuals:57-61,69): of the nf values of each array only those on the Dirichlet /
+ * Neumann faces enter the result.  fcfv_set_mesh therefore lists these faces (device pass over bc, sorted ids), and every
+ * HOST array of per-face boundary data (fcfv_set_face_data and all calls that take VxDir ... SyxNeu) crosses PCIe as its
+ * values on the listed faces (gather into a page-locked slot, one small copy, scatter on the device) instead of nf
+ * doubles.  mode 0: off (whole arrays), 1 (default): lists when both are short (<= nf/16 and <= 2^18 faces -- every mesh
+ * of the reference: boundary faces are O(sqrt(nf))), 2: always.  Entries of the device arrays on other faces keep what
+ * they held (zeros after allocation); no kernel reads them, fcfv_get_data returns them as they are.  Device-pointer
+ * arguments are copied whole as before.  Changing the mode on a handle with a mesh rebuilds the lists. */
+int fcfv_sparse_face_data(fcfv_t* h, int mode);
+/* *active = 1 when lists are in use for the resident mesh; their lengths (-1 when inactive); number of list uploads so
+ * far.  Any pointer may be NULL. */
+int fcfv_sparse_face_info(fcfv_t* h, int* active, int64_t* n_dirichlet, int64_t* n_neumann, int64_t* uploads);
+
 /* ---- a5/a6/a7: ElementAssemblyLoop[NEW] + Sparsify (Discretisation:102-202,210-347,355-364)
  * alpha/beta/Z: NULL = use the device-resident result of the last fcfv_compute_local.
  * Uses mesh.τ as resident (fcfv_compute_local / fcfv_update_fields).  Result: device CSR of

@@ -697,6 +697,7 @@ def test_staged_pageable_copies_give_identical_results(monkeypatch, api, oracle)
     from fcfv_nme23_b200 import lib as L
     case = cases.Case("LowRes", "inclusion", 0, "Gradient")
     ref = {}
+    monkeypatch.setenv("FCFV_SPARSE_FACE_DATA", "0")      # whole per-face arrays: they are part of what is staged here
     for tag, env in (("direct", "0"), ("staged", "1024")):
         monkeypatch.setenv("FCFV_STAGED_MIN_BYTES", env)
         m, d = cases.build(case)

@@ -16,6 +16,13 @@ def api():
     return api
 
 
+@pytest.fixture(autouse=True)
+def whole_face_arrays(monkeypatch):
+    """The byte counts below are those of whole per-face arrays; the face lists (tests/test_sparse_face_data.py) would
+    replace the VDir / Neumann uploads by a few values each."""
+    monkeypatch.setenv("FCFV_SPARSE_FACE_DATA", "0")
+
+
 def three_calls(api, mesh, d, case, mutate=None):
     """The three calls of a reference driver through the mirror; `mutate(d)` runs between ComputeFCFV and the assembly."""
     from fcfv_nme23_b200 import lib as L

@@ -16,7 +16,7 @@ assemble their own rows with no data-path communication, NCCL all-reduces the si
 `value`   : device-resident pipeline, inputs already in HBM (timed with CUDA events on the
             library's stream, max over ranks).  Inputs (>40 GB) are far larger than L2 (126 MB).
 `e2e`     : the same step through the reference-facing C-ABI calls with HOST (pinned) buffers:
-            fcfv_set_mesh + fcfv_compute_local + fcfv_assemble + fcfv_residuals, H2D of every input
+            fcfv_compute_fcfv (mesh + ComputeFCFV) + fcfv_assemble + fcfv_residuals, H2D of every input
             and D2H of alpha/beta/Z/tau + nnz + norms inside the timed region.  The assembled CSR
             stays on the device (north_star: the GPU path ends at device-resident CSR).
 `roofline`: dominant kernel (k_asm_fill), algorithmic bytes / CUDA-event time vs the measured HBM peak.
@@ -620,8 +620,8 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
     """The same step through the reference-facing host-buffer calls, exactly as the shims (julia/FCFV_B200.jl,
     fcfv_nme23_b200/api.py) issue them for the three calls of a driver (SolKzFCFV.jl:150,155,205):
 
-        ComputeFCFV            -> [first call on a mesh: fcfv_set_mesh | later: fcfv_new_epoch], fcfv_update_fields(ke, delta,
-                                  tau_e, tau), fcfv_compute_local_ex
+        ComputeFCFV            -> fcfv_compute_fcfv: [first call on a mesh: the mesh arrays | later: fcfv_new_epoch and the
+                                  mutable fields ke, delta, tau_e] + sources / boundary data up, alpha / beta / Z / tau down
         ElementAssemblyLoopNEW -> fcfv_update_fields(...), fcfv_assemble(alpha, beta, Z, VDir, sigmaNeu)
         ComputeResiduals..._o1 -> fcfv_update_fields(...), fcfv_residuals(Vh, Pe, alpha, beta, Z, sources, VDir, sigmaNeu)
 
@@ -657,22 +657,24 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
     def three_calls(h, P, Dd, out, nel, with_mesh=True, ownership=True, cached=True):
         def refresh(tau=True):
             h.check(lib.fcfv_update_fields(h._h, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, ptr(out["tau"]) if tau else None))
-        if with_mesh:       # first call on an FCFV_Mesh object (or a driver that rebuilds its mesh): the mesh goes up
-            h.check(lib.fcfv_set_mesh(h._h, nel, P["bc"].numel(), ptr(P["e2f"]), ptr(P["bc"]), ptr(P["Ω"]), ptr(P["n_x"]), ptr(P["n_y"]),
-                                      ptr(P["Γ"]), ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel))
-            if world > 1 and ownership:
-                h.check(lib.fcfv_set_ownership(h._h, ptr(P["eo"]), ptr(P["fo"]), nel_g, nf_g, None))
         sig = [ptr(Dd[k]) for k in ("sxx", "syy", "sxy", "syx")]
         loc = [ptr(out[k]) for k in ("alpha", "beta", "Z")]
-        # ComputeFCFV
-        if cached and not with_mesh:      # the shims skip this right after they have uploaded the mesh themselves
+        nf_ = P["bc"].numel()
+        # ComputeFCFV = ONE library call (fcfv_compute_fcfv).  First call on an FCFV_Mesh object (or a driver that rebuilds
+        # its mesh): the mesh goes up in front of the element kernel; later calls: only the mutable fields ke, delta, tau_e
+        send_mesh = with_mesh
+        if with_mesh and world > 1 and ownership:       # partitioned mesh of one rank: ownership masks go up between the
+            h.check(lib.fcfv_set_mesh(h._h, nel, nf_, ptr(P["e2f"]), ptr(P["bc"]), ptr(P["Ω"]), ptr(P["n_x"]), ptr(P["n_y"]),   # mesh and the call
+                                      ptr(P["Γ"]), ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel))
+            h.check(lib.fcfv_set_ownership(h._h, ptr(P["eo"]), ptr(P["fo"]), nel_g, nf_g, None))
+            send_mesh = False
+        elif cached and not with_mesh:      # the shims skip this right after they have uploaded the mesh themselves
             h.check(lib.fcfv_new_epoch(h._h))
-        orph = C.c_int(1)
-        h.check(lib.fcfv_has_orphan_faces(h._h, C.byref(orph)))
-        refresh(bool(orph.value))         # ComputeFCFV overwrites tau on every face that has an element: mesh.tau only goes up
-                                          # in front of it when the mesh has faces without elements
-        h.check(lib.fcfv_compute_local_ex(h._h, form, 1.0, ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), *sig,
-                                          *loc, ptr(out["tau"])))
+        geo = [ptr(P[k]) for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ")] if send_mesh else [None] * 6
+        # mesh.tau goes in as well: the library reads it only when the mesh has faces without elements (ComputeFCFV
+        # overwrites every other entry)
+        h.check(lib.fcfv_compute_fcfv(h._h, nel, nf_, *geo, ptr(P["ke"]), ptr(P["δ"]), ptr(P["τe"]), nel, ptr(out["tau"]), form, 1.0,
+                                      ptr(Dd["sex"]), ptr(Dd["sey"]), ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), *sig, *loc, ptr(out["tau"])))
         # ElementAssemblyLoopNEW
         refresh()
         h.check(lib.fcfv_assemble(h._h, VARIANT, form, 1.0, *loc, ptr(Dd["VxDir"]), ptr(Dd["VyDir"]), *sig, 0, C.byref(nnz[0]),
@@ -784,10 +786,13 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
                           "note": "same calls with fcfv_upload_cache(0): every call sends every array it is given"},
             "single_process_multi_gpu_handle": single,
             "fused_pass": fused_res,
-            "api": "per pass: fcfv_set_mesh, then what the shims issue for ComputeFCFV / ElementAssemblyLoopNEW / ComputeResidualsFCFV_Stokes_o1 "
-                   "(fcfv_new_epoch + fcfv_update_fields + fcfv_compute_local_ex | fcfv_update_fields + fcfv_assemble | fcfv_update_fields + "
-                   "fcfv_residuals) with pinned host buffers and the upload cache on; byte counts from fcfv_transfer_stats (all ranks); "
-                   "CSR left device-resident"}
+            "face_lists": dict(zip(("active", "dirichlet_faces", "neumann_faces", "list_uploads"), h.sparse_face_info())),
+            "compute_fcfv_pipelined_calls": h.pipelined_calls,
+            "api": "per pass what the shims issue for ComputeFCFV / ElementAssemblyLoopNEW / ComputeResidualsFCFV_Stokes_o1: "
+                   "fcfv_compute_fcfv (with the mesh arrays: first call on a mesh object; mesh_resident: fcfv_new_epoch + the mutable "
+                   "fields only) | fcfv_update_fields + fcfv_assemble | fcfv_update_fields + fcfv_residuals, with pinned host buffers "
+                   "and the upload cache on; VxDir / VyDir / Neumann arrays cross the link as their values on the Dirichlet / "
+                   "Neumann faces (fcfv_sparse_face_data); byte counts from fcfv_transfer_stats (all ranks); CSR left device-resident"}
 
 
 _RESULT_FD = None

@@ -148,6 +148,11 @@ class Handle:
         return int(self.lib.fcfv_staged_copies(self._h))
 
     @property
+    def pipelined_calls(self):
+        """``fcfv_compute_fcfv`` calls that ran as an upload | kernel | download pipeline over element chunks."""
+        return int(self.lib.fcfv_pipelined_calls(self._h))
+
+    @property
     def device_bytes(self):
         return int(self.lib.fcfv_device_bytes(self._h))
 
@@ -202,6 +207,30 @@ class Handle:
         if getattr(mesh, "elem_owned", None) is not None or getattr(mesh, "face_owned", None) is not None:
             self.set_ownership(mesh.elem_owned, mesh.face_owned, getattr(mesh, "nel_global", 0),
                                getattr(mesh, "nf_global", 0), getattr(mesh, "tau_ref", None))
+
+    def compute_fcfv(self, mesh, send_mesh, Formulation, A, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu):
+        """``fcfv_compute_fcfv``: ComputeFCFV(mesh, ...) as one call -- the mesh (``send_mesh``) or only its mutable fields
+        ke, δ, τe go up in front of the element kernel; α, β, Ζ and mesh.τ come back."""
+        a = _Arg()
+        nel, nf = int(mesh.nel), int(mesh.nf)
+        taue = mesh.τe if mesh.τe is not None else (np.zeros(nel) if send_mesh else None)
+        ntaue = 0 if taue is None else (int(np.size(taue)) if not hasattr(taue, "numel") else int(taue.numel()))
+        al, be, Z = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")
+        tau = np.empty(nf)
+        geo = ([a.i(mesh.e2f, 3 * nel), a.i(mesh.bc, nf), a.d(mesh.Ω, nel), a.d(mesh.n_x, 3 * nel), a.d(mesh.n_y, 3 * nel),
+                a.d(mesh.Γ, 3 * nel)] if send_mesh else [None] * 6)
+        # the Neumann arrays the reference's ComputeFCFV receives and ignores go up while the results come down
+        self.check(self.lib.fcfv_compute_fcfv(
+            self._h, nel, nf, *geo, a.d(mesh.ke, nel), a.d(mesh.δ, nel), a.d(taue, nel), ntaue, a.d(mesh.τ, nf),
+            formulation_id(Formulation), float(A), a.d(sex, nel), a.d(sey, nel), a.d(VxDir, nf), a.d(VyDir, nf), a.d(SxxNeu, nf),
+            a.d(SyyNeu, nf), a.d(SxyNeu, nf), a.d(SyxNeu, nf), _out(al), _out(be), _out(Z), _out(tau)))
+        a.done(self)
+        if send_mesh:
+            self.nel, self.nf = nel, nf
+            flag = C.c_int(0)
+            self.check(self.lib.fcfv_has_orphan_faces(self._h, C.byref(flag)))
+            self.has_orphans = bool(flag.value)
+        return al, be, Z, tau
 
     def update_fields(self, ke=None, delta=None, taue=None, tau=None):
         a = _Arg()
@@ -413,21 +442,30 @@ def partition_part(e2f, nf, nparts, part):
     return eg, fg, eo, fo
 
 
+def _new_handle(mesh, device=None) -> Handle:
+    ngpus = int(getattr(mesh, "ngpus", None) or DEFAULT_GPUS)
+    h = Handle(0 if device is None else device, ngpus=ngpus)
+    h.upload_cache(CACHE_INPUTS)
+    return h
+
+
+def _warn_numbering(mesh, h):
+    if h.ngpus == 1 and h.nel >= 100_000 and getattr(mesh, "elem_owned", None) is None:
+        span, off = h.numbering_locality()
+        if span > 0.05 or off > 0.05:
+            import warnings
+            warnings.warn(f"mesh numbering has little locality (element span {span:.2f}, face offset {off:.2f} of the mesh): "
+                          "the GPU passes run 3-7x faster after mesh.renumber_elements(hilbert_elements) / "
+                          "mesh.renumber_faces(first_seen_faces)", stacklevel=4)
+
+
 def handle_for(mesh, device=None, tau=True) -> Handle:
     h = getattr(mesh, "_fcfv_handle", None)
     if h is None:
-        ngpus = int(getattr(mesh, "ngpus", None) or DEFAULT_GPUS)
-        h = Handle(0 if device is None else device, ngpus=ngpus)
-        h.upload_cache(CACHE_INPUTS)
+        h = _new_handle(mesh, device)
         h.set_mesh(mesh, tau=tau)
         mesh._fcfv_handle = h
-        if ngpus == 1 and h.nel >= 100_000 and getattr(mesh, "elem_owned", None) is None:
-            span, off = h.numbering_locality()
-            if span > 0.05 or off > 0.05:
-                import warnings
-                warnings.warn(f"mesh numbering has little locality (element span {span:.2f}, face offset {off:.2f} of the mesh): "
-                              "the GPU passes run 3-7x faster after mesh.renumber_elements(hilbert_elements) / "
-                              "mesh.renumber_faces(first_seen_faces)", stacklevel=3)
+        _warn_numbering(mesh, h)
     return h
 
 
@@ -458,20 +496,19 @@ def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τ
     arrays and τr are accepted and unused, as in the reference."""
     if mesh.τ is None:
         mesh.τ = np.zeros(mesh.nf)
-    fresh = getattr(mesh, "_fcfv_handle", None) is None
-    h = handle_for(mesh, tau=False)
-    if not fresh:            # first call of a driver pass: whatever the caller changed since the last one goes up again
-        h.new_epoch()        # (a handle made just now has uploaded the mesh fields in this very call)
-    _refresh(mesh, h, tau=getattr(h, "has_orphans", True))
-    nel, nf = h.nel, h.nf
-    a = _Arg()
-    al, be, Z = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")
-    tau = np.empty(nf)
-    # the Neumann arrays the reference's ComputeFCFV receives and ignores go up while the results come down
-    h.check(h.lib.fcfv_compute_local_ex(h._h, formulation_id(Formulation), float(A), a.d(sex, nel), a.d(sey, nel),
-                                        a.d(VxDir, nf), a.d(VyDir, nf), a.d(SxxNeu, nf), a.d(SyyNeu, nf), a.d(SxyNeu, nf),
-                                        a.d(SyxNeu, nf), _out(al), _out(be), _out(Z), _out(tau)))
-    a.done(h)
+    h = getattr(mesh, "_fcfv_handle", None)
+    partitioned = getattr(mesh, "elem_owned", None) is not None or getattr(mesh, "face_owned", None) is not None
+    send_mesh = h is None and not partitioned
+    if h is None and partitioned:      # ownership masks go up between the mesh and the first call (fcfv_set_ownership)
+        h = handle_for(mesh, tau=False)
+    elif h is None:
+        h = _new_handle(mesh)
+    else:                    # first call of a driver pass: whatever the caller changed since the last one goes up again
+        h.new_epoch()
+    al, be, Z, tau = h.compute_fcfv(mesh, send_mesh, Formulation, A, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu)
+    if send_mesh:
+        mesh._fcfv_handle = h
+        _warn_numbering(mesh, h)
     mesh.τ = tau
     return al, be, Z
 

@@ -162,6 +162,7 @@ struct fcfv_handle {
     cudaEvent_t fstage_ev[6] = {};
     bool fstage_busy[6] = {};
     long long sparse_uploads = 0;
+    long long pipelined_calls = 0;    // fcfv_compute_fcfv calls that ran as a chunk pipeline (diagnostics / tests)
     // nccl
     NcclApi nccl;
     void* comm = nullptr;
@@ -814,6 +815,7 @@ int64_t fcfv_staged_copies(fcfv_t* h) {
     if (h->multi) multi_each(h, [&](fcfv_t* q) { n += q->staged_copies; });
     return n;
 }
+int64_t fcfv_pipelined_calls(fcfv_t* h) { return h ? (int64_t)h->pipelined_calls : 0; }
 int64_t fcfv_device_bytes(fcfv_t* h) {
     if (!h) return 0;
     int64_t n = (int64_t)h->bytes;
@@ -822,17 +824,13 @@ int64_t fcfv_device_bytes(fcfv_t* h) {
 }
 
 // -------------------------------------------------------------------------------------------------
-int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const int64_t* bc, const double* Omega,
-                  const double* nx, const double* ny, const double* Gamma, const double* ke, const double* delta,
-                  const double* taue, int64_t ntaue) {
-    if (!h) return FCFV_ERR_INVALID;
-    if (h->multi) return multi_set_mesh(h, nel, nf, e2f, bc, Omega, nx, ny, Gamma, ke, delta, taue, ntaue);
+namespace {
+// First half of fcfv_set_mesh: connectivity and tags (everything the face -> element map, the connectivity records, the
+// tag words and the boundary-face lists are built from).  have_mesh stays false until the fields have arrived.
+int set_mesh_connectivity(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const int64_t* bc) {
     CU(cudaSetDevice(h->device));
     if (nel < 0 || nf < 0 || nel >= (1LL << 29) || nf >= (1LL << 30))
         return fail(h, FCFV_ERR_INVALID, "mesh size out of range (nel=%lld < 2^29, nf=%lld < 2^30 required)", (long long)nel, (long long)nf);
-    if (!e2f || !bc || !Omega || !nx || !ny || !Gamma || !ke || !delta)
-        return fail(h, FCFV_ERR_INVALID, "fcfv_set_mesh: null mesh array");
-    if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
     h->have_mesh = false; h->have_local = false;
     new_epoch(h);        // a new mesh: nothing that is resident mirrors a host array any more
     h->coef_variant = -1;
@@ -852,17 +850,6 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     TRY(upload(h, h->tmp, bc, sizeof(int64_t) * nf));
     TRY(ensure(h, h->bc, (size_t)nf));
     LAUNCH(h, k_convert_bc, nblocks(nf, 256), 256, P<long long>(h->tmp), P<int8_t>(h->bc), (int)nf);
-    TRY(upload(h, h->Om, Omega, sizeof(double) * nel));
-    TRY(upload(h, h->nx, nx, sizeof(double) * 3 * nel));
-    TRY(upload(h, h->ny, ny, sizeof(double) * 3 * nel));
-    TRY(upload(h, h->G, Gamma, sizeof(double) * 3 * nel));
-    // the mutable fields are remembered by the upload cache: the field refresh of the first ComputeFCFV on this mesh
-    // (fcfv_update_fields in the same epoch) does not send them a second time
-    TRY(upload_cached(h, h->ke, ke, sizeof(double) * nel));
-    TRY(upload_cached(h, h->dl, delta, sizeof(double) * nel));
-    TRY(ensure(h, h->taue, sizeof(double) * nel));
-    if (taue) TRY(upload_cached(h, h->taue, taue, sizeof(double) * nel));
-    else { h->taue.hm.epoch = -1; CU(cudaMemsetAsync(h->taue.p, 0, sizeof(double) * nel, h->stream)); }
     TRY(alloc_mesh_dependent(h));
     CU(cudaMemsetAsync(h->tau.p, 0, sizeof(double) * nf, h->stream));
     TRY(build_f2e(h));
@@ -874,6 +861,31 @@ int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const 
     if (flag & 1) return fail(h, FCFV_ERR_INVALID, "e2f contains a face id outside 1..nf");
     if (flag & 2) return fail(h, FCFV_ERR_INVALID, "a face is referenced by more than two (element, local face) pairs");
     if (flag & 4) return fail(h, FCFV_ERR_INVALID, "two elements share more than one face (or an element lists a face twice)");
+    return FCFV_OK;
+}
+}  // namespace
+
+int fcfv_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const int64_t* bc, const double* Omega,
+                  const double* nx, const double* ny, const double* Gamma, const double* ke, const double* delta,
+                  const double* taue, int64_t ntaue) {
+    if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) return multi_set_mesh(h, nel, nf, e2f, bc, Omega, nx, ny, Gamma, ke, delta, taue, ntaue);
+    if (!e2f || !bc || !Omega || !nx || !ny || !Gamma || !ke || !delta)
+        return fail(h, FCFV_ERR_INVALID, "fcfv_set_mesh: null mesh array");
+    if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
+    TRY(set_mesh_connectivity(h, nel, nf, e2f, bc));
+    TRY(upload(h, h->Om, Omega, sizeof(double) * nel));
+    TRY(upload(h, h->nx, nx, sizeof(double) * 3 * nel));
+    TRY(upload(h, h->ny, ny, sizeof(double) * 3 * nel));
+    TRY(upload(h, h->G, Gamma, sizeof(double) * 3 * nel));
+    // the mutable fields are remembered by the upload cache: the field refresh of the first ComputeFCFV on this mesh
+    // (fcfv_update_fields in the same epoch) does not send them a second time
+    TRY(upload_cached(h, h->ke, ke, sizeof(double) * nel));
+    TRY(upload_cached(h, h->dl, delta, sizeof(double) * nel));
+    TRY(ensure(h, h->taue, sizeof(double) * nel));
+    if (taue) TRY(upload_cached(h, h->taue, taue, sizeof(double) * nel));
+    else { h->taue.hm.epoch = -1; CU(cudaMemsetAsync(h->taue.p, 0, sizeof(double) * nel, h->stream)); }
+    TRY(sync(h));
     h->have_mesh = true;
     return FCFV_OK;
 }
@@ -1155,13 +1167,14 @@ int fcfv_set_local(fcfv_t* h, const double* alpha, const double* beta, const dou
 // -------------------------------------------------------------------------------------------------
 namespace {
 template <int FORM, int COEF>
-void launch_local(fcfv_t* h, double A) {
+void launch_local(fcfv_t* h, double A, long long e0 = 0, long long e1 = -1) {
     const MeshView M = mesh_view(h);
     double* c = P<double>(h->coef);
+    if (e1 < 0) e1 = h->nel;
     // mesh.τ is set by the element kernel (one writer per face: its highest adjacent element)
-    TLAUNCH(h, T_LOCAL, (k_local<FORM, COEF>), nblocks(h->nel), kBlock, M, P<double>(h->sex), P<double>(h->sey), P<double>(h->VxDir),
+    TLAUNCH(h, T_LOCAL, (k_local<FORM, COEF>), nblocks(e1 - e0), kBlock, M, P<double>(h->sex), P<double>(h->sey), P<double>(h->VxDir),
             P<double>(h->VyDir), A, P<double>(h->alpha), P<double>(h->beta), P<double>(h->Z), P<double>(h->tau), COEF >= 0 ? c : nullptr,
-            COEF >= 0 ? c + (size_t)h->nel : nullptr);
+            COEF >= 0 ? c + (size_t)h->nel : nullptr, (int)e0, (int)e1);
 }
 
 // coef_variant: FCFV_LOOP_OLD / FCFV_LOOP_NEW = the assembly of that loop follows (fcfv_run_pipeline): the element kernel
@@ -1280,6 +1293,142 @@ int fcfv_compute_local_ex(fcfv_t* h, int formulation, double A, const double* se
     rc = tail();
     h->async = was_async;
     const int rc2 = local_downloaded(h, alpha, beta, Z, tau);     // both streams are drained whatever happened above
+    return rc ? rc : rc2;
+}
+
+namespace {
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+constexpr int kLocalChunks = 8;
+
+// One ComputeFCFV with everything it needs still on the host, as a pipeline over element chunks: while chunk c of the
+// per-element inputs goes up, the element kernel runs on chunk c-1 and alpha / beta / Z of chunk c-2 come down -- both
+// directions of the link stay busy and the kernel costs nothing.  The element kernel reads, per element, only
+// element-indexed arrays (geometry, tau_e, sources) besides the connectivity / tag records (complete before the first chunk)
+// and VxDir / VyDir on Dirichlet faces (sent first); ke and delta are not read by it at all and follow the last chunk,
+// under the tail of the downloads.  Only page-locked (or registered) host memory can be copied asynchronously, so this path
+// needs every array to be that; the caller falls back to the plain sequence otherwise.
+template <int FORM>
+int compute_fcfv_chunks(fcfv_t* h, bool mesh, const double* Omega, const double* nx, const double* ny, const double* Gamma,
+                        const double* ke, const double* delta, const double* taue, const double* tau_in, double A, const double* sex,
+                        const double* sey, const double* VxDir, const double* VyDir, const double* const sig[4], double* alpha,
+                        double* beta, double* Z, double* tau) {
+    const long long nel = h->nel, nf = h->nf;
+    const size_t be = sizeof(double) * (size_t)nel;
+    if (!h->stream_out) {
+        CU(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    }
+    if (tau_in && h->has_orphans) TRY(upload_cached(h, h->tau, tau_in, sizeof(double) * nf));   // faces without elements keep the caller's tau
+    TRY(fcfv_set_face_data(h, VxDir, VyDir, nullptr, nullptr, nullptr, nullptr));
+    struct In { DBuf* b; const double* src; int ncol; bool skip; } ins[7] = {
+        {&h->Om, mesh ? Omega : nullptr, 1, false}, {&h->nx, mesh ? nx : nullptr, 3, false}, {&h->ny, mesh ? ny : nullptr, 3, false},
+        {&h->G, mesh ? Gamma : nullptr, 3, false}, {&h->taue, taue, 1, false}, {&h->sex, sex, 1, false}, {&h->sey, sey, 1, false}};
+    for (In& in : ins) {
+        TRY(ensure(h, *in.b, be * in.ncol));
+        if (!in.src) { in.skip = true; continue; }
+        in.skip = cache_hit(h, *in.b, in.src, be * in.ncol);     // resident mesh: an array the device already mirrors stays
+        if (in.skip) { h->cache_hits++; h->cache_hit_bytes += (long long)(be * in.ncol); }
+        else in.b->hm.epoch = -1;
+    }
+    if (mesh && !taue) { h->taue.hm.epoch = -1; CU(cudaMemsetAsync(h->taue.p, 0, be, h->stream)); }
+    h->alpha.hm.epoch = h->beta.hm.epoch = h->Z.hm.epoch = h->tau.hm.epoch = -1;      // rewritten on the device
+    h->coef_variant = -1;
+    long long chunk = (nel + kLocalChunks - 1) / kLocalChunks;
+    chunk = std::max<long long>(kBlock, (chunk + kBlock - 1) / kBlock * kBlock);
+    struct Out { double* dst; const DBuf* b; int ncol; } outs[3] = {{alpha, &h->alpha, 1}, {beta, &h->beta, 2}, {Z, &h->Z, 4}};
+    for (long long e0 = 0; e0 < nel; e0 += chunk) {
+        const long long e1 = std::min(nel, e0 + chunk);
+        const size_t off = sizeof(double) * (size_t)e0, len = sizeof(double) * (size_t)(e1 - e0);
+        for (const In& in : ins) {
+            if (in.skip) continue;
+            for (int c = 0; c < in.ncol; c++)
+                TRY(copy(h, (char*)in.b->p + c * be + off, (const char*)in.src + c * be + off, len));
+        }
+        launch_local<FORM, -1>(h, A, e0, e1);
+        CU(cudaEventRecord(h->ev_out, h->stream));
+        CU(cudaStreamWaitEvent(h->stream_out, h->ev_out, 0));
+        for (const Out& o : outs) {
+            if (!o.dst) continue;
+            for (int c = 0; c < o.ncol; c++)
+                CU(cudaMemcpyAsync((char*)o.dst + c * be + off, (const char*)o.b->p + c * be + off, len, cudaMemcpyDeviceToHost, h->stream_out));
+            h->d2h_bytes += (long long)(len * o.ncol);
+        }
+    }
+    CU(cudaGetLastError());
+    if (tau && nf) {          // complete once every chunk has run (a face's tau comes from its highest element)
+        CU(cudaMemcpyAsync(tau, h->tau.p, sizeof(double) * (size_t)nf, cudaMemcpyDeviceToHost, h->stream_out));
+        h->d2h_bytes += (long long)(sizeof(double) * nf);
+    }
+    // what the element kernel does not read goes up under the tail of the downloads
+    if (ke) TRY(upload_cached(h, h->ke, ke, be));
+    if (delta) {
+        const long long hits = h->cache_hits;
+        TRY(upload_cached(h, h->dl, delta, be));
+        if (h->cache_hits == hits) h->delta_dirty = true;
+    }
+    if (h->cache_on) {
+        for (const In& in : ins)       // the chunks together are the whole array: it is a mirror from now on
+            if (!in.skip && in.b != &h->Om && in.b != &h->nx && in.b != &h->ny && in.b != &h->G)
+                in.b->hm = HostMirror{in.src, be * in.ncol, fingerprint(in.src, be * in.ncol), h->epoch};
+        if (sig[0] || sig[1] || sig[2] || sig[3]) TRY(fcfv_set_face_data(h, nullptr, nullptr, sig[0], sig[1], sig[2], sig[3]));
+    }
+    h->have_sources = true;
+    h->have_local = true;
+    return FCFV_OK;
+}
+}  // namespace
+
+// set_mesh (e2f != NULL) or field refresh (e2f == NULL: the mesh is resident) + ComputeFCFV in one call: what the shims issue
+// for ComputeFCFV(mesh, ...).  Same results as fcfv_set_mesh / fcfv_update_fields followed by fcfv_compute_local_ex.
+int fcfv_compute_fcfv(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const int64_t* bc, const double* Omega, const double* nx,
+                      const double* ny, const double* Gamma, const double* ke, const double* delta, const double* taue, int64_t ntaue,
+                      const double* tau_in, int formulation, double A, const double* sex, const double* sey, const double* VxDir,
+                      const double* VyDir, const double* sxxNeu, const double* syyNeu, const double* sxyNeu, const double* syxNeu,
+                      double* alpha, double* beta, double* Z, double* tau) {
+    if (!h) return FCFV_ERR_INVALID;
+    TRY(check_form(h, formulation));
+    const bool mesh = e2f != nullptr;
+    if (mesh && (!bc || !Omega || !nx || !ny || !Gamma || !ke || !delta)) return fail(h, FCFV_ERR_INVALID, "fcfv_compute_fcfv: null mesh array");
+    if (!mesh) { TRY(need(h, h->have_mesh, "fcfv_compute_fcfv: no mesh resident and none given")); nel = h->nel; nf = h->nf; }
+    if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
+    if (!sex || !sey || !VxDir || !VyDir) return fail(h, FCFV_ERR_INVALID, "fcfv_compute_fcfv: null source / Dirichlet array");
+    long long min_nel = 1LL << 20;          // below that a pass is a few milliseconds whichever way it is issued
+    if (const char* v = getenv("FCFV_PIPELINE_MIN_NEL")) min_nel = atoll(v);
+    bool chunks = !h->multi && nel >= min_nel && nel >= 2 * kBlock;
+    const void* arrays[] = {Omega, nx, ny, Gamma, ke, delta, taue, sex, sey, alpha, beta, Z, tau};
+    for (size_t k = 0; k < sizeof arrays / sizeof arrays[0] && chunks; k++) {
+        const bool mesh_only = k < 4;
+        if (arrays[k] && (mesh || !mesh_only) && !is_pinned_host(arrays[k])) chunks = false;
+    }
+    if (!chunks) {
+        if (mesh) {
+            TRY(fcfv_set_mesh(h, nel, nf, e2f, bc, Omega, nx, ny, Gamma, ke, delta, taue, ntaue));
+            if (tau_in && !h->multi && h->has_orphans) TRY(fcfv_update_fields(h, nullptr, nullptr, nullptr, 0, tau_in));
+            if (tau_in && h->multi && multi_has_orphans(h)) TRY(fcfv_update_fields(h, nullptr, nullptr, nullptr, 0, tau_in));
+        } else {
+            const bool orph = h->multi ? multi_has_orphans(h) != 0 : h->has_orphans;
+            TRY(fcfv_update_fields(h, ke, delta, taue, ntaue, orph ? tau_in : nullptr));
+        }
+        return fcfv_compute_local_ex(h, formulation, A, sex, sey, VxDir, VyDir, sxxNeu, syyNeu, sxyNeu, syxNeu, alpha, beta, Z, tau);
+    }
+    if (mesh) TRY(set_mesh_connectivity(h, nel, nf, e2f, bc));
+    CU(cudaSetDevice(h->device));
+    h->pipelined_calls++;
+    const bool was_async = h->async;
+    h->async = true;
+    h->have_mesh = true;            // the entries used below ask for it; withdrawn again if the fields do not arrive
+    const double* const sig[4] = {sxxNeu, syyNeu, sxyNeu, syxNeu};
+    int rc = formulation == FCFV_GRADIENT
+                 ? compute_fcfv_chunks<kGradient>(h, mesh, Omega, nx, ny, Gamma, ke, delta, taue, tau_in, A, sex, sey, VxDir, VyDir, sig, alpha, beta, Z, tau)
+                 : compute_fcfv_chunks<kSymmetricGradient>(h, mesh, Omega, nx, ny, Gamma, ke, delta, taue, tau_in, A, sex, sey, VxDir, VyDir, sig, alpha, beta, Z, tau);
+    h->async = was_async;
+    const int rc2 = local_downloaded(h, alpha, beta, Z, tau);
+    if (rc && mesh) h->have_mesh = false;
     return rc ? rc : rc2;
 }
 

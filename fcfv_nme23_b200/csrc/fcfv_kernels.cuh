@@ -520,10 +520,11 @@ __global__ void __launch_bounds__(kBlock)
 k_local(MeshView M, const double* __restrict__ sex, const double* __restrict__ sey,
         const double* __restrict__ VxDir, const double* __restrict__ VyDir, double A, double* __restrict__ alpha,
         double* __restrict__ beta, double* __restrict__ Z, double* __restrict__ tau, double* __restrict__ ia,
-        double* __restrict__ c11) {
-    const int e = blockIdx.x * kBlock + threadIdx.x;
+        double* __restrict__ c11, int e0, int e1) {
+    // elements [e0, e1): the whole mesh, or one chunk of a ComputeFCFV whose inputs are still arriving (fcfv_compute_fcfv)
+    const int e = e0 + blockIdx.x * kBlock + threadIdx.x;
     const int nel = M.nel;
-    if (e >= nel) return;
+    if (e >= e1) return;
     double G[3], nx[3], ny[3], vx[3], vy[3];
     bool dir[3];
     int fid[3];

@@ -90,6 +90,7 @@ def load():
         "fcfv_pass": [vp, ci, ci, dbl, ci] + [vp] * 11 + [vp] * 4 + [ci, P(i64), P(i64), P(i64), vp],
         "fcfv_numbering_locality": [vp, P(dbl), P(dbl)],
         "fcfv_compute_local_ex": [vp, ci, dbl] + [vp] * 12,
+        "fcfv_compute_fcfv": [vp, i64, i64] + [vp] * 9 + [i64, vp, ci, dbl] + [vp] * 12,
         "fcfv_upload_cache": [vp, ci],
         "fcfv_has_orphan_faces": [vp, P(ci)],
         "fcfv_new_epoch": [vp],
@@ -138,6 +139,8 @@ def load():
     lib.fcfv_kernel_launches.restype = i64
     lib.fcfv_staged_copies.argtypes = [vp]
     lib.fcfv_staged_copies.restype = i64
+    lib.fcfv_pipelined_calls.argtypes = [vp]
+    lib.fcfv_pipelined_calls.restype = i64
     lib.fcfv_device_bytes.argtypes = [vp]
     lib.fcfv_device_bytes.restype = i64
     _lib = lib

@@ -138,6 +138,26 @@ int fcfv_compute_local_ex(fcfv_t* h, int formulation, double A, const double* se
                           const double* sxyNeu, const double* syxNeu, double* alpha, double* beta, double* Z,
                           double* tau);
 
+/* ComputeFCFV(mesh, ...) as ONE call (DiscretisationFCFV_Stokes.jl:8-44 on the mesh of CreateMeshFCFV.jl:10-44): what the
+ * shims issue for it.
+ *   e2f != NULL: the mesh goes up first (= fcfv_set_mesh(nel, nf, e2f, bc, Omega, nx, ny, Gamma, ke, delta, taue, ntaue));
+ *   e2f == NULL: the mesh is resident, nel / nf and the geometry arguments are ignored and ke / delta / taue (each may be
+ *                NULL = unchanged) are refreshed (= fcfv_update_fields);
+ *   tau_in     : mesh.tau as it stands, or NULL; only read when the mesh has faces no element references (every other entry
+ *                is overwritten, Discretisation:40);
+ * then = fcfv_compute_local_ex.  Results are those of the separate calls, bit for bit.  When every array is page-locked (or
+ * registered) host memory and nel >= 2^20 (FCFV_PIPELINE_MIN_NEL overrides), the call runs as a pipeline over 8 element
+ * chunks: connectivity and tags first (the records are built on the device), VxDir / VyDir on the Dirichlet faces, then per
+ * chunk geometry + tau_e + sources up | element kernel | alpha, beta, Z down on a second stream, and ke / delta (which the
+ * element kernel does not read) and the Neumann arrays under the tail of the downloads -- both directions of PCIe stay busy.
+ * Otherwise (pageable or device memory, small meshes, multi-GPU handles) it issues the separate calls. */
+int fcfv_compute_fcfv(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const int64_t* bc, const double* Omega,
+                      const double* nx, const double* ny, const double* Gamma, const double* ke, const double* delta,
+                      const double* taue, int64_t ntaue, const double* tau_in, int formulation, double A,
+                      const double* sex, const double* sey, const double* VxDir, const double* VyDir, const double* sxxNeu,
+                      const double* syyNeu, const double* sxyNeu, const double* syxNeu, double* alpha, double* beta,
+                      double* Z, double* tau);
+
 /* ---- upload cache ---------------------------------------------------------------------------------
  * A driver hands the same host arrays to ComputeFCFV, ElementAssemblyLoop[NEW] and ComputeResidualsFCFV_Stokes_o1
  * (examples/SolKzFCFV.jl:150,155,205: VxDir / VyDir three times, the Neumann arrays and the sources twice, and
@@ -287,6 +307,7 @@ int64_t fcfv_kernel_launches(fcfv_t* h);    /* kernels launched by this handle s
  * threads through page-locked staging buffers when a transfer is 8 MiB or larger (FCFV_STAGED_MIN_BYTES overrides the
  * threshold, 0 disables); the call still returns with the host side of the copy complete.  Number of such copies: */
 int64_t fcfv_staged_copies(fcfv_t* h);
+int64_t fcfv_pipelined_calls(fcfv_t* h);    /* fcfv_compute_fcfv calls that ran as a chunk pipeline */
 int64_t fcfv_device_bytes(fcfv_t* h);       /* device memory currently held by the handle */
 
 /* ---- synthetic structured mesh S(n) generated on the device (bench / large tests) --------

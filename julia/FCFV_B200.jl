@@ -94,19 +94,14 @@ end
 f64(x) = convert(Array{Float64}, x)
 i64(x) = convert(Array{Int64}, x)
 
-function handle_for(mesh)
-    haskey(HANDLES, mesh) && return HANDLES[mesh]
+function new_handle()
     h = Handle()
     check(h, ccall((:fcfv_upload_cache, LIB), Cint, (Ptr{Cvoid}, Cint), h.ptr, CACHE_INPUTS[] ? 1 : 0))
-    e2f, bc = i64(mesh.e2f), i64(mesh.bc)
-    Ω, nx, ny, Γ, ke, δ = f64(mesh.Ω), f64(mesh.n_x), f64(mesh.n_y), f64(mesh.Γ), f64(mesh.ke), f64(mesh.δ)
-    τe = ismissing(mesh.τe) ? zeros(mesh.nel) : f64(mesh.τe)       # may have nf entries (v2.jl:127)
-    GC.@preserve e2f bc Ω nx ny Γ ke δ τe begin
-        check(h, ccall((:fcfv_set_mesh, LIB), Cint,
-            (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
-            h.ptr, mesh.nel, mesh.nf, e2f, bc, Ω, nx, ny, Γ, ke, δ, τe, length(τe)))
-    end
+    return h
+end
+
+# after the mesh has gone up (fcfv_set_mesh, or fcfv_compute_fcfv with the mesh arrays): sizes, orphan flag, numbering check
+function adopt!(h::Handle, mesh)
     h.nel, h.nf = mesh.nel, mesh.nf
     orph = Ref{Cint}(1)
     check(h, ccall((:fcfv_has_orphan_faces, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}), h.ptr, orph))
@@ -120,6 +115,21 @@ function handle_for(mesh)
         end
     end
     return h
+end
+
+function handle_for(mesh)
+    haskey(HANDLES, mesh) && return HANDLES[mesh]
+    h = new_handle()
+    e2f, bc = i64(mesh.e2f), i64(mesh.bc)
+    Ω, nx, ny, Γ, ke, δ = f64(mesh.Ω), f64(mesh.n_x), f64(mesh.n_y), f64(mesh.Γ), f64(mesh.ke), f64(mesh.δ)
+    τe = ismissing(mesh.τe) ? zeros(mesh.nel) : f64(mesh.τe)       # may have nf entries (v2.jl:127)
+    GC.@preserve e2f bc Ω nx ny Γ ke δ τe begin
+        check(h, ccall((:fcfv_set_mesh, LIB), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+            h.ptr, mesh.nel, mesh.nf, e2f, bc, Ω, nx, ny, Γ, ke, δ, τe, length(τe)))
+    end
+    return adopt!(h, mesh)
 end
 
 # The drivers mutate mesh.ke / δ / τe / τ after the mesh is built (v2.jl:44,127; SolKzFCFV.jl:25,149):
@@ -158,25 +168,37 @@ function MeshGeometry!(mesh, τr; numbering::Integer = 0)
     return mesh
 end
 
-"""src/DiscretisationFCFV_Stokes.jl:8-44"""
+"""src/DiscretisationFCFV_Stokes.jl:8-44.  One library call (fcfv_compute_fcfv): on the first call for a mesh object the mesh
+goes up in front of the element kernel, later only its mutable fields ke, δ, τe (v2.jl:44,127; SolKzFCFV.jl:25,149); with
+page-locked arrays (PinArrays) and a large mesh the call runs as an upload | kernel | download pipeline over element chunks."""
 function ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τr, Formulation)
     ismissing(mesh.τ) && (mesh.τ = zeros(mesh.nf))      # LoadExternalMesh leaves τ missing
     fresh = !haskey(HANDLES, mesh)
-    h = handle_for(mesh)
+    h = fresh ? new_handle() : HANDLES[mesh]
     fresh || new_epoch!(h)              # first call of a driver pass: everything the driver may have changed goes up again
-    refresh!(h, mesh; tau = h.orphans)  # (a handle made just now has uploaded the mesh fields in this very call)
     nel, nf = mesh.nel, mesh.nf
+    e2f, bc = fresh ? (i64(mesh.e2f), i64(mesh.bc)) : (Int64[], Int64[])
+    Ω, nx, ny, Γ = fresh ? (f64(mesh.Ω), f64(mesh.n_x), f64(mesh.n_y), f64(mesh.Γ)) : (Float64[], Float64[], Float64[], Float64[])
+    ke, δ, τin = f64(mesh.ke), f64(mesh.δ), f64(mesh.τ)
+    τe = ismissing(mesh.τe) ? zeros(nel) : f64(mesh.τe)       # may have nf entries (v2.jl:127)
     α, β, Ζ, τ = zeros(nel), zeros(nel, 2), zeros(nel, 2, 2), zeros(nf)
     sx, sy, vx, vy = f64(sex), f64(sey), f64(VxDir), f64(VyDir)
     sxx, syy, sxy, syx = f64(SxxNeu), f64(SyyNeu), f64(SxyNeu), f64(SyxNeu)
+    pi64(a) = isempty(a) ? Ptr{Int64}(C_NULL) : pointer(a)
+    pf64(a) = isempty(a) ? Ptr{Float64}(C_NULL) : pointer(a)
     # the Neumann arrays (received and ignored by the reference) go up while α, β, Ζ, τ come down
-    GC.@preserve sx sy vx vy sxx syy sxy syx α β Ζ τ begin
-        check(h, ccall((:fcfv_compute_local_ex, LIB), Cint,
-            (Ptr{Cvoid}, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-            h.ptr, form_id(Formulation), A, sx, sy, vx, vy, sxx, syy, sxy, syx, α, β, Ζ, τ))
+    GC.@preserve e2f bc Ω nx ny Γ ke δ τe τin sx sy vx vy sxx syy sxy syx α β Ζ τ begin
+        check(h, ccall((:fcfv_compute_fcfv, LIB), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Float64,
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h.ptr, nel, nf, pi64(e2f), pi64(bc), pf64(Ω), pf64(nx), pf64(ny), pf64(Γ), ke, δ, τe, length(τe), τin,
+            form_id(Formulation), A, sx, sy, vx, vy, sxx, syy, sxy, syx, α, β, Ζ, τ))
     end
-    forget_temps!(h, (sex, sx), (sey, sy), (VxDir, vx), (VyDir, vy), (SxxNeu, sxx), (SyyNeu, syy), (SxyNeu, sxy), (SyxNeu, syx))
+    fresh && adopt!(h, mesh)
+    forget_temps!(h, (mesh.ke, ke), (mesh.δ, δ), (mesh.τe, τe), (mesh.τ, τin),
+                  (sex, sx), (sey, sy), (VxDir, vx), (VyDir, vy), (SxxNeu, sxx), (SyyNeu, syy), (SxyNeu, sxy), (SyxNeu, syx))
     mesh.τ = τ
     return α, β, Ζ
 end

@@ -82,6 +82,8 @@ def test_only_the_listed_values_cross_the_link(api):
     h.set_mesh(m)
     assert h.sparse_face_info()[:3] == (True, nd, nn)
     ptr = lambda x: C.c_void_p(np.ascontiguousarray(x).ctypes.data)
+    h.check(h.lib.fcfv_set_sources(h._h, ptr(d["sex"]), ptr(d["sey"])))           # fcfv_get_data wants every array set
+    h.check(h.lib.fcfv_set_solution(h._h, ptr(d["Vxh"]), ptr(d["Vyh"]), ptr(d["Pe"])))
     up0 = h.transfer_stats()[0]
     h.check(h.lib.fcfv_set_face_data(h._h, ptr(d["VxDir"]), ptr(d["VyDir"]), *[ptr(s) for s in d["neu"]]))
     assert h.transfer_stats()[0] - up0 == 8 * (2 * nd + 4 * nn)

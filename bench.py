@@ -581,7 +581,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- e2e through the host-buffer C ABI ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, h, rank, world, total_el, barrier)
+        e2e = run_e2e(args, h, rank, world, total_el, barrier, norms)
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -616,7 +616,7 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_e2e(args, hdev, rank, world, total_el, barrier):
+def run_e2e(args, hdev, rank, world, total_el, barrier, norms_device):
     """The same step through the reference-facing host-buffer calls, exactly as the shims (julia/FCFV_B200.jl,
     fcfv_nme23_b200/api.py) issue them for the three calls of a driver (SolKzFCFV.jl:150,155,205):
 
@@ -711,6 +711,12 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
     steps = max(1, min(args.steps, 3))
     progress("e2e: three calls with set_mesh")
     dt, h2d, d2h, hit = timed_host(step, steps)
+    # same inputs, same kernels: the norms that came back through the host-buffer calls are those of the device-resident pass
+    nd = np.asarray(norms_device, dtype=np.float64)
+    scale = np.maximum(np.abs(nd), 1e-300)
+    check = {"max_rel_vs_device_pipeline": float(np.max(np.abs(norms - nd) / scale)), "tolerance": 1e-12,
+             "nnz": [int(x.value) for x in nnz[:2]]}
+    check["ok"] = bool(check["max_rel_vs_device_pipeline"] <= 1e-12)
     # same pass on a mesh that is already resident (second and later passes on one FCFV_Mesh object)
     progress("e2e: three calls, mesh resident")
     dt2, h2d2, d2h2, hit2 = timed_host(lambda: step(with_mesh=False), steps)
@@ -786,6 +792,7 @@ def run_e2e(args, hdev, rank, world, total_el, barrier):
                           "note": "same calls with fcfv_upload_cache(0): every call sends every array it is given"},
             "single_process_multi_gpu_handle": single,
             "fused_pass": fused_res,
+            "result_check": check,
             "face_lists": dict(zip(("active", "dirichlet_faces", "neumann_faces", "list_uploads"), h.sparse_face_info())),
             "compute_fcfv_pipelined_calls": h.pipelined_calls,
             "api": "per pass what the shims issue for ComputeFCFV / ElementAssemblyLoopNEW / ComputeResidualsFCFV_Stokes_o1: "

@@ -190,6 +190,12 @@ int multi_export(fcfv_t*, int, int, void*, void*, double*);
 int multi_export_rhs(fcfv_t*, double*, double*);
 int multi_run_residuals(fcfv_t*, int, int, double*, double*);
 int multi_unsupported(fcfv_t*, const char*);
+int multi_element_values(fcfv_t*, const double*, const double*, const double*, const double*, const double*, double*, double*, double*, double*,
+                         double*);
+int multi_ph_residual(fcfv_t*, const double*, const double*, double*, double*, double*);
+int multi_ph_update_p(fcfv_t*, double, const double*, double*);
+int multi_ph_fusc(fcfv_t*, double, const double*, double*);
+int multi_center_pressure(fcfv_t*, double*, double*);
 int multi_has_orphans(fcfv_t*);
 double multi_asm_seconds(fcfv_t*);
 fcfv_t* multi_part0(fcfv_t*);
@@ -1969,7 +1975,7 @@ int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, c
 int fcfv_element_values(fcfv_t* h, const double* Vxh, const double* Vyh, const double* alpha, const double* beta,
                         const double* Z, double* Vxe, double* Vye, double* Txxe, double* Tyye, double* Txye) {
     if (!h) return FCFV_ERR_INVALID;
-    if (h->multi) return multi_unsupported(h, "fcfv_element_values");
+    if (h->multi) return multi_element_values(h, Vxh, Vyh, alpha, beta, Z, Vxe, Vye, Txxe, Tyye, Txye);
     TRY(need(h, h->have_mesh, "fcfv_element_values: no mesh set"));
     CU(cudaSetDevice(h->device));
     const long long nel = h->nel, nf = h->nf;
@@ -2014,7 +2020,7 @@ int ph_inputs(fcfv_t* h, const double* u, const double* p, double** du, double**
 
 int fcfv_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, double* rp, double* nrm) {
     if (!h) return FCFV_ERR_INVALID;
-    if (h->multi) return multi_unsupported(h, "fcfv_ph_residual");
+    if (h->multi) return multi_ph_residual(h, u, p, ru, rp, nrm);
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_residual: nothing assembled"));
     if (!u || !p) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_residual: null u or p");
     CU(cudaSetDevice(h->device));
@@ -2051,7 +2057,7 @@ int fcfv_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, do
 
 int fcfv_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p) {
     if (!h) return FCFV_ERR_INVALID;
-    if (h->multi) return multi_unsupported(h, "fcfv_ph_update_p");
+    if (h->multi) return multi_ph_update_p(h, gamma, u, p);
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_update_p: nothing assembled"));
     if (!u || !p) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_update_p: null u or p");
     CU(cudaSetDevice(h->device));
@@ -2066,7 +2072,7 @@ int fcfv_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p) {
 
 int fcfv_center_pressure(fcfv_t* h, double* Pe, double* mean) {
     if (!h) return FCFV_ERR_INVALID;
-    if (h->multi) return multi_unsupported(h, "fcfv_center_pressure");
+    if (h->multi) return multi_center_pressure(h, Pe, mean);
     TRY(need(h, h->have_mesh, "fcfv_center_pressure: no mesh set"));
     if (!Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_center_pressure: null Pe");
     CU(cudaSetDevice(h->device));
@@ -2093,7 +2099,7 @@ int fcfv_center_pressure(fcfv_t* h, double* Pe, double* mean) {
 
 int fcfv_ph_fusc(fcfv_t* h, double gamma, const double* p, double* fusc) {
     if (!h) return FCFV_ERR_INVALID;
-    if (h->multi) return multi_unsupported(h, "fcfv_ph_fusc");
+    if (h->multi) return multi_ph_fusc(h, gamma, p, fusc);
     TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_fusc: nothing assembled"));
     if (!p || !fusc) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_fusc: null p or fusc");
     CU(cudaSetDevice(h->device));

@@ -797,6 +797,128 @@ int multi_run_residuals(fcfv_t* h, int formulation, int tau_mode, double* sumsq,
     return multi_finish(h);
 }
 
+// ---- element values and the Powell-Hestenes lines on a multi-GPU handle ----------------------------------------------
+// Global arrays in and out: the inputs are restricted to every part (owned + ghost entries), the part-level entry runs on
+// its device, and each part returns the entries it owns.  Nothing here is on the hot path (post-processing / the outer
+// iteration around a host factorisation), so the outputs come back through part-local host temporaries.
+Part& part_of(fcfv_t* h, fcfv_t* q) {
+    for (Part& Pt : h->multi->parts)
+        if (Pt.h == q) return Pt;
+    return h->multi->parts[0];
+}
+
+int multi_element_values(fcfv_t* h, const double* Vxh, const double* Vyh, const double* alpha, const double* beta, const double* Z,
+                         double* Vxe, double* Vye, double* Txxe, double* Tyye, double* Txye) {
+    TRY(need(h, h->have_mesh, "fcfv_element_values: no mesh set"));
+    if ((Vxh == nullptr) != (Vyh == nullptr)) return fail(h, FCFV_ERR_INVALID, "fcfv_element_values: pass both Vxh and Vyh or neither");
+    if (alpha || beta || Z) {
+        if (!alpha || !beta || !Z) return fail(h, FCFV_ERR_INVALID, "fcfv_element_values: pass alpha, beta and Z together (or none of them)");
+        TRY(multi_set_local(h, alpha, beta, Z));
+    }
+    TRY(need(h, h->have_local, "fcfv_element_values: local coefficients missing"));
+    TRY(need(h, Vxh != nullptr || h->have_solution, "fcfv_element_values: no face velocities (fcfv_set_solution)"));
+    double* out[5] = {Vxe, Vye, Txxe, Tyye, Txye};
+    auto run = [&](fcfv_t* q, const double* vx, const double* vy) -> int {
+        Part& Pt = part_of(h, q);
+        const size_t ne = Pt.elems.size();
+        uvec<double> loc[5];
+        double* lp[5];
+        for (int k = 0; k < 5; k++) { if (out[k]) loc[k].resize(ne); lp[k] = out[k] ? loc[k].data() : nullptr; }
+        TRY(fcfv_element_values(q, vx, vy, nullptr, nullptr, nullptr, lp[0], lp[1], lp[2], lp[3], lp[4]));
+        for (int k = 0; k < 5; k++)
+            if (out[k]) put_owned(out[k], h->nel, Pt.elems, Pt.own_e, 1, lp[k]);
+        return FCFV_OK;
+    };
+    if (Vxh) {
+        TRY(multi_scatter(h, {{Vxh, 'f', 1, nullptr}, {Vyh, 'f', 1, nullptr}},
+                          [&](fcfv_t* q, const std::vector<const double*>& a) { return run(q, a[0], a[1]); }));
+        h->Vxh.hm.epoch = h->Vyh.hm.epoch = -1;      // the parts' face velocities were replaced behind the cache's back
+        h->have_solution = true;
+        return FCFV_OK;
+    }
+    return for_parts(h, [&](int, Part& Pt) -> int { return run(Pt.h, nullptr, nullptr); });
+}
+
+int multi_ph_residual(fcfv_t* h, const double* u, const double* p, double* ru, double* rp, double* nrm) {
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_residual: nothing assembled"));
+    if (!u || !p) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_residual: null u or p");
+    if (ru)      // rows of faces no element references: empty, fu = 0
+        for (int64_t f : h->multi->unref) { ru[f] = 0.0; ru[(size_t)h->nf + f] = 0.0; }
+    TRY(multi_scatter(h, {{u, 'f', 2, nullptr}, {p, 'e', 1, nullptr}}, [&](fcfv_t* q, const std::vector<const double*>& a) -> int {
+        Part& Pt = part_of(h, q);
+        uvec<double> lru(ru ? 2 * Pt.faces.size() : 0), lrp(rp ? Pt.elems.size() : 0);
+        TRY(fcfv_ph_residual(q, a[0], a[1], ru ? lru.data() : nullptr, rp ? lrp.data() : nullptr, nullptr));
+        if (ru) put_owned(ru, h->nf, Pt.faces, Pt.own_f, 2, lru.data());
+        if (rp) put_owned(rp, h->nel, Pt.elems, Pt.own_e, 1, lrp.data());
+        return FCFV_OK;
+    }));
+    if (nrm) {
+        // every part has left the sums of squares over ITS rows / elements at sumsq[6..7]
+        TRY(multi_allreduce(h, [](fcfv_t* q) -> double* { return P<double>(q->sumsq) + 6; }, 2));
+        fcfv_t* q = h->multi->parts[0].h;
+        double hs[2];
+        CU(cudaSetDevice(q->device));
+        CU(cudaMemcpyAsync(hs, P<double>(q->sumsq) + 6, sizeof hs, cudaMemcpyDeviceToHost, q->stream));
+        TRY(multi_sync(h));
+        nrm[0] = sqrt(hs[0]); nrm[1] = sqrt(hs[1]);
+    }
+    return FCFV_OK;
+}
+
+int multi_ph_update_p(fcfv_t* h, double gamma, const double* u, double* p) {
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_update_p: nothing assembled"));
+    if (!u || !p) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_update_p: null u or p");
+    return multi_scatter(h, {{u, 'f', 2, nullptr}, {p, 'e', 1, nullptr}}, [&](fcfv_t* q, const std::vector<const double*>& a) -> int {
+        Part& Pt = part_of(h, q);
+        uvec<double> lp(Pt.elems.size());
+        TRY(copy(q, lp.data(), a[1], sizeof(double) * lp.size()));     // the part's slice of p (host or device) ...
+        TRY(sync(q));
+        TRY(fcfv_ph_update_p(q, gamma, a[0], lp.data()));              // ... updated in place
+        put_owned(p, h->nel, Pt.elems, Pt.own_e, 1, lp.data());
+        return FCFV_OK;
+    });
+}
+
+int multi_ph_fusc(fcfv_t* h, double gamma, const double* p, double* fusc) {
+    TRY(need(h, h->Kuu.nnz != -1, "fcfv_ph_fusc: nothing assembled"));
+    if (!p || !fusc) return fail(h, FCFV_ERR_INVALID, "fcfv_ph_fusc: null p or fusc");
+    // w = (gamma ke / Omega) fp - p is needed on the ghost elements of a part as well, and fp of an element is only formed
+    // by the part that owns it: collect it and hand every part its slice (owned entries are rewritten with their own values)
+    uvec<double> fpg((size_t)h->nel);
+    TRY(multi_export_rhs(h, nullptr, fpg.data()));
+    TRY(multi_scatter(h, {{fpg.data(), 'e', 1, nullptr}}, [&](fcfv_t* q, const std::vector<const double*>& a) -> int {
+        TRY(copy(q, q->fp.p, a[0], sizeof(double) * (size_t)q->nel));
+        return sync(q);
+    }));
+    for (int64_t f : h->multi->unref) { fusc[f] = 0.0; fusc[(size_t)h->nf + f] = 0.0; }
+    return multi_scatter(h, {{p, 'e', 1, nullptr}}, [&](fcfv_t* q, const std::vector<const double*>& a) -> int {
+        Part& Pt = part_of(h, q);
+        uvec<double> lf(2 * Pt.faces.size());
+        TRY(fcfv_ph_fusc(q, gamma, a[0], lf.data()));
+        put_owned(fusc, h->nf, Pt.faces, Pt.own_f, 2, lf.data());
+        return FCFV_OK;
+    });
+}
+
+// Pe .-= mean(Pe) (SolversFCFV_Stokes.jl:20) on the host: the array is the caller's and nothing of it is resident
+int multi_center_pressure(fcfv_t* h, double* Pe, double* mean) {
+    TRY(need(h, h->have_mesh, "fcfv_center_pressure: no mesh set"));
+    if (!Pe) return fail(h, FCFV_ERR_INVALID, "fcfv_center_pressure: null Pe");
+    if (is_device(Pe)) return fail(h, FCFV_ERR_INVALID, "a multi-GPU handle takes host arrays");
+    const int64_t n = h->nel;
+    // pairwise sums over fixed blocks (deterministic, close to what one GPU forms)
+    double total = 0.0;
+    for (int64_t b = 0; b < n; b += 4096) {
+        double s = 0.0;
+        for (int64_t e = b; e < std::min(n, b + 4096); e++) s += Pe[e];
+        total += s;
+    }
+    const double m = n > 0 ? total / (double)n : 0.0;
+    for (int64_t e = 0; e < n; e++) Pe[e] = Pe[e] - m;
+    if (mean) *mean = m;
+    return FCFV_OK;
+}
+
 double multi_asm_seconds(fcfv_t* h) { return h->multi->asm_seconds; }
 int multi_has_orphans(fcfv_t* h) { return h->multi->unref.empty() ? 0 : 1; }
 fcfv_t* multi_part0(fcfv_t* h) { return h->multi->parts[0].h; }

@@ -44,12 +44,32 @@ def _run(case, ngpus, mesh_data=None):
     sc = api.SchurComplement(g, 1.0e4)
     out["Kuusc"] = h.export_csc(L.KUUSC)
     out["nnz_sc"] = sc.nnz
+    # post-processing and the Powell-Hestenes lines (global arrays in and out on either kind of handle)
+    rng = np.random.default_rng(11)
+    u, p = rng.standard_normal(2 * g.nf), rng.standard_normal(g.nel)
+    out["ev"] = api.ComputeElementValues(g, d["Vxh"], d["Vyh"], d["Pe"], a, b, Z, d["VxDir"], d["VyDir"], case.form)
+    out["ph_res"] = api.ph_residual(g, u, p)
+    out["ph_p"] = api.ph_update_p(g, 1.0e3, u, p)
+    out["ph_fusc"] = api.ph_fusc(g, 1.0e3, p)
+    out["center"] = api.center_pressure(g, d["Pe"])
     if ngpus > 1:
         info, sec = h.partition_info()
         assert sum(i[2] for i in info) == g.nel and all(i[0] >= i[2] and i[1] >= i[3] for i in info) and sec >= 0.0
         out["ghosts"] = sum(i[0] - i[2] for i in info)
     h.close()
     return out
+
+
+def same_post_processing(got, ref):
+    """Element values, ru / rp / p update / fusc: every entry is computed by the part that owns it from the same operands
+    (bit for bit); norms and the pressure mean are sums taken in another order (1e-12)."""
+    for x, y in zip(got["ev"], ref["ev"]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(got["ph_res"][0], ref["ph_res"][0]) and np.array_equal(got["ph_res"][1], ref["ph_res"][1])
+    assert np.all(np.abs(got["ph_res"][2] - ref["ph_res"][2]) <= TOL * ref["ph_res"][2])
+    assert np.array_equal(got["ph_p"], ref["ph_p"]) and np.array_equal(got["ph_fusc"], ref["ph_fusc"])
+    scale = max(1.0, np.abs(ref["center"][0]).max())
+    assert np.all(np.abs(got["center"][0] - ref["center"][0]) <= TOL * scale) and abs(got["center"][1] - ref["center"][1]) <= TOL * scale
 
 
 CASES = [cases.Case("LowRes", "inclusion", 0, "Gradient", neumann=True), cases.Case("H2", "solkz", 1, "SymmetricGradient", tau_r=10.0),
@@ -74,6 +94,7 @@ def test_multi_handle_equals_single_gpu(case, ngpus, monkeypatch):
         big = r > 1e-9 * r.max()
         assert np.all(np.abs(n[big] - r[big]) <= TOL * r[big]) and np.all(np.abs(n[~big] - r[~big]) <= TOL * r.max()), m
     assert got["ghosts"] > 0
+    same_post_processing(got, ref)
 
 
 @pytest.mark.parametrize("ngpus", [2, 3])
@@ -90,6 +111,7 @@ def test_multi_handle_random_mesh(ngpus, monkeypatch):
     for k in ("Kuu", "Kup", "Muu", "Kuusc"):
         for x, y in zip(got[k], ref[k]):
             assert np.array_equal(x, y), k
+    same_post_processing(got, ref)
 
 
 @pytest.mark.parametrize("max_runs", ["0", "3"])

@@ -712,7 +712,15 @@ int fcfv_sparse_face_data(fcfv_t* h, int mode) {
     if (!h) return FCFV_ERR_INVALID;
     if (mode < 0 || mode > 2) return fail(h, FCFV_ERR_INVALID, "fcfv_sparse_face_data: mode must be 0 (off), 1 (auto) or 2 (always)");
     h->sparse_mode = mode;
-    if (h->multi) { multi_each(h, [&](fcfv_t* q) { q->sparse_mode = mode; }); return FCFV_OK; }
+    if (h->multi) {      // every part keeps its own lists (of its local faces)
+        int rc = FCFV_OK;
+        multi_each(h, [&](fcfv_t* q) {
+            q->sparse_mode = mode;
+            if (rc == FCFV_OK && q->have_mesh && cudaSetDevice(q->device) == cudaSuccess) rc = build_face_lists(q);
+            if (rc != FCFV_OK) h->err = q->err;
+        });
+        return rc;
+    }
     if (h->have_mesh) { CU(cudaSetDevice(h->device)); TRY(build_face_lists(h)); }
     return FCFV_OK;
 }

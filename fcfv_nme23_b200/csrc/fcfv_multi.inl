@@ -166,42 +166,55 @@ void put_owned(T* g, int64_t ld, const std::vector<int64_t>& idx, const std::vec
 
 // ---- the partitioner (C++ port of what one rank of a torchrun job does in fcfv_nme23_b200/partition.py) ------------
 // lo / hi: lowest / highest adjacent element of every face (-1: none).  Returns false on an out-of-range face id.
-bool face_adjacency(int64_t nel, int64_t nf, const int64_t* e2f, std::vector<int64_t>& lo, std::vector<int64_t>& hi) {
+// 32-bit ids (a multi-GPU handle takes nel < 2^31) in storage that is not zeroed on allocation: the worker threads that
+// fill it with -1 are the first to touch it, so the page faults of the two nf-sized arrays run in parallel.
+// The walks themselves are plain loops: in ascending element order the first visitor of a face is its lowest element, in
+// descending order its highest -- two threads, no atomics (a compare-and-swap per visit on many threads was measured 8x
+// slower than one plain walk: the locked operations serialise the memory pipeline).
+using AdjVec = uvec<int32_t>;
+bool face_adjacency(int64_t nel, int64_t nf, const int64_t* e2f, AdjVec& lo, AdjVec& hi) {
     lo.resize((size_t)nf);
     hi.resize((size_t)nf);
-    // element ranges on several threads; a face is touched by at most two elements, so the compare-and-swap loops below
-    // almost never retry
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)(hw ? hw : 1u), 16, nel / 65536 + 1}));
-    std::vector<int> bad(nt, 0);
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)(hw ? hw : 1u), 16, nf / 262144 + 1}));
     auto fill = [&](int t) {
         const int64_t f0 = nf * t / nt, f1 = nf * (t + 1) / nt;
         for (int64_t f = f0; f < f1; f++) { lo[f] = -1; hi[f] = -1; }
     };
-    auto scan = [&](int t) {
-        const int64_t a = nel * t / nt, b = nel * (t + 1) / nt;
-        for (int64_t e = a; e < b; e++)
-            for (int i = 0; i < 3; i++) {
-                const int64_t f = e2f[(size_t)i * nel + e] - 1;
-                if (f < 0 || f >= nf) { bad[t] = 1; return; }
-                int64_t o = __atomic_load_n(&lo[f], __ATOMIC_RELAXED);
-                while ((o < 0 || e < o) && !__atomic_compare_exchange_n(&lo[f], &o, e, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-                o = __atomic_load_n(&hi[f], __ATOMIC_RELAXED);
-                while (e > o && !__atomic_compare_exchange_n(&hi[f], &o, e, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-            }
-    };
-    auto run = [&](auto&& fn) {
+    {
         std::vector<std::thread> th;
         for (int t = 1; t < nt; t++) {
-            try { th.emplace_back(fn, t); } catch (...) { fn(t); }
+            try { th.emplace_back(fill, t); } catch (...) { fill(t); }
         }
-        fn(0);
+        fill(0);
         for (auto& x : th) x.join();
+    }
+    bool bad_lo = false, bad_hi = false;
+    auto walk_lo = [&]() {
+        for (int64_t e = 0; e < nel; e++)
+            for (int i = 0; i < 3; i++) {
+                const int64_t f = e2f[(size_t)i * nel + e] - 1;
+                if (f < 0 || f >= nf) { bad_lo = true; return; }
+                if (lo[f] < 0) lo[f] = (int32_t)e;
+            }
     };
-    run(fill);
-    run(scan);
-    for (int b : bad) if (b) return false;
-    return true;
+    auto walk_hi = [&]() {
+        for (int64_t e = nel - 1; e >= 0; e--)
+            for (int i = 0; i < 3; i++) {
+                const int64_t f = e2f[(size_t)i * nel + e] - 1;
+                if (f < 0 || f >= nf) { bad_hi = true; return; }
+                if (hi[f] < 0) hi[f] = (int32_t)e;
+            }
+    };
+    try {
+        std::thread other(walk_hi);
+        walk_lo();
+        other.join();
+    } catch (...) {      // no second thread to be had
+        walk_lo();
+        walk_hi();
+    }
+    return !(bad_lo || bad_hi);
 }
 
 // ascending ids with a mark in [lo, hi]
@@ -218,7 +231,7 @@ void collect_marked(const std::vector<uint8_t>& mark, int64_t lo, int64_t hi, st
 // highest neighbour of every face of an owned / A element, so that the local last-writer rule reproduces the
 // global mesh.tau on every column the owned rows touch.  Sets are kept as byte marks over the id range they span
 // (no sorting: the ids come out ascending from a scan).
-void build_part(int64_t nel, int64_t nf, const int64_t* e2f, const std::vector<int64_t>& lo, const std::vector<int64_t>& hi,
+void build_part(int64_t nel, int64_t nf, const int64_t* e2f, const AdjVec& lo, const AdjVec& hi,
                 int p, int np, Part& P) {
     const int64_t e0 = (int64_t)p * nel / np, e1 = (int64_t)(p + 1) * nel / np;
     auto in_range = [&](int64_t e) { return e >= e0 && e < e1; };
@@ -363,7 +376,7 @@ int multi_set_mesh(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, const
     h->rp64 = 20 * nf >= (1LL << 31);
     h->Kuu.nnz = h->Kup.nnz = h->Muu.nnz = h->Kuusc.nnz = -1;
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<int64_t> lo, hi;
+    AdjVec lo, hi;
     if (!face_adjacency(nel, nf, e2f, lo, hi)) return fail(h, FCFV_ERR_INVALID, "e2f contains a face id outside 1..nf");
     TRY(for_parts(h, [&](int p, Part& Pt) -> int {
         build_part(nel, nf, e2f, lo, hi, p, np, Pt);
@@ -1002,7 +1015,8 @@ int fcfv_partition_info(fcfv_t* h, int part, int64_t* nel_local, int64_t* nf_loc
 int fcfv_partition_part(int64_t nel, int64_t nf, const int64_t* e2f, int nparts, int part, int64_t* nel_local, int64_t* nf_local,
                         int64_t* elem_global, int64_t* face_global, uint8_t* elem_owned, uint8_t* face_owned) {
     if (!e2f || nel < 0 || nf < 0 || nparts < 1 || part < 0 || part >= nparts) return FCFV_ERR_INVALID;
-    std::vector<int64_t> lo, hi;
+    if (nel >= (1LL << 31)) return FCFV_ERR_INVALID;
+    AdjVec lo, hi;
     if (!face_adjacency(nel, nf, e2f, lo, hi)) return FCFV_ERR_INVALID;
     Part Pt;
     build_part(nel, nf, e2f, lo, hi, part, nparts, Pt);

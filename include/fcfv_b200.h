@@ -53,8 +53,10 @@ int fcfv_create(fcfv_t** h, int device);
  * faces with no data-path communication, bit-identical to the single-GPU rows; fcfv_export concatenates them into the global
  * CSR / Julia CSC.  One NCCL communicator per device (ncclCommInitAll), used for one grouped all-reduce of the six residual
  * sums per evaluation.  Supported: set_mesh, update_fields, set_* / run_* / get_local / get_nnz, compute_local, assemble,
- * schur, export (CSR0, CSC1_INT64), export_rhs, residuals (norms), run_pipeline, pass, geometry / first_seen_faces /
- * hilbert_elements (first device).  Everything else returns FCFV_ERR_STATE.  ngpus == 1 gives a plain single-GPU handle. */
+ * compute_fcfv, schur, export (CSR0, CSC1_INT64), export_rhs, residuals (norms), run_pipeline, pass, element_values, ph_residual /
+ * ph_update_p / ph_fusc / center_pressure, geometry / first_seen_faces / hilbert_elements (first device).  What hands out
+ * device pointers or part-local state (device_csr, device_rhs, get_mesh, get_data, generate_structured, set_ownership, comm_*)
+ * returns FCFV_ERR_STATE.  ngpus == 1 gives a plain single-GPU handle. */
 int fcfv_create_multi(fcfv_t** h, int ngpus);
 int fcfv_num_devices(fcfv_t* h);
 /* What part `part` of a multi-GPU handle holds after fcfv_set_mesh: local / owned element and face counts (local - owned =

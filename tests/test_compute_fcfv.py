@@ -174,3 +174,40 @@ def test_argument_errors(api):
                                  *[None] * 4, *[None] * 4)
     assert rc != 0 and b"null mesh array" in h.lib.fcfv_last_error(h._h)
     h.close()
+
+
+def test_default_threshold_on_a_million_elements(api):
+    """S(520): 1 081 600 elements, above the library's own pipeline threshold (2^20) -- eight chunks of 135 296 elements, arrays
+    of 8.7-26 MB, no test hook: the page-locked call gives the results of the separate calls from pageable memory."""
+    import torch
+    from fcfv_nme23_b200.mesh import FCFV_Mesh
+    h = api.Handle(0)
+    h.generate_structured(520, setting="inclusion", tau_r=2.0, neumann_south=True)
+    M0, D0 = h.get_mesh(), h.get_data()
+    h.close()
+    nel, nf = M0["Ω"].size, M0["bc"].size
+    assert nel >= 1 << 20
+    m = FCFV_Mesh(nel=nel, nf=nf, nf_el=3)
+    for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe"):
+        setattr(m, k, M0[k])
+    neu = [D0[k] for k in ("sxx", "syy", "sxy", "syx")]
+    a, b, Z = api.ComputeFCFV(m, D0["sex"], D0["sey"], D0["VxDir"], D0["VyDir"], *neu, 2.0, "Gradient")     # pageable: separate calls
+    h0 = api.handle_for(m)
+    assert h0.pipelined_calls == 0
+    tau0 = m.τ.copy()
+    h0.close()
+    keep = []
+    def pin(x):
+        t, v = pinned(x); keep.append(t); return v
+    A = {k: pin(M0[k]) for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe")}
+    D = {k: pin(v) for k, v in D0.items()}
+    out = [pin(np.zeros(nel)), pin(np.zeros(2 * nel)), pin(np.zeros(4 * nel)), pin(np.zeros(nf))]
+    h1 = api.Handle(0)
+    h1.upload_cache(True)
+    h1.check(h1.lib.fcfv_compute_fcfv(h1._h, nel, nf, *[ptr(A[k]) for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe")], nel, None,
+                                      api.formulation_id("Gradient"), 1.0, ptr(D["sex"]), ptr(D["sey"]), ptr(D["VxDir"]), ptr(D["VyDir"]),
+                                      *[ptr(D[k]) for k in ("sxx", "syy", "sxy", "syx")], *[ptr(x) for x in out]))
+    assert h1.pipelined_calls == 1
+    assert np.array_equal(out[0], a) and np.array_equal(out[1], b.reshape(-1, order="F")) and np.array_equal(out[2], Z.reshape(-1, order="F"))
+    assert np.array_equal(out[3], tau0)
+    h1.close()

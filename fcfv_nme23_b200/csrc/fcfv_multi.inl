@@ -281,6 +281,8 @@ void build_part(int64_t nel, int64_t nf, const int64_t* e2f, const AdjVec& lo, c
     P.eown.resize(P.elems.size());
     P.fown.resize(P.faces.size());
     P.own_e.clear(); P.own_f.clear();
+    P.own_e.reserve((size_t)std::max<int64_t>(0, e1 - e0));      // exactly the owned elements; most faces of a part are owned
+    P.own_f.reserve(P.faces.size());
     for (size_t k = 0; k < P.elems.size(); k++) {
         P.eown[k] = in_range(P.elems[k]) ? 1 : 0;
         if (P.eown[k]) P.own_e.push_back((int64_t)k);

@@ -1319,6 +1319,16 @@ bool is_pinned_host(const void* p) {
 
 constexpr int kLocalChunks = 8;
 
+// the chunk pipeline needs a mesh worth the trouble and arrays that can be copied asynchronously (page-locked / registered)
+bool chunk_pipeline_ok(fcfv_t* h, long long nel, std::initializer_list<const void*> arrays) {
+    long long min_nel = 1LL << 20;          // below that a pass is a few milliseconds whichever way it is issued
+    if (const char* v = getenv("FCFV_PIPELINE_MIN_NEL")) min_nel = atoll(v);
+    if (h->multi || nel < min_nel || nel < 2 * kBlock) return false;
+    for (const void* p : arrays)
+        if (p && !is_pinned_host(p)) return false;
+    return true;
+}
+
 // One ComputeFCFV with everything it needs still on the host, as a pipeline over element chunks: while chunk c of the
 // per-element inputs goes up, the element kernel runs on chunk c-1 and alpha / beta / Z of chunk c-2 come down -- both
 // directions of the link stay busy and the kernel costs nothing.  The element kernel reads, per element, only
@@ -1352,7 +1362,8 @@ int compute_fcfv_chunks(fcfv_t* h, bool mesh, const double* Omega, const double*
     if (mesh && !taue) { h->taue.hm.epoch = -1; CU(cudaMemsetAsync(h->taue.p, 0, be, h->stream)); }
     h->alpha.hm.epoch = h->beta.hm.epoch = h->Z.hm.epoch = h->tau.hm.epoch = -1;      // rewritten on the device
     h->coef_variant = -1;
-    long long chunk = (nel + kLocalChunks - 1) / kLocalChunks;
+    const int nchunks = nel >= (1LL << 24) ? 2 * kLocalChunks : kLocalChunks;     // large meshes: shorter fill and drain of the pipeline
+    long long chunk = (nel + nchunks - 1) / nchunks;
     chunk = std::max<long long>(kBlock, (chunk + kBlock - 1) / kBlock * kBlock);
     struct Out { double* dst; const DBuf* b; int ncol; } outs[3] = {{alpha, &h->alpha, 1}, {beta, &h->beta, 2}, {Z, &h->Z, 4}};
     for (long long e0 = 0; e0 < nel; e0 += chunk) {
@@ -1411,14 +1422,8 @@ int fcfv_compute_fcfv(fcfv_t* h, int64_t nel, int64_t nf, const int64_t* e2f, co
     if (!mesh) { TRY(need(h, h->have_mesh, "fcfv_compute_fcfv: no mesh resident and none given")); nel = h->nel; nf = h->nf; }
     if (taue && ntaue < nel) return fail(h, FCFV_ERR_INVALID, "taue has %lld entries, need at least nel=%lld", (long long)ntaue, (long long)nel);
     if (!sex || !sey || !VxDir || !VyDir) return fail(h, FCFV_ERR_INVALID, "fcfv_compute_fcfv: null source / Dirichlet array");
-    long long min_nel = 1LL << 20;          // below that a pass is a few milliseconds whichever way it is issued
-    if (const char* v = getenv("FCFV_PIPELINE_MIN_NEL")) min_nel = atoll(v);
-    bool chunks = !h->multi && nel >= min_nel && nel >= 2 * kBlock;
-    const void* arrays[] = {Omega, nx, ny, Gamma, ke, delta, taue, sex, sey, alpha, beta, Z, tau};
-    for (size_t k = 0; k < sizeof arrays / sizeof arrays[0] && chunks; k++) {
-        const bool mesh_only = k < 4;
-        if (arrays[k] && (mesh || !mesh_only) && !is_pinned_host(arrays[k])) chunks = false;
-    }
+    const bool chunks = mesh ? chunk_pipeline_ok(h, nel, {Omega, nx, ny, Gamma, ke, delta, taue, sex, sey, alpha, beta, Z, tau})
+                             : chunk_pipeline_ok(h, nel, {ke, delta, taue, sex, sey, alpha, beta, Z, tau});
     if (!chunks) {
         if (mesh) {
             TRY(fcfv_set_mesh(h, nel, nf, e2f, bc, Omega, nx, ny, Gamma, ke, delta, taue, ntaue));
@@ -1954,12 +1959,25 @@ int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, c
     CU(cudaSetDevice(h->device));
     const bool was_async = h->async;
     h->async = true;
+    TRY(check_form(h, formulation));
     auto body = [&]() -> int {
-        TRY(fcfv_set_sources(h, sex, sey));
-        TRY(fcfv_set_face_data(h, VxDir, VyDir, nullptr, nullptr, nullptr, nullptr));
-        TRY(fcfv_run_local(h, formulation, A));
-        // outputs of the element kernel go down while the rest goes up
-        TRY(download_local_async(h, alpha, beta, Z, tau));
+        if (sex && sey && chunk_pipeline_ok(h, h->nel, {sex, sey, alpha, beta, Z, tau})) {
+            // sources up | element kernel | alpha, beta, Z down, chunk by chunk (fcfv_compute_fcfv); the downloads then keep
+            // running under the assembly and the upload of the solution
+            const double* const none[4] = {nullptr, nullptr, nullptr, nullptr};
+            h->pipelined_calls++;
+            TRY(formulation == FCFV_GRADIENT
+                    ? compute_fcfv_chunks<kGradient>(h, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, A, sex, sey, VxDir,
+                                                     VyDir, none, alpha, beta, Z, tau)
+                    : compute_fcfv_chunks<kSymmetricGradient>(h, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, A, sex,
+                                                              sey, VxDir, VyDir, none, alpha, beta, Z, tau));
+        } else {
+            TRY(fcfv_set_sources(h, sex, sey));
+            TRY(fcfv_set_face_data(h, VxDir, VyDir, nullptr, nullptr, nullptr, nullptr));
+            TRY(fcfv_run_local(h, formulation, A));
+            // outputs of the element kernel go down while the rest goes up
+            TRY(download_local_async(h, alpha, beta, Z, tau));
+        }
         TRY(fcfv_set_face_data(h, nullptr, nullptr, sxxNeu, syyNeu, sxyNeu, syxNeu));   // NULL = keep what is resident
         TRY(fcfv_run_assemble(h, variant, formulation, A, want_muu));
         TRY(fcfv_set_solution(h, Vxh, Vyh, Pe));

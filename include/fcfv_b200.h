@@ -148,7 +148,7 @@ int fcfv_compute_local_ex(fcfv_t* h, int formulation, double A, const double* se
  *   tau_in     : mesh.tau as it stands, or NULL; only read when the mesh has faces no element references (every other entry
  *                is overwritten, Discretisation:40);
  * then = fcfv_compute_local_ex.  Results are those of the separate calls, bit for bit.  When every array is page-locked (or
- * registered) host memory and nel >= 2^20 (FCFV_PIPELINE_MIN_NEL overrides), the call runs as a pipeline over 8 element
+ * registered) host memory and nel >= 2^20 (FCFV_PIPELINE_MIN_NEL overrides), the call runs as a pipeline over 8 (16 from 2^24 elements) element
  * chunks: connectivity and tags first (the records are built on the device), VxDir / VyDir on the Dirichlet faces, then per
  * chunk geometry + tau_e + sources up | element kernel | alpha, beta, Z down on a second stream, and ke / delta (which the
  * element kernel does not read) and the Neumann arrays under the tail of the downloads -- both directions of PCIe stay busy.

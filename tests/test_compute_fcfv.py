@@ -211,3 +211,43 @@ def test_default_threshold_on_a_million_elements(api):
     assert np.array_equal(out[0], a) and np.array_equal(out[1], b.reshape(-1, order="F")) and np.array_equal(out[2], Z.reshape(-1, order="F"))
     assert np.array_equal(out[3], tau0)
     h1.close()
+
+
+def test_fcfv_pass_takes_the_chunk_pipeline_with_page_locked_arrays(api, monkeypatch):
+    """fcfv_pass (the three calls in one): its ComputeFCFV part runs as the chunk pipeline when the arrays allow it; same
+    outputs as from pageable arrays."""
+    from fcfv_nme23_b200 import lib as L
+    case = cases.Case("H2", "inclusion", 1, "SymmetricGradient", neumann=True)
+    form = api.formulation_id(case.form)
+    res = []
+    for pinned_arrays in (False, True):
+        monkeypatch.setenv("FCFV_PIPELINE_MIN_NEL", "1")
+        m, d = cases.build(case)
+        nel, nf = m.nel, m.nf
+        keep = []
+        def conv(x):
+            if not pinned_arrays:
+                return np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1, order="F"))
+            t, v = pinned(np.asarray(x, dtype=np.float64)); keep.append(t); return v
+        h = api.Handle(0)
+        h.upload_cache(True)
+        h.set_mesh(m)
+        D = {k: conv(d[k]) for k in ("sex", "sey", "VxDir", "VyDir", "Vxh", "Vyh", "Pe")}
+        S = [conv(s) for s in d["neu"]]
+        out = [conv(np.zeros(nel)), conv(np.zeros(2 * nel)), conv(np.zeros(4 * nel)), conv(np.zeros(nf))]
+        nnz = [C.c_int64(0) for _ in range(3)]
+        norms = np.zeros(6)
+        h.check(h.lib.fcfv_pass(h._h, case.variant, form, 1.0, L.TAU_FACE, ptr(D["sex"]), ptr(D["sey"]), ptr(D["VxDir"]), ptr(D["VyDir"]),
+                                *[ptr(s) for s in S], ptr(D["Vxh"]), ptr(D["Vyh"]), ptr(D["Pe"]), *[ptr(x) for x in out], 1,
+                                C.byref(nnz[0]), C.byref(nnz[1]), C.byref(nnz[2]), ptr(norms)))
+        assert h.pipelined_calls == (1 if pinned_arrays else 0)
+        fu, fp = h.export_rhs()
+        res.append(dict(out=[x.copy() for x in out], K=h.export_csr(L.KUU), P=h.export_csr(L.KUP), M=h.export_csr(L.MUU), fu=fu, fp=fp,
+                        norms=norms.copy(), nnz=[x.value for x in nnz]))
+        h.close()
+    a, b = res
+    for x, y in zip(a["out"], b["out"]):
+        assert np.array_equal(x, y)
+    for k in ("K", "P", "M"):
+        assert_csr_equal(a[k], b[k], k)
+    assert np.array_equal(a["fu"], b["fu"]) and np.array_equal(a["fp"], b["fp"]) and np.array_equal(a["norms"], b["norms"]) and a["nnz"] == b["nnz"]

@@ -830,6 +830,24 @@ int64_t fcfv_staged_copies(fcfv_t* h) {
     return n;
 }
 int64_t fcfv_pipelined_calls(fcfv_t* h) { return h ? (int64_t)h->pipelined_calls : 0; }
+int64_t fcfv_debug_bounds_violations(void) {
+#if FCFV_BOUNDS_CHECK
+    // summed over every device this process has used (the counter is a per-device symbol)
+    int n = 0, cur = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || cudaGetDevice(&cur) != cudaSuccess) return -2;
+    long long total = 0;
+    for (int d = 0; d < n; d++) {
+        unsigned long long v = 0;
+        if (cudaSetDevice(d) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpyFromSymbol(&v, g_bounds_violations, sizeof v) != cudaSuccess) { cudaGetLastError(); continue; }
+        total += (long long)v;
+    }
+    cudaSetDevice(cur);
+    return total;
+#else
+    return -1;      // not a bounds-checked build
+#endif
+}
 int64_t fcfv_device_bytes(fcfv_t* h) {
     if (!h) return 0;
     int64_t n = (int64_t)h->bytes;
@@ -1487,9 +1505,9 @@ int launch_assemble(fcfv_t* h, double A, double gamma) {
     TLAUNCH(h, T_COUNT, (k_asm_count<VARIANT, FORM, EXTRA, ANISO>), nblk, kAsmBlock, M, L, Cf, D, A, sums, nblk);
     TLAUNCH(h, T_SCAN, k_scan_local, dim3(nchunks, kNumSums), 1024, sums, local, nblk, nchunks, chunk_tot);
     Csr& X = EXTRA == kExtraSchur ? h->Kuusc : h->Muu;   // third block
-    CsrOut ouu{h->Kuu.rowptr.p, P<int>(h->Kuu.col), P<double>(h->Kuu.val)};
-    CsrOut oup{h->Kup.rowptr.p, P<int>(h->Kup.col), P<double>(h->Kup.val)};
-    CsrOut oex{X.rowptr.p, P<int>(X.col), P<double>(X.val)};
+    CsrOut ouu{h->Kuu.rowptr.p, P<int>(h->Kuu.col), P<double>(h->Kuu.val), (long long)(h->Kuu.val.cap / sizeof(double))};
+    CsrOut oup{h->Kup.rowptr.p, P<int>(h->Kup.col), P<double>(h->Kup.val), (long long)(h->Kup.val.cap / sizeof(double))};
+    CsrOut oex{X.rowptr.p, P<int>(X.col), P<double>(X.val), (long long)(X.val.cap / sizeof(double))};
     if (h->rp64) {
         TLAUNCH(h, T_SCAN, k_scan_chunks<long long>, 1, 32, chunk_tot, chunk_base, nchunks, P<long long>(h->totals),
                 (long long*)ouu.rowptr, (long long*)oup.rowptr, (long long*)oex.rowptr, M.nf, (int)(EXTRA != kExtraNone), EXTRA == kExtraSchur ? 9 : 8);

@@ -27,6 +27,26 @@ struct int4 { int x, y, z, w; };
 
 namespace fcfv {
 
+// Bounds-checked build (make variant NAME=bounds DEFS=-DFCFV_BOUNDS_CHECK=1; compute-sanitizer is closed on the GPU pool): every
+// staged shared-memory index, every global segment the fill pass flushes, every gathered element / face id and every flux slot
+// is compared with the capacity of its array; violations are counted, not trapped (fcfv_debug_bounds_violations).
+#ifndef FCFV_BOUNDS_CHECK
+#define FCFV_BOUNDS_CHECK 0
+#endif
+#if FCFV_BOUNDS_CHECK && defined(__CUDACC__)
+__device__ unsigned long long g_bounds_violations = 0ull;
+FCFV_HD void check_index(long long i, long long n) {
+#if defined(__CUDA_ARCH__)
+    if (i < 0 || i >= n) atomicAdd(&g_bounds_violations, 1ull);
+#else
+    (void)i; (void)n;
+#endif
+}
+#define FCFV_CHECK_INDEX(i, n) ::fcfv::check_index((long long)(i), (long long)(n))
+#else
+#define FCFV_CHECK_INDEX(i, n) do { } while (0)
+#endif
+
 struct MeshView {
     int nel, nf;
     const int* e2f;
@@ -126,9 +146,11 @@ template <int VARIANT, bool ANISO, int EXTRA, bool NATURAL = false>
 FCFV_HD void load_face_elem(const MeshView& M, const LocalView& L, const CoefView& Cf, const FaceConn& C, bool second, int e, int i,
                             FaceElem& E) {
     const int nel = M.nel;
+    FCFV_CHECK_INDEX(e, nel);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int g = k == 0 ? C.k[0] : (second ? C.k[2 + k] : C.k[k]);
+        FCFV_CHECK_INDEX(g, M.nf);
         E.g[k] = g;
         E.bc[k] = k == 0 ? C.bc[0] : (second ? C.bc[2 + k] : C.bc[k]);
         E.tau[k] = M.tau[g];
@@ -373,7 +395,7 @@ __global__ void k_bc_face_lists(int nf, const int8_t* __restrict__ bc, int cap, 
 // dst[idx[k]] = packed[k]: the values of a per-face array on the listed faces
 __global__ void k_scatter_faces(int n, const int* __restrict__ idx, const double* __restrict__ packed, double* __restrict__ dst) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) dst[idx[k]] = packed[k];
+    if (k < n) dst[idx[k]] = packed[k];       // idx comes from k_bc_face_lists (< nf by construction)
 }
 
 __global__ void k_f2e_init(int2* __restrict__ f2e, int* __restrict__ cnt, int nf) {
@@ -754,7 +776,7 @@ __global__ void k_scan_chunks(const long long* __restrict__ chunk_tot, long long
 // Recomputes the rows, takes the block-local exclusive scan of the row lengths, stages the block's
 // compacted entries in shared memory (x rows in the lower half, y rows in the upper half) and
 // writes them to the CSR arrays as two contiguous, fully coalesced segments.
-struct CsrOut { void* rowptr; int* col; double* val; };
+struct CsrOut { void* rowptr; int* col; double* val; long long cap; };   // cap: entries col / val can hold (bounds-checked build)
 
 // The segment [base, base+count) of a CSR array leaves shared memory through the TMA unit: ONE
 // thread issues a bulk copy (cp.async.bulk shared -> global) per array, so the flush costs no LSU
@@ -774,6 +796,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // middle part by TMA (called by one thread)
 __device__ __forceinline__ void flush_segment_bulk(const double* sval, const int* scol, int count, long long base, const CsrOut& O) {
+    if (count > 0) { FCFV_CHECK_INDEX(base, O.cap); FCFV_CHECK_INDEX(base + count - 1, O.cap); }
     {
         const int sh = (int)(base & 1), end = sh + count;
         const int q0 = 2 * sh, q1 = end & ~1;
@@ -856,6 +879,9 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
         int* cx = scol + cfield(off, 0) + (int)(bux & 3);
         int* cy = scol + kHalf + cfield(off, 1) + (int)(buy & 3);
         rows_emit_uu(R, V, nf, [&](int comp, int pos, int col, double v) {
+            FCFV_CHECK_INDEX((comp == 0 ? vx : vy) + pos - (sval + (comp == 0 ? 0 : kHalf)), kHalf);
+            FCFV_CHECK_INDEX((comp == 0 ? cx : cy) + pos - (scol + (comp == 0 ? 0 : kHalf)), kHalf);
+            FCFV_CHECK_INDEX(col, 2 * nf);
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });
@@ -866,6 +892,9 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
         int* cx = pcol + cfield(off, 2) + (int)(bpx & 3);
         int* cy = pcol + kHalfP + cfield(off, 3) + (int)(bpy & 3);
         rows_emit_up(R, V.kpx, V.kpy, [&](int comp, int pos, int col, double v) {   // columns = element ids, ascending
+            FCFV_CHECK_INDEX((comp == 0 ? vx : vy) + pos - (pval + (comp == 0 ? 0 : kHalfP)), kHalfP);
+            FCFV_CHECK_INDEX((comp == 0 ? cx : cy) + pos - (pcol + (comp == 0 ? 0 : kHalfP)), kHalfP);
+            FCFV_CHECK_INDEX(col, M.nel);
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });
@@ -895,6 +924,9 @@ k_asm_fill(MeshView M, LocalView L, CoefView Cf, FaceDataView D, double A, const
         int* cx = scol + cfield(off, 4) + (int)(bmx & 3);
         int* cy = scol + kHalf + cfield(off, 5) + (int)(bmy & 3);
         rows_emit_ex<EXTRA>(R, V, nf, [&](int comp, int pos, int col, double v) {
+            FCFV_CHECK_INDEX((comp == 0 ? vx : vy) + pos - (sval + (comp == 0 ? 0 : kHalf)), kHalf);
+            FCFV_CHECK_INDEX((comp == 0 ? cx : cy) + pos - (scol + (comp == 0 ? 0 : kHalf)), kHalf);
+            FCFV_CHECK_INDEX(col, 2 * nf);
             if (comp == 0) { vx[pos] = v; cx[pos] = col; }
             else { vy[pos] = v; cy[pos] = col; }
         });
@@ -966,6 +998,7 @@ k_res_elem(MeshView M, LocalView L, FaceDataView D, SolutionView S, const double
         for (int i = 0; i < 3; i++) {
             const double2 v = make_double2(r.Fg1[i][0], r.Fg1[i][1]);
             sF[3 * threadIdx.x + i] = v;
+            FCFV_CHECK_INDEX(fid[i], M.nf);
             if (((adj >> (9 * i)) & 511) == kAdjNone)          // cut face: slot of this side (the highest element is side 1)
                 reinterpret_cast<double2*>(Fg)[(size_t)2 * fid[i] + ((tags >> (12 + i)) & 1)] = v;
         }

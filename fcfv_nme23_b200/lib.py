@@ -139,6 +139,8 @@ def load():
     lib.fcfv_kernel_launches.restype = i64
     lib.fcfv_staged_copies.argtypes = [vp]
     lib.fcfv_staged_copies.restype = i64
+    lib.fcfv_debug_bounds_violations.argtypes = []
+    lib.fcfv_debug_bounds_violations.restype = i64
     lib.fcfv_pipelined_calls.argtypes = [vp]
     lib.fcfv_pipelined_calls.restype = i64
     lib.fcfv_device_bytes.argtypes = [vp]

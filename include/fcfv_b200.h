@@ -310,6 +310,10 @@ int64_t fcfv_kernel_launches(fcfv_t* h);    /* kernels launched by this handle s
  * threshold, 0 disables); the call still returns with the host side of the copy complete.  Number of such copies: */
 int64_t fcfv_staged_copies(fcfv_t* h);
 int64_t fcfv_pipelined_calls(fcfv_t* h);    /* fcfv_compute_fcfv calls that ran as a chunk pipeline */
+/* Bounds-checked build of the library (make -C fcfv_nme23_b200/csrc variant NAME=bounds DEFS=-DFCFV_BOUNDS_CHECK=1): number of
+ * out-of-range shared-memory staging indices, flushed CSR segments, gathered element / face ids and flux slots seen so far on
+ * all devices of the process; -1 in a normal build (the checks are compiled out). */
+int64_t fcfv_debug_bounds_violations(void);
 int64_t fcfv_device_bytes(fcfv_t* h);       /* device memory currently held by the handle */
 
 /* ---- synthetic structured mesh S(n) generated on the device (bench / large tests) --------

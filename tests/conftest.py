@@ -50,3 +50,21 @@ def emu():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                                "-o", so, srcs[0]])
     return ctypes.CDLL(so)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """With a bounds-checked build of the library (FCFV_LIB=.../libfcfv_b200_bounds.so, see include/fcfv_b200.h) the GPU suite
+    ends with the number of out-of-range indices its kernels saw: anything but 0 fails the run."""
+    if not _has_gpu():
+        return
+    try:
+        from fcfv_nme23_b200 import lib as L
+        if L._lib is None:
+            return
+        n = int(L._lib.fcfv_debug_bounds_violations())
+    except Exception:
+        return
+    if n >= 0:
+        print(f"\n[fcfv] bounds-checked build: {n} out-of-range indices seen by the kernels of this run")
+        if n > 0:
+            session.exitstatus = 1

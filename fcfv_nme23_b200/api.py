@@ -208,15 +208,22 @@ class Handle:
             self.set_ownership(mesh.elem_owned, mesh.face_owned, getattr(mesh, "nel_global", 0),
                                getattr(mesh, "nf_global", 0), getattr(mesh, "tau_ref", None))
 
-    def compute_fcfv(self, mesh, send_mesh, Formulation, A, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu):
+    def compute_fcfv(self, mesh, send_mesh, Formulation, A, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, out=None):
         """``fcfv_compute_fcfv``: ComputeFCFV(mesh, ...) as one call -- the mesh (``send_mesh``) or only its mutable fields
-        ke, δ, τe go up in front of the element kernel; α, β, Ζ and mesh.τ come back."""
+        ke, δ, τe go up in front of the element kernel; α, β, Ζ and mesh.τ come back.  ``out = (α, β, Ζ, τ)``: caller's arrays
+        (column-major; page-locked ones -- ``host_register`` -- let the call run as a pipeline)."""
         a = _Arg()
         nel, nf = int(mesh.nel), int(mesh.nf)
         taue = mesh.τe if mesh.τe is not None else (np.zeros(nel) if send_mesh else None)
         ntaue = 0 if taue is None else (int(np.size(taue)) if not hasattr(taue, "numel") else int(taue.numel()))
-        al, be, Z = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")
-        tau = np.empty(nf)
+        if out is None:
+            al, be, Z = np.empty(nel), np.empty((nel, 2), order="F"), np.empty((nel, 2, 2), order="F")
+            tau = np.empty(nf)
+        else:
+            al, be, Z, tau = out
+            for x, n in ((al, nel), (be, 2 * nel), (Z, 4 * nel), (tau, nf)):
+                if x.dtype != np.float64 or x.size != n or not (x.flags.f_contiguous or x.flags.c_contiguous and x.ndim == 1):
+                    raise ValueError("out arrays must be float64, column-major and of sizes nel, (nel, 2), (nel, 2, 2), nf")
         geo = ([a.i(mesh.e2f, 3 * nel), a.i(mesh.bc, nf), a.d(mesh.Ω, nel), a.d(mesh.n_x, 3 * nel), a.d(mesh.n_y, 3 * nel),
                 a.d(mesh.Γ, 3 * nel)] if send_mesh else [None] * 6)
         # the Neumann arrays the reference's ComputeFCFV receives and ignores go up while the results come down
@@ -490,10 +497,12 @@ def mesh_geometry(mesh, τr, device=0):
     return mesh
 
 
-def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τr, Formulation, A=A_DEFAULT):
+def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τr, Formulation, A=A_DEFAULT, out=None):
     """src/DiscretisationFCFV_Stokes.jl:8-44.  Returns α (nel), β (nel x 2), Ζ (nel x 2 x 2) and
     overwrites ``mesh.τ`` (allocated when missing, as after ``LoadExternalMesh``).  The Neumann
-    arrays and τr are accepted and unused, as in the reference."""
+    arrays and τr are accepted and unused, as in the reference.  ``out = (α, β, Ζ, τ)`` (optional, not in the reference):
+    write into the caller's arrays instead of fresh ones -- with page-locked inputs and outputs (``Handle.host_register``) a large
+    mesh then runs through the library's upload | kernel | download pipeline."""
     if mesh.τ is None:
         mesh.τ = np.zeros(mesh.nf)
     h = getattr(mesh, "_fcfv_handle", None)
@@ -505,7 +514,7 @@ def ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τ
         h = _new_handle(mesh)
     else:                    # first call of a driver pass: whatever the caller changed since the last one goes up again
         h.new_epoch()
-    al, be, Z, tau = h.compute_fcfv(mesh, send_mesh, Formulation, A, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu)
+    al, be, Z, tau = h.compute_fcfv(mesh, send_mesh, Formulation, A, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, out=out)
     if send_mesh:
         mesh._fcfv_handle = h
         _warn_numbering(mesh, h)

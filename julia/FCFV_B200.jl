@@ -172,6 +172,17 @@ end
 goes up in front of the element kernel, later only its mutable fields ke, δ, τe (v2.jl:44,127; SolKzFCFV.jl:25,149); with
 page-locked arrays (PinArrays) and a large mesh the call runs as an upload | kernel | download pipeline over element chunks."""
 function ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu, τr, Formulation)
+    nel, nf = mesh.nel, mesh.nf
+    return ComputeFCFV!(zeros(nel), zeros(nel, 2), zeros(nel, 2, 2), zeros(nf), mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNeu,
+                        τr, Formulation)
+end
+
+"""    ComputeFCFV!(α, β, Ζ, τ, mesh, sex, ..., Formulation)
+
+The same into the caller's arrays (not in the reference): with inputs and outputs page-locked once (`PinArrays`), a large mesh runs
+through the library's upload | kernel | download pipeline instead of one staged copy after the other.  `mesh.τ` becomes `τ`."""
+function ComputeFCFV!(α::Array{Float64}, β::Array{Float64}, Ζ::Array{Float64}, τ::Array{Float64}, mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu,
+                      SxyNeu, SyxNeu, τr, Formulation)
     ismissing(mesh.τ) && (mesh.τ = zeros(mesh.nf))      # LoadExternalMesh leaves τ missing
     fresh = !haskey(HANDLES, mesh)
     h = fresh ? new_handle() : HANDLES[mesh]
@@ -181,7 +192,7 @@ function ComputeFCFV(mesh, sex, sey, VxDir, VyDir, SxxNeu, SyyNeu, SxyNeu, SyxNe
     Ω, nx, ny, Γ = fresh ? (f64(mesh.Ω), f64(mesh.n_x), f64(mesh.n_y), f64(mesh.Γ)) : (Float64[], Float64[], Float64[], Float64[])
     ke, δ, τin = f64(mesh.ke), f64(mesh.δ), f64(mesh.τ)
     τe = ismissing(mesh.τe) ? zeros(nel) : f64(mesh.τe)       # may have nf entries (v2.jl:127)
-    α, β, Ζ, τ = zeros(nel), zeros(nel, 2), zeros(nel, 2, 2), zeros(nf)
+    (length(α) == nel && length(β) == 2nel && length(Ζ) == 4nel && length(τ) == nf) || error("ComputeFCFV!: output arrays of sizes nel, nel x 2, nel x 2 x 2, nf expected")
     sx, sy, vx, vy = f64(sex), f64(sey), f64(VxDir), f64(VyDir)
     sxx, syy, sxy, syx = f64(SxxNeu), f64(SyyNeu), f64(SxyNeu), f64(SyxNeu)
     pi64(a) = isempty(a) ? Ptr{Int64}(C_NULL) : pointer(a)

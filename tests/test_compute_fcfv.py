@@ -251,3 +251,34 @@ def test_fcfv_pass_takes_the_chunk_pipeline_with_page_locked_arrays(api, monkeyp
     for k in ("K", "P", "M"):
         assert_csr_equal(a[k], b[k], k)
     assert np.array_equal(a["fu"], b["fu"]) and np.array_equal(a["fp"], b["fp"]) and np.array_equal(a["norms"], b["norms"]) and a["nnz"] == b["nnz"]
+
+
+def test_mirror_with_registered_arrays_takes_the_pipeline(api, monkeypatch):
+    """api.ComputeFCFV(..., out=(α, β, Ζ, τ)) on NumPy arrays that were page-locked with host_register: the call reaches the
+    chunk pipeline through the mirror (what ComputeFCFV! + PinArrays give a Julia driver)."""
+    monkeypatch.setenv("FCFV_PIPELINE_MIN_NEL", "1")
+    case = cases.Case("H2", "solkz", 1, "SymmetricGradient", tau_r=10.0)
+    m0, d0 = cases.build(case)
+    ref = api.ComputeFCFV(m0, d0["sex"], d0["sey"], d0["VxDir"], d0["VyDir"], *d0["neu"], case.tau_r, case.form)
+    assert api.handle_for(m0).pipelined_calls == 0
+    m, d = cases.build(case)
+    for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe"):
+        v = np.asarray(getattr(m, k))
+        setattr(m, k, np.asfortranarray(v, dtype=np.int64 if k in ("e2f", "bc") else np.float64))
+    m.τ = np.zeros(m.nf)
+    out = (np.zeros(m.nel), np.zeros((m.nel, 2), order="F"), np.zeros((m.nel, 2, 2), order="F"), np.zeros(m.nf))
+    reg = api.Handle(0)
+    arrays = [getattr(m, k) for k in ("e2f", "bc", "Ω", "n_x", "n_y", "Γ", "ke", "δ", "τe", "τ")] + [d[k] for k in ("sex", "sey", "VxDir", "VyDir")] + list(out)
+    reg.host_register(*arrays)
+    try:
+        a, b, Z = api.ComputeFCFV(m, d["sex"], d["sey"], d["VxDir"], d["VyDir"], *d["neu"], case.tau_r, case.form, out=out)
+        h = api.handle_for(m)
+        assert h.pipelined_calls == 1 and a is out[0] and m.τ is out[3]
+        for x, y in zip((a, b, Z), ref):
+            assert np.array_equal(x, y)
+        assert np.array_equal(m.τ, m0.τ)
+        h.close()
+    finally:
+        reg.host_unregister(*arrays)
+        reg.close()
+    api.handle_for(m0).close()

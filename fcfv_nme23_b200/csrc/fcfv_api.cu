@@ -1492,7 +1492,14 @@ int launch_assemble(fcfv_t* h, double A, double gamma) {
     int* local = P<int>(h->bases);
     long long* chunk_tot = P<long long>(h->chunks);
     long long* chunk_base = chunk_tot + (size_t)kNumSums * nchunks;
-    TLAUNCH(h, T_OTHER, k_asm_fp, nblocks((h->nf + 3) / 4, 256), 256, M, D, P<double>(h->fp));   // fp was zeroed by the caller
+    // fp was zeroed by the caller; only Dirichlet faces contribute: walk their list when the mesh has one
+    if (h->sparse_faces) {
+        if (!h->dir_list.empty())
+            TLAUNCH(h, T_OTHER, k_asm_fp_listed, nblocks((long long)h->dir_list.size(), 256), 256, M, D, P<int>(h->dir_idx), (int)h->dir_list.size(),
+                    P<double>(h->fp));
+    } else {
+        TLAUNCH(h, T_OTHER, k_asm_fp, nblocks((h->nf + 3) / 4, 256), 256, M, D, P<double>(h->fp));
+    }
     if (!ANISO && EXTRA != kExtraSchur && h->coef_variant == VARIANT) {
         // 1/alpha and c11 were written by the element kernel of this pass (fcfv_run_pipeline)
     } else if (!ANISO && EXTRA != kExtraSchur && (h->nel & 1) == 0 && h->nel > 0)

@@ -668,6 +668,25 @@ k_asm_fp(MeshView M, FaceDataView D, double* __restrict__ fp) {
     }
 }
 
+// the same over the list of Dirichlet faces (fcfv_sparse_face_data: a few thousand of the mesh's millions): one thread per
+// listed face
+__global__ void __launch_bounds__(256)
+k_asm_fp_listed(MeshView M, FaceDataView D, const int* __restrict__ dir_idx, int n, double* __restrict__ fp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int f = dir_idx[k];
+    const int2 pr = M.f2e[f];
+    if (pr.x < 0) return;
+    for (int s2 = 0; s2 < 2; s2++) {
+        if (s2 == 1 && pr.y == pr.x) break;
+        const int code = s2 == 0 ? pr.x : pr.y;
+        const int e = code >> 2, i = code & 3;
+        if (!(M.ebc[e] & kOwnedElem)) continue;
+        double v;
+        if (face_fp(M, D, e, i, v)) fp[e] = v;
+    }
+}
+
 // row lengths of a face packed in one 64-bit word: Kuu x, Kuu y (11 bits: <= 1280 per block),
 // Kup x, Kup y (9 bits: <= 256), third block x, y (11 bits)
 __device__ __forceinline__ int cshift(int q) { return q == 0 ? 0 : q == 1 ? 11 : q == 2 ? 22 : q == 3 ? 31 : q == 4 ? 40 : 51; }

@@ -727,6 +727,16 @@ int fcfv_sparse_face_data(fcfv_t* h, int mode) {
 
 int fcfv_sparse_face_info(fcfv_t* h, int* active, int64_t* n_dirichlet, int64_t* n_neumann, int64_t* uploads) {
     if (!h) return FCFV_ERR_INVALID;
+    if (h->multi) {      // lists in use when every part has them; lengths summed over the parts (ghost faces count once per part)
+        bool all = true;
+        int64_t nd = 0, nn = 0, up = 0;
+        multi_each(h, [&](fcfv_t* q) { all = all && q->sparse_faces; nd += (int64_t)q->dir_list.size(); nn += (int64_t)q->neu_list.size(); up += q->sparse_uploads; });
+        if (active) *active = all ? 1 : 0;
+        if (n_dirichlet) *n_dirichlet = all ? nd : -1;
+        if (n_neumann) *n_neumann = all ? nn : -1;
+        if (uploads) *uploads = up;
+        return FCFV_OK;
+    }
     if (active) *active = h->sparse_faces ? 1 : 0;
     if (n_dirichlet) *n_dirichlet = h->sparse_faces ? (int64_t)h->dir_list.size() : -1;
     if (n_neumann) *n_neumann = h->sparse_faces ? (int64_t)h->neu_list.size() : -1;
@@ -1981,10 +1991,10 @@ int fcfv_pass(fcfv_t* h, int variant, int formulation, double A, int tau_mode, c
         return fcfv_residuals(h, formulation, tau_mode, Vxh, Vyh, Pe, nullptr, nullptr, nullptr, sex, sey, VxDir, VyDir, sxxNeu, syyNeu, sxyNeu,
                               syxNeu, norms, nullptr, nullptr, nullptr);
     }
+    TRY(check_form(h, formulation));
     CU(cudaSetDevice(h->device));
     const bool was_async = h->async;
     h->async = true;
-    TRY(check_form(h, formulation));
     auto body = [&]() -> int {
         if (sex && sey && chunk_pipeline_ok(h, h->nel, {sex, sey, alpha, beta, Z, tau})) {
             // sources up | element kernel | alpha, beta, Z down, chunk by chunk (fcfv_compute_fcfv); the downloads then keep

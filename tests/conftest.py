@@ -47,8 +47,10 @@ def emu():
     srcs = [os.path.join(TESTS, "host_emulation.cpp")] + [
         os.path.join(ROOT, "fcfv_nme23_b200", "csrc", f) for f in ("fcfv_math.cuh", "fcfv_kernels.cuh", "fcfv_generate.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        tmp = f"{so}.{os.getpid()}.tmp"          # several xdist workers may rebuild at once: each writes its own file,
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas",
-                               "-o", so, srcs[0]])
+                               "-o", tmp, srcs[0]])
+        os.replace(tmp, so)                      # and the rename is atomic
     return ctypes.CDLL(so)
 
 

@@ -305,7 +305,7 @@ int fcfv_num_timers(void);
 const char* fcfv_timer_name(int k);
 int fcfv_get_timers(fcfv_t* h, double* ms, int64_t* calls);
 int64_t fcfv_kernel_launches(fcfv_t* h);    /* kernels launched by this handle so far */
-/* Host arrays that are neither page-locked nor registered (plain Julia / NumPy arrays) are copied by up to eight worker
+/* Host arrays that are neither page-locked nor registered (plain Julia / NumPy arrays) are copied by up to sixteen worker
  * threads through page-locked staging buffers when a transfer is 8 MiB or larger (FCFV_STAGED_MIN_BYTES overrides the
  * threshold, 0 disables); the call still returns with the host side of the copy complete.  Number of such copies: */
 int64_t fcfv_staged_copies(fcfv_t* h);

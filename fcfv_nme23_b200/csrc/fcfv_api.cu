@@ -98,6 +98,7 @@ struct fcfv_handle {
     cudaStream_t stream_out = nullptr;   // device-to-host copies of fcfv_pass, concurrent with its uploads
     cudaEvent_t ev_out = nullptr;
     long long staged_copies = 0;      // copies that went through the Stager (diagnostics / tests)
+    int stage_share = 1;              // parts of a multi-GPU handle copy concurrently: each takes its share of the host's threads
     size_t staged_min_bytes = 8u << 20;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -362,7 +363,7 @@ int copy_staged(fcfv_t* h, void* dev, void* host, size_t bytes, bool to_device) 
     cudaError_t err[kStageThreads];
     std::thread th[kStageThreads];
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nt = (int)std::max(1u, std::min((unsigned)kStageThreads, hw ? hw : 1u));
+    const int nt = (int)std::max(1u, std::min((unsigned)kStageThreads, (hw ? hw : 1u) / (unsigned)std::max(1, h->stage_share)));
     const size_t per = ((bytes / nt) + 255) & ~(size_t)255;
     for (int t = 0; t < kStageThreads; t++) {
         const size_t lo = t < nt ? std::min(bytes, per * t) : bytes, hi = t >= nt - 1 ? bytes : std::min(bytes, per * (t + 1));

@@ -982,7 +982,10 @@ int fcfv_create_multi(fcfv_t** out, int ngpus) {
     if (!h->multi) { delete h; return FCFV_ERR_ALLOC; }
     h->multi->parts.resize(ngpus);
     int rc = FCFV_OK;
-    for (int p = 0; p < ngpus && !rc; p++) rc = fcfv_create(&h->multi->parts[p].h, p % count);
+    for (int p = 0; p < ngpus && !rc; p++) {
+        rc = fcfv_create(&h->multi->parts[p].h, p % count);
+        if (!rc) h->multi->parts[p].h->stage_share = ngpus;      // the parts copy concurrently (for_parts): they share the host's threads
+    }
     if (!rc && !oversub) rc = multi_load_nccl(h);
     if (!rc && !oversub) {
         std::vector<int> devs(ngpus);

@@ -31,6 +31,12 @@ def test_binding_covers_header():
         assert getattr(lib, s).restype is not None or s in ("fcfv_stream",), s
 
 
+def test_shipped_library_is_not_the_bounds_checked_build():
+    """fcfv_debug_bounds_violations: -1 = the index checks are compiled out (the build the benchmarks run); the checked
+    variant (make variant NAME=bounds DEFS=-DFCFV_BOUNDS_CHECK=1) returns a count >= 0 and is run by tools/gpu_bounds.sh."""
+    assert L.load().fcfv_debug_bounds_violations() == -1
+
+
 def test_library_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", L.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))

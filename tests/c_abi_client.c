@@ -12,7 +12,8 @@ int main(void) {
                     (void*)fcfv_block_size, (void*)fcfv_export, (void*)fcfv_export_rhs, (void*)fcfv_device_csr, (void*)fcfv_device_rhs,
                     (void*)fcfv_residuals, (void*)fcfv_element_values, (void*)fcfv_ph_residual, (void*)fcfv_ph_update_p,
                     (void*)fcfv_ph_fusc, (void*)fcfv_center_pressure, (void*)fcfv_run_local, (void*)fcfv_run_assemble,
-                    (void*)fcfv_run_residuals, (void*)fcfv_run_pipeline, (void*)fcfv_generate_structured, (void*)fcfv_comm_init};
+                    (void*)fcfv_run_residuals, (void*)fcfv_run_pipeline, (void*)fcfv_generate_structured, (void*)fcfv_comm_init,
+                    (void*)fcfv_compute_fcfv, (void*)fcfv_sparse_face_data, (void*)fcfv_sparse_face_info, (void*)fcfv_debug_bounds_violations};
     for (unsigned k = 0; k < sizeof syms / sizeof syms[0]; k++)
         if (!syms[k]) return 2;
     fcfv_t* h = NULL;
@@ -26,8 +27,16 @@ int main(void) {
     double alpha[1], beta[2], Z[4], tau[3], fu[6], fp[1], val[6];
     int64_t nuu = 0, nup = 0, nmu = 0, colptr[7], rowval[6];
     double sec = 0.0;
-    int rc = fcfv_set_mesh(h, 1, 3, e2f, bc, Om, nx, ny, G, ke, dl, taue, 1);
+    /* ComputeFCFV(mesh, ...) as the shims issue it: one call that takes the mesh with it ... */
+    double alpha1[1], beta1[2], Z1[4], tau1[3];
+    int rc = fcfv_compute_fcfv(h, 1, 3, e2f, bc, Om, nx, ny, G, ke, dl, taue, 1, NULL, FCFV_GRADIENT, 1.0, zero1, zero1, Vx, Vy, zero3, zero3,
+                               zero3, zero3, alpha1, beta1, Z1, tau1);
+    /* ... and the separate calls it stands for */
+    if (!rc) rc = fcfv_set_mesh(h, 1, 3, e2f, bc, Om, nx, ny, G, ke, dl, taue, 1);
     if (!rc) rc = fcfv_compute_local(h, FCFV_GRADIENT, 1.0, zero1, zero1, Vx, Vy, alpha, beta, Z, tau);
+    if (!rc && !(alpha1[0] == alpha[0] && beta1[0] == beta[0] && beta1[1] == beta[1] && Z1[0] == Z[0] && Z1[3] == Z[3] && tau1[2] == tau[2])) {
+        printf("fcfv_compute_fcfv differs from fcfv_set_mesh + fcfv_compute_local\n"); fcfv_destroy(h); return 1;
+    }
     if (!rc) rc = fcfv_assemble(h, FCFV_LOOP_OLD, FCFV_GRADIENT, 1.0, NULL, NULL, NULL, Vx, Vy, zero3, zero3, zero3, zero3, 0, &nuu, &nup, &nmu, &sec);
     if (!rc) rc = fcfv_export(h, FCFV_KUU, FCFV_CSC1_INT64, colptr, rowval, val);
     if (!rc) rc = fcfv_export_rhs(h, fu, fp);

@@ -142,3 +142,76 @@ def test_face_numbering_of_the_dat_converter():
     je2f, jxf, jyf, jbc = R.number_faces(T.J(xv), T.J(yv), T.JArr(np.asfortranarray(e2v)), int(e2v.shape[0]))
     assert np.array_equal(je2f.a, e2f) and np.array_equal(jxf.a, xf) and np.array_equal(jyf.a, yf)
     assert np.array_equal(jbc.a, bc)
+
+
+def _ph_line(text):
+    """One statement of StokesSolvers! (src/SolversFCFV_Stokes.jl) as a Python statement over NumPy vectors and SciPy sparse
+    matrices.  Rule table (anything else is refused): broadcast dots disappear (`.=`, `.-`, `.+`, `.*`, `./` act elementwise on
+    vectors, as NumPy's operators do); `x .+= y` -> `x = x + y`; `A*x` of a sparse matrix is SciPy's `*` (matrix product);
+    `A'` -> `A.T`; `spdiagm(v)` -> diagonal sparse matrix; `mesh.Ω` stays an attribute."""
+    import re
+    s = T._strip_comment(text).strip()
+    if not s:
+        return None
+    m = re.match(r"^(\w+)\s*\.\+=\s*(.*)$", s)
+    if m:
+        s = f"{m.group(1)} = {m.group(1)} + ({m.group(2)})"
+    s = s.replace(".=", "=")
+    for op in (".-", ".+", ".*", "./"):
+        s = s.replace(op, op[1])
+    s = re.sub(r"(\w)'", r"\1.T", s)
+    if re.search(r"[@!?:\[\]{}|&^]|\bfor\b|\bif\b|\bend\b", s):
+        raise ValueError(f"construct outside the rule table: {text!r}")
+    return s
+
+
+@pytest.mark.parametrize("case", [cases.Case("LowRes", "inclusion", 0, "Gradient", neumann=True), cases.Case("H1", "solkz", 1, "SymmetricGradient", tau_r=10.0)],
+                         ids=lambda c: c.name)
+def test_powell_hestenes_lines_from_the_source_text(case):
+    """a9: the lines of StokesSolvers! the GPU path replaces (SolversFCFV_Stokes.jl:6 Kpu, :23-25 Schur complement, :40-41 ru / rp,
+    :47 fusc, :49 pressure update), read from the reference's text and executed with SciPy's sparse algebra, against the oracle's
+    restatement: 1e-12 (sums are taken in another order); the Schur complement's stored pattern exactly."""
+    import os
+    import types
+    import scipy.sparse as sp
+    path = os.path.join(T.REFERENCE, "src", "SolversFCFV_Stokes.jl")
+    m, d = cases.build(case)
+    a, b, Z, Kuu3, Muu3, Kup3, fu, fp = _oracle(case, m, d)
+    nel, nf = m.nel, m.nf
+    rng = np.random.default_rng(7)
+    u0, p0 = rng.standard_normal(2 * nf), rng.standard_normal(nel)
+    penalty = 1.0e3
+    env = dict(Kuu=O.csc_to_scipy(Kuu3, (2 * nf, 2 * nf)), Kup=O.csc_to_scipy(Kup3, (2 * nf, nel)), fu=np.asarray(fu, dtype=float).ravel(),
+               fp=np.asarray(fp, dtype=float).ravel(), u=u0.copy(), p=p0.copy(), penalty=penalty, mesh=types.SimpleNamespace(ke=m.ke, Ω=m.Ω),
+               spdiagm=lambda v: sp.diags(np.asarray(v)).tocsc(), ru=None, rp=None, fusc=None)
+    sig = [ln for k, ln in T.extract_lines(path, 6, 6)][0]
+    kpu = re_default(sig, "Kpu")                                   # the keyword default `Kpu=-Kup'`
+    env["Kpu"] = eval(_ph_line(kpu), {}, env)
+    for first, last in ((23, 25), (40, 41), (47, 47), (49, 49)):
+        for k, ln in T.extract_lines(path, first, last):
+            st = _ph_line(ln)
+            if st:
+                exec(st, {}, env)
+    Kc, Pc = Kuu3, Kup3
+    ru, rp, nrm = O.ph_residual(m, Kc, Pc, fu, fp, u0, p0)
+    tol = lambda ref: 1e-12 * max(1.0, np.abs(ref).max())
+    assert np.abs(env["ru"] - ru).max() <= tol(ru) and np.abs(env["rp"] - rp).max() <= tol(rp)
+    assert abs(np.linalg.norm(env["ru"]) - nrm[0]) <= 1e-12 * nrm[0] and abs(np.linalg.norm(env["rp"]) - nrm[1]) <= 1e-12 * nrm[1]
+    fusc = O.ph_fusc(m, Pc, fu, fp, penalty, p0)
+    assert np.abs(env["fusc"] - fusc).max() <= tol(fusc)
+    pn = O.ph_update_p(m, Pc, fp, penalty, u0, p0)
+    assert np.abs(env["p"] - pn).max() <= tol(pn)
+    sc = O.csc_to_scipy(O.schur_complement(m, Kc, Pc, penalty), (2 * nf, 2 * nf))
+    ref = env["Kuusc"].tocsc()
+    ref.eliminate_zeros()                                           # Julia's sparse `.-` stores no zeros (dropzeros semantics)
+    ref.sort_indices(); sc.sort_indices()
+    assert np.array_equal(ref.indptr, sc.indptr) and np.array_equal(ref.indices, sc.indices)
+    assert np.abs(ref.data - sc.data).max() <= 1e-12 * np.abs(sc.data).max()
+
+
+def re_default(signature, name):
+    """`name=<expr>` out of a Julia keyword-argument list (up to the next top-level comma)."""
+    import re
+    m = re.search(rf"\b{name}\s*=\s*([^,;)]+)", signature)
+    assert m, signature
+    return m.group(1).strip()

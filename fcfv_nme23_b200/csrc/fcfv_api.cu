@@ -568,7 +568,11 @@ int build_face_lists(fcfv_t* h) {
             if (h->fstage_busy[k]) { CU(cudaEventSynchronize(h->fstage_ev[k])); h->fstage_busy[k] = false; }
         if (h->fstage) { CU(cudaFreeHost(h->fstage)); h->fstage = nullptr; h->fstage_cap = 0; }
         const size_t cap2 = need + need / 2 + 64;
-        CU(cudaHostAlloc((void**)&h->fstage, sizeof(double) * 6 * cap2, cudaHostAllocDefault));
+        if (cudaHostAlloc((void**)&h->fstage, sizeof(double) * 6 * cap2, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();         // no page-locked memory to be had: the boundary arrays keep going up whole
+            h->fstage = nullptr;
+            return FCFV_OK;
+        }
         h->fstage_cap = cap2;
     }
     TRY(ensure(h, h->fpack, sizeof(double) * 6 * h->fstage_cap));

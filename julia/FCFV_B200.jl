@@ -10,7 +10,7 @@ module FCFV_B200
 
 using SparseArrays, Printf
 
-export ComputeFCFV, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
+export ComputeFCFV, ComputeFCFV!, ElementAssemblyLoop, ElementAssemblyLoopNEW, ComputeResidualsFCFV_Stokes_o1, ComputeElementValues,
        SchurComplement, MeshGeometry!, PHResidual, PHUpdateP!, PHFusc, CenterPressure!, RenumberFacesFirstSeen!,
        RenumberElementsHilbert!, PrepareNumbering!, PinArrays, FusedPass, release!, NGPUS, CACHE_INPUTS, new_epoch!
 
